@@ -1,0 +1,127 @@
+"""ctypes binding of libdeepdish_b200.so (the C ABI declared in include/deepdish_b200.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing any operator
+raises.  Build it with ``python -m deepdish_b200.build`` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdeepdish_b200.so")
+
+DD_OK, DD_ERR_INVALID, DD_ERR_CUDA, DD_ERR_CAPACITY = 0, -1, -2, -3
+DD_MAX_LABELS = 128
+FLAG_TRACK_OVERFLOW, FLAG_DET_OVERFLOW, FLAG_LSAP_INFEASIBLE = 1, 2, 4
+
+_i32, _f64, _u64, _vp = ctypes.c_int32, ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p
+
+
+class TrackerConfig(ctypes.Structure):
+    _fields_ = [("n_streams", _i32), ("max_tracks", _i32), ("max_dets", _i32), ("budget", _i32),
+                ("feat_dim", _i32), ("n_labels", _i32), ("max_age", _i32), ("n_init", _i32),
+                ("max_cosine_distance", _f64), ("max_iou_distance", _f64),
+                ("label_motorbike", _i32), ("label_bicycle", _i32),
+                ("label_rank", _i32 * DD_MAX_LABELS)]
+
+
+LAYOUT_FIELDS = ["n_tracks", "next_id", "n_deleted", "err", "order", "deleted", "counts", "mean", "cov",
+                 "track_id", "hits", "age", "tsu", "state", "gal_len", "gal_pos", "gal", "lab_cnt",
+                 "lab_sum", "path_n", "path_last", "path_crossed", "gate", "cost", "det_xyah",
+                 "det_featn", "det_slot", "det_kind"]
+
+
+class TrackerLayout(ctypes.Structure):
+    _fields_ = [("total_bytes", _u64)] + [(n, _u64) for n in LAYOUT_FIELDS]
+
+
+def field_specs(cfg):
+    """name -> (dtype string, shape) of every array in the state blob."""
+    S, T, D, B, C = cfg.n_streams, cfg.max_tracks, cfg.max_dets, cfg.budget, cfg.n_labels
+    DW = (D + 31) // 32
+    i, f, d = "int32", "float32", "float64"
+    return {
+        "n_tracks": (i, (S,)), "next_id": (i, (S,)), "n_deleted": (i, (S,)), "err": (i, (S,)),
+        "order": (i, (S, T)), "deleted": (i, (S, T)), "counts": ("int64", (S, C, 4)),
+        "mean": (d, (S, T, 8)), "cov": (d, (S, T, 8, 8)), "track_id": (i, (S, T)),
+        "hits": (i, (S, T)), "age": (i, (S, T)), "tsu": (i, (S, T)), "state": (i, (S, T)),
+        "gal_len": (i, (S, T)), "gal_pos": (i, (S, T)), "gal": (f, (S, T, B, 128)),
+        "lab_cnt": (i, (S, T, C)), "lab_sum": (d, (S, T, C)), "path_n": (i, (S, T)),
+        "path_last": (d, (S, T, 2)), "path_crossed": (i, (S, T)), "gate": (i, (S, T, DW)),
+        "cost": (f, (S, T, D)), "det_xyah": (d, (S, D, 4)), "det_featn": (f, (S, D, 128)),
+        "det_slot": (i, (S, D)), "det_kind": (i, (S, D)),
+    }
+
+
+def make_config(n_streams, max_tracks, max_dets, budget, labels, max_age=30, n_init=3,
+                max_cosine_distance=0.2, max_iou_distance=0.7):
+    """Fill a dd_tracker_config from Python values; ``labels`` is the ordered list of label names."""
+    labels = list(labels)
+    if not 0 < len(labels) <= DD_MAX_LABELS:
+        raise ValueError("need 1..%d labels" % DD_MAX_LABELS)
+    if budget is None:
+        raise ValueError("the batched tracker needs a finite nn_budget (gallery ring capacity)")
+    cfg = TrackerConfig()
+    cfg.n_streams, cfg.max_tracks, cfg.max_dets, cfg.budget = n_streams, max_tracks, max_dets, budget
+    cfg.feat_dim, cfg.n_labels, cfg.max_age, cfg.n_init = 128, len(labels), max_age, n_init
+    cfg.max_cosine_distance, cfg.max_iou_distance = max_cosine_distance, max_iou_distance
+    cfg.label_motorbike = labels.index("motorbike") if "motorbike" in labels else -1
+    cfg.label_bicycle = labels.index("bicycle") if "bicycle" in labels else -1
+    ranks = {n: r for r, n in enumerate(sorted(labels))}
+    for k, n in enumerate(labels):
+        cfg.label_rank[k] = ranks[n]
+    return cfg
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library or raise -- never falls back to a CPU implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("deepdish_b200: CUDA library %s is missing; build it with "
+                           "`python -m deepdish_b200.build` (nvcc, sm_100a). There is no CPU fallback."
+                           % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.dd_version.restype = ctypes.c_char_p
+    cfgp, layp = ctypes.POINTER(TrackerConfig), ctypes.POINTER(TrackerLayout)
+    sigs = {
+        "dd_tracker_layout_query": [cfgp, layp],
+        "dd_tracker_init": [_vp, cfgp, _vp],
+        "dd_tracker_predict": [_vp, cfgp, _vp],
+        "dd_tracker_update": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+        "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
+        "dd_tracker_count_reduce": [_vp, cfgp, _vp, _vp],
+        "dd_tracker_status": [_vp, cfgp, ctypes.POINTER(_i32), _vp],
+        "dd_kalman_initiate": [_vp, _vp, _vp, _i32, _vp],
+        "dd_kalman_predict": [_vp, _vp, _i32, _vp],
+        "dd_kalman_project": [_vp, _vp, _vp, _vp, _i32, _vp],
+        "dd_kalman_update": [_vp, _vp, _vp, _i32, _vp],
+        "dd_kalman_gating_distance": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
+        "dd_nn_distance": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
+        "dd_iou_cost": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
+        "dd_lsap": [_vp, _i32, _i32, _i32, _vp, _vp, _vp],
+        "dd_set_difference_order": [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
+        "dd_intersection": [_vp, _i32, _vp, _vp],
+        "dd_nms": [_vp, _vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp],
+        "dd_yolo_decode": [_vp, _i32, ctypes.c_float, _i32, _i32, _i32, _i32, _vp, ctypes.c_float,
+                           _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc == DD_OK:
+        return
+    msg = {DD_ERR_INVALID: "invalid argument", DD_ERR_CUDA: "CUDA error",
+           DD_ERR_CAPACITY: "capacity exceeded"}.get(rc, "error %d" % rc)
+    if rc == DD_ERR_INVALID:
+        raise ValueError("%s: %s" % (what, msg))
+    raise RuntimeError("%s: %s" % (what, msg))

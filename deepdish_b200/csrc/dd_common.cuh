@@ -1,0 +1,140 @@
+// dd_common.cuh -- thread-group abstraction + exact-arithmetic helpers shared by all kernels.
+//
+// Every kernel body is a template over a "group" G: the set of threads that cooperate on one unit
+// of work (a track, a stream, a frame).  On the device G is a warp (WarpG) or a whole CTA (BlockG).
+// tests/hostemu compiles the very same bodies with HostG (one lane, all collectives trivial) into a
+// host library so the serial logic (scipy-exact LSAP, CPython set order, lifecycle) can be checked
+// on a machine without a GPU.  HostG is test scaffolding only: the product library never runs it.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define DD_HD __host__ __device__ __forceinline__
+#define DD_D __device__ __forceinline__
+#else
+#define DD_HD inline
+#define DD_D inline
+struct alignas(16) float4 { float x, y, z, w; };      // host emulation build only
+#endif
+
+// ---- f64/f32 arithmetic that must round like numpy's element-wise ops (no FMA contraction) -------
+// The library is compiled with -fmad=false; these wrappers additionally pin the intent where an
+// operation order decides a thresholded (bit-exact) output.
+#if defined(__CUDA_ARCH__)
+DD_D double dd_mul(double a, double b) { return __dmul_rn(a, b); }
+DD_D double dd_add(double a, double b) { return __dadd_rn(a, b); }
+DD_D double dd_sub(double a, double b) { return __dsub_rn(a, b); }
+DD_D double dd_div(double a, double b) { return __ddiv_rn(a, b); }
+DD_D double dd_sqrt(double a) { return __dsqrt_rn(a); }
+DD_D float dd_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+DD_D float dd_mulf(float a, float b) { return __fmul_rn(a, b); }
+DD_D float dd_addf(float a, float b) { return __fadd_rn(a, b); }
+DD_D float dd_subf(float a, float b) { return __fsub_rn(a, b); }
+DD_D float dd_divf(float a, float b) { return __fdiv_rn(a, b); }
+DD_D float dd_sqrtf(float a) { return __fsqrt_rn(a); }
+#else
+inline double dd_mul(double a, double b) { volatile double r = a * b; return r; }
+inline double dd_add(double a, double b) { return a + b; }
+inline double dd_sub(double a, double b) { return a - b; }
+inline double dd_div(double a, double b) { return a / b; }
+inline double dd_sqrt(double a) { return sqrt(a); }
+inline float dd_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
+inline float dd_mulf(float a, float b) { volatile float r = a * b; return r; }
+inline float dd_addf(float a, float b) { return a + b; }
+inline float dd_subf(float a, float b) { return a - b; }
+inline float dd_divf(float a, float b) { return a / b; }
+inline float dd_sqrtf(float a) { return sqrtf(a); }
+#endif
+
+DD_HD double dd_max(double a, double b) { return a > b ? a : b; }   // np.maximum for non-NaN input
+DD_HD double dd_min(double a, double b) { return a < b ? a : b; }
+#if defined(__CUDA_ARCH__)
+DD_D int dd_ctz(unsigned w) { return __ffs((int)w) - 1; }
+#else
+inline int dd_ctz(unsigned w) { return __builtin_ctz(w); }
+#endif
+DD_HD int dd_imin(int a, int b) { return a < b ? a : b; }
+DD_HD int dd_imax(int a, int b) { return a > b ? a : b; }
+
+// (value, preference) pair used by the LSAP column scan: lower value wins, ties -> higher pref.
+struct DDKey {
+    double val;
+    int pref;
+};
+DD_HD bool dd_key_better(const DDKey& a, const DDKey& b) {   // is a strictly better than b
+    return (a.val < b.val) || (a.val == b.val && a.pref > b.pref);
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------- WarpG
+struct WarpG {
+    static constexpr int NL = 32;
+    int lane;
+    __device__ explicit WarpG() : lane(threadIdx.x & 31) {}
+    __device__ void sync() const { __syncwarp(); }
+    __device__ float sum(float v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ int sum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+    __device__ int imax(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ int imin(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ float fmax(float v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = ::fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ unsigned bor(unsigned v) const { return __reduce_or_sync(0xffffffffu, v); }
+    __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+    // exclusive prefix count of a per-lane predicate + total (ordered compaction)
+    __device__ int scan_excl(bool p, int& total) const {
+        unsigned m = __ballot_sync(0xffffffffu, p);
+        total = __popc(m);
+        return __popc(m & ((1u << lane) - 1u));
+    }
+    __device__ DDKey best(DDKey k) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            DDKey t;
+            t.val = __shfl_xor_sync(0xffffffffu, k.val, o);
+            t.pref = __shfl_xor_sync(0xffffffffu, k.pref, o);
+            if (dd_key_better(t, k)) k = t;
+        }
+        return k;
+    }
+};
+
+// ---------------------------------------------------------------------------------------- BlockG
+// Whole CTA; collectives go through a small shared-memory scratch supplied by the kernel.
+struct BlockG {
+    int lane;      // thread index in the CTA
+    int nl;        // blockDim.x
+    __device__ explicit BlockG() : lane(threadIdx.x), nl(blockDim.x) {}
+    __device__ void sync() const { __syncthreads(); }
+};
+#endif
+
+// ---------------------------------------------------------------------------------------- HostG
+struct HostG {
+    static constexpr int NL = 1;
+    int lane = 0;
+    int nl = 1;
+    void sync() const {}
+    float sum(float v) const { return v; }
+    double sum(double v) const { return v; }
+    int sum(int v) const { return v; }
+    int imax(int v) const { return v; }
+    int imin(int v) const { return v; }
+    float fmax(float v) const { return v; }
+    unsigned bor(unsigned v) const { return v; }
+    bool any(bool p) const { return p; }
+    int scan_excl(bool p, int& total) const { total = p ? 1 : 0; return 0; }
+    DDKey best(DDKey k) const { return k; }
+};

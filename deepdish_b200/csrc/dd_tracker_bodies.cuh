@@ -1,0 +1,651 @@
+// dd_tracker_bodies.cuh -- per-unit bodies of the batched DeepSORT tick (group-generic, see dd_common.cuh).
+//
+//   dd_prep_det        (stream, det)    Detection.to_xyah + feature normalisation
+//   dd_predict_track   (stream, track)  Track.predict
+//   dd_gate_cosine     (stream, track)  gating_distance + gallery min cosine distance for gated pairs
+//   dd_match_stream    (stream)         matching cascade + IoU stage + track lifecycle
+//   dd_apply_det       (stream, det)    Kalman update / initiate + gallery append + label vote
+//   dd_countline       (stream)         count-line crossing + per-label counters
+#pragma once
+#include "dd_view.h"
+#include "dd_kalman.cuh"
+#include "dd_lsap.cuh"
+
+#define DD_INFTY_COST 1e5          // deep_sort/linear_assignment.py:8
+
+#if defined(__CUDA_ARCH__)
+DD_D void dd_atomic_add_ll(long long* p, long long v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+DD_D void dd_atomic_or(int* p, int v) { atomicOr(p, v); }
+#else
+inline void dd_atomic_add_ll(long long* p, long long v) { *p += v; }
+inline void dd_atomic_or(int* p, int v) { *p |= v; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Detection.to_xyah (deep_sort/detection.py:43-50) and b / |b| (deep_sort/nn_matching.py:53).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+DD_HD void dd_prep_det(const G& g, const DDView& V, int s, int d, const double* det_tlwh,
+                       const float* det_feat, const int* det_count) {
+    int nd = det_count[s];
+    if (nd > V.D) nd = V.D;
+    if (d >= nd) return;
+    const size_t sd = (size_t)s * V.D + d;
+    if (g.lane == 0) {
+        const double* b = det_tlwh + sd * 4;
+        double* o = V.det_xyah + sd * 4;
+        o[0] = dd_add(b[0], dd_div(b[2], 2.0));
+        o[1] = dd_add(b[1], dd_div(b[3], 2.0));
+        o[2] = dd_div(b[2], b[3]);
+        o[3] = b[3];
+    }
+    const float4* f4 = (const float4*)(det_feat + sd * DD_FEAT_DIM);
+    float4* o4 = (float4*)(V.det_featn + sd * DD_FEAT_DIM);
+    float ss = 0.f;
+    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) {
+        const float4 x = f4[k];
+        ss = dd_fmaf(x.x, x.x, ss); ss = dd_fmaf(x.y, x.y, ss);
+        ss = dd_fmaf(x.z, x.z, ss); ss = dd_fmaf(x.w, x.w, ss);
+    }
+    const float nrm = dd_sqrtf(g.sum(ss));
+    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) {
+        float4 x = f4[k];
+        x.x = dd_divf(x.x, nrm); x.y = dd_divf(x.y, nrm);
+        x.z = dd_divf(x.z, nrm); x.w = dd_divf(x.w, nrm);
+        o4[k] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Track.predict (deep_sort/track.py:113-125).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+DD_HD void dd_predict_track(const G& g, const DDView& V, int s, int t) {
+    if (t >= V.n_tracks[s]) return;
+    const size_t slot = (size_t)s * V.T + V.order[(size_t)s * V.T + t];
+    dd_kf_predict(g, V.mean + slot * 8, V.cov + slot * 64);
+    if (g.lane == 0) {
+        V.age[slot] += 1;
+        V.tsu[slot] += 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate-first appearance cost for one confirmed track:
+//   gate bit d  = not (gating_distance > chi2inv95[4])     (linear_assignment.py:182-189)
+//   cost[d]     = min over the track's gallery of 1 - a.b   (nn_matching.py:78-96), only where the
+//                 gate bit is set -- every other entry of the reference cost matrix is overwritten
+//                 with INFTY_COST before it is read, so it is never computed here.
+// Gallery rows are unit vectors (normalised when appended); each lane owns one float4 of the 128-d
+// row, up to DD_CH candidates share one pass over the gallery.
+// ------------------------------------------------------------------------------------------------
+#define DD_CH 4
+template <class G>
+DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* det_count) {
+    if (t >= V.n_tracks[s]) return;
+    const size_t slot = (size_t)s * V.T + V.order[(size_t)s * V.T + t];
+    if (V.state[slot] != DD_STATE_CONFIRMED) return;
+    int nd = det_count[s];
+    if (nd > V.D) nd = V.D;
+    const double* mean = V.mean + slot * 8;
+    double S[16], L[16];
+    dd_kf_project_cov(mean, V.cov + slot * 64, S);
+    dd_chol4(S, L);
+    const double pm[4] = {mean[0], mean[1], mean[2], mean[3]};
+    const int glen = V.gal_len[slot];
+    const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
+    constexpr int KP = (DD_FEAT_DIM / 4) / G::NL;          // float4 chunks per lane (1 on a warp)
+    for (int base = 0; base < nd; base += 32) {
+        unsigned word = 0;
+        const int lim = dd_imin(base + 32, nd);
+        for (int j = base + g.lane; j < lim; j += G::NL) {
+            const double d2 = dd_maha_sq(L, pm, V.det_xyah + ((size_t)s * V.D + j) * 4);
+            if (!(d2 > DD_CHI2INV95_4)) word |= 1u << (j - base);
+        }
+        word = g.bor(word);
+        if (g.lane == 0) V.gate[slot * V.DW + (base >> 5)] = word;
+        while (word) {
+            int cj[DD_CH];
+            int nc = 0;
+            while (word && nc < DD_CH) {
+                const int b = dd_ctz(word);
+                word &= word - 1;
+                cj[nc++] = base + b;
+            }
+            float4 q[DD_CH][KP];
+            for (int c = 0; c < DD_CH; ++c) {
+                const float4* f4 = (const float4*)(V.det_featn + ((size_t)s * V.D + cj[c < nc ? c : 0]) * DD_FEAT_DIM);
+                int kk = 0;
+                for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) q[c][kk] = f4[k];
+            }
+            float best[DD_CH];
+            for (int c = 0; c < DD_CH; ++c) best[c] = -3.0e38f;
+            for (int gi = 0; gi < glen; ++gi) {
+                float p[DD_CH];
+                for (int c = 0; c < DD_CH; ++c) p[c] = 0.f;
+                int kk = 0;
+                for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
+                    const float4 a = gal4[(size_t)gi * (DD_FEAT_DIM / 4) + k];
+#pragma unroll
+                    for (int c = 0; c < DD_CH; ++c) {
+                        p[c] = dd_fmaf(a.x, q[c][kk].x, p[c]);
+                        p[c] = dd_fmaf(a.y, q[c][kk].y, p[c]);
+                        p[c] = dd_fmaf(a.z, q[c][kk].z, p[c]);
+                        p[c] = dd_fmaf(a.w, q[c][kk].w, p[c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < DD_CH; ++c) {
+                    const float tot = g.sum(p[c]);
+                    best[c] = tot > best[c] ? tot : best[c];
+                }
+            }
+            if (g.lane == 0)
+                for (int c = 0; c < nc; ++c) V.cost[slot * V.D + cj[c]] = dd_subf(1.0f, best[c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-stream matching + lifecycle.  Shared-memory plan (bytes, n = max(T, D)):
+//   LSAP scratch | trk_slot[T] trk_tsu[T] trk_det[T] rows[T] lista[T] listb[T] | cols/undA[D] undB[D]
+//   | trk_state[T] flag[T] (bytes) | three set tables of dd_set_table_slots(T) shorts
+// ------------------------------------------------------------------------------------------------
+struct DDMatchSmem {
+    DDLsapScratch ls;
+    short *trk_slot, *trk_tsu, *trk_det, *rows, *lista, *listb, *undA, *undB, *r2c, *c2r;
+    unsigned char *trk_state, *flag;
+    short *tabA, *tabB, *tabC;
+    int tab_cap;
+};
+
+DD_HD size_t dd_match_smem_bytes(int T, int D) {
+    const int n = T > D ? T : D;
+    size_t b = dd_lsap_scratch_bytes(n);
+    b += (size_t)T * 2 * 6 + (size_t)D * 2 * 2 + (size_t)n * 2 * 2;
+    b += (size_t)T * 2;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)dd_set_table_slots(T) * 2 * 3;
+    return (b + 15) & ~(size_t)15;
+}
+
+DD_HD void dd_match_carve(char* mem, int T, int D, DDMatchSmem& m) {
+    const int n = T > D ? T : D;
+    dd_lsap_carve(mem, n, m.ls);
+    char* p = mem + dd_lsap_scratch_bytes(n);
+    m.trk_slot = (short*)p; p += T * 2;
+    m.trk_tsu = (short*)p; p += T * 2;
+    m.trk_det = (short*)p; p += T * 2;
+    m.rows = (short*)p; p += T * 2;
+    m.lista = (short*)p; p += T * 2;
+    m.listb = (short*)p; p += T * 2;
+    m.undA = (short*)p; p += D * 2;
+    m.undB = (short*)p; p += D * 2;
+    m.r2c = (short*)p; p += n * 2;
+    m.c2r = (short*)p; p += n * 2;
+    m.trk_state = (unsigned char*)p; p += T;
+    m.flag = (unsigned char*)p; p += T;
+    p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    m.tab_cap = dd_set_table_slots(T);
+    m.tabA = (short*)p; p += m.tab_cap * 2;
+    m.tabB = (short*)p; p += m.tab_cap * 2;
+    m.tabC = (short*)p;
+}
+
+// cost functors: (r, c) are positions in the rows[] / cols[] lists of the current sub-problem.
+struct DDCosineCost {      // tracker.py:97-105 + linear_assignment.py:57
+    const unsigned* gate;  // stream base [T, DW]
+    const float* cost;     // stream base [T, D]
+    const short *trk_slot, *rows, *cols;
+    int D, DW;
+    double thr, clip;
+    DD_HD double raw(int r, int c) const {
+        const int slot = trk_slot[rows[r]];
+        const int d = cols[c];
+        const bool pass = (gate[slot * DW + (d >> 5)] >> (d & 31)) & 1u;
+        return pass ? (double)cost[slot * D + d] : DD_INFTY_COST;
+    }
+    DD_HD double operator()(int r, int c) const {
+        const double v = raw(r, c);
+        return v > thr ? clip : v;
+    }
+};
+
+struct DDIouCost {         // iou_matching.py:7-81 + linear_assignment.py:57
+    const double* mean;    // stream base [T, 8]
+    const double* det_tlwh;// stream base [D, 4]
+    const short *trk_slot, *trk_tsu, *rows, *cols;
+    double thr, clip;
+    DD_HD double raw(int r, int c) const {
+        const int t = rows[r];
+        if (trk_tsu[t] > 1) return DD_INFTY_COST;
+        const double* m = mean + (size_t)trk_slot[t] * 8;
+        // Track.to_tlwh (track.py:84-97)
+        const double w = dd_mul(m[2], m[3]), h = m[3];
+        const double x = dd_sub(m[0], dd_div(w, 2.0)), y = dd_sub(m[1], dd_div(h, 2.0));
+        const double* b = det_tlwh + (size_t)cols[c] * 4;
+        const double tlx = dd_max(x, b[0]), tly = dd_max(y, b[1]);
+        const double brx = dd_min(dd_add(x, w), dd_add(b[0], b[2]));
+        const double bry = dd_min(dd_add(y, h), dd_add(b[1], b[3]));
+        const double iw = dd_max(0.0, dd_sub(brx, tlx)), ih = dd_max(0.0, dd_sub(bry, tly));
+        const double inter = dd_mul(iw, ih);
+        const double uni = dd_sub(dd_add(dd_mul(w, h), dd_mul(b[2], b[3])), inter);
+        return dd_sub(1.0, dd_div(inter, uni));
+    }
+    DD_HD double operator()(int r, int c) const {
+        const double v = raw(r, c);
+        return v > thr ? clip : v;
+    }
+};
+
+template <class F>
+struct DDTransposed {
+    const F& f;
+    DD_HD explicit DDTransposed(const F& f_) : f(f_) {}
+    DD_HD double operator()(int i, int j) const { return f(j, i); }
+};
+
+// linear_assignment.py:11-75.  rows[nr] = track indices, cols = *und (ordered unmatched detections,
+// nund entries).  Records matches in trk_det[], rewrites *und / nund with the new ordered
+// unmatched-detection list.  Returns 0 or -1 (infeasible).
+template <class G, class F>
+DD_HD int dd_min_cost_matching(const G& g, const F& cost, double thr, DDMatchSmem& m, int nr,
+                               short*& und, short*& und_next, int& nund) {
+    const int nc = nund;
+    if (nr == 0 || nc == 0) return 0;
+    int rc;
+    if (nc < nr) {
+        DDTransposed<F> ct(cost);
+        rc = dd_lsap_solve(g, nc, nr, ct, m.ls);
+        for (int c = g.lane; c < nc; c += G::NL) m.c2r[c] = m.ls.col4row[c];
+        for (int r = g.lane; r < nr; r += G::NL) m.r2c[r] = m.ls.row4col[r];
+    } else {
+        rc = dd_lsap_solve(g, nr, nc, cost, m.ls);
+        for (int r = g.lane; r < nr; r += G::NL) m.r2c[r] = m.ls.col4row[r];
+        for (int c = g.lane; c < nc; c += G::NL) m.c2r[c] = m.ls.row4col[c];
+    }
+    g.sync();
+    if (rc != 0) return rc;
+    int n2 = 0;
+    for (int base = 0; base < nc; base += G::NL) {       // columns without a row, in column order
+        const int c = base + g.lane;
+        const bool p = c < nc && m.c2r[c] < 0;
+        int tot;
+        const int pos = g.scan_excl(p, tot);
+        if (p) und_next[n2 + pos] = und[c];
+        n2 += tot;
+    }
+    for (int base = 0; base < nr; base += G::NL) {       // assigned but over threshold, in row order
+        const int r = base + g.lane;
+        bool p = false;
+        int c = -1;
+        if (r < nr) {
+            c = m.r2c[r];
+            if (c >= 0) {
+                p = cost(r, c) > thr;
+                if (!p) m.trk_det[m.rows[r]] = und[c];
+            }
+        }
+        int tot;
+        const int pos = g.scan_excl(p, tot);
+        if (p) und_next[n2 + pos] = und[c];
+        n2 += tot;
+    }
+    g.sync();
+    short* t = und; und = und_next; und_next = t;
+    nund = n2;
+    return 0;
+}
+
+template <class G>
+DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det_tlwh,
+                           const int* det_count, int* out_det_track_id, char* smem) {
+    DDMatchSmem m;
+    dd_match_carve(smem, V.T, V.D, m);
+    const size_t sT = (size_t)s * V.T, sD = (size_t)s * V.D;
+    int nd = det_count[s];
+    if (nd > V.D) {
+        nd = V.D;
+        if (g.lane == 0) V.err[s] |= DD_FLAG_DET_OVERFLOW;
+    }
+    if (nd < 0) nd = 0;
+    const int nT = V.n_tracks[s];
+    // slots deleted by the previous update become free now
+    {
+        const int ndel = V.n_deleted[s];
+        for (int k = g.lane; k < ndel; k += G::NL) V.state[sT + V.deleted[sT + k]] = DD_STATE_FREE;
+    }
+    for (int t = g.lane; t < nT; t += G::NL) {
+        const int slot = V.order[sT + t];
+        m.trk_slot[t] = (short)slot;
+        m.trk_tsu[t] = (short)V.tsu[sT + slot];
+        m.trk_state[t] = (unsigned char)V.state[sT + slot];
+        m.trk_det[t] = -1;
+    }
+    for (int d = g.lane; d < nd; d += G::NL) m.undA[d] = (short)d;
+    g.sync();
+    short *und = m.undA, *und_next = m.undB;
+    int nund = nd;
+    int infeasible = 0;
+
+    // ---- confirmed tracks (tracker.py:108-111) -> lista, and the deepest occupied cascade level
+    int nconf = 0, max_tsu = 0;
+    for (int base = 0; base < nT; base += G::NL) {
+        const int t = base + g.lane;
+        const bool p = t < nT && m.trk_state[t] == DD_STATE_CONFIRMED;
+        int tot;
+        const int pos = g.scan_excl(p, tot);
+        if (p) {
+            m.lista[nconf + pos] = (short)t;
+            max_tsu = dd_imax(max_tsu, (int)m.trk_tsu[t]);
+        }
+        nconf += tot;
+    }
+    max_tsu = g.imax(max_tsu);
+    g.sync();
+
+    // ---- matching cascade (linear_assignment.py:121-139)
+    {
+        DDCosineCost cc;
+        cc.gate = V.gate + sT * V.DW; cc.cost = V.cost + sT * V.D;
+        cc.trk_slot = m.trk_slot; cc.rows = m.rows; cc.D = V.D; cc.DW = V.DW;
+        cc.thr = V.thr_cos; cc.clip = dd_add(V.thr_cos, 1e-5);
+        const int depth = dd_imin(V.max_age, max_tsu);
+        for (int level = 0; level < depth; ++level) {
+            if (nund == 0) break;
+            int nr = 0;
+            for (int base = 0; base < nconf; base += G::NL) {
+                const int k = base + g.lane;
+                const bool p = k < nconf && m.trk_tsu[m.lista[k]] == 1 + level;
+                int tot;
+                const int pos = g.scan_excl(p, tot);
+                if (p) m.rows[nr + pos] = m.lista[k];
+                nr += tot;
+            }
+            g.sync();
+            if (nr == 0) continue;
+            cc.cols = und;
+            if (dd_min_cost_matching(g, cc, V.thr_cos, m, nr, und, und_next, nund) != 0) infeasible = 1;
+        }
+    }
+
+    // ---- unmatched confirmed tracks in CPython set order (linear_assignment.py:140)
+    int n_unm_a = 0;
+    {
+        int nmatched = 0;
+        for (int k = g.lane; k < nT; k += G::NL) m.flag[k] = 0;
+        g.sync();
+        for (int k = g.lane; k < nconf; k += G::NL) {
+            const int t = m.lista[k];
+            if (m.trk_det[t] >= 0) { m.flag[t] = 1; ++nmatched; }
+        }
+        nmatched = g.sum(nmatched);
+        g.sync();
+        if (g.lane == 0)
+            n_unm_a = dd_set_difference_order_serial(m.lista, nconf, m.flag, nmatched, m.listb,
+                                                     m.tabA, m.tabB, m.tabC, m.tab_cap);
+        n_unm_a = g.imax(n_unm_a);
+        g.sync();
+    }
+
+    // ---- IoU stage rows: unconfirmed (ascending) + set-ordered unmatched confirmed with tsu == 1
+    int nr = 0;
+    for (int base = 0; base < nT; base += G::NL) {
+        const int t = base + g.lane;
+        const bool p = t < nT && m.trk_state[t] != DD_STATE_CONFIRMED;
+        int tot;
+        const int pos = g.scan_excl(p, tot);
+        if (p) m.rows[nr + pos] = (short)t;
+        nr += tot;
+    }
+    for (int base = 0; base < n_unm_a; base += G::NL) {
+        const int k = base + g.lane;
+        const bool p = k < n_unm_a && m.trk_tsu[m.listb[k]] == 1;
+        int tot;
+        const int pos = g.scan_excl(p, tot);
+        if (p) m.rows[nr + pos] = m.listb[k];
+        nr += tot;
+    }
+    g.sync();
+    {
+        DDIouCost ic;
+        ic.mean = V.mean + sT * 8; ic.det_tlwh = det_tlwh + sD * 4;
+        ic.trk_slot = m.trk_slot; ic.trk_tsu = m.trk_tsu; ic.rows = m.rows; ic.cols = und;
+        ic.thr = V.thr_iou; ic.clip = dd_add(V.thr_iou, 1e-5);
+        if (dd_min_cost_matching(g, ic, V.thr_iou, m, nr, und, und_next, nund) != 0) infeasible = 1;
+    }
+    if (infeasible && g.lane == 0) V.err[s] |= DD_FLAG_LSAP_INFEASIBLE;
+
+    // ---- lifecycle (tracker.py:72-81, track.py:127-152,190-196)
+    for (int d = g.lane; d < V.D; d += G::NL) {
+        V.det_kind[sD + d] = 0;
+        V.det_slot[sD + d] = -1;
+        if (out_det_track_id) out_det_track_id[sD + d] = -1;
+    }
+    g.sync();
+    for (int t = g.lane; t < nT; t += G::NL) {
+        const size_t slot = sT + m.trk_slot[t];
+        const int d = m.trk_det[t];
+        int st = m.trk_state[t];
+        if (d >= 0) {
+            const int hits = V.hits[slot] + 1;
+            V.hits[slot] = hits;
+            V.tsu[slot] = 0;
+            if (st == DD_STATE_TENTATIVE && hits >= V.n_init) st = DD_STATE_CONFIRMED;
+            V.det_kind[sD + d] = 1;
+            V.det_slot[sD + d] = m.trk_slot[t];
+            if (out_det_track_id) out_det_track_id[sD + d] = V.track_id[slot];
+        } else {
+            if (st == DD_STATE_TENTATIVE) st = DD_STATE_DELETED;
+            else if (m.trk_tsu[t] > V.max_age) st = DD_STATE_DELETED;
+        }
+        V.state[slot] = st;
+        m.trk_state[t] = (unsigned char)st;
+    }
+    g.sync();
+    // free slots in ascending slot order -> lista
+    int nfree = 0;
+    for (int base = 0; base < V.T; base += G::NL) {
+        const int k = base + g.lane;
+        const bool p = k < V.T && V.state[sT + k] == DD_STATE_FREE;
+        int tot;
+        const int pos = g.scan_excl(p, tot);
+        if (p) m.lista[nfree + pos] = (short)k;
+        nfree += tot;
+    }
+    g.sync();
+    int nnew = nund;
+    if (nnew > nfree) {
+        nnew = nfree;
+        if (g.lane == 0) V.err[s] |= DD_FLAG_TRACK_OVERFLOW;
+    }
+    const int id0 = V.next_id[s];
+    for (int k = g.lane; k < nnew; k += G::NL) {          // tracker.py:135-138, ids in list order
+        const int d = und[k];
+        const size_t slot = sT + m.lista[k];
+        V.track_id[slot] = id0 + k;
+        V.hits[slot] = 1;
+        V.age[slot] = 1;
+        V.tsu[slot] = 0;
+        V.state[slot] = DD_STATE_TENTATIVE;
+        V.det_kind[sD + d] = 2;
+        V.det_slot[sD + d] = m.lista[k];
+        if (out_det_track_id) out_det_track_id[sD + d] = id0 + k;
+    }
+    // stable split of the old list into live / deleted (tracker.py:80-81), then append new tracks
+    int nlive = 0, ndel = 0;
+    for (int base = 0; base < nT; base += G::NL) {
+        const int t = base + g.lane;
+        const bool in = t < nT;
+        const bool dead = in && m.trk_state[t] == DD_STATE_DELETED;
+        int tot_l, tot_d;
+        const int pl = g.scan_excl(in && !dead, tot_l);
+        const int pd = g.scan_excl(dead, tot_d);
+        if (in && !dead) V.order[sT + nlive + pl] = m.trk_slot[t];
+        if (dead) V.deleted[sT + ndel + pd] = m.trk_slot[t];
+        nlive += tot_l;
+        ndel += tot_d;
+    }
+    g.sync();
+    for (int k = g.lane; k < nnew; k += G::NL) V.order[sT + nlive + k] = m.lista[k];
+    if (g.lane == 0) {
+        V.n_tracks[s] = nlive + nnew;
+        V.n_deleted[s] = ndel;
+        V.next_id[s] = id0 + nnew;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-detection state update: Track.update (track.py:127-152) or Tracker._initiate_track
+// (tracker.py:135-138 -> kalman_filter.py:55-86, track.py:67-82), then the gallery append that
+// metric.partial_fit performs (nn_matching.py:137-154; ring of `budget` unit vectors) and the label
+// vote.  scratch: >= 64 doubles per group.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+DD_HD void dd_apply_det(const G& g, const DDView& V, int s, int d, const float* det_conf,
+                        const int* det_label, double* scratch) {
+    const size_t sd = (size_t)s * V.D + d;
+    const int kind = V.det_kind[sd];
+    if (kind == 0) return;
+    const size_t slot = (size_t)s * V.T + V.det_slot[sd];
+    const double* z = V.det_xyah + sd * 4;
+    if (kind == 1) {
+        dd_kf_update(g, V.mean + slot * 8, V.cov + slot * 64, z, scratch);
+    } else {
+        dd_kf_initiate(g, z, V.mean + slot * 8, V.cov + slot * 64);
+        for (int c = g.lane; c < V.C; c += G::NL) {
+            V.lab_cnt[slot * V.C + c] = 0;
+            V.lab_sum[slot * V.C + c] = 0.0;
+        }
+        if (g.lane == 0) {
+            V.gal_len[slot] = 0;
+            V.gal_pos[slot] = 0;
+            V.path_n[slot] = 0;
+            V.path_crossed[slot] = 0;
+        }
+        g.sync();
+    }
+    const int pos = V.gal_pos[slot];
+    const int len = V.gal_len[slot];
+    const float4* src = (const float4*)(V.det_featn + sd * DD_FEAT_DIM);
+    float4* dst = (float4*)(V.gal + (slot * (size_t)V.B + pos) * DD_FEAT_DIM);
+    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) dst[k] = src[k];
+    g.sync();
+    if (g.lane == 0) {
+        V.gal_pos[slot] = (pos + 1 == V.B) ? 0 : pos + 1;
+        V.gal_len[slot] = len < V.B ? len + 1 : V.B;
+        int lbl = det_label[sd];
+        if (lbl < 0) lbl = 0;
+        if (lbl >= V.C) lbl = V.C - 1;
+        V.lab_cnt[slot * V.C + lbl] += 1;
+        V.lab_sum[slot * V.C + lbl] = dd_add(V.lab_sum[slot * V.C + lbl], (double)det_conf[sd]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Count-line (tools/intersection.py:4-24, deepdish.py:1041-1112,1303-1312, track.py:154-188).
+// ------------------------------------------------------------------------------------------------
+DD_HD double dd_cross2(double a0, double a1, double b0, double b1) {
+    return dd_sub(dd_mul(a0, b1), dd_mul(a1, b0));
+}
+
+// intersection(p, pr, q, qs) with points given as (x, y) pairs.
+DD_HD bool dd_segments_intersect(double px, double py, double prx, double pry, double qx, double qy,
+                                 double qsx, double qsy) {
+    const double eps = 2.220446049250313e-16;            // sys.float_info.epsilon
+    const double rx = dd_sub(prx, px), ry = dd_sub(pry, py);
+    const double sx = dd_sub(qsx, qx), sy = dd_sub(qsy, qy);
+    const double rxs = dd_cross2(rx, ry, sx, sy);
+    const double qmpx = dd_sub(qx, px), qmpy = dd_sub(qy, py);
+    const double qpxr = dd_cross2(qmpx, qmpy, rx, ry);
+    if (fabs(rxs) < eps) {
+        if (fabs(qpxr) < eps) {
+            const double rr = dd_add(dd_mul(rx, rx), dd_mul(ry, ry));
+            const double ax = dd_div(rx, rr), ay = dd_div(ry, rr);
+            double t0 = dd_add(dd_mul(qmpx, ax), dd_mul(qmpy, ay));
+            double t1 = dd_add(t0, dd_add(dd_mul(sx, ax), dd_mul(sy, ay)));
+            if (t0 > t1) { const double tmp = t0; t0 = t1; t1 = tmp; }
+            return !(t1 < 0.0 || t0 > 1.0);
+        }
+        return false;
+    }
+    const double t = dd_div(dd_cross2(qmpx, qmpy, sx, sy), rxs);
+    const double u = dd_div(qpxr, rxs);
+    return 0.0 <= t && t <= 1.0 && 0.0 <= u && u <= 1.0;
+}
+
+// Track.get_label (track.py:154-188): Dirichlet-expected vote, reverse (value, name) order,
+// motorbike/bicycle rule.  Returns the label index (or -1 when the track has no votes).
+DD_HD int dd_get_label(const DDView& V, size_t slot) {
+    const int* cnt = V.lab_cnt + slot * V.C;
+    const double* sum = V.lab_sum + slot * V.C;
+    double tot_c = 0.0, tot_a = 0.0;
+    for (int c = 0; c < V.C; ++c)
+        if (cnt[c] > 0) {
+            tot_c = dd_add(tot_c, (double)cnt[c]);
+            tot_a = dd_add(tot_a, dd_div(sum[c], (double)cnt[c]));
+        }
+    const double den = dd_add(tot_c, tot_a);
+    int b1 = -1, b2 = -1;
+    double v1 = 0.0, v2 = 0.0;
+    for (int c = 0; c < V.C; ++c) {
+        if (cnt[c] <= 0) continue;
+        const double v = dd_div(dd_add(dd_div(sum[c], (double)cnt[c]), (double)cnt[c]), den);
+        const bool gt1 = b1 < 0 || v > v1 || (v == v1 && V.label_rank[c] > V.label_rank[b1]);
+        if (gt1) {
+            b2 = b1; v2 = v1;
+            b1 = c; v1 = v;
+        } else {
+            const bool gt2 = b2 < 0 || v > v2 || (v == v2 && V.label_rank[c] > V.label_rank[b2]);
+            if (gt2) { b2 = c; v2 = v; }
+        }
+    }
+    if (b2 >= 0 && b1 == V.lbl_motorbike && b2 == V.lbl_bicycle && V.lbl_motorbike >= 0)
+        return (v1 > dd_mul(v2, 4.0)) ? b1 : b2;
+    return b1;
+}
+
+template <class G>
+DD_HD void dd_countline(const G& g, const DDView& V, int s, const double* line) {
+    const size_t sT = (size_t)s * V.T;
+    const double p1x = line[0], p1y = line[1], q1x = line[2], q1y = line[3];
+    long long* cnt = V.counts + (size_t)s * V.C * 4;
+    // deleted tracks (deepdish.py:1041-1044): only the LAST one's result survives the overwrite
+    const int ndel = V.n_deleted[s];
+    if (g.lane == 0 && ndel > 0) {
+        const size_t slot = sT + V.deleted[sT + ndel - 1];
+        if (V.path_n[slot] > 1 && V.path_crossed[slot]) {
+            const int l = dd_get_label(V, slot);
+            if (l >= 0) dd_atomic_add_ll(cnt + l * 4 + 3, 1);
+        }
+    }
+    const int nT = V.n_tracks[s];
+    for (int t = g.lane; t < nT; t += G::NL) {
+        const size_t slot = sT + V.order[sT + t];
+        if (V.state[slot] != DD_STATE_CONFIRMED || V.tsu[slot] > 1) continue;
+        const double* m = V.mean + slot * 8;
+        // Track.to_tlbr (track.py:84-111) and the bottom-centre point (deepdish.py:1060-1063)
+        const double w = dd_mul(m[2], m[3]), h = m[3];
+        const double x = dd_sub(m[0], dd_div(w, 2.0)), y = dd_sub(m[1], dd_div(h, 2.0));
+        const double x2 = dd_add(x, w), y2 = dd_add(y, h);
+        const double bx = dd_div(dd_add(x, x2), 2.0), by = y2;
+        const int n = V.path_n[slot];
+        if (n >= 1) {
+            const double lx = V.path_last[slot * 2], ly = V.path_last[slot * 2 + 1];
+            // p2 = latest, q2 = previous (deepdish.py:1073-1075)
+            const double cp = dd_cross2(dd_sub(q1x, p1x), dd_sub(q1y, p1y), dd_sub(lx, bx), dd_sub(ly, by));
+            if (dd_segments_intersect(p1x, p1y, q1x, q1y, bx, by, lx, ly)) {
+                const int l = dd_get_label(V, slot);
+                if (l >= 0) {
+                    dd_atomic_add_ll(cnt + l * 4 + (cp >= 0.0 ? 0 : 1), 1);
+                    dd_atomic_add_ll(cnt + l * 4 + 2, 1);
+                }
+            }
+            // any_intersection walks the path forwards: segment (previous, latest)
+            if (dd_segments_intersect(p1x, p1y, q1x, q1y, lx, ly, bx, by)) V.path_crossed[slot] = 1;
+        }
+        V.path_last[slot * 2] = bx;
+        V.path_last[slot * 2 + 1] = by;
+        V.path_n[slot] = n + 1;
+    }
+}

@@ -1,0 +1,209 @@
+/* deepdish_b200.h -- C ABI of the B200-native tracking-by-detection hot path of AdaptiveCity/deepdish.
+ *
+ * Drop-in boundary.  The reference is 100 % Python and has no FFI of its own;
+ * each entry point below names the reference interface (file:line under /root/reference) whose
+ * arithmetic it replaces.  The reference-side binding a maintainer would add is a ctypes stub, shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `host_`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous
+ *     with respect to the host, outputs are valid after the stream is synchronised;
+ *   - return value: DD_OK or a negative DD_ERR_* code; nothing is thrown across the ABI;
+ *   - the caller (PyTorch, cudaMalloc, ...) owns every buffer; the library keeps no global state;
+ *   - row-major, densely packed arrays; f64 = double, f32 = float, i32 = int32_t, i64 = int64_t.
+ */
+#ifndef DEEPDISH_B200_H
+#define DEEPDISH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_OK             0
+#define DD_ERR_INVALID   (-1)   /* bad argument (size, NULL, unsupported feature dim ...)            */
+#define DD_ERR_CUDA      (-2)   /* a CUDA runtime call / launch failed                               */
+#define DD_ERR_CAPACITY  (-3)   /* T > max_tracks or D > max_dets: never silently truncated          */
+
+#define DD_MAX_LABELS   128
+#define DD_FEAT_DIM     128     /* MARS re-ID feature width (tools/generate_detections.py:137-140)   */
+
+/* track states, deep_sort/track.py:15-17 (0 = slot unused) */
+#define DD_STATE_FREE       0
+#define DD_STATE_TENTATIVE  1
+#define DD_STATE_CONFIRMED  2
+#define DD_STATE_DELETED    3
+
+/* per-stream error bits in the `err` state array (sticky; read with dd_tracker_status) */
+#define DD_FLAG_TRACK_OVERFLOW  1   /* needed more than max_tracks slots              */
+#define DD_FLAG_DET_OVERFLOW    2   /* det_count[s] > max_dets                        */
+#define DD_FLAG_LSAP_INFEASIBLE 4   /* scipy would raise ValueError (NaN / inf cost)  */
+
+const char* dd_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched DeepSORT tracker: S independent streams, one `deep_sort.tracker.Tracker` each.
+ * Replaces deep_sort/tracker.py:40-138 (+ track.py, kalman_filter.py, nn_matching.py,
+ * iou_matching.py, linear_assignment.py and scipy.optimize.linear_sum_assignment underneath).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dd_tracker_config {
+    int32_t n_streams;          /* S                                                                */
+    int32_t max_tracks;         /* Tmax: slots per stream (live + deleted-this-tick + new)          */
+    int32_t max_dets;           /* Dmax: detections per stream per tick                             */
+    int32_t budget;             /* nn_budget: gallery vectors kept per track (nn_matching.py:150)   */
+    int32_t feat_dim;           /* must be DD_FEAT_DIM                                              */
+    int32_t n_labels;           /* C <= DD_MAX_LABELS                                               */
+    int32_t max_age;            /* tracker.py:40 (deepdish.py:1418 default 60)                      */
+    int32_t n_init;             /* tracker.py:40                                                    */
+    double  max_cosine_distance;/* metric.matching_threshold (deepdish.py:1412 default 0.2)         */
+    double  max_iou_distance;   /* tracker.py:40 default 0.7                                        */
+    int32_t label_motorbike;    /* label ids for the track.py:175-183 special case, -1 if absent    */
+    int32_t label_bicycle;
+    int32_t label_rank[DD_MAX_LABELS]; /* rank of each label NAME in ascending string order
+                                          (tie-break of the reverse sort in track.py:170)           */
+} dd_tracker_config;
+
+/* Byte offsets of every array inside the caller-owned state blob (all multiples of 256). */
+typedef struct dd_tracker_layout {
+    uint64_t total_bytes;
+    /* per stream */
+    uint64_t n_tracks;      /* i32 [S]            live tracks                                       */
+    uint64_t next_id;       /* i32 [S]            tracker.py:49 _next_id                            */
+    uint64_t n_deleted;     /* i32 [S]            len(tracker.deleted_tracks)                       */
+    uint64_t err;           /* i32 [S]            DD_FLAG_* bits                                    */
+    uint64_t order;         /* i32 [S,Tmax]       slot of the k-th live track (creation order)      */
+    uint64_t deleted;       /* i32 [S,Tmax]       slots deleted by the last update (creation order) */
+    uint64_t counts;        /* i64 [S,C,4]        pos, neg, int, del per label                      */
+    /* per slot */
+    uint64_t mean;          /* f64 [S,Tmax,8]                                                       */
+    uint64_t cov;           /* f64 [S,Tmax,8,8]                                                     */
+    uint64_t track_id;      /* i32 [S,Tmax]                                                         */
+    uint64_t hits;          /* i32 [S,Tmax]                                                         */
+    uint64_t age;           /* i32 [S,Tmax]                                                         */
+    uint64_t tsu;           /* i32 [S,Tmax]       time_since_update                                 */
+    uint64_t state;         /* i32 [S,Tmax]       DD_STATE_*                                        */
+    uint64_t gal_len;       /* i32 [S,Tmax]       valid gallery vectors (<= budget)                 */
+    uint64_t gal_pos;       /* i32 [S,Tmax]       ring write position                               */
+    uint64_t gal;           /* f32 [S,Tmax,budget,128]  unit-normalised features (ring)             */
+    uint64_t lab_cnt;       /* i32 [S,Tmax,C]     votes per label (track.py:75-80,147-151)          */
+    uint64_t lab_sum;       /* f64 [S,Tmax,C]     sum of confidences per label                      */
+    uint64_t path_n;        /* i32 [S,Tmax]       points in the count-line path db                  */
+    uint64_t path_last;     /* f64 [S,Tmax,2]     last bottom-centre point                          */
+    uint64_t path_crossed;  /* i32 [S,Tmax]       any path segment crossed the line                 */
+    /* per-tick scratch / outputs */
+    uint64_t gate;          /* u32 [S,Tmax,ceil(Dmax/32)]  bit d set: d^2 <= chi2inv95[4]           */
+    uint64_t cost;          /* f32 [S,Tmax,Dmax]  min cosine distance (valid where gate bit set)    */
+    uint64_t det_xyah;      /* f64 [S,Dmax,4]                                                       */
+    uint64_t det_featn;     /* f32 [S,Dmax,128]   unit-normalised detection features                */
+    uint64_t det_slot;      /* i32 [S,Dmax]       slot the detection was applied to                 */
+    uint64_t det_kind;      /* i32 [S,Dmax]       0 none, 1 Kalman update, 2 new track              */
+} dd_tracker_layout;
+
+/* Host-only arithmetic: fills `host_out`.  No CUDA call. */
+int dd_tracker_layout_query(const dd_tracker_config* host_cfg, dd_tracker_layout* host_out);
+
+/* Zero the blob and set _next_id = 1 (tracker.py:46-49). */
+int dd_tracker_init(void* state, const dd_tracker_config* host_cfg, void* stream);
+
+/* Tracker.predict (tracker.py:51-57 -> track.py:113-125 -> kalman_filter.py:88-123). */
+int dd_tracker_predict(void* state, const dd_tracker_config* host_cfg, void* stream);
+
+/* Tracker.update (tracker.py:59-93): gating + cosine cost, matching cascade, IoU stage, Kalman update,
+ * mark_missed, _initiate_track, deleted/live split, partial_fit.
+ *   det_tlwh  f64 [S,Dmax,4]   Detection.tlwh        (detection.py:30)
+ *   det_conf  f32 [S,Dmax]     Detection.confidence
+ *   det_label i32 [S,Dmax]     index into the label list
+ *   det_feat  f32 [S,Dmax,128] Detection.feature
+ *   det_count i32 [S]          detections present this tick (<= Dmax)
+ *   out_det_track_id i32 [S,Dmax]  (may be NULL) track id each detection was matched to / created as */
+int dd_tracker_update(void* state, const dd_tracker_config* host_cfg,
+                      const double* det_tlwh, const float* det_conf, const int32_t* det_label,
+                      const float* det_feat, const int32_t* det_count,
+                      int32_t* out_det_track_id, void* stream);
+
+/* Count-line step (deepdish.py:1035-1114 counting part, :1303-1312; tools/intersection.py:4-30).
+ *   line f64 [S,4] (x1,y1,x2,y2 per stream) or, with line_per_stream = 0, one f64[4] for all streams. */
+int dd_tracker_countline(void* state, const dd_tracker_config* host_cfg, const double* line,
+                         int line_per_stream, void* stream);
+
+/* Sum the per-stream counters into out_counts i64 [C,4] (the tensor handed to the NCCL all-reduce). */
+int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int64_t* out_counts,
+                            void* stream);
+
+/* OR of all per-stream DD_FLAG_* bits -> *host_flags.  Synchronises `stream`. */
+int dd_tracker_status(void* state, const dd_tracker_config* host_cfg, int32_t* host_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone batched operators behind the per-function deep_sort API.
+ * ---------------------------------------------------------------------------------------------- */
+/* KalmanFilter.initiate (kalman_filter.py:55-86): xyah f64[n,4] -> mean f64[n,8], cov f64[n,64]. */
+int dd_kalman_initiate(const double* xyah, double* mean, double* cov, int32_t n, void* stream);
+/* KalmanFilter.predict (kalman_filter.py:88-123), in place. */
+int dd_kalman_predict(double* mean, double* cov, int32_t n, void* stream);
+/* KalmanFilter.project (kalman_filter.py:125-152): -> pmean f64[n,4], pcov f64[n,16]. */
+int dd_kalman_project(const double* mean, const double* cov, double* pmean, double* pcov, int32_t n,
+                      void* stream);
+/* KalmanFilter.update (kalman_filter.py:154-186), in place, one measurement per track. */
+int dd_kalman_update(double* mean, double* cov, const double* xyah, int32_t n, void* stream);
+/* KalmanFilter.gating_distance (kalman_filter.py:188-229): n tracks x m measurements -> f64[n,m]. */
+int dd_kalman_gating_distance(const double* mean, const double* cov, const double* xyah, int32_t n,
+                              int32_t m, int32_t only_position, double* out, void* stream);
+
+/* NearestNeighborDistanceMetric.distance (nn_matching.py:156-177), dense.
+ *   gallery f32 [G,128] raw sample vectors, gal_offsets i32 [n+1] (target i owns rows off[i]..off[i+1]),
+ *   feats f32 [m,128] raw, out f64 [n,m].  metric: 0 = cosine (nn_matching.py:78-96),
+ *   1 = euclidean (nn_matching.py:57-75). */
+int dd_nn_distance(const float* gallery, const int32_t* gal_offsets, const float* feats, int32_t n,
+                   int32_t m, int32_t metric, double* out, void* stream);
+
+/* iou_matching.iou_cost (iou_matching.py:42-81): track_tlwh f64[n,4], tsu i32[n], det_tlwh f64[m,4]
+ * -> f64[n,m] (1 - IoU, rows with tsu > 1 = 1e5). */
+int dd_iou_cost(const double* track_tlwh, const int32_t* tsu, const double* det_tlwh, int32_t n,
+                int32_t m, double* out, void* stream);
+
+/* scipy.optimize.linear_sum_assignment as called at linear_assignment.py:58, INCLUDING scipy's
+ * tie-breaking (scipy 1.18.1 rectangular_lsap.cpp).  cost f64 [b,nr,nc]; out_col4row i32 [b,nr]
+ * (-1 = row unassigned, only when nr > nc); out_status i32 [b] (0 ok, 1 infeasible). */
+int dd_lsap(const double* cost, int32_t b, int32_t nr, int32_t nc, int32_t* out_col4row,
+            int32_t* out_status, void* stream);
+
+/* Iteration order of CPython 3.12 `list(set(a) - set(m))` (linear_assignment.py:140) for batches of
+ * small non-negative ints: a i32 [b,na_max] with na i32 [b]; m i32 [b,nm_max] with nm i32 [b];
+ * out i32 [b,na_max], out_n i32 [b].  Values must be < 4096. */
+int dd_set_difference_order(const int32_t* a, const int32_t* na, int32_t na_max, const int32_t* m,
+                            const int32_t* nm, int32_t nm_max, int32_t b, int32_t* out,
+                            int32_t* out_n, void* stream);
+
+/* tools/intersection.py:4-24 for n segment pairs: seg f64 [n,8] = p,pr,q,qs -> out i32 [n]. */
+int dd_intersection(const double* seg, int32_t n, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detector post-processing.
+ * ---------------------------------------------------------------------------------------------- */
+/* preprocessing.non_max_suppression (deep_sort/preprocessing.py:6-73), one block per frame.
+ *   boxes f64 [b,nmax,4] tlwh, scores f32 [b,nmax] (unique per frame), counts i32 [b],
+ *   out_keep i32 [b,nmax] original indices in pick order (descending score), out_nkeep i32 [b]. */
+int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int32_t b, int32_t nmax,
+           double max_overlap, int32_t* out_keep, int32_t* out_nkeep, void* stream);
+
+/* YOLOV5.detect_image post-processing (tools/yolov5.py:115-146) fused with the box filter
+ * (deepdish.py:946-955) for b frames:
+ *   head: f32 [b,na,5+nc], or u8 with (scale, zero_point) when head_is_u8 != 0 (yolov5.py:115-118);
+ *   wanted u8 [nc] (1 = label in wanted_labels); img_w/img_h = PIL image size (yolov5.py:98,131);
+ *   frame_w/frame_h = camera viewport of the box filter (deepdish.py:945).
+ *   Candidates are emitted in ascending anchor order, at most ncap per frame (more -> DD_FLAG_DET_OVERFLOW
+ *   in out_flags[b]):  out_tlwh f64 [b,ncap,4] integer-valued boxes after the filter, out_score f32,
+ *   out_class i32, out_anchor i32, out_count i32 [b]. */
+int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t zero_point, int32_t b,
+                   int32_t na, int32_t nc, const uint8_t* wanted, float score_thr, int32_t img_w,
+                   int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap, double* out_tlwh,
+                   float* out_score, int32_t* out_class, int32_t* out_anchor, int32_t* out_count,
+                   int32_t* out_flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPDISH_B200_H */

@@ -1,0 +1,68 @@
+"""Shared parity harness: drive the oracle (one Trkr per stream) next to a batched implementation
+(CUDA BatchedTracker or the host emulation) on the same Scene and compare every tick."""
+import numpy as np
+
+from oracle import deepsort as od, countline as oc
+
+LABELS3 = ["person", "bicycle", "car"]
+
+
+class OracleStreams:
+    def __init__(self, n_streams, labels, budget=100, max_age=30, n_init=3, max_cos=0.2, max_iou=0.7,
+                 line=None, port=False):
+        self.labels = list(labels)
+        kw = dict(lsap=od.lsap_port, set_order=od.cpython_set_difference_order) if port else {}
+        self.trk = [od.Trkr(od.Metric("cosine", max_cos, budget), max_iou, max_age, n_init, **kw)
+                    for _ in range(n_streams)]
+        line = oc.default_line(640, 480) if line is None else np.asarray(line, float).reshape(2, 2)
+        self.cnt = [oc.LineCounter(line, self.labels) for _ in range(n_streams)]
+        self.det_ids = None
+
+    def step(self, batch, streams=None):
+        """batch: deepdish_b200.scene.SceneBatch on the host.  Returns per-stream det->track id lists."""
+        out = []
+        for s, (t, c) in enumerate(zip(self.trk, self.cnt)):
+            tlwh, conf, lab, feat = batch.stream(s if streams is None else streams[s])
+            dets = [od.Det(tlwh[i], self.labels[lab[i]], conf[i], feat[i]) for i in range(len(conf))]
+            t.trace = {}
+            t.predict()
+            t.update(dets)
+            c.step(t)
+            ids = [-1] * len(dets)
+            for tid, d in t.trace["match_ids"]:
+                ids[d] = tid
+            nxt = t._next_id - len(t.trace["unmatched_detections"])
+            for k, d in enumerate(t.trace["unmatched_detections"]):
+                ids[d] = nxt + k
+            out.append(ids)
+        self.det_ids = out
+        return out
+
+
+def compare_stream(o_trk, o_cnt, view, s, labels, rtol=1e-4, gallery=True):
+    """Compare oracle tracker/counter of one stream with the SoA state `view` (dict of numpy arrays)."""
+    n = int(view["n_tracks"][s])
+    slots = view["order"][s, :n]
+    assert n == len(o_trk.tracks), (s, n, len(o_trk.tracks))
+    assert [int(x) for x in view["track_id"][s, slots]] == [t.track_id for t in o_trk.tracks]
+    assert [int(x) for x in view["state"][s, slots]] == [t.state for t in o_trk.tracks]
+    assert [int(x) for x in view["hits"][s, slots]] == [t.hits for t in o_trk.tracks]
+    assert [int(x) for x in view["age"][s, slots]] == [t.age for t in o_trk.tracks]
+    assert [int(x) for x in view["tsu"][s, slots]] == [t.time_since_update for t in o_trk.tracks]
+    nd = int(view["n_deleted"][s])
+    dsl = view["deleted"][s, :nd]
+    assert [int(x) for x in view["track_id"][s, dsl]] == [t.track_id for t in o_trk.deleted_tracks]
+    assert int(view["next_id"][s]) == o_trk._next_id
+    if n:
+        om = np.stack([t.mean for t in o_trk.tracks])
+        ocv = np.stack([t.covariance for t in o_trk.tracks])
+        np.testing.assert_allclose(view["mean"][s, slots], om, rtol=rtol, atol=1e-9)
+        np.testing.assert_allclose(view["cov"][s, slots], ocv, rtol=rtol, atol=1e-12)
+    if gallery:
+        for k, t in enumerate(o_trk.tracks):
+            sl = slots[k]
+            if t.is_confirmed():
+                g = np.asarray(o_trk.metric.samples[t.track_id])
+                assert int(view["gal_len"][s, sl]) == len(g)
+    if o_cnt is not None:
+        np.testing.assert_array_equal(view["counts"][s], o_cnt.counts(labels))
