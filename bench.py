@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- tracked stream-frames/s of the batched tracking-by-detection tick on B200.
+
+Workload (BASELINE.json configs[2], "C3"): 1024 concurrent camera streams per GPU x ~50 detections
+per frame, 128-d features, nn_budget 100, max_age 60: Tracker.predict + Tracker.update (gating +
+gallery cosine + matching cascade + IoU stage + Kalman update + lifecycle) + count-line + count
+reduction (+ NCCL all-reduce of the [C,4] counters when N > 1).  A "step" is one tick over all
+streams of this rank.  Streams shard across ranks with no data-path collective ("weak" scaling:
+1024 streams per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # CUDA arm
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # CPU reference arm
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LABELS = ["person", "bicycle", "car"]
+S_PER_GPU = 1024
+N_OBJECTS = 50
+DMAX = 64
+TMAX = 128
+BUDGET = 100
+MAX_AGE = 60
+PREROLL = 110          # setup ticks so galleries reach the budget
+WORKLOAD = ("C3: %d streams/GPU x ~%d dets/frame, 128-d feats, nn_budget %d, max_age %d, "
+            "predict+cascade+IoU+Kalman update+countline+count reduce" % (S_PER_GPU, N_OBJECTS, BUDGET, MAX_AGE))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (the oracle port of the reference's numpy/scipy path; the reference itself is
+# pure Python and cannot travel to the GPU box -- see DESIGN.md).  One stream per worker process.
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, preroll, warm, steps = args
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    import torch
+    torch.set_num_threads(1)
+    from deepdish_b200.scene import Scene
+    from oracle import deepsort as od, countline as oc
+    sc = Scene(1, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=seed)
+    trk = od.Trkr(od.Metric("cosine", 0.2, BUDGET), 0.7, MAX_AGE, 3)
+    cnt = oc.LineCounter(oc.default_line(640, 480), LABELS)
+    frames = []
+    for _ in range(preroll + warm + steps):
+        frames.append(sc.step().stream(0))
+
+    def tick(fr):
+        tlwh, conf, lab, feat = fr
+        dets = [od.Det(tlwh[i], LABELS[lab[i]], conf[i], feat[i]) for i in range(len(conf))]
+        trk.predict()
+        trk.update(dets)
+        cnt.step(trk)
+
+    for fr in frames[:preroll + warm]:
+        tick(fr)
+    t0 = time.perf_counter()
+    for fr in frames[preroll + warm:]:
+        tick(fr)
+    return time.perf_counter() - t0
+
+
+def cpu_reference(steps, warm, preroll=100, workers=None):
+    import multiprocessing as mp
+    cores = workers or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(1000 + i, preroll, warm, steps) for i in range(cores)])
+    wall = max(times)
+    return {"value": cores * steps / wall, "unit": "stream-frames/s", "cores": cores, "kind": "port",
+            "sample": "%d streams (1 per core) x %d frames after %d pre-roll frames, oracle port of the "
+                      "reference numpy/scipy path, BLAS threads 1" % (cores, steps, preroll + warm),
+            "ms_per_step": 1e3 * wall / steps}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.2 <= ts <= t1 + 0.2):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from deepdish_b200.batched import BatchedTracker
+    from deepdish_b200.scene import Scene
+    K, W = args.steps, args.warmup
+    S = S_PER_GPU
+
+    # CPU baseline first (rank 0, N=1 only) -- before the GPU is busy, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(steps=60, warm=0, preroll=100)
+
+    bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev)
+    scene = Scene(S, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=1234 + rank, device=dev)
+    for _ in range(PREROLL):
+        bt.step(scene.step())
+    bt.reduce_counts()
+    bt.check()
+    frames = [scene.step() for _ in range(W + K)]             # inputs resident in HBM
+    e2e_dev = [scene.step() for _ in range(W + K)]
+    torch.cuda.synchronize()
+
+    def tick(b, ev=None):
+        bt.predict()
+        if ev is None:
+            bt.update(b.tlwh, b.conf, b.label, b.feat, b.count)
+        else:
+            bt.update_profiled(b.tlwh, b.conf, b.label, b.feat, b.count, ev)
+        bt.countline()
+        bt.all_reduce_counts()
+
+    for b in frames[:W]:
+        tick(b)
+    evs = [bt.new_events(5) for _ in range(K)]
+    g0 = int(bt.gallery_vectors().sum())
+    conf0 = int(((bt.v["state"] == 2).sum()))
+    dets = sum(int(b.count.sum()) for b in frames[W:])
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    start.record()
+    for i, b in enumerate(frames[W:]):
+        tick(b, evs[i])
+    end.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms = start.elapsed_time(end)
+    g1 = int(bt.gallery_vectors().sum())
+    conf1 = int(((bt.v["state"] == 2).sum()))
+    bt.check()
+    stage = [0.0, 0.0, 0.0, 0.0]
+    for ev in evs:
+        for j in range(4):
+            stage[j] += bt.elapsed_ms(ev[j], ev[j + 1]) / K
+    # ---- end-to-end through the public API with pinned host buffers
+    host = [b.to("cpu").pin() for b in e2e_dev]
+    del e2e_dev
+    ids_host = torch.empty((S, DMAX), dtype=torch.int32).pin_memory()
+    cnt_host = torch.empty((len(LABELS), 4), dtype=torch.int64).pin_memory()
+    for hb in host[:W]:
+        ids, cnt = bt.step_host(hb)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    es.record()
+    for hb in host[W:]:
+        ids, cnt = bt.step_host(hb)
+        ids_host.copy_(ids, non_blocking=True)
+        cnt_host.copy_(cnt, non_blocking=True)
+    ee.record()
+    torch.cuda.synchronize()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - tw0)
+    e2e_ms = max(es.elapsed_time(ee), e2e_wall_ms)
+    bt.check()
+    h2d = host[0].nbytes()
+    d2h = ids_host.numel() * 4 + cnt_host.numel() * 8
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(g0 + g1) / 2, float(conf0 + conf1) / 2, float(dets)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_all, e2e_all = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        G, TC = float(tot[0]) / world, float(tot[1]) / world            # per GPU, per tick
+        Dn = float(tot[2]) / world / K
+        gc_bytes = 512.0 * G + 512.0 * Dn + 576.0 * TC + 32.0 * Dn
+        gc_ms = stage[1]
+        achieved = gc_bytes / (gc_ms * 1e-3) / 1e9
+        tick_bytes = 512.0 * (G + Dn + Dn) + 1152.0 * (TC * 1.1) + 44.0 * Dn
+        out = {
+            "metric": "tracked stream-frames/s", "value": S * world * K / (ms_all * 1e-3),
+            "unit": "stream-frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_all / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (Kalman/gating/IoU/LSAP/count-line) + f32 (cosine)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "max_tracks": TMAX, "max_dets": DMAX,
+                       "preroll_ticks": PREROLL, "gallery_vectors_per_stream": G / S,
+                       "confirmed_tracks_per_stream": TC / S, "dets_per_frame": Dn / S,
+                       "l2": "inputs larger than L2: %.2f GB of galleries streamed per tick" % (512 * G / 1e9)},
+            "e2e": {"value": S * world * K / (e2e_all * 1e-3), "unit": "stream-frames/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K},
+            "gpu_launches": K * 7,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_gate_cosine", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": gc_bytes, "ms_per_launch": gc_ms,
+                         "tick_bytes": tick_bytes, "tick_frac": tick_bytes / (ms_all / K * 1e-3) / 1e9 / peak},
+            "stage_ms": {"prep": stage[0], "gate_cosine": stage[1], "match": stage[2], "apply": stage[3],
+                         "tick_total": ms_all / K},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(steps=args.steps, warm=args.warmup, preroll=100)
+    out = {"impl": "reference", "metric": "tracked stream-frames/s", "value": r["value"],
+           "unit": "stream-frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64 (Kalman/gating/IoU/LSAP/count-line) + f32 (cosine)", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "sample": r["sample"]},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": "stream-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,11 @@ def lib():
         "dd_tracker_init": [_vp, cfgp, _vp],
         "dd_tracker_predict": [_vp, cfgp, _vp],
         "dd_tracker_update": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+        "dd_tracker_update_profiled": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       ctypes.POINTER(_vp)],
+        "dd_event_create": [ctypes.POINTER(_vp)],
+        "dd_event_destroy": [_vp],
+        "dd_event_elapsed_ms": [_vp, _vp, ctypes.POINTER(ctypes.c_float)],
         "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
         "dd_tracker_count_reduce": [_vp, cfgp, _vp, _vp],
         "dd_tracker_status": [_vp, cfgp, ctypes.POINTER(_i32), _vp],

@@ -131,29 +131,67 @@ int dd_tracker_predict(void* state, const dd_tracker_config* cfg, void* stream) 
     return DD_OK;
 }
 
-int dd_tracker_update(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
-                      const float* det_conf, const int32_t* det_label, const float* det_feat,
-                      const int32_t* det_count, int32_t* out_det_track_id, void* stream) {
+static int dd_update_impl(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                          const float* det_conf, const int32_t* det_label, const float* det_feat,
+                          const int32_t* det_count, int32_t* out_det_track_id, cudaStream_t st,
+                          cudaEvent_t* ev) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
     if (!det_tlwh || !det_conf || !det_label || !det_feat || !det_count) return DD_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    k_prep<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_tlwh, det_feat, det_count);
-    DD_CHECK_LAUNCH();
-    k_gate_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
-    DD_CHECK_LAUNCH();
     const size_t smem = dd_match_smem_bytes(V.T, V.D);
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) return DD_ERR_INVALID;
         if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return DD_ERR_CUDA;
     }
+    if (ev) cudaEventRecord(ev[0], st);
+    k_prep<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_tlwh, det_feat, det_count);
+    DD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[1], st);
+    k_gate_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
+    DD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[2], st);
     k_match<<<V.S, 32, smem, st>>>(V, det_tlwh, det_count, out_det_track_id);
     DD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[3], st);
     k_apply<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_conf, det_label);
     DD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[4], st);
     return DD_OK;
+}
+
+int dd_tracker_update(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                      const float* det_conf, const int32_t* det_label, const float* det_feat,
+                      const int32_t* det_count, int32_t* out_det_track_id, void* stream) {
+    return dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count,
+                          out_det_track_id, (cudaStream_t)stream, nullptr);
+}
+
+int dd_tracker_update_profiled(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                               const float* det_conf, const int32_t* det_label, const float* det_feat,
+                               const int32_t* det_count, int32_t* out_det_track_id, void* stream,
+                               void* const* host_events5) {
+    if (!host_events5) return DD_ERR_INVALID;
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; ++i) ev[i] = (cudaEvent_t)host_events5[i];
+    return dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count,
+                          out_det_track_id, (cudaStream_t)stream, ev);
+}
+
+int dd_event_create(void** host_out) {
+    if (!host_out) return DD_ERR_INVALID;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return DD_ERR_CUDA;
+    *host_out = (void*)e;
+    return DD_OK;
+}
+
+int dd_event_destroy(void* ev) { return cudaEventDestroy((cudaEvent_t)ev) == cudaSuccess ? DD_OK : DD_ERR_CUDA; }
+
+int dd_event_elapsed_ms(void* start, void* end, float* host_ms) {
+    if (!host_ms) return DD_ERR_INVALID;
+    return cudaEventElapsedTime(host_ms, (cudaEvent_t)start, (cudaEvent_t)end) == cudaSuccess ? DD_OK : DD_ERR_CUDA;
 }
 
 int dd_tracker_countline(void* state, const dd_tracker_config* cfg, const double* line,

@@ -124,6 +124,18 @@ int dd_tracker_update(void* state, const dd_tracker_config* host_cfg,
                       const float* det_feat, const int32_t* det_count,
                       int32_t* out_det_track_id, void* stream);
 
+/* dd_tracker_update that also records five caller-supplied CUDA events on `stream`: before the
+ * detection prep kernel and after each of prep / gate+cosine / match / apply (no synchronisation), so a
+ * benchmark can time each kernel inside its own timed region.  host_events5: host array of 5 events
+ * made by dd_event_create. */
+int dd_tracker_update_profiled(void* state, const dd_tracker_config* host_cfg,
+                               const double* det_tlwh, const float* det_conf, const int32_t* det_label,
+                               const float* det_feat, const int32_t* det_count,
+                               int32_t* out_det_track_id, void* stream, void* const* host_events5);
+int dd_event_create(void** host_out);
+int dd_event_destroy(void* ev);
+int dd_event_elapsed_ms(void* start, void* end, float* host_ms);   /* both events must have completed */
+
 /* Count-line step (deepdish.py:1035-1114 counting part, :1303-1312; tools/intersection.py:4-30).
  *   line f64 [S,4] (x1,y1,x2,y2 per stream) or, with line_per_stream = 0, one f64[4] for all streams. */
 int dd_tracker_countline(void* state, const dd_tracker_config* host_cfg, const double* line,
@@ -172,7 +184,7 @@ int dd_lsap(const double* cost, int32_t b, int32_t nr, int32_t nc, int32_t* out_
 
 /* Iteration order of CPython 3.12 `list(set(a) - set(m))` (linear_assignment.py:140) for batches of
  * small non-negative ints: a i32 [b,na_max] with na i32 [b]; m i32 [b,nm_max] with nm i32 [b];
- * out i32 [b,na_max], out_n i32 [b].  Values must be < 4096. */
+ * out i32 [b,na_max], out_n i32 [b].  Values must be < 1024. */
 int dd_set_difference_order(const int32_t* a, const int32_t* na, int32_t na_max, const int32_t* m,
                             const int32_t* nm, int32_t nm_max, int32_t b, int32_t* out,
                             int32_t* out_n, void* stream);
