@@ -79,7 +79,97 @@ DD_HD void dd_predict_track(const G& g, const DDView& V, int s, int t) {
 // Gallery rows are unit vectors (normalised when appended); each lane owns one float4 of the 128-d
 // row, up to DD_CH candidates share one pass over the gallery.
 // ------------------------------------------------------------------------------------------------
-#define DD_CH 4
+#define DD_CH 4          // candidates sharing one pass over the gallery
+#define DD_ROWS 8        // gallery rows in flight per pass step (8 x 512 B = 4 KB of loads per warp)
+
+// Cross-lane sum of N = DD_ROWS * NC per-lane partials v[r * NC + c] by a transposing butterfly
+// (N-1 + log2(32/N) shuffles instead of 5 N), folded into a running maximum over rows per candidate.
+// WarpG: after the butterfly lane L owns the total of value index idx(L) = top log2(N) bits of L, so its
+// candidate is idx(L) % NC; the running maximum lives in acc[0] and dd_fold_finish combines lanes.
+// HostG: one lane owns everything, acc[c] is the maximum for candidate c.
+#if defined(__CUDACC__)
+template <int NC>
+__device__ __forceinline__ void dd_fold_max(const WarpG& g, float (&v)[DD_ROWS * NC], float (&acc)[NC]) {
+    constexpr int N = DD_ROWS * NC;
+    int n = N, o = 16;
+#pragma unroll
+    for (; n > 1; n >>= 1, o >>= 1) {
+        const bool up = (g.lane & o) != 0;
+        const int half = n >> 1;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+#pragma unroll
+    for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    acc[0] = v[0] > acc[0] ? v[0] : acc[0];
+}
+template <int NC>
+__device__ __forceinline__ void dd_fold_finish(const WarpG& g, float (&acc)[NC], float (&best)[NC]) {
+    constexpr int N = DD_ROWS * NC;
+    constexpr int SH = N >= 32 ? 0 : (N == 16 ? 1 : (N == 8 ? 2 : 3));     // idx(L) = L >> SH
+    const int mine = (g.lane >> SH) % NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) best[c] = g.fmax(mine == c ? acc[0] : -3.0e38f);
+}
+#endif
+template <int NC>
+inline void dd_fold_max(const HostG&, float (&v)[DD_ROWS * NC], float (&acc)[NC]) {
+    for (int r = 0; r < DD_ROWS; ++r)
+        for (int c = 0; c < NC; ++c) acc[c] = v[r * NC + c] > acc[c] ? v[r * NC + c] : acc[c];
+}
+template <int NC>
+inline void dd_fold_finish(const HostG&, float (&acc)[NC], float (&best)[NC]) {
+    for (int c = 0; c < NC; ++c) best[c] = acc[c];
+}
+
+// max over the gallery rows of row . q[c] for NC query vectors; rows are unit vectors, each lane owns
+// float4 chunk(s) of the 128-d row.  Rows past glen re-read the last row (duplicates do not change a max).
+template <class G, int NC>
+DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
+                          const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
+    constexpr int KP = (DD_FEAT_DIM / 4) / G::NL;          // float4 chunks per lane (1 on a warp)
+    float4 q[NC][KP];
+    for (int c = 0; c < NC; ++c) {
+        int kk = 0;
+        for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) q[c][kk] = qp[c][k];
+    }
+    float acc[NC];
+    for (int c = 0; c < NC; ++c) acc[c] = -3.0e38f;
+    for (int g0 = 0; g0 < glen; g0 += DD_ROWS) {
+        float v[DD_ROWS * NC];
+#pragma unroll
+        for (int i = 0; i < DD_ROWS * NC; ++i) v[i] = 0.f;
+        int kk = 0;
+        for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
+            float4 a[DD_ROWS];
+#pragma unroll
+            for (int r = 0; r < DD_ROWS; ++r) {
+                const int row = dd_imin(g0 + r, glen - 1);
+                a[r] = gal4[(size_t)row * (DD_FEAT_DIM / 4) + k];
+            }
+#pragma unroll
+            for (int r = 0; r < DD_ROWS; ++r)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float p = v[r * NC + c];
+                    p = dd_fmaf(a[r].x, q[c][kk].x, p);
+                    p = dd_fmaf(a[r].y, q[c][kk].y, p);
+                    p = dd_fmaf(a[r].z, q[c][kk].z, p);
+                    p = dd_fmaf(a[r].w, q[c][kk].w, p);
+                    v[r * NC + c] = p;
+                }
+        }
+        dd_fold_max<NC>(g, v, acc);
+    }
+    float b[NC];
+    dd_fold_finish<NC>(g, acc, b);
+    for (int c = 0; c < NC; ++c) best[c] = b[c];
+}
+
 template <class G>
 DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* det_count) {
     if (t >= V.n_tracks[s]) return;
@@ -94,7 +184,6 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
     const double pm[4] = {mean[0], mean[1], mean[2], mean[3]};
     const int glen = V.gal_len[slot];
     const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
-    constexpr int KP = (DD_FEAT_DIM / 4) / G::NL;          // float4 chunks per lane (1 on a warp)
     for (int base = 0; base < nd; base += 32) {
         unsigned word = 0;
         const int lim = dd_imin(base + 32, nd);
@@ -112,33 +201,18 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
                 word &= word - 1;
                 cj[nc++] = base + b;
             }
-            float4 q[DD_CH][KP];
-            for (int c = 0; c < DD_CH; ++c) {
-                const float4* f4 = (const float4*)(V.det_featn + ((size_t)s * V.D + cj[c < nc ? c : 0]) * DD_FEAT_DIM);
-                int kk = 0;
-                for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) q[c][kk] = f4[k];
-            }
+            const float4* qp[DD_CH];
+            for (int c = 0; c < DD_CH; ++c)
+                qp[c] = (const float4*)(V.det_featn + ((size_t)s * V.D + cj[c < nc ? c : 0]) * DD_FEAT_DIM);
             float best[DD_CH];
-            for (int c = 0; c < DD_CH; ++c) best[c] = -3.0e38f;
-            for (int gi = 0; gi < glen; ++gi) {
-                float p[DD_CH];
-                for (int c = 0; c < DD_CH; ++c) p[c] = 0.f;
-                int kk = 0;
-                for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
-                    const float4 a = gal4[(size_t)gi * (DD_FEAT_DIM / 4) + k];
-#pragma unroll
-                    for (int c = 0; c < DD_CH; ++c) {
-                        p[c] = dd_fmaf(a.x, q[c][kk].x, p[c]);
-                        p[c] = dd_fmaf(a.y, q[c][kk].y, p[c]);
-                        p[c] = dd_fmaf(a.z, q[c][kk].z, p[c]);
-                        p[c] = dd_fmaf(a.w, q[c][kk].w, p[c]);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < DD_CH; ++c) {
-                    const float tot = g.sum(p[c]);
-                    best[c] = tot > best[c] ? tot : best[c];
-                }
+            if (glen <= 0) {
+                for (int c = 0; c < DD_CH; ++c) best[c] = -3.0e38f;
+            } else if (nc == 1) {
+                dd_cosine_pass<G, 1>(g, gal4, glen, qp, best);
+            } else if (nc == 2) {
+                dd_cosine_pass<G, 2>(g, gal4, glen, qp, best);
+            } else {
+                dd_cosine_pass<G, 4>(g, gal4, glen, qp, best);
             }
             if (g.lane == 0)
                 for (int c = 0; c < nc; ++c) V.cost[slot * V.D + cj[c]] = dd_subf(1.0f, best[c]);

@@ -496,7 +496,11 @@ class Trkr:
         feats = np.array([dets[i].feature for i in det_indices])
         targets = np.array([tracks[i].track_id for i in track_indices])
         cost = self.metric.distance(feats, targets)
-        return gate_cost_matrix(cost, tracks, dets, track_indices, det_indices)
+        cost = gate_cost_matrix(cost, tracks, dets, track_indices, det_indices)
+        if self.trace is not None:
+            self.trace.setdefault("gated_costs", []).append(
+                ([int(t) for t in targets], [int(d) for d in det_indices], cost.copy()))
+        return cost
 
     def _match(self, dets):
         """tracker.py:95-133."""

@@ -98,3 +98,114 @@ def load():
             _loaded[n.replace(".", "_")] = None
             _loaded[n.replace(".", "_") + "_error"] = repr(e)
     return types.SimpleNamespace(**_loaded)
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own counting code: Pipeline.process_results (deepdish.py:1035-1139) driven
+# without camera / MQTT / web app.  Build container only.
+# ------------------------------------------------------------------------------------------------
+_pipeline_mod = None
+
+
+def load_pipeline_module():
+    """Load /root/reference/deepdish.py (not the deepdish/ package) with I/O dependencies stubbed."""
+    global _pipeline_mod
+    if _pipeline_mod is not None:
+        return _pipeline_mod
+    load()
+    import importlib.util
+
+    def stub(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _Any:
+        def __init__(self, *a, **k):
+            pass
+
+        def __getattr__(self, n):
+            return _Any()
+
+        def __call__(self, *a, **k):
+            return _Any()
+
+        def route(self, *a, **k):
+            return lambda f: f
+
+        before_serving = after_serving = route
+
+    stub("cameratransform")
+    stub("uvloop", install=lambda: None)
+    stub("aiofiles")
+    stub("gmqtt", Client=_Any)
+    stub("quart", Quart=_Any, Response=_Any, current_app=_Any())
+    stub("hypercorn")
+    stub("hypercorn.asyncio", serve=lambda *a, **k: None)
+    stub("hypercorn.config", Config=_Any)
+    spec = importlib.util.spec_from_file_location("deepdish_main_ref", os.path.join(REFERENCE_ROOT, "deepdish.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _pipeline_mod = mod
+    return mod
+
+
+class RefCounter:
+    """Runs the reference's Pipeline.process_results on a reference Tracker, one frame at a time."""
+
+    def __init__(self, tracker, labels, line):
+        import asyncio
+        mod = load_pipeline_module()
+        P = mod.Pipeline
+        p = object.__new__(P)
+        p.running = True
+        p.args = types.SimpleNamespace(object_annotation="none", mqtt_verbosity=0)
+        p.tracker = tracker
+        from deepdish.framerecords import FrameRecords
+        p.framerec = FrameRecords({})
+        p.db = {}
+        p.cameracountline = np.asarray(line, dtype=float).reshape(2, 2)
+        p.trackdata_ratios = (1, 1)
+        p.cam = None
+        p.topdownview = None
+        p.data_lock = asyncio.Lock()
+        p.wanted_labels = list(labels)
+        p.poscount = {l: 0 for l in labels}
+        p.negcount = {l: 0 for l in labels}
+        p.intcount = {l: 0 for l in labels}
+        p.delcount = {l: 0 for l in labels}
+        p.mqtt = None
+        p.log = None
+        p.cpu_temp_file = None
+        p.output = None
+        p.framenum_committed = 0
+        self.p, self.mod, self.labels = p, mod, list(labels)
+        self.frame = 0
+
+    def step(self, detections):
+        import asyncio
+        import contextlib
+        import io
+        p = self.p
+
+        class QIn:
+            async def get(self_inner):
+                return (self.frame, detections, [self.mod.FrameInfo(0.0, self.frame)], 0.0)
+
+        class QOut:
+            async def put(self_inner, item):
+                p.running = False
+
+        p.running = True
+        with contextlib.redirect_stdout(io.StringIO()):
+            asyncio.run(p.process_results(QIn(), QOut()))
+        self.frame += 1
+
+    def counts(self):
+        p = self.p
+        return np.array([[p.poscount[l], p.negcount[l], p.intcount[l], p.delcount[l]] for l in self.labels],
+                        dtype=np.int64)

@@ -66,3 +66,25 @@ def compare_stream(o_trk, o_cnt, view, s, labels, rtol=1e-4, gallery=True):
                 assert int(view["gal_len"][s, sl]) == len(g)
     if o_cnt is not None:
         np.testing.assert_array_equal(view["counts"][s], o_cnt.counts(labels))
+
+
+def compare_costs(o_trk, view_pre, view_post, s, rtol=1e-4, atol=2e-6):
+    """Gated appearance costs of the last update: oracle (per cascade level, before clipping) against the
+    CUDA gate bits + f32 min-cosine costs.  view_pre: track_id/order/n_tracks BEFORE the update (slot of a
+    track id); view_post: gate / cost arrays after it.  Returns the number of gate-passing pairs checked."""
+    n = int(view_pre["n_tracks"][s])
+    slot_of = {int(view_pre["track_id"][s, sl]): int(sl) for sl in view_pre["order"][s, :n]}
+    checked = 0
+    for tids, dets, cost in o_trk.trace.get("gated_costs", []):
+        for r, tid in enumerate(tids):
+            sl = slot_of[tid]
+            for c, d in enumerate(dets):
+                bit = (int(view_post["gate"][s, sl, d >> 5]) >> (d & 31)) & 1
+                if cost[r, c] >= 1e5:
+                    assert bit == 0, (tid, d)
+                else:
+                    assert bit == 1, (tid, d)
+                    got = float(view_post["cost"][s, sl, d])
+                    assert abs(got - cost[r, c]) <= atol + rtol * abs(cost[r, c]), (tid, d, got, cost[r, c])
+                    checked += 1
+    return checked

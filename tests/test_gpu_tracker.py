@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from deepdish_b200.scene import Scene
-from tests.parity import OracleStreams, compare_stream, LABELS3
+from tests.parity import OracleStreams, compare_stream, compare_costs, LABELS3
 
 pytestmark = pytest.mark.gpu
 
@@ -77,3 +77,24 @@ def test_empty_frames_and_capacity_flags():
         bt.check()
     with pytest.raises(ValueError):
         bt.update(z["tlwh"].float(), z["conf"], z["label"], z["feat"], z["count"])
+
+
+def test_gated_cost_matrices_match_oracle():
+    """Distance matrices: every (track, detection) the reference would not gate out has the same
+    min-cosine cost within 1e-4 relative (+2e-6 absolute: the reference's own BLAS summation noise)."""
+    from deepdish_b200.batched import BatchedTracker
+    S = 4
+    bt = BatchedTracker(S, LABELS3, max_tracks=128, max_dets=64, budget=100, max_age=60)
+    orc = OracleStreams(S, LABELS3, budget=100, max_age=60)
+    sc = Scene(S, 50, 64, n_labels=3, seed=21)
+    checked = 0
+    for f in range(50):
+        b = sc.step()
+        pre = bt.host_view(["n_tracks", "order", "track_id"])
+        orc.step(b)
+        bt.step(b.to("cuda"))
+        if f >= 5 and f % 3 == 0:
+            post = bt.host_view(["gate", "cost"])
+            for s in range(S):
+                checked += compare_costs(orc.trk[s], pre, post, s)
+    assert checked > 1000
