@@ -1,0 +1,199 @@
+"""Thin torch wrappers over the stand-alone C-ABI operators (device tensors in, device tensors out).
+
+These are what the per-function ``deep_sort`` mirror (deepdish_b200/deep_sort/*.py) and the detector
+adapters call.  Every function launches on the current CUDA stream of the tensors' device and returns
+without synchronising.  No CPU implementation exists behind any of them.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _dev(x, dtype, device="cuda"):
+    """Host array / tensor -> contiguous CUDA tensor of `dtype`."""
+    if isinstance(x, torch.Tensor):
+        t = x.to(device=device, dtype=dtype)
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
+    return t.contiguous()
+
+
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError("deepdish_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------- Kalman
+def kalman_initiate(xyah):
+    """KalmanFilter.initiate (kalman_filter.py:55-86).  xyah f64 [n,4] -> mean [n,8], cov [n,8,8]."""
+    _need_cuda(xyah)
+    n = xyah.shape[0]
+    mean = torch.empty((n, 8), dtype=torch.float64, device=xyah.device)
+    cov = torch.empty((n, 8, 8), dtype=torch.float64, device=xyah.device)
+    _lib.check(_lib.lib().dd_kalman_initiate(xyah.data_ptr(), mean.data_ptr(), cov.data_ptr(), n,
+                                             _stream(xyah.device)), "dd_kalman_initiate")
+    return mean, cov
+
+
+def kalman_predict_(mean, cov):
+    """KalmanFilter.predict (kalman_filter.py:88-123), in place."""
+    _need_cuda(mean)
+    _lib.check(_lib.lib().dd_kalman_predict(mean.data_ptr(), cov.data_ptr(), mean.shape[0],
+                                            _stream(mean.device)), "dd_kalman_predict")
+    return mean, cov
+
+
+def kalman_project(mean, cov):
+    """KalmanFilter.project (kalman_filter.py:125-152) -> pmean [n,4], pcov [n,4,4]."""
+    _need_cuda(mean)
+    n = mean.shape[0]
+    pm = torch.empty((n, 4), dtype=torch.float64, device=mean.device)
+    pc = torch.empty((n, 4, 4), dtype=torch.float64, device=mean.device)
+    _lib.check(_lib.lib().dd_kalman_project(mean.data_ptr(), cov.data_ptr(), pm.data_ptr(), pc.data_ptr(), n,
+                                            _stream(mean.device)), "dd_kalman_project")
+    return pm, pc
+
+
+def kalman_update_(mean, cov, xyah):
+    """KalmanFilter.update (kalman_filter.py:154-186), in place, one measurement per row."""
+    _need_cuda(mean)
+    _lib.check(_lib.lib().dd_kalman_update(mean.data_ptr(), cov.data_ptr(), xyah.data_ptr(), mean.shape[0],
+                                           _stream(mean.device)), "dd_kalman_update")
+    return mean, cov
+
+
+def kalman_gating_distance(mean, cov, xyah, only_position=False):
+    """KalmanFilter.gating_distance (kalman_filter.py:188-229): n tracks x m measurements -> [n,m]."""
+    _need_cuda(mean)
+    n, m = mean.shape[0], xyah.shape[0]
+    out = torch.empty((n, m), dtype=torch.float64, device=mean.device)
+    _lib.check(_lib.lib().dd_kalman_gating_distance(mean.data_ptr(), cov.data_ptr(), xyah.data_ptr(), n, m,
+                                                    1 if only_position else 0, out.data_ptr(),
+                                                    _stream(mean.device)), "dd_kalman_gating_distance")
+    return out
+
+
+# ------------------------------------------------------------------------------------- metric / IoU
+def nn_distance(gallery, offsets, feats, metric="cosine"):
+    """NearestNeighborDistanceMetric.distance (nn_matching.py:156-177): gallery f32 [G,128] grouped by
+    offsets i32 [n+1], feats f32 [m,128] -> f64 [n,m]."""
+    _need_cuda(feats)
+    n, m = offsets.shape[0] - 1, feats.shape[0]
+    out = torch.zeros((n, m), dtype=torch.float64, device=feats.device)
+    code = {"cosine": 0, "euclidean": 1}[metric]
+    _lib.check(_lib.lib().dd_nn_distance(gallery.data_ptr() if gallery.numel() else None, offsets.data_ptr(),
+                                         feats.data_ptr(), n, m, code, out.data_ptr(), _stream(feats.device)),
+               "dd_nn_distance")
+    return out
+
+
+def iou_cost(track_tlwh, tsu, det_tlwh):
+    """iou_matching.iou_cost (iou_matching.py:42-81) -> f64 [n,m]."""
+    _need_cuda(track_tlwh)
+    n, m = track_tlwh.shape[0], det_tlwh.shape[0]
+    out = torch.zeros((n, m), dtype=torch.float64, device=track_tlwh.device)
+    _lib.check(_lib.lib().dd_iou_cost(track_tlwh.data_ptr(), tsu.data_ptr(), det_tlwh.data_ptr(), n, m,
+                                      out.data_ptr(), _stream(track_tlwh.device)), "dd_iou_cost")
+    return out
+
+
+# ------------------------------------------------------------------------------------- assignment
+def lsap(cost):
+    """scipy.optimize.linear_sum_assignment with scipy's tie-breaking (linear_assignment.py:58).
+    cost f64 [b,nr,nc] -> col4row i32 [b,nr] (-1 = unassigned row), status i32 [b]."""
+    _need_cuda(cost)
+    b, nr, nc = cost.shape
+    out = torch.full((b, nr), -1, dtype=torch.int32, device=cost.device)
+    st = torch.zeros((b,), dtype=torch.int32, device=cost.device)
+    _lib.check(_lib.lib().dd_lsap(cost.data_ptr(), b, nr, nc, out.data_ptr(), st.data_ptr(),
+                                  _stream(cost.device)), "dd_lsap")
+    return out, st
+
+
+def linear_sum_assignment(cost):
+    """Drop-in for scipy's function on ONE host matrix: returns (row_ind, col_ind) numpy arrays."""
+    c = np.asarray(cost, dtype=np.float64)
+    if c.ndim != 2:
+        raise ValueError("expected a matrix (2-D array), got a %r array" % (c.shape,))
+    if c.size == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    if np.isnan(c).any() or np.isneginf(c).any():
+        raise ValueError("matrix contains invalid numeric entries")
+    out, st = lsap(_dev(c[None], torch.float64))
+    if int(st[0]) != 0:
+        raise ValueError("cost matrix is infeasible")
+    col = out[0].cpu().numpy().astype(np.int64)
+    rows = np.nonzero(col >= 0)[0]
+    return rows.astype(np.int64), col[rows]
+
+
+def set_difference_order(a, na, m, nm):
+    """CPython `list(set(a) - set(m))` iteration order for batches of small ints (device tensors)."""
+    _need_cuda(a)
+    b, na_max = a.shape
+    out = torch.zeros((b, na_max), dtype=torch.int32, device=a.device)
+    on = torch.zeros((b,), dtype=torch.int32, device=a.device)
+    _lib.check(_lib.lib().dd_set_difference_order(a.data_ptr(), na.data_ptr(), na_max, m.data_ptr(), nm.data_ptr(),
+                                                  m.shape[1], b, out.data_ptr(), on.data_ptr(),
+                                                  _stream(a.device)), "dd_set_difference_order")
+    return out, on
+
+
+def segments_intersect(seg):
+    """tools/intersection.py:4-24 for seg f64 [n,8] = (p, pr, q, qs) -> i32 [n]."""
+    _need_cuda(seg)
+    out = torch.zeros((seg.shape[0],), dtype=torch.int32, device=seg.device)
+    _lib.check(_lib.lib().dd_intersection(seg.data_ptr(), seg.shape[0], out.data_ptr(), _stream(seg.device)),
+               "dd_intersection")
+    return out
+
+
+# ------------------------------------------------------------------------------------- detection
+def nms(boxes, scores, counts, max_overlap):
+    """preprocessing.non_max_suppression for b frames (preprocessing.py:6-73).
+    boxes f64 [b,nmax,4] tlwh, scores f32 [b,nmax], counts i32 [b] -> keep i32 [b,nmax], nkeep i32 [b]."""
+    _need_cuda(boxes)
+    b, nmax = scores.shape
+    keep = torch.full((b, nmax), -1, dtype=torch.int32, device=boxes.device)
+    nkeep = torch.zeros((b,), dtype=torch.int32, device=boxes.device)
+    _lib.check(_lib.lib().dd_nms(boxes.data_ptr(), scores.data_ptr(), counts.data_ptr(), b, nmax,
+                                 float(max_overlap), keep.data_ptr(), nkeep.data_ptr(), _stream(boxes.device)),
+               "dd_nms")
+    return keep, nkeep
+
+
+def yolo_decode(head, wanted_mask, score_thr=0.25, img_size=(640, 480), frame_size=(640, 480), ncap=1024,
+                quant=None):
+    """YOLOv5 head decode + box filter for b frames (tools/yolov5.py:115-146, deepdish.py:946-955).
+    head f32 [b,na,5+nc] (or u8 with quant=(scale, zero_point)); wanted_mask u8 [nc].
+    Returns dict(tlwh f64 [b,ncap,4], score f32, cls i32, anchor i32, count i32 [b], flags i32 [b])."""
+    _need_cuda(head)
+    b, na, rw = head.shape
+    nc = rw - 5
+    dev = head.device
+    out = dict(tlwh=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
+               score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
+               cls=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
+               anchor=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
+               count=torch.zeros((b,), dtype=torch.int32, device=dev),
+               flags=torch.zeros((b,), dtype=torch.int32, device=dev))
+    is_u8 = head.dtype == torch.uint8
+    if is_u8 and quant is None:
+        raise ValueError("u8 head needs quant=(scale, zero_point)")
+    if not is_u8 and head.dtype != torch.float32:
+        raise ValueError("head must be float32 or uint8")
+    scale, zp = quant if is_u8 else (1.0, 0)
+    _lib.check(_lib.lib().dd_yolo_decode(head.data_ptr(), 1 if is_u8 else 0, float(scale), int(zp), b, na, nc,
+                                         wanted_mask.data_ptr(), float(score_thr), int(img_size[0]),
+                                         int(img_size[1]), int(frame_size[0]), int(frame_size[1]), ncap,
+                                         out["tlwh"].data_ptr(), out["score"].data_ptr(), out["cls"].data_ptr(),
+                                         out["anchor"].data_ptr(), out["count"].data_ptr(),
+                                         out["flags"].data_ptr(), _stream(dev)), "dd_yolo_decode")
+    return out

@@ -1,0 +1,275 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in the build
+container.  TEST INFRASTRUCTURE -- run as ``python -m oracle.make_golden`` from the repo root.
+
+Every fixture stores the inputs (or, for the long trajectories, the Scene seed plus a checksum of the
+regenerated inputs) and the reference's outputs.  tests/test_golden.py checks the oracle against
+them on any machine (the reference tree is not needed there); the GPU tests check the CUDA path
+against the same files.
+"""
+import hashlib
+import os
+
+import numpy as np
+
+from oracle import refload, countline as oc, detect as odet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+LABELS3 = ["person", "bicycle", "car"]
+
+
+def scene_checksum(batches):
+    h = hashlib.sha256()
+    for b in batches:
+        for k in ("tlwh", "conf", "label", "feat", "count"):
+            h.update(np.ascontiguousarray(getattr(b, k).numpy()).tobytes())
+    return h.hexdigest()
+
+
+def run_reference_tracker(R, batches, labels, budget, max_age, n_init=3, tcap=64):
+    """Reference Tracker + the reference's own Pipeline.process_results on one stream."""
+    metric = R.deep_sort_nn_matching.NearestNeighborDistanceMetric("cosine", 0.2, budget)
+    trk = R.deep_sort_tracker.Tracker(metric, max_iou_distance=0.7, max_age=max_age, n_init=n_init)
+    cnt = refload.RefCounter(trk, labels, oc.default_line(640, 480))
+    F, D = len(batches), batches[0].tlwh.shape[1]
+    det_ids = np.full((F, D), -1, np.int32)
+    n_tracks = np.zeros(F, np.int32)
+    ids = np.full((F, tcap), -1, np.int32)
+    states = np.zeros((F, tcap), np.int32)
+    tsu = np.zeros((F, tcap), np.int32)
+    means = np.zeros((F, tcap, 8))
+    covs = np.zeros((F, tcap, 8, 8))
+    deleted = np.full((F, tcap), -1, np.int32)
+    counts = np.zeros((F, len(labels), 4), np.int64)
+    track_labels = np.full((F, tcap), -1, np.int32)
+    for f, b in enumerate(batches):
+        tlwh, conf, lab, feat = b.stream(0)
+        dets = [R.deep_sort_detection.Detection(tlwh[i], labels[lab[i]], conf[i], feat[i])
+                for i in range(len(conf))]
+        trk.predict()
+        before = {id(t): t for t in trk.tracks}
+        prev_next = trk._next_id
+        trk.update(dets)
+        cnt.step(dets)
+        # det -> track id: a detection object is appended to track.detections on update / creation
+        for t in trk.tracks + trk.deleted_tracks:
+            d = t.detections[-1]
+            if t.time_since_update == 0 and d in dets:
+                det_ids[f, dets.index(d)] = t.track_id
+        assert trk._next_id >= prev_next
+        n = len(trk.tracks)
+        assert n <= tcap
+        n_tracks[f] = n
+        for k, t in enumerate(trk.tracks):
+            ids[f, k], states[f, k], tsu[f, k] = t.track_id, t.state, t.time_since_update
+            means[f, k], covs[f, k] = t.mean, t.covariance
+            track_labels[f, k] = labels.index(t.get_label())
+        for k, t in enumerate(trk.deleted_tracks):
+            deleted[f, k] = t.track_id
+        counts[f] = cnt.counts()
+    return dict(det_ids=det_ids, n_tracks=n_tracks, ids=ids, states=states, tsu=tsu, means=means,
+                covs=covs, deleted=deleted, counts=counts, track_labels=track_labels)
+
+
+def golden_tracker(R, name, seed, n_obj, dmax, frames, budget, max_age, store_inputs, **scene_kw):
+    from deepdish_b200.scene import Scene
+    sc = Scene(1, n_obj, dmax, n_labels=3, seed=seed, **scene_kw)
+    batches = [sc.step() for _ in range(frames)]
+    out = run_reference_tracker(R, batches, LABELS3, budget, max_age)
+    out.update(seed=seed, n_obj=n_obj, dmax=dmax, frames=frames, budget=budget, max_age=max_age,
+               checksum=scene_checksum(batches),
+               scene_kw=np.array(sorted(scene_kw.items()), dtype=object) if scene_kw else np.zeros(0))
+    if store_inputs:
+        out.update(in_tlwh=np.stack([b.tlwh[0].numpy() for b in batches]),
+                   in_conf=np.stack([b.conf[0].numpy() for b in batches]),
+                   in_label=np.stack([b.label[0].numpy() for b in batches]),
+                   in_feat=np.stack([b.feat[0].numpy() for b in batches]),
+                   in_count=np.stack([b.count.numpy()[0] for b in batches]))
+    else:
+        out["means"] = out["means"][::10].copy()       # keep the file small: every 10th frame
+        out["covs"] = out["covs"][-1:].copy()
+    np.savez_compressed(os.path.join(OUT, name), **{k: v for k, v in out.items()}, allow_pickle=True)
+    print(name, "next ids", int(out["ids"].max()), "counts", out["counts"][-1].tolist())
+
+
+def golden_kalman(R):
+    rng = np.random.default_rng(0)
+    kf = R.deep_sort_kalman_filter.KalmanFilter()
+    n, m = 40, 25
+    z0 = np.c_[rng.uniform(0, 600, n), rng.uniform(0, 400, n), rng.uniform(0.2, 0.8, n), rng.uniform(40, 100, n)]
+    init = [kf.initiate(z) for z in z0]
+    mean = np.stack([a for a, _ in init]); cov = np.stack([b for _, b in init])
+    seq_mean, seq_cov, zs = [mean.copy()], [cov.copy()], []
+    for it in range(5):
+        pr = [kf.predict(mean[i], cov[i]) for i in range(n)]
+        mean = np.stack([a for a, _ in pr]); cov = np.stack([b for _, b in pr])
+        seq_mean.append(mean.copy()); seq_cov.append(cov.copy())
+        z = mean[:, :4] + rng.normal(0, 1, (n, 4)) * [2, 2, 0.01, 2]
+        zs.append(z)
+        up = [kf.update(mean[i], cov[i], z[i]) for i in range(n)]
+        mean = np.stack([a for a, _ in up]); cov = np.stack([b for _, b in up])
+        seq_mean.append(mean.copy()); seq_cov.append(cov.copy())
+    proj = [kf.project(mean[i], cov[i]) for i in range(n)]
+    meas = np.c_[rng.uniform(0, 600, m), rng.uniform(0, 400, m), rng.uniform(0.2, 0.8, m), rng.uniform(40, 100, m)]
+    meas[:10] = mean[:10, :4] + rng.normal(0, 1.5, (10, 4)) * [1, 1, 0.01, 1]
+    g4 = np.stack([kf.gating_distance(mean[i], cov[i], meas) for i in range(n)])
+    g2 = np.stack([kf.gating_distance(mean[i], cov[i], meas, True) for i in range(n)])
+    np.savez_compressed(os.path.join(OUT, "kalman.npz"), z0=z0, seq_mean=np.stack(seq_mean),
+                        seq_cov=np.stack(seq_cov), zs=np.stack(zs), pmean=np.stack([a for a, _ in proj]),
+                        pcov=np.stack([b for _, b in proj]), meas=meas, gating4=g4, gating2=g2)
+    print("kalman.npz")
+
+
+def golden_metric_iou(R):
+    rng = np.random.default_rng(1)
+    nn = R.deep_sort_nn_matching
+    lens = [1, 3, 100, 17, 64]
+    gal = [rng.normal(size=(l, 128)).astype(np.float32) * np.float32(rng.uniform(0.5, 2)) for l in lens]
+    feats = rng.normal(size=(23, 128)).astype(np.float32)
+    feats[3] = gal[2][40] + 0.01 * rng.normal(size=128).astype(np.float32)
+    feats[5] = gal[4][7] + 0.05 * rng.normal(size=128).astype(np.float32)
+    cos = np.stack([nn._nn_cosine_distance(g, feats) for g in gal])
+    euc = np.stack([nn._nn_euclidean_distance(g, feats) for g in gal])
+    n, m = 30, 21
+    trk = np.c_[rng.uniform(0, 500, n), rng.uniform(0, 300, n), rng.uniform(20, 80, n), rng.uniform(40, 120, n)]
+    det = np.floor(np.c_[rng.uniform(0, 500, m), rng.uniform(0, 300, m), rng.uniform(20, 80, m), rng.uniform(40, 120, m)])
+    det[:10] = np.floor(trk[:10]) + 1
+    iou = np.stack([R.deep_sort_iou_matching.iou(trk[i], det) for i in range(n)])
+    np.savez_compressed(os.path.join(OUT, "metric_iou.npz"), gallery=np.concatenate(gal),
+                        offsets=np.r_[0, np.cumsum(lens)].astype(np.int32), feats=feats, cosine=cos,
+                        euclidean=euc, trk_tlwh=trk, det_tlwh=det, iou=iou)
+    print("metric_iou.npz")
+
+
+def golden_nms(R):
+    rng = np.random.default_rng(2)
+    cases = []
+    for case in range(40):
+        n = int(rng.integers(0, 120)) if case else 0
+        k = max(1, n // 4)
+        cx, cy = rng.uniform(40, 600, k), rng.uniform(40, 440, k)
+        pick = rng.integers(0, k, n)
+        x = np.clip(cx[pick] + rng.normal(0, 6, n), 0, 630).astype(np.int64)
+        y = np.clip(cy[pick] + rng.normal(0, 6, n), 0, 470).astype(np.int64)
+        w = rng.integers(10, 60, n); h = rng.integers(20, 120, n)
+        boxes = np.stack([x, y, w, h], axis=1).astype(np.int64).reshape(n, 4)
+        scores = (0.25 + 0.75 * (rng.permutation(n) + rng.uniform(0.1, 0.9, n)) / max(n, 1)).astype(np.float32)
+        assert len(np.unique(scores)) == n
+        thr = [0.6, 0.3, 0.9][case % 3]
+        keep = R.deep_sort_preprocessing.non_max_suppression(boxes, thr, scores)
+        cases.append((boxes, scores, thr, np.array(keep, dtype=np.int32)))
+    nmax = max(len(c[0]) for c in cases)
+    B = len(cases)
+    boxes = np.zeros((B, nmax, 4)); scores = np.zeros((B, nmax), np.float32)
+    counts = np.zeros(B, np.int32); thr = np.zeros(B); keep = np.full((B, nmax), -1, np.int32)
+    nkeep = np.zeros(B, np.int32)
+    for i, (b, s, t, k) in enumerate(cases):
+        n = len(b)
+        boxes[i, :n], scores[i, :n], counts[i], thr[i] = b, s, n, t
+        keep[i, :len(k)], nkeep[i] = k, len(k)
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), boxes=boxes, scores=scores, counts=counts, thr=thr,
+                        keep=keep, nkeep=nkeep)
+    print("nms.npz", nkeep.tolist())
+
+
+def synth_yolo_head(rng, frames, na, nc=80, hot=0.02):
+    """[frames, na, 5+nc] f32 head in the TFLite export's format (normalised xywh, obj, cls)."""
+    h = np.empty((frames, na, 5 + nc), np.float32)
+    h[..., 0:2] = rng.uniform(0.05, 0.9, (frames, na, 2))
+    h[..., 2:4] = rng.uniform(0.01, 0.2, (frames, na, 2))
+    h[..., 4] = rng.beta(0.5, 8, (frames, na))
+    h[..., 5:] = rng.beta(0.5, 4, (frames, na, nc))
+    hotmask = rng.random((frames, na)) < hot          # a few confident rows
+    h[..., 4][hotmask] = rng.uniform(0.5, 1.0, hotmask.sum())
+    cls = rng.integers(0, 6, hotmask.sum())
+    rows = np.argwhere(hotmask)
+    h[rows[:, 0], rows[:, 1], 5 + cls] = rng.uniform(0.5, 1.0, len(rows))
+    return h
+
+
+def golden_yolo(R):
+    from PIL import Image
+    os.environ["DEEPDISHHOME"] = refload.REFERENCE_ROOT
+    rng = np.random.default_rng(3)
+    frames, na = 3, 1600
+    head = synth_yolo_head(rng, frames, na)
+    head[2, :, 4] *= 0.2                                   # a frame with no survivors
+    head[0, 5, :4] = [0.5, 0.5, 0.99, 0.99]                # a huge box: rejected by the area filter
+    head[0, 5, 4] = 0.9; head[0, 5, 5] = 0.9
+    wanted = ["person", "bicycle", "car", "motorbike"]
+    det = R.tools_yolov5.YOLOV5(wanted_labels=wanted, model_file="synthetic.tflite")
+    names = [det.labels[i] for i in range(80)]
+    img = Image.new("RGB", (640, 480))
+    out = {}
+    for f in range(frames):
+        refload.FakeInterpreter.outputs = [head[f:f + 1]]
+        boxes, labels, scores = det.detect_image(img)
+        out["tlwh%d" % f] = np.array(boxes, np.float32).reshape(-1, 4)
+        out["cls%d" % f] = np.array([names.index(l) for l in labels], np.int32)
+        out["score%d" % f] = np.array(scores, np.float32)
+        # downstream: box filter (restated from deepdish.py:946-955) + the reference's own NMS
+        ib, kept = odet.box_filter(boxes, 640, 480)
+        sc = np.array(scores, np.float32)[kept]
+        keep = R.deep_sort_preprocessing.non_max_suppression(np.array(ib), 0.6, sc) if len(ib) else []
+        out["fbox%d" % f] = ib
+        out["fidx%d" % f] = kept
+        out["keep%d" % f] = np.array(keep, np.int32)
+    np.savez_compressed(os.path.join(OUT, "yolo.npz"), head=head, wanted=np.array(wanted),
+                        names=np.array(names), **out)
+    print("yolo.npz", [len(out["tlwh%d" % f]) for f in range(frames)], [len(out["keep%d" % f]) for f in range(frames)])
+
+
+def golden_ssd_post(R):
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    label_path = os.path.join(refload.REFERENCE_ROOT, "detectors", "mobilenet", "labels.txt")
+    names = [l.strip() for l in open(label_path)]
+    wanted = ["person", "bicycle", "car", "motorcycle", "bus"]
+    refload.FakeInterpreter.input_shape = (1, 300, 300, 3)
+    refload.FakeInterpreter.outputs = [np.zeros((1, 10, 4), np.float32), np.zeros((1, 10), np.float32),
+                                       np.zeros((1, 10), np.float32), np.zeros(1, np.float32)]
+    det = R.tools_ssd_mobilenet.SSD_MOBILENET(wanted_labels=wanted, model_file="x.tflite", label_file=label_path)
+    img = Image.new("RGB", (640, 480))
+    cases = 60
+    ob = np.zeros((cases, 10, 4), np.float32); ocl = np.zeros((cases, 10), np.float32)
+    osc = np.zeros((cases, 10), np.float32)
+    res = {}
+    for c in range(cases):
+        k = 3
+        cy, cx = rng.uniform(0.2, 0.8, k), rng.uniform(0.2, 0.8, k)
+        p = rng.integers(0, k, 10)
+        y0 = cy[p] + rng.normal(0, 0.02, 10); x0 = cx[p] + rng.normal(0, 0.02, 10)
+        hh = rng.uniform(0.1, 0.3, 10); ww = rng.uniform(0.05, 0.2, 10)
+        ob[c] = np.stack([y0, x0, y0 + hh, x0 + ww], 1)
+        ocl[c] = rng.choice([0, 1, 2, 3, 5, 16, 40], 10).astype(np.float32)
+        osc[c] = np.sort(rng.uniform(0.2, 1.0, 10).astype(np.float32))[::-1]
+        refload.FakeInterpreter.outputs = [ob[c:c + 1].copy(), ocl[c:c + 1].copy(), osc[c:c + 1].copy(),
+                                           np.array([10], np.float32)]
+        boxes, labels, scores = det.detect_image(img)
+        res["tlwh%d" % c] = np.array(boxes, float).reshape(-1, 4)
+        res["lab%d" % c] = np.array([names.index(l) for l in labels], np.int32)
+        res["score%d" % c] = np.array(scores, np.float32)
+    refload.FakeInterpreter.input_shape = (1, 640, 640, 3)
+    np.savez_compressed(os.path.join(OUT, "ssd_post.npz"), op_boxes=ob, op_classes=ocl, op_scores=osc,
+                        names=np.array(names), wanted=np.array(wanted), **res)
+    print("ssd_post.npz", sum(len(res["lab%d" % c]) for c in range(cases)))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = refload.load()
+    golden_kalman(R)
+    golden_metric_iou(R)
+    golden_nms(R)
+    golden_yolo(R)
+    golden_ssd_post(R)
+    golden_tracker(R, "tracker_small.npz", seed=101, n_obj=12, dmax=16, frames=100, budget=20, max_age=30,
+                   store_inputs=True)
+    golden_tracker(R, "tracker_c1.npz", seed=102, n_obj=20, dmax=24, frames=300, budget=100, max_age=60,
+                   store_inputs=False)
+    golden_tracker(R, "tracker_delcount.npz", seed=103, n_obj=10, dmax=12, frames=240, budget=100, max_age=5,
+                   store_inputs=False, clutter_mean=0.0, respawn_prob=0.03)
+
+
+if __name__ == "__main__":
+    main()

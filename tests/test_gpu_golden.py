@@ -1,0 +1,105 @@
+"""GPU parity against fixtures produced by the UNMODIFIED reference (tests/golden/, oracle/make_golden.py):
+the CUDA path is compared with the reference's own outputs, not only with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests import goldens
+from tests.goldens import LABELS3
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["tracker_small.npz", "tracker_c1.npz", "tracker_delcount.npz"])
+def test_tracker_vs_reference_fixture(name):
+    from deepdish_b200.batched import BatchedTracker
+    g = goldens.load(name)
+    batches = goldens.tracker_batches(g)
+    if batches is None:
+        pytest.skip("regenerated inputs do not match the fixture checksum")
+    D = int(g["dmax"])
+    bt = BatchedTracker(1, LABELS3, max_tracks=96, max_dets=D, budget=int(g["budget"]), max_age=int(g["max_age"]))
+    stored = "in_feat" in g.files
+    for f, b in enumerate(batches):
+        got = bt.step(b.to("cuda")).cpu().numpy()[0]
+        n = int(b.count[0])
+        assert list(got[:n]) == list(g["det_ids"][f, :n]), f
+        v = bt.host_view(["n_tracks", "order", "track_id", "state", "tsu", "n_deleted", "deleted", "mean", "cov", "counts"])
+        nt = int(v["n_tracks"][0]); sl = v["order"][0, :nt]
+        assert nt == int(g["n_tracks"][f])
+        assert list(v["track_id"][0, sl]) == list(g["ids"][f, :nt])
+        assert list(v["state"][0, sl]) == list(g["states"][f, :nt])
+        assert list(v["tsu"][0, sl]) == list(g["tsu"][f, :nt])
+        dl = v["deleted"][0, :int(v["n_deleted"][0])]
+        assert list(v["track_id"][0, dl]) == [x for x in g["deleted"][f] if x >= 0]
+        np.testing.assert_array_equal(v["counts"][0], g["counts"][f])
+        if stored:
+            np.testing.assert_allclose(v["mean"][0, sl], g["means"][f, :nt], rtol=1e-4, atol=1e-9)
+            np.testing.assert_allclose(v["cov"][0, sl], g["covs"][f, :nt], rtol=1e-4, atol=1e-12)
+        elif f % 10 == 0:
+            np.testing.assert_allclose(v["mean"][0, sl], g["means"][f // 10, :nt], rtol=1e-4, atol=1e-9)
+    bt.check()
+    if name == "tracker_delcount.npz":
+        assert int(v["counts"][0, :, 3].sum()) > 0       # the del counter was exercised
+
+
+def test_nms_vs_reference_fixture():
+    from deepdish_b200 import ops
+    g = goldens.load("nms.npz")
+    B = len(g["counts"])
+    for thr in np.unique(g["thr"]):
+        sel = np.nonzero(g["thr"] == thr)[0]
+        keep, nkeep = ops.nms(ops._dev(g["boxes"][sel], torch.float64), ops._dev(g["scores"][sel], torch.float32),
+                              ops._dev(g["counts"][sel], torch.int32), float(thr))
+        keep, nkeep = keep.cpu().numpy(), nkeep.cpu().numpy()
+        for k, i in enumerate(sel):
+            assert nkeep[k] == g["nkeep"][i]
+            assert list(keep[k, :nkeep[k]]) == list(g["keep"][i, :g["nkeep"][i]]), i
+
+
+def test_yolo_decode_vs_reference_fixture():
+    from deepdish_b200 import ops
+    g = goldens.load("yolo.npz")
+    names, wanted = list(g["names"]), list(g["wanted"])
+    mask = torch.tensor([1 if n in wanted else 0 for n in names], dtype=torch.uint8, device="cuda")
+    head = torch.from_numpy(g["head"]).cuda()
+    out = ops.yolo_decode(head, mask, 0.25, (640, 480), (640, 480), ncap=256)
+    keep, nkeep = ops.nms(out["tlwh"], out["score"], out["count"], 0.6)
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    keep, nkeep = keep.cpu().numpy(), nkeep.cpu().numpy()
+    for f in range(head.shape[0]):
+        n = int(o["count"][f])
+        fidx = g["fidx%d" % f]                       # rows of the reference output that pass the box filter
+        assert n == len(fidx)
+        np.testing.assert_array_equal(o["tlwh"][f, :n], g["fbox%d" % f].reshape(-1, 4).astype(np.float64))
+        np.testing.assert_array_equal(o["score"][f, :n], g["score%d" % f][fidx])
+        np.testing.assert_array_equal(o["cls"][f, :n], g["cls%d" % f][fidx])
+        assert np.all(np.diff(o["anchor"][f, :n]) > 0)
+        assert list(keep[f, :nkeep[f]]) == list(g["keep%d" % f])
+    assert int(o["flags"].sum()) == 0
+
+
+def test_kalman_metric_iou_vs_reference_fixture():
+    from deepdish_b200 import ops
+    g = goldens.load("kalman.npz")
+    mean, cov = ops.kalman_initiate(ops._dev(g["z0"], torch.float64))
+    np.testing.assert_array_equal(mean.cpu().numpy(), g["seq_mean"][0])
+    np.testing.assert_array_equal(cov.cpu().numpy(), g["seq_cov"][0])
+    k = 0
+    for it in range(5):
+        ops.kalman_predict_(mean, cov); k += 1
+        np.testing.assert_allclose(mean.cpu().numpy(), g["seq_mean"][k], rtol=1e-9)
+        np.testing.assert_allclose(cov.cpu().numpy(), g["seq_cov"][k], rtol=1e-7, atol=1e-13)
+        ops.kalman_update_(mean, cov, ops._dev(g["zs"][it], torch.float64)); k += 1
+        np.testing.assert_allclose(mean.cpu().numpy(), g["seq_mean"][k], rtol=1e-9)
+        np.testing.assert_allclose(cov.cpu().numpy(), g["seq_cov"][k], rtol=1e-7, atol=1e-13)
+    meas = ops._dev(g["meas"], torch.float64)
+    np.testing.assert_allclose(ops.kalman_gating_distance(mean, cov, meas).cpu().numpy(), g["gating4"], rtol=1e-7)
+    np.testing.assert_allclose(ops.kalman_gating_distance(mean, cov, meas, True).cpu().numpy(), g["gating2"], rtol=1e-7)
+    m = goldens.load("metric_iou.npz")
+    gal, off, feats = ops._dev(m["gallery"], torch.float32), ops._dev(m["offsets"], torch.int32), ops._dev(m["feats"], torch.float32)
+    np.testing.assert_allclose(ops.nn_distance(gal, off, feats, "cosine").cpu().numpy(), m["cosine"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(ops.nn_distance(gal, off, feats, "euclidean").cpu().numpy(), m["euclidean"], rtol=1e-4, atol=5e-4)
+    cost = ops.iou_cost(ops._dev(m["trk_tlwh"], torch.float64), torch.ones(len(m["trk_tlwh"]), dtype=torch.int32, device="cuda"),
+                        ops._dev(m["det_tlwh"], torch.float64))
+    np.testing.assert_array_equal(cost.cpu().numpy(), 1. - m["iou"])

@@ -1,0 +1,76 @@
+"""CPU tests of the kernel bodies' serial logic through the host emulation (tests/hostemu): the same
+source files the CUDA kernels are built from, compiled with a one-lane group.  Not a product path."""
+import random
+
+import numpy as np
+from scipy.optimize import linear_sum_assignment
+
+from deepdish_b200 import _lib as L
+from deepdish_b200.scene import Scene
+from oracle import deepsort as od
+from tests.hostemu import driver as hd
+from tests.parity import OracleStreams, compare_stream, compare_costs, LABELS3
+
+
+def _matrices(rng, n):
+    for trial in range(n):
+        nr, nc = rng.integers(1, 14), rng.integers(1, 14)
+        kind = trial % 4
+        if kind == 0:
+            c = rng.integers(0, 4, (nr, nc)).astype(float)
+        elif kind == 1:
+            c = rng.random((nr, nc)); c[c > 0.3] = 0.20001
+        elif kind == 2:
+            c = np.full((nr, nc), 0.20001)
+            for i in range(min(nr, nc)):
+                if rng.random() < 0.7:
+                    c[i, rng.integers(0, nc)] = rng.random() * 0.2
+        else:
+            c = rng.random((nr, nc))
+        yield c
+
+
+def test_lsap_device_code_and_oracle_port_match_scipy():
+    rng = np.random.default_rng(0)
+    for c in _matrices(rng, 1500):
+        r, cc = linear_sum_assignment(c)
+        exp = np.full(c.shape[0], -1); exp[r] = cc
+        rc, out = hd.lsap(c)
+        assert rc == 0 and np.array_equal(exp, out)
+        pr, pc = od.lsap_port(c)
+        assert np.array_equal(pr, r) and np.array_equal(pc, cc)
+
+
+def test_set_difference_order_matches_cpython():
+    random.seed(1)
+    for trial in range(6000):
+        n = random.randint(0, 200)
+        a = list(range(n)) if trial % 5 else random.sample(range(300), min(n, 250))
+        m = random.sample(a, random.randint(0, len(a))) if trial % 3 else random.sample(a, min(len(a), random.randint(0, 6)))
+        exp = list(set(a) - set(m))
+        assert hd.set_difference_order(a, m) == exp
+        if trial % 5:
+            assert od.cpython_set_difference_order(n, m) == exp
+
+
+def test_trajectory_parity_host_emulation():
+    S = 3
+    cfg = L.make_config(S, 64, 24, 100, LABELS3, max_age=30)
+    emu = hd.HostEmuTracker(cfg)
+    orc = OracleStreams(S, LABELS3, max_age=30)
+    sc = Scene(S, 20, 24, n_labels=3, seed=7)
+    checked = 0
+    for f in range(70):
+        b = sc.step()
+        pre = {k: emu.v[k].copy() for k in ("n_tracks", "order", "track_id")}
+        ids = orc.step(b)
+        emu.predict()
+        got = emu.update(b.tlwh.numpy(), b.conf.numpy(), b.label.numpy(), b.feat.numpy(), b.count.numpy())
+        emu.countline()
+        for s in range(S):
+            n = int(b.count[s])
+            assert list(got[s, :n]) == ids[s], (f, s)
+            compare_stream(orc.trk[s], orc.cnt[s], emu.v, s, LABELS3)
+            if f > 5:
+                checked += compare_costs(orc.trk[s], pre, emu.v, s)
+    assert checked > 500 and int(emu.v["err"].sum()) == 0
