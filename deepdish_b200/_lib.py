@@ -98,6 +98,7 @@ def lib():
         "dd_event_destroy": [_vp],
         "dd_event_elapsed_ms": [_vp, _vp, ctypes.POINTER(ctypes.c_float)],
         "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
+        "dd_tracker_tick": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
         "dd_tracker_count_reduce": [_vp, cfgp, _vp, _vp],
         "dd_tracker_status": [_vp, cfgp, ctypes.POINTER(_i32), _vp],
         "dd_kalman_initiate": [_vp, _vp, _vp, _i32, _vp],

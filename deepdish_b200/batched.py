@@ -2,10 +2,17 @@
 
 The batched extension of the reference's ``deep_sort.tracker.Tracker``: same
 ``predict()`` / ``update(detections)`` call sequence (tracker.py:51-93), plus the count-line step of
-``Pipeline.process_results`` (deepdish.py:1035-1114).  All state lives in one caller-owned device
-blob whose layout is defined by the C ABI (include/deepdish_b200.h); this class only allocates it
-with torch, passes raw pointers + the current CUDA stream to libdeepdish_b200.so, and exposes typed
-torch views for inspection.  There is no CPU path.
+``Pipeline.process_results`` (deepdish.py:1035-1114).  All state lives in caller-owned device blobs
+whose layout is defined by the C ABI (include/deepdish_b200.h); this class only allocates them with
+torch, passes raw pointers + a CUDA stream to libdeepdish_b200.so, and exposes typed torch views for
+inspection.  There is no CPU path.
+
+Stream chunks.  Streams never interact, so the S streams can be split into ``n_chunks`` contiguous
+chunks, each with its own state blob and its own CUDA stream.  A chunk's tick is a strictly ordered
+kernel sequence on its stream; different chunks overlap freely, so the latency-bound per-stream
+matching kernel of one chunk runs under the HBM-bound gallery kernel of another, also across tick
+boundaries.  ``step(..., join=False)`` only enqueues; ``join()`` makes the caller's stream wait for
+every chunk.  With ``n_chunks=1`` everything runs on the caller's current stream.
 """
 import ctypes
 
@@ -17,78 +24,176 @@ _DT = {"int32": torch.int32, "int64": torch.int64, "float32": torch.float32,
        "float64": torch.float64}
 
 
+class _Chunk:
+    """One contiguous block of streams: config, state blob, typed views, CUDA stream."""
+
+    def __init__(self, owner, lo, hi, stream):
+        self.lo, self.hi = lo, hi
+        self.stream = stream
+        o = owner
+        self.cfg = _lib.make_config(hi - lo, o.max_tracks, o.max_dets, o.budget, o.labels, max_age=o.max_age,
+                                    n_init=o.n_init, max_cosine_distance=o.max_cosine_distance,
+                                    max_iou_distance=o.max_iou_distance)
+        self.cfgp = ctypes.byref(self.cfg)
+        self.lay = _lib.TrackerLayout()
+        _lib.check(o.lib.dd_tracker_layout_query(self.cfgp, ctypes.byref(self.lay)), "dd_tracker_layout_query")
+        self.blob = torch.empty(self.lay.total_bytes, dtype=torch.uint8, device=o.device)
+        self.state = self.blob.data_ptr()
+        self.v = {}
+        for name, (dt, shape) in _lib.field_specs(self.cfg).items():
+            off = getattr(self.lay, name)
+            n = torch.empty((), dtype=_DT[dt]).element_size()
+            for d in shape:
+                n *= d
+            self.v[name] = self.blob[off:off + n].view(_DT[dt]).view(shape)
+        self.done = torch.cuda.Event()
+        self.staging = None
+
+
+class _CatView:
+    """``bt.v[name]``: the state array of all streams (concatenation over chunks; a view when there
+    is a single chunk).  Read-only for n_chunks > 1."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def __getitem__(self, name):
+        o = self._o
+        if len(o.chunks) == 1:
+            return o.chunks[0].v[name]
+        o.join()
+        return torch.cat([c.v[name] for c in o.chunks], dim=0)
+
+    def __iter__(self):
+        return iter(self._o.chunks[0].v)
+
+    def keys(self):
+        return self._o.chunks[0].v.keys()
+
+
 class BatchedTracker:
     def __init__(self, n_streams, labels, max_tracks=128, max_dets=64, budget=100,
                  max_cosine_distance=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
-                 line=None, frame_size=(640, 480), device="cuda"):
+                 line=None, frame_size=(640, 480), device="cuda", n_chunks=1):
         self.lib = _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedTracker runs on a CUDA device only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.labels = list(labels)
-        self.cfg = _lib.make_config(n_streams, max_tracks, max_dets, budget, self.labels,
-                                    max_age=max_age, n_init=n_init,
-                                    max_cosine_distance=max_cosine_distance,
-                                    max_iou_distance=max_iou_distance)
-        self.lay = _lib.TrackerLayout()
-        _lib.check(self.lib.dd_tracker_layout_query(ctypes.byref(self.cfg), ctypes.byref(self.lay)),
-                   "dd_tracker_layout_query")
-        self.blob = torch.empty(self.lay.total_bytes, dtype=torch.uint8, device=self.device)
-        self.v = {}
-        for name, (dt, shape) in _lib.field_specs(self.cfg).items():
-            off = getattr(self.lay, name)
-            n = 1
-            for d in shape:
-                n *= d
-            n *= torch.empty((), dtype=_DT[dt]).element_size()
-            self.v[name] = self.blob[off:off + n].view(_DT[dt]).view(shape)
+        self.n_streams, self.max_tracks, self.max_dets, self.budget = n_streams, max_tracks, max_dets, budget
+        self.max_age, self.n_init = max_age, n_init
+        self.max_cosine_distance, self.max_iou_distance = max_cosine_distance, max_iou_distance
+        n_chunks = max(1, min(int(n_chunks), n_streams))
+        from .sharding import shard_range
+        self.chunks = []
+        with torch.cuda.device(self.device):
+            for i in range(n_chunks):
+                lo, hi = shard_range(n_streams, i, n_chunks)
+                st = None if n_chunks == 1 else torch.cuda.Stream(device=self.device)
+                self.chunks.append(_Chunk(self, lo, hi, st))
+        self.cfg = self.chunks[0].cfg if n_chunks == 1 else _lib.make_config(
+            n_streams, max_tracks, max_dets, budget, self.labels, max_age=max_age, n_init=n_init,
+            max_cosine_distance=max_cosine_distance, max_iou_distance=max_iou_distance)
+        self.v = _CatView(self)
         if line is None:                      # deepdish.py:739-744
             w, h = frame_size
             line = (float(int(w / 2)), 0.0, float(int(w / 2)), float(int(h)))
         lt = torch.as_tensor(line, dtype=torch.float64)
         self.line_per_stream = 1 if lt.dim() == 2 else 0
         self.line = lt.to(self.device).contiguous()
-        S, D = n_streams, max_dets
+        S, D, C = n_streams, max_dets, len(self.labels)
         self.det_track_id = torch.full((S, D), -1, dtype=torch.int32, device=self.device)
-        self.total_counts = torch.zeros((len(self.labels), 4), dtype=torch.int64, device=self.device)
-        self._cfgp = ctypes.byref(self.cfg)
-        self._state = self.blob.data_ptr()
-        _lib.check(self.lib.dd_tracker_init(self._state, self._cfgp, self._stream()), "dd_tracker_init")
+        self.partial_counts = torch.zeros((2, n_chunks, C, 4), dtype=torch.int64, device=self.device)
+        self.total_counts = torch.zeros((C, 4), dtype=torch.int64, device=self.device)
+        self._tick = 0
+        self._sum_done = [None, None]
+        torch.cuda.synchronize(self.device)
+        for c in self.chunks:
+            _lib.check(self.lib.dd_tracker_init(c.state, c.cfgp, self._sp(c)), "dd_tracker_init")
+        self.join()
 
     # ------------------------------------------------------------------------------------------
-    def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    def _cur(self):
+        return torch.cuda.current_stream(self.device)
 
+    def _sp(self, c):
+        s = c.stream if c.stream is not None else self._cur()
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def _fork(self, tensors=()):
+        """Chunk streams wait for everything already enqueued on the caller's stream."""
+        if len(self.chunks) == 1:
+            return
+        ev = self._cur().record_event()
+        for c in self.chunks:
+            c.stream.wait_event(ev)
+            for t in tensors:
+                t.record_stream(c.stream)
+
+    def _mark(self):
+        if len(self.chunks) > 1:
+            for c in self.chunks:
+                c.done.record(c.stream)
+
+    def join(self):
+        """Make the caller's current stream wait for all chunk streams (no host synchronisation)."""
+        if len(self.chunks) == 1:
+            return
+        cur = self._cur()
+        for c in self.chunks:
+            c.done.record(c.stream)
+            cur.wait_event(c.done)
+
+    def _line_ptr(self, c):
+        return self.line.data_ptr() + (c.lo * 32 if self.line_per_stream else 0)
+
+    def _check_batch(self, tlwh, conf, label, feat, count):
+        S, D = self.n_streams, self.max_dets
+        for t, dt, shape in ((tlwh, torch.float64, (S, D, 4)), (conf, torch.float32, (S, D)),
+                             (label, torch.int32, (S, D)), (feat, torch.float32, (S, D, 128)),
+                             (count, torch.int32, (S,))):
+            if t.dtype != dt or tuple(t.shape) != shape or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("expected contiguous CUDA %s %s, got %s %s on %s"
+                                 % (dt, shape, t.dtype, tuple(t.shape), t.device))
+
+    @staticmethod
+    def _ptrs(c, tlwh, conf, label, feat, count, ids):
+        D = conf.shape[1]
+        lo = c.lo
+        return (tlwh.data_ptr() + lo * D * 32, conf.data_ptr() + lo * D * 4, label.data_ptr() + lo * D * 4,
+                feat.data_ptr() + lo * D * 512, count.data_ptr() + lo * 4, ids.data_ptr() + lo * D * 4)
+
+    # ------------------------------------------------------------------------------------------
     def predict(self):
         """Tracker.predict for every stream (tracker.py:51-57)."""
-        _lib.check(self.lib.dd_tracker_predict(self._state, self._cfgp, self._stream()),
-                   "dd_tracker_predict")
+        self._fork()
+        for c in self.chunks:
+            _lib.check(self.lib.dd_tracker_predict(c.state, c.cfgp, self._sp(c)), "dd_tracker_predict")
+        self.join()
 
     def update(self, tlwh, conf, label, feat, count):
         """Tracker.update for every stream (tracker.py:59-93).
 
         tlwh f64 [S,Dmax,4], conf f32 [S,Dmax], label i32 [S,Dmax], feat f32 [S,Dmax,128], count i32 [S]
         -- device tensors, padded.  Returns det_track_id i32 [S,Dmax] (device; -1 = padding)."""
-        S, D = self.cfg.n_streams, self.cfg.max_dets
-        for t, dt, shape in ((tlwh, torch.float64, (S, D, 4)), (conf, torch.float32, (S, D)),
-                             (label, torch.int32, (S, D)), (feat, torch.float32, (S, D, 128)),
-                             (count, torch.int32, (S,))):
-            if t.dtype != dt or tuple(t.shape) != shape or not t.is_cuda or not t.is_contiguous():
-                raise ValueError("update(): expected contiguous CUDA %s %s, got %s %s on %s"
-                                 % (dt, shape, t.dtype, tuple(t.shape), t.device))
-        _lib.check(self.lib.dd_tracker_update(
-            self._state, self._cfgp, tlwh.data_ptr(), conf.data_ptr(), label.data_ptr(),
-            feat.data_ptr(), count.data_ptr(), self.det_track_id.data_ptr(), self._stream()),
-            "dd_tracker_update")
+        self._check_batch(tlwh, conf, label, feat, count)
+        self._fork((tlwh, conf, label, feat, count))
+        for c in self.chunks:
+            p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
+            _lib.check(self.lib.dd_tracker_update(c.state, c.cfgp, *p, self._sp(c)), "dd_tracker_update")
+        self.join()
         return self.det_track_id
 
     def update_profiled(self, tlwh, conf, label, feat, count, events5):
-        """update() that records 5 CUDA events (see dd_tracker_update_profiled); events5 = ctypes
-        array of handles from new_events()."""
-        _lib.check(self.lib.dd_tracker_update_profiled(
-            self._state, self._cfgp, tlwh.data_ptr(), conf.data_ptr(), label.data_ptr(),
-            feat.data_ptr(), count.data_ptr(), self.det_track_id.data_ptr(), self._stream(), events5),
-            "dd_tracker_update_profiled")
+        """update() that records 5 CUDA events (see dd_tracker_update_profiled); single chunk only."""
+        if len(self.chunks) != 1:
+            raise RuntimeError("update_profiled needs n_chunks=1")
+        c = self.chunks[0]
+        p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
+        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events5),
+                   "dd_tracker_update_profiled")
         return self.det_track_id
 
     def new_events(self, n=5):
@@ -106,59 +211,134 @@ class BatchedTracker:
 
     def countline(self):
         """Count-line step (deepdish.py:1041-1112) on the state left by update()."""
-        _lib.check(self.lib.dd_tracker_countline(self._state, self._cfgp, self.line.data_ptr(),
-                                                 self.line_per_stream, self._stream()),
-                   "dd_tracker_countline")
+        self._fork()
+        for c in self.chunks:
+            _lib.check(self.lib.dd_tracker_countline(c.state, c.cfgp, self._line_ptr(c), self.line_per_stream,
+                                                     self._sp(c)), "dd_tracker_countline")
+        self.join()
 
-    def step(self, batch):
-        """predict + update + countline for one SceneBatch-like object (device tensors)."""
-        self.predict()
-        ids = self.update(batch.tlwh, batch.conf, batch.label, batch.feat, batch.count)
-        self.countline()
-        return ids
+    def step(self, batch, join=True, reduce=False):
+        """One tick (predict + update + count-line [+ per-chunk count reduction]) for a SceneBatch-like
+        object of device tensors: one fused C call per chunk.  join=False only enqueues (call join())."""
+        tlwh, conf, label, feat, count = batch.tlwh, batch.conf, batch.label, batch.feat, batch.count
+        self._check_batch(tlwh, conf, label, feat, count)
+        self._fork((tlwh, conf, label, feat, count))
+        par = self._tick & 1
+        multi = len(self.chunks) > 1
+        if reduce and multi and self._sum_done[par] is not None:
+            for c in self.chunks:              # partial_counts[par] of tick-2 must have been summed
+                c.stream.wait_event(self._sum_done[par])
+        for i, c in enumerate(self.chunks):
+            p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
+            out = self.partial_counts[par, i].data_ptr() if reduce else None
+            _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream,
+                                                out, self._sp(c)), "dd_tracker_tick")
+        self._mark()
+        if reduce:
+            self._sum_partials(par)
+        self._tick += 1
+        if join:
+            self.join()
+        return self.det_track_id
 
-    def step_host(self, host_batch):
-        """End-to-end entry: pinned HOST batch -> H2D -> tick -> device-side count reduction.
-        Returns (det_track_id, total_counts) device tensors; the caller reads them back."""
-        dev = host_batch.to(self.device, non_blocking=True)
-        ids = self.step(dev)
-        return ids, self.reduce_counts()
+    def _sum_partials(self, par):
+        """caller's stream: wait for the chunks' partial counters of this tick, sum them."""
+        cur = self._cur()
+        multi = len(self.chunks) > 1
+        if multi:
+            for c in self.chunks:
+                cur.wait_event(c.done)
+        torch.sum(self.partial_counts[par], dim=0, out=self.total_counts)
+        if multi:
+            self._sum_done[par] = cur.record_event()
+
+    def step_host(self, host_batch, out_ids_host=None):
+        """End-to-end tick from a pinned HOST batch: per chunk and on the chunk's stream, H2D copy of its
+        slice into a staging buffer, the tick, the partial count reduction and (optionally) the D2H copy
+        of its det->track ids into the pinned ``out_ids_host``.  Returns total_counts (device, summed on the
+        caller's stream)."""
+        D = self.max_dets
+        par = self._tick & 1
+        multi = len(self.chunks) > 1
+        if multi and self._sum_done[par] is not None:
+            for c in self.chunks:
+                c.stream.wait_event(self._sum_done[par])
+        src = (host_batch.tlwh, host_batch.conf, host_batch.label, host_batch.feat, host_batch.count)
+        for i, c in enumerate(self.chunks):
+            n = c.hi - c.lo
+            st = c.stream if multi else self._cur()
+            with torch.cuda.stream(st):
+                if c.staging is None:
+                    c.staging = (torch.empty((n, D, 4), dtype=torch.float64, device=self.device),
+                                 torch.empty((n, D), dtype=torch.float32, device=self.device),
+                                 torch.empty((n, D), dtype=torch.int32, device=self.device),
+                                 torch.empty((n, D, 128), dtype=torch.float32, device=self.device),
+                                 torch.empty((n,), dtype=torch.int32, device=self.device))
+                for dst, s in zip(c.staging, src):
+                    dst.copy_(s[c.lo:c.hi], non_blocking=True)
+                t, cf, lb, ft, ct = c.staging
+                ids = self.det_track_id[c.lo:c.hi]
+                _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, t.data_ptr(), cf.data_ptr(), lb.data_ptr(),
+                                                    ft.data_ptr(), ct.data_ptr(), ids.data_ptr(),
+                                                    self._line_ptr(c), self.line_per_stream,
+                                                    self.partial_counts[par, i].data_ptr(),
+                                                    ctypes.c_void_p(st.cuda_stream)), "dd_tracker_tick")
+                if out_ids_host is not None:
+                    out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
+        self._mark()
+        self._sum_partials(par)
+        self._tick += 1
+        return self.total_counts
 
     def reduce_counts(self):
         """Sum the per-stream counters -> i64 [C,4] (pos, neg, int, del per label), this GPU only."""
-        _lib.check(self.lib.dd_tracker_count_reduce(self._state, self._cfgp,
-                                                    self.total_counts.data_ptr(), self._stream()),
-                   "dd_tracker_count_reduce")
+        self._fork()
+        par = self._tick & 1
+        multi = len(self.chunks) > 1
+        if multi and self._sum_done[par] is not None:
+            for c in self.chunks:
+                c.stream.wait_event(self._sum_done[par])
+        for i, c in enumerate(self.chunks):
+            _lib.check(self.lib.dd_tracker_count_reduce(c.state, c.cfgp, self.partial_counts[par, i].data_ptr(),
+                                                        self._sp(c)), "dd_tracker_count_reduce")
+        self._mark()
+        self._sum_partials(par)
+        self._tick += 1
         return self.total_counts
 
-    def all_reduce_counts(self):
-        """reduce_counts() followed by the NCCL all-reduce over ranks (the only collective)."""
-        t = self.reduce_counts()
+    def all_reduce_counts(self, reduced=False):
+        """[C,4] counters summed over streams and, over NCCL, ranks (the path's only collective).
+        reduced=True: total_counts already holds this tick's local sum (step(reduce=True) / step_host)."""
+        t = self.total_counts if reduced else self.reduce_counts()
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
     def status(self):
-        flags = ctypes.c_int32(0)
-        _lib.check(self.lib.dd_tracker_status(self._state, self._cfgp, ctypes.byref(flags),
-                                              self._stream()), "dd_tracker_status")
-        return flags.value
+        self.join()
+        out = 0
+        for c in self.chunks:
+            flags = ctypes.c_int32(0)
+            _lib.check(self.lib.dd_tracker_status(c.state, c.cfgp, ctypes.byref(flags), self._sp(c)),
+                       "dd_tracker_status")
+            out |= flags.value
+        return out
 
     def check(self):
         """Raise if any stream overflowed its capacities (never silently truncated)."""
         f = self.status()
         if f & _lib.FLAG_TRACK_OVERFLOW:
-            raise RuntimeError("track capacity exceeded (max_tracks=%d)" % self.cfg.max_tracks)
+            raise RuntimeError("track capacity exceeded (max_tracks=%d)" % self.max_tracks)
         if f & _lib.FLAG_DET_OVERFLOW:
-            raise RuntimeError("detection capacity exceeded (max_dets=%d)" % self.cfg.max_dets)
+            raise RuntimeError("detection capacity exceeded (max_dets=%d)" % self.max_dets)
         if f & _lib.FLAG_LSAP_INFEASIBLE:
             raise ValueError("cost matrix is infeasible")
 
     # ------------------------------------------------------------------------------------------
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
-        names = names or [n for n in self.v if n not in ("gal", "cost", "gate", "det_featn")]
+        names = names or [n for n in self.v.keys() if n not in ("gal", "cost", "gate", "det_featn")]
         out = {}
         for n in names:
             t = self.v[n]
@@ -169,11 +349,14 @@ class BatchedTracker:
 
     def gallery_vectors(self):
         """Total gallery vectors of confirmed live tracks (G in SURVEY.md section 8d), per stream."""
-        S, T = self.cfg.n_streams, self.cfg.max_tracks
-        valid = torch.arange(T, device=self.device)[None, :] < self.v["n_tracks"][:, None]
-        rows = torch.arange(S, device=self.device)[:, None].expand(S, T)[valid]
-        slots = self.v["order"].long()[valid]
-        live = torch.zeros((S, T), dtype=torch.bool, device=self.device)
-        live[rows, slots] = True
-        conf = live & (self.v["state"] == 2)
-        return (self.v["gal_len"] * conf).sum(dim=1)
+        self.join()
+        outs = []
+        for c in self.chunks:
+            S, T = c.hi - c.lo, self.max_tracks
+            valid = torch.arange(T, device=self.device)[None, :] < c.v["n_tracks"][:, None]
+            rows = torch.arange(S, device=self.device)[:, None].expand(S, T)[valid]
+            slots = c.v["order"].long()[valid]
+            live = torch.zeros((S, T), dtype=torch.bool, device=self.device)
+            live[rows, slots] = True
+            outs.append((c.v["gal_len"] * (live & (c.v["state"] == 2))).sum(dim=1))
+        return torch.cat(outs)

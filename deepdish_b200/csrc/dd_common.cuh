@@ -99,16 +99,25 @@ struct WarpG {
         total = __popc(m);
         return __popc(m & ((1u << lane) - 1u));
     }
+    // Warp-wide best key in 3 REDUX ops: min over an order-preserving 64-bit image of the double
+    // (hi word, then lo word among the hi-minimal lanes), then max pref among the value-minimal lanes.
+    // -0.0 is folded into +0.0 first so that bit equality == IEEE equality (NaN sorts above +inf).
     __device__ DDKey best(DDKey k) const {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            DDKey t;
-            t.val = __shfl_xor_sync(0xffffffffu, k.val, o);
-            t.pref = __shfl_xor_sync(0xffffffffu, k.pref, o);
-            if (dd_key_better(t, k)) k = t;
-        }
-        return k;
+        long long b = __double_as_longlong(k.val + 0.0);
+        unsigned long long key = (unsigned long long)b ^ ((unsigned long long)(b >> 63) | 0x8000000000000000ull);
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+        const bool tie = (hi == mhi) && (lo == mlo);
+        const int mp = __reduce_max_sync(0xffffffffu, tie ? k.pref : (int)0x80000000);
+        key = ((unsigned long long)mhi << 32) | mlo;
+        key = (key & 0x8000000000000000ull) ? (key ^ 0x8000000000000000ull) : ~key;
+        DDKey r;
+        r.val = __longlong_as_double((long long)key);
+        r.pref = mp;
+        return r;
     }
+    __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
 };
 
 // ---------------------------------------------------------------------------------------- BlockG
@@ -135,6 +144,7 @@ struct HostG {
     float fmax(float v) const { return v; }
     unsigned bor(unsigned v) const { return v; }
     bool any(bool p) const { return p; }
+    bool all(bool p) const { return p; }
     int scan_excl(bool p, int& total) const { total = p ? 1 : 0; return 0; }
     DDKey best(DDKey k) const { return k; }
 };

@@ -81,30 +81,42 @@ DD_HD void dd_kf_project_cov(const double* mean, const double* cov, double* S) {
         }
 }
 
-// Lower Cholesky factor of a 4x4 (or leading n x n) SPD matrix, row-major, full storage.
-DD_HD void dd_chol4(const double* S, double* L, int n = 4) {
-    for (int i = 0; i < 16; ++i) L[i] = 0.0;
-    for (int j = 0; j < n; ++j) {
+// Lower Cholesky factor of the leading N x N block of a 4x4 SPD matrix (row-major, stride 4), fully
+// unrolled so L lives in registers; rinv[j] = 1 / L[j][j] is returned so the triangular solves multiply
+// by a reciprocal instead of dividing (LAPACK/OpenBLAS trsm kernels do the same; results differ from a
+// true division by <= 1 ulp, far inside the 1e-4 Kalman tolerance and the same for every code path here).
+template <int N>
+DD_HD void dd_chol(const double* S, double* L, double* rinv) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
         double d = S[j * 4 + j];
+#pragma unroll
         for (int k = 0; k < j; ++k) d = dd_sub(d, dd_mul(L[j * 4 + k], L[j * 4 + k]));
         const double ljj = dd_sqrt(d);
         L[j * 4 + j] = ljj;
-        for (int i = j + 1; i < n; ++i) {
+        const double r = dd_div(1.0, ljj);
+        rinv[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
             double v = S[i * 4 + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) v = dd_sub(v, dd_mul(L[i * 4 + k], L[j * 4 + k]));
-            L[i * 4 + j] = dd_div(v, ljj);
+            L[i * 4 + j] = dd_mul(v, r);
         }
     }
 }
 
 // kalman_filter.py:223-228 -- squared Mahalanobis distance of one measurement: solve L z = d.
-DD_HD double dd_maha_sq(const double* L, const double* pmean, const double* meas, int n = 4) {
-    double z[4];
+template <int N>
+DD_HD double dd_maha_sq(const double* L, const double* rinv, const double* pmean, const double* meas) {
+    double z[N];
     double acc = 0.0;
-    for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
         double v = dd_sub(meas[i], pmean[i]);
+#pragma unroll
         for (int k = 0; k < i; ++k) v = dd_sub(v, dd_mul(L[i * 4 + k], z[k]));
-        z[i] = dd_div(v, L[i * 4 + i]);
+        z[i] = dd_mul(v, rinv[i]);
         const double sq = dd_mul(z[i], z[i]);
         acc = (i == 0) ? sq : dd_add(acc, sq);
     }
@@ -116,31 +128,37 @@ template <class G>
 DD_HD void dd_kf_update(const G& g, double* mean, double* cov, const double* z, double* scratch) {
     double* Ksh = scratch;        // gain K [8][4]
     double* Msh = scratch + 32;   // S K^T  [4][8]
-    double S[16], L[16];
+    double S[16], L[16], rinv[4];
     dd_kf_project_cov(mean, cov, S);
-    dd_chol4(S, L);
+    dd_chol<4>(S, L, rinv);
     double innov[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) innov[i] = dd_sub(z[i], mean[i]);
     // K[c][:] = S^-1 (P H^T)^T[:, c]  -> cho_solve with rhs column c = P[c][0..3]
     for (int c = g.lane; c < 8; c += G::NL) {
         double y[4], x[4];
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
             double v = cov[c * 8 + i];
+#pragma unroll
             for (int k = 0; k < i; ++k) v = dd_sub(v, dd_mul(L[i * 4 + k], y[k]));
-            y[i] = dd_div(v, L[i * 4 + i]);
+            y[i] = dd_mul(v, rinv[i]);
         }
+#pragma unroll
         for (int i = 3; i >= 0; --i) {
             double v = y[i];
+#pragma unroll
             for (int k = i + 1; k < 4; ++k) v = dd_sub(v, dd_mul(L[k * 4 + i], x[k]));
-            x[i] = dd_div(v, L[i * 4 + i]);
+            x[i] = dd_mul(v, rinv[i]);
         }
+#pragma unroll
         for (int i = 0; i < 4; ++i) Ksh[c * 4 + i] = x[i];
     }
     g.sync();
     for (int e = g.lane; e < 32; e += G::NL) {       // M = S K^T
         const int i = e >> 3, j = e & 7;
         double v = dd_mul(S[i * 4 + 0], Ksh[j * 4 + 0]);
+#pragma unroll
         for (int k = 1; k < 4; ++k) v = dd_add(v, dd_mul(S[i * 4 + k], Ksh[j * 4 + k]));
         Msh[e] = v;
     }
@@ -151,6 +169,7 @@ DD_HD void dd_kf_update(const G& g, double* mean, double* cov, const double* z, 
     for (int e = g.lane; e < 64; e += G::NL, ++n) {  // P - K M
         const int a = e >> 3, b = e & 7;
         double v = dd_mul(Ksh[a * 4 + 0], Msh[0 * 8 + b]);
+#pragma unroll
         for (int i = 1; i < 4; ++i) v = dd_add(v, dd_mul(Ksh[a * 4 + i], Msh[i * 8 + b]));
         outv[n] = dd_sub(cov[e], v);
     }
@@ -158,6 +177,7 @@ DD_HD void dd_kf_update(const G& g, double* mean, double* cov, const double* z, 
     n = 0;
     for (int j = g.lane; j < 8; j += G::NL, ++n) {   // mean + innov . K^T
         double v = dd_mul(innov[0], Ksh[j * 4 + 0]);
+#pragma unroll
         for (int i = 1; i < 4; ++i) v = dd_add(v, dd_mul(innov[i], Ksh[j * 4 + i]));
         mnew[n] = dd_add(mean[j], v);
     }

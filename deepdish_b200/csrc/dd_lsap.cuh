@@ -235,3 +235,20 @@ DD_HD int dd_set_difference_order_serial(const short* a, int na, const unsigned 
         if (R[i]) out[n_out++] = (short)(R[i] - 1);
     return n_out;
 }
+
+// Fast path for the case the tracker always produces: a = [0, 1, ..., n-1].
+// set(range(n)) places key k in slot k at every table size (k < fill <= 3/5 mask), so its slot order is
+// ascending and only the survivors matter:
+//   (n >> 2) > nm  : set_copy_and_difference -> ascending survivors (caller already has them);
+//   otherwise      : the survivors, in ascending order, are inserted into a fresh set with CPython's
+//                    growth rule and read back in slot order (dd_set_order_from_survivors).
+DD_HD int dd_set_order_from_survivors(const short* surv_asc, int k, short* out, short* bufA, short* bufB) {
+    short *R = bufA, *Rt = bufB;
+    int maskR = 7, fillR = 0;
+    for (int i = 0; i < 8; ++i) R[i] = 0;
+    for (int i = 0; i < k; ++i) dd_set_add(R, Rt, maskR, fillR, surv_asc[i]);
+    int n_out = 0;
+    for (int i = 0; i <= maskR; ++i)
+        if (R[i]) out[n_out++] = (short)(R[i] - 1);
+    return n_out;
+}

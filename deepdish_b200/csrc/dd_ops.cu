@@ -54,12 +54,16 @@ k_kf_gating(const double* __restrict__ mean, const double* __restrict__ cov, con
     if (w >= n) return;
     const int lane = threadIdx.x & 31;
     const double* mu = mean + (size_t)w * 8;
-    double S[16], L[16];
+    double S[16], L[16], rinv[4];
     dd_kf_project_cov(mu, cov + (size_t)w * 64, S);
-    const int dim = only_position ? 2 : 4;
-    dd_chol4(S, L, dim);
     const double pm[4] = {mu[0], mu[1], mu[2], mu[3]};
-    for (int j = lane; j < m; j += 32) out[(size_t)w * m + j] = dd_maha_sq(L, pm, xyah + (size_t)j * 4, dim);
+    if (only_position) {
+        dd_chol<2>(S, L, rinv);
+        for (int j = lane; j < m; j += 32) out[(size_t)w * m + j] = dd_maha_sq<2>(L, rinv, pm, xyah + (size_t)j * 4);
+    } else {
+        dd_chol<4>(S, L, rinv);
+        for (int j = lane; j < m; j += 32) out[(size_t)w * m + j] = dd_maha_sq<4>(L, rinv, pm, xyah + (size_t)j * 4);
+    }
 }
 
 // one warp per (target, query): nn_matching.py:31-54 (normalise rows, 1 - a.b) / :5-28 (pdist).
@@ -166,7 +170,19 @@ k_set_diff(const int* __restrict__ a, const int* __restrict__ na, int na_max, co
     for (int i = lane; i < k; i += 32) flag[mm[(size_t)p * nm_max + i] & 1023] = 1;
     __syncwarp();
     int cnt = 0;
-    if (lane == 0) cnt = dd_set_difference_order_serial(av, n, flag, k, ov, tA, tB, tC, cap);
+    if (lane == 0) {
+        bool contig = true;
+        for (int i = 0; i < n; ++i) contig = contig && av[i] == i;
+        if (contig) {                       // the path the tracker takes (dd_match_stream)
+            short* surv = tC;
+            int ns = 0;
+            for (int i = 0; i < n; ++i) if (!flag[i]) surv[ns++] = (short)i;
+            if ((n >> 2) > k) { for (int i = 0; i < ns; ++i) ov[i] = surv[i]; cnt = ns; }
+            else cnt = dd_set_order_from_survivors(surv, ns, ov, tA, tB);
+        } else {
+            cnt = dd_set_difference_order_serial(av, n, flag, k, ov, tA, tB, tC, cap);
+        }
+    }
     cnt = __shfl_sync(0xffffffffu, cnt, 0);
     __syncwarp();
     for (int i = lane; i < cnt; i += 32) out[(size_t)p * na_max + i] = ov[i];

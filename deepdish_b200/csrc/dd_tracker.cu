@@ -205,6 +205,28 @@ int dd_tracker_countline(void* state, const dd_tracker_config* cfg, const double
     return DD_OK;
 }
 
+int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                    const float* det_conf, const int32_t* det_label, const float* det_feat,
+                    const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                    int line_per_stream, int64_t* out_counts, void* stream) {
+    DDView V;
+    int rc = dd_make_view(state, cfg, &V);
+    if (rc != DD_OK) return rc;
+    if (!line) return DD_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_predict<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V);
+    DD_CHECK_LAUNCH();
+    rc = dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, st, nullptr);
+    if (rc != DD_OK) return rc;
+    k_countline<<<warps_to_blocks(V.S), DD_WARPS * 32, 0, st>>>(V, line, line_per_stream);
+    DD_CHECK_LAUNCH();
+    if (out_counts) {
+        k_count_reduce<<<V.C * 4, 256, 0, st>>>(V.counts, V.S, V.C * 4, (long long*)out_counts);
+        DD_CHECK_LAUNCH();
+    }
+    return DD_OK;
+}
+
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* cfg, int64_t* out_counts, void* stream) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);

@@ -178,9 +178,9 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
     int nd = det_count[s];
     if (nd > V.D) nd = V.D;
     const double* mean = V.mean + slot * 8;
-    double S[16], L[16];
+    double S[16], L[16], rinv[4];
     dd_kf_project_cov(mean, V.cov + slot * 64, S);
-    dd_chol4(S, L);
+    dd_chol<4>(S, L, rinv);
     const double pm[4] = {mean[0], mean[1], mean[2], mean[3]};
     const int glen = V.gal_len[slot];
     const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
@@ -188,7 +188,7 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
         unsigned word = 0;
         const int lim = dd_imin(base + 32, nd);
         for (int j = base + g.lane; j < lim; j += G::NL) {
-            const double d2 = dd_maha_sq(L, pm, V.det_xyah + ((size_t)s * V.D + j) * 4);
+            const double d2 = dd_maha_sq<4>(L, rinv, pm, V.det_xyah + ((size_t)s * V.D + j) * 4);
             if (!(d2 > DD_CHI2INV95_4)) word |= 1u << (j - base);
         }
         word = g.bor(word);
@@ -231,6 +231,7 @@ struct DDMatchSmem {
     unsigned char *trk_state, *flag;
     short *tabA, *tabB, *tabC;
     int tab_cap;
+    double* tbox;      // [T][5]  x, y, x2, y2, area of the IoU-stage rows (Track.to_tlwh, track.py:84-97)
 };
 
 DD_HD size_t dd_match_smem_bytes(int T, int D) {
@@ -240,6 +241,8 @@ DD_HD size_t dd_match_smem_bytes(int T, int D) {
     b += (size_t)T * 2;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)dd_set_table_slots(T) * 2 * 3;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)T * 5 * 8;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -263,7 +266,9 @@ DD_HD void dd_match_carve(char* mem, int T, int D, DDMatchSmem& m) {
     m.tab_cap = dd_set_table_slots(T);
     m.tabA = (short*)p; p += m.tab_cap * 2;
     m.tabB = (short*)p; p += m.tab_cap * 2;
-    m.tabC = (short*)p;
+    m.tabC = (short*)p; p += m.tab_cap * 2;
+    p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    m.tbox = (double*)p;
 }
 
 // cost functors: (r, c) are positions in the rows[] / cols[] lists of the current sub-problem.
@@ -286,24 +291,20 @@ struct DDCosineCost {      // tracker.py:97-105 + linear_assignment.py:57
 };
 
 struct DDIouCost {         // iou_matching.py:7-81 + linear_assignment.py:57
-    const double* mean;    // stream base [T, 8]
+    const double* tbox;    // [nr][5] per row: x, y, x2, y2, area (INFTY rows: area < 0)
     const double* det_tlwh;// stream base [D, 4]
-    const short *trk_slot, *trk_tsu, *rows, *cols;
+    const short* cols;
     double thr, clip;
     DD_HD double raw(int r, int c) const {
-        const int t = rows[r];
-        if (trk_tsu[t] > 1) return DD_INFTY_COST;
-        const double* m = mean + (size_t)trk_slot[t] * 8;
-        // Track.to_tlwh (track.py:84-97)
-        const double w = dd_mul(m[2], m[3]), h = m[3];
-        const double x = dd_sub(m[0], dd_div(w, 2.0)), y = dd_sub(m[1], dd_div(h, 2.0));
+        const double* t = tbox + r * 5;
+        if (t[4] < 0.0) return DD_INFTY_COST;          // time_since_update > 1 (iou_matching.py:74-76)
         const double* b = det_tlwh + (size_t)cols[c] * 4;
-        const double tlx = dd_max(x, b[0]), tly = dd_max(y, b[1]);
-        const double brx = dd_min(dd_add(x, w), dd_add(b[0], b[2]));
-        const double bry = dd_min(dd_add(y, h), dd_add(b[1], b[3]));
+        const double tlx = dd_max(t[0], b[0]), tly = dd_max(t[1], b[1]);
+        const double brx = dd_min(t[2], dd_add(b[0], b[2]));
+        const double bry = dd_min(t[3], dd_add(b[1], b[3]));
         const double iw = dd_max(0.0, dd_sub(brx, tlx)), ih = dd_max(0.0, dd_sub(bry, tly));
         const double inter = dd_mul(iw, ih);
-        const double uni = dd_sub(dd_add(dd_mul(w, h), dd_mul(b[2], b[3])), inter);
+        const double uni = dd_sub(dd_add(t[4], dd_mul(b[2], b[3])), inter);
         return dd_sub(1.0, dd_div(inter, uni));
     }
     DD_HD double operator()(int r, int c) const {
@@ -446,19 +447,42 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
     // ---- unmatched confirmed tracks in CPython set order (linear_assignment.py:140)
     int n_unm_a = 0;
     {
-        int nmatched = 0;
-        for (int k = g.lane; k < nT; k += G::NL) m.flag[k] = 0;
-        g.sync();
-        for (int k = g.lane; k < nconf; k += G::NL) {
-            const int t = m.lista[k];
-            if (m.trk_det[t] >= 0) { m.flag[t] = 1; ++nmatched; }
+        // ascending survivors by ordered compaction; is the confirmed list 0..nconf-1 (always, in this flow)?
+        bool contig = true;
+        int nsurv = 0;
+        for (int base = 0; base < nconf; base += G::NL) {
+            const int k = base + g.lane;
+            bool p = false;
+            if (k < nconf) {
+                const int t = m.lista[k];
+                contig = contig && (t == k);
+                p = m.trk_det[t] < 0;
+            }
+            int tot;
+            const int pos = g.scan_excl(p, tot);
+            if (p) m.rows[nsurv + pos] = m.lista[k];
+            nsurv += tot;
         }
-        nmatched = g.sum(nmatched);
+        contig = g.all(contig);
+        const int nmatched = nconf - nsurv;
         g.sync();
-        if (g.lane == 0)
-            n_unm_a = dd_set_difference_order_serial(m.lista, nconf, m.flag, nmatched, m.listb,
-                                                     m.tabA, m.tabB, m.tabC, m.tab_cap);
-        n_unm_a = g.imax(n_unm_a);
+        if (contig && ((nconf >> 2) > nmatched || nsurv <= 1)) {
+            for (int k = g.lane; k < nsurv; k += G::NL) m.listb[k] = m.rows[k];
+            n_unm_a = nsurv;
+        } else if (contig) {
+            if (g.lane == 0) n_unm_a = dd_set_order_from_survivors(m.rows, nsurv, m.listb, m.tabA, m.tabB);
+            n_unm_a = g.imax(n_unm_a);
+        } else {
+            for (int k = g.lane; k < nT; k += G::NL) m.flag[k] = 0;
+            g.sync();
+            for (int k = g.lane; k < nconf; k += G::NL)
+                if (m.trk_det[m.lista[k]] >= 0) m.flag[m.lista[k]] = 1;
+            g.sync();
+            if (g.lane == 0)
+                n_unm_a = dd_set_difference_order_serial(m.lista, nconf, m.flag, nmatched, m.listb,
+                                                         m.tabA, m.tabB, m.tabC, m.tab_cap);
+            n_unm_a = g.imax(n_unm_a);
+        }
         g.sync();
     }
 
@@ -481,10 +505,19 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
         nr += tot;
     }
     g.sync();
-    {
+    if (nr > 0 && nund > 0) {
+        for (int r = g.lane; r < nr; r += G::NL) {       // Track.to_tlwh of every IoU row, once
+            const int t = m.rows[r];
+            const double* mu = V.mean + (sT + m.trk_slot[t]) * 8;
+            const double w = dd_mul(mu[2], mu[3]), h = mu[3];
+            const double x = dd_sub(mu[0], dd_div(w, 2.0)), y = dd_sub(mu[1], dd_div(h, 2.0));
+            double* o = m.tbox + r * 5;
+            o[0] = x; o[1] = y; o[2] = dd_add(x, w); o[3] = dd_add(y, h);
+            o[4] = m.trk_tsu[t] > 1 ? -1.0 : dd_mul(w, h);
+        }
+        g.sync();
         DDIouCost ic;
-        ic.mean = V.mean + sT * 8; ic.det_tlwh = det_tlwh + sD * 4;
-        ic.trk_slot = m.trk_slot; ic.trk_tsu = m.trk_tsu; ic.rows = m.rows; ic.cols = und;
+        ic.tbox = m.tbox; ic.det_tlwh = det_tlwh + sD * 4; ic.cols = und;
         ic.thr = V.thr_iou; ic.clip = dd_add(V.thr_iou, 1e-5);
         if (dd_min_cost_matching(g, ic, V.thr_iou, m, nr, und, und_next, nund) != 0) infeasible = 1;
     }

@@ -141,6 +141,13 @@ int dd_event_elapsed_ms(void* start, void* end, float* host_ms);   /* both event
 int dd_tracker_countline(void* state, const dd_tracker_config* host_cfg, const double* line,
                          int line_per_stream, void* stream);
 
+/* One whole tick in one call: dd_tracker_predict + dd_tracker_update + dd_tracker_countline and, when
+ * out_counts != NULL, dd_tracker_count_reduce (7 kernel launches on `stream`). */
+int dd_tracker_tick(void* state, const dd_tracker_config* host_cfg, const double* det_tlwh,
+                    const float* det_conf, const int32_t* det_label, const float* det_feat,
+                    const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                    int line_per_stream, int64_t* out_counts, void* stream);
+
 /* Sum the per-stream counters into out_counts i64 [C,4] (the tensor handed to the NCCL all-reduce). */
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int64_t* out_counts,
                             void* stream);

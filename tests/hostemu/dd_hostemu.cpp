@@ -100,8 +100,18 @@ int ddh_set_difference_order(const int32_t* a, int na, const int32_t* m, int nm,
     for (int i = 0; i < na; ++i) av[i] = (short)a[i];
     const int cap = dd_set_table_slots(na > 0 ? na : 1);
     std::vector<short> A(cap), B(cap), C(cap);
-    const int n = dd_set_difference_order_serial(av.data(), na, flag.data(), nm, o.data(), A.data(),
-                                                 B.data(), C.data(), cap);
+    bool contig = true;
+    for (int i = 0; i < na; ++i) contig = contig && a[i] == i;
+    int n;
+    if (contig) {
+        std::vector<short> surv;
+        for (int i = 0; i < na; ++i) if (!flag[i]) surv.push_back((short)i);
+        if ((na >> 2) > nm) { n = (int)surv.size(); for (int i = 0; i < n; ++i) o[i] = surv[i]; }
+        else n = dd_set_order_from_survivors(surv.data(), (int)surv.size(), o.data(), A.data(), B.data());
+    } else {
+        n = dd_set_difference_order_serial(av.data(), na, flag.data(), nm, o.data(), A.data(), B.data(),
+                                           C.data(), cap);
+    }
     for (int i = 0; i < n; ++i) out[i] = o[i];
     return n;
 }

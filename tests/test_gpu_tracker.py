@@ -98,3 +98,35 @@ def test_gated_cost_matrices_match_oracle():
             for s in range(S):
                 checked += compare_costs(orc.trk[s], pre, post, s)
     assert checked > 1000
+
+
+def test_stream_chunks_pipelined_and_step_host():
+    """n_chunks > 1 (chunk streams, enqueue-only steps, pinned-host entry) gives the same ids / state /
+    counters as the oracle, and the chunked count reduction equals the sum over streams."""
+    from deepdish_b200.batched import BatchedTracker
+    S = 7
+    bt = BatchedTracker(S, LABELS3, max_tracks=64, max_dets=24, budget=30, max_age=30, n_chunks=3)
+    orc = OracleStreams(S, LABELS3, budget=30, max_age=30)
+    sc = Scene(S, 16, 24, n_labels=3, seed=31)
+    ids_host = torch.empty((S, 24), dtype=torch.int32).pin_memory()
+    for f in range(60):
+        b = sc.step()
+        ids = orc.step(b)
+        if f % 2 == 0:
+            bt.step(b.to("cuda"), join=False, reduce=True)
+            bt.join()
+            got = bt.det_track_id.cpu().numpy()
+        else:
+            bt.step_host(b.pin(), ids_host)
+            bt.join()
+            torch.cuda.synchronize()
+            got = ids_host.numpy().copy()
+        for s in range(S):
+            n = int(b.count[s])
+            assert list(got[s, :n]) == ids[s], (f, s)
+        exp = sum(c.counts(LABELS3) for c in orc.cnt)
+        np.testing.assert_array_equal(bt.total_counts.cpu().numpy(), exp)
+    v = bt.host_view()
+    for s in range(S):
+        compare_stream(orc.trk[s], orc.cnt[s], v, s, LABELS3)
+    bt.check()
