@@ -166,6 +166,9 @@ def gpu_arm(args):
         cpu = cpu_reference(steps=60, warm=0, preroll=100)
 
     P = args.chunks
+    if args.gate_impl is not None:
+        from deepdish_b200 import _lib
+        _lib.check(_lib.lib().dd_tuning_set(0, args.gate_impl), "dd_tuning_set")
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
                         n_chunks=P)
     scene = Scene(S, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=1234 + rank, device=dev)
@@ -243,7 +246,7 @@ def gpu_arm(args):
 
     # ---- per-kernel pass: the same K ticks on a single-stream (n_chunks=1) tracker so that CUDA events
     #      between the kernels measure each kernel alone (rank 0 only; roofline of the dominant kernel)
-    stage = [0.0, 0.0, 0.0, 0.0]
+    stage = [0.0, 0.0, 0.0, 0.0, 0.0]
     single_ms = None
     if rank == 0:
         del bt
@@ -251,7 +254,7 @@ def gpu_arm(args):
         bt1 = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev)
         for b in pre + frames[:W]:
             bt1.step(b)
-        evs = [bt1.new_events(5) for _ in range(K)]
+        evs = [bt1.new_events(6) for _ in range(K)]
         s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         s1.record()
@@ -264,7 +267,7 @@ def gpu_arm(args):
         torch.cuda.synchronize()
         single_ms = s1.elapsed_time(e1)
         for ev in evs:
-            for j in range(4):
+            for j in range(5):
                 stage[j] += bt1.elapsed_ms(ev[j], ev[j + 1]) / K
         bt1.check()
         del bt1
@@ -280,8 +283,8 @@ def gpu_arm(args):
         peak, peak_src = load_peaks()
         G, TC = float(tot[0]) / world, float(tot[1]) / world            # per GPU, per tick
         Dn = float(tot[2]) / world / K
-        gc_bytes = 512.0 * G + 512.0 * Dn + 576.0 * TC + 32.0 * Dn
-        gc_ms = stage[1]
+        gc_bytes = 512.0 * G + 512.0 * Dn + 16.0 * TC
+        gc_ms = stage[2]
         achieved = gc_bytes / (gc_ms * 1e-3) / 1e9
         tick_bytes = 512.0 * (G + Dn + Dn) + 1152.0 * (TC * 1.1) + 44.0 * Dn
         out = {
@@ -295,14 +298,14 @@ def gpu_arm(args):
                        "l2": "inputs larger than L2: %.2f GB of galleries streamed per tick" % (512 * G / 1e9)},
             "e2e": {"value": S * world * K / (e2e_all * 1e-3), "unit": "stream-frames/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K},
-            "gpu_launches": K * 7 * P,
+            "gpu_launches": K * 8 * P,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_gate_cosine", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_cosine", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": gc_bytes, "ms_per_launch": gc_ms,
                          "tick_bytes": tick_bytes, "tick_frac": tick_bytes / (ms_all / K * 1e-3) / 1e9 / peak},
             "stage_ms": {"pass": "same K ticks, n_chunks=1, CUDA events between kernels", "prep": stage[0],
-                         "gate_cosine": stage[1], "match": stage[2], "apply": stage[3],
+                         "gate": stage[1], "cosine": stage[2], "match": stage[3], "apply": stage[4],
                          "tick_total_single_stream": single_ms / K, "tick_total_pipelined": ms_all / K},
             "cpu_baseline": cpu,
         }
@@ -333,6 +336,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gate-impl", type=int, default=None, help="A/B knob: 1 TMA-staged gallery pass, 0 direct loads")
     ap.add_argument("--chunks", type=int, default=4, help="stream chunks pipelined on separate CUDA streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

@@ -27,7 +27,7 @@ class TrackerConfig(ctypes.Structure):
 LAYOUT_FIELDS = ["n_tracks", "next_id", "n_deleted", "err", "order", "deleted", "counts", "mean", "cov",
                  "track_id", "hits", "age", "tsu", "state", "gal_len", "gal_pos", "gal", "lab_cnt",
                  "lab_sum", "path_n", "path_last", "path_crossed", "gate", "cost", "det_xyah",
-                 "det_featn", "det_slot", "det_kind"]
+                 "det_featn", "det_slot", "det_kind", "cdesc"]
 
 
 class TrackerLayout(ctypes.Structure):
@@ -48,7 +48,7 @@ def field_specs(cfg):
         "lab_cnt": (i, (S, T, C)), "lab_sum": (d, (S, T, C)), "path_n": (i, (S, T)),
         "path_last": (d, (S, T, 2)), "path_crossed": (i, (S, T)), "gate": (i, (S, T, DW)),
         "cost": (f, (S, T, D)), "det_xyah": (d, (S, D, 4)), "det_featn": (f, (S, D, 128)),
-        "det_slot": (i, (S, D)), "det_kind": (i, (S, D)),
+        "det_slot": (i, (S, D)), "det_kind": (i, (S, D)), "cdesc": (i, (S, T, 2)),
     }
 
 
@@ -94,6 +94,7 @@ def lib():
         "dd_tracker_update": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
         "dd_tracker_update_profiled": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        ctypes.POINTER(_vp)],
+        "dd_tuning_set": [_i32, _i32],
         "dd_event_create": [ctypes.POINTER(_vp)],
         "dd_event_destroy": [_vp],
         "dd_event_elapsed_ms": [_vp, _vp, ctypes.POINTER(ctypes.c_float)],

@@ -186,17 +186,17 @@ class BatchedTracker:
         self.join()
         return self.det_track_id
 
-    def update_profiled(self, tlwh, conf, label, feat, count, events5):
-        """update() that records 5 CUDA events (see dd_tracker_update_profiled); single chunk only."""
+    def update_profiled(self, tlwh, conf, label, feat, count, events6):
+        """update() that records 6 CUDA events (see dd_tracker_update_profiled); single chunk only."""
         if len(self.chunks) != 1:
             raise RuntimeError("update_profiled needs n_chunks=1")
         c = self.chunks[0]
         p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
-        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events5),
+        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events6),
                    "dd_tracker_update_profiled")
         return self.det_track_id
 
-    def new_events(self, n=5):
+    def new_events(self, n=6):
         arr = (ctypes.c_void_p * n)()
         for i in range(n):
             h = ctypes.c_void_p()

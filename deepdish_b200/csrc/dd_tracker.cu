@@ -3,7 +3,8 @@
 // Launch shapes (S streams, T = max_tracks, D = max_dets):
 //   k_prep         one warp per (stream, detection)       4 warps / CTA
 //   k_predict      one warp per (stream, track index)     4 warps / CTA
-//   k_gate_cosine  one warp per (stream, track index)     4 warps / CTA   <- the HBM-bound kernel
+//   k_gate         one warp per (stream, track index)     4 warps / CTA
+//   k_cosine       one warp per (stream, track index)     4 warps / CTA   <- the HBM-bound kernel
 //   k_match        one warp per stream                    1 warp  / CTA, dynamic shared memory
 //   k_apply        one warp per (stream, detection)       4 warps / CTA
 //   k_countline    one warp per stream                    4 warps / CTA
@@ -35,12 +36,131 @@ __global__ void __launch_bounds__(DD_WARPS * 32) k_predict(const DDView V) {
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
-k_gate_cosine(const DDView V, const int* __restrict__ det_count) {
+k_gate(const DDView V, const int* __restrict__ det_count) {
     const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
     if (w >= V.S * V.T) return;
     WarpG g;
-    dd_gate_cosine(g, V, w / V.T, w % V.T, det_count);
+    dd_gate_track(g, V, w / V.T, w % V.T, det_count);
 }
+
+__global__ void __launch_bounds__(DD_WARPS * 32, 7)
+k_cosine(const DDView V, const int* __restrict__ det_count) {
+    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    if (w >= V.S * V.T) return;
+    WarpG g;
+    DDDirectPass<WarpG> pass;
+    dd_cosine_track(g, V, w / V.T, w % V.T, det_count, pass);
+}
+
+// ---- TMA-staged gallery pass ---------------------------------------------------------------------
+// Each warp owns a ring of DD_STAGES shared-memory stages of DD_ROWS gallery rows (4 KB) with one
+// mbarrier per stage.  Lane 0 issues 1-D bulk copies (cp.async.bulk global -> shared, completion on the
+// stage's mbarrier); loads in flight live in shared memory instead of registers, so a warp keeps
+// DD_STAGES x 4 KB outstanding at ~70 registers/thread and the SM holds several such warps.
+#define DD_STAGES 4
+#define DD_STAGE_BYTES (DD_ROWS * DD_FEAT_DIM * 4)
+
+__device__ __forceinline__ unsigned dd_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dd_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dd_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dd_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dd_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dd_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(dd_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dd_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(dd_smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+struct DDTmaPass {
+    float4* ring;                 // [DD_STAGES][DD_ROWS][32] float4, this warp's
+    unsigned long long* bars;     // [DD_STAGES]
+    unsigned phase;               // bit s = parity the next wait on stage s expects
+
+    template <int NC>
+    __device__ __forceinline__ void run(const WarpG& g, const float4* gal4, int glen,
+                                        const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
+        constexpr int N = DD_ROWS * NC;
+        float4 q[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) q[c] = qp[c][g.lane];
+        float acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = -3.0e38f;
+        const int nchunk = (glen + DD_ROWS - 1) / DD_ROWS;
+        const char* src = (const char*)gal4;
+        if (g.lane == 0) {
+            const int pre = nchunk < DD_STAGES ? nchunk : DD_STAGES;
+            for (int c = 0; c < pre; ++c) {
+                const int rows = min(DD_ROWS, glen - c * DD_ROWS);
+                dd_mbar_expect_tx(bars + c, rows * 512);
+                dd_bulk_g2s(ring + c * (DD_ROWS * 32), src + (size_t)c * DD_STAGE_BYTES, rows * 512, bars + c);
+            }
+        }
+        int st = 0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            dd_mbar_wait(bars + st, (phase >> st) & 1u);
+            phase ^= 1u << st;
+            const int rows = min(DD_ROWS, glen - ch * DD_ROWS);
+            const float4* stage = ring + st * (DD_ROWS * 32);
+            float4 a[DD_ROWS];
+#pragma unroll
+            for (int r = 0; r < DD_ROWS; ++r) a[r] = stage[min(r, rows - 1) * 32 + g.lane];
+            __syncwarp();                                   // every lane has read the stage
+            const int nxt = ch + DD_STAGES;
+            if (g.lane == 0 && nxt < nchunk) {
+                const int nrows = min(DD_ROWS, glen - nxt * DD_ROWS);
+                dd_mbar_expect_tx(bars + st, nrows * 512);
+                dd_bulk_g2s(ring + st * (DD_ROWS * 32), src + (size_t)nxt * DD_STAGE_BYTES, nrows * 512, bars + st);
+            }
+            float v[N];
+#pragma unroll
+            for (int r = 0; r < DD_ROWS; ++r)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float p = dd_fmaf(a[r].x, q[c].x, 0.f);
+                    p = dd_fmaf(a[r].y, q[c].y, p);
+                    p = dd_fmaf(a[r].z, q[c].z, p);
+                    p = dd_fmaf(a[r].w, q[c].w, p);
+                    v[r * NC + c] = p;
+                }
+            dd_fold_max<NC, N>(g, v, acc);
+            st = (st + 1 == DD_STAGES) ? 0 : st + 1;
+        }
+        float b[NC];
+        dd_fold_finish<NC, N>(g, acc, b);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) best[c] = b[c];
+    }
+};
+
+__global__ void __launch_bounds__(DD_WARPS * 32)
+k_cosine_tma(const DDView V, const int* __restrict__ det_count) {
+    extern __shared__ __align__(128) char smem[];
+    const int wi = threadIdx.x >> 5;
+    const int w = blockIdx.x * DD_WARPS + wi;
+    if (w >= V.S * V.T) return;
+    WarpG g;
+    DDTmaPass pass;
+    pass.ring = (float4*)(smem + (size_t)wi * DD_STAGES * DD_STAGE_BYTES);
+    pass.bars = (unsigned long long*)(smem + (size_t)DD_WARPS * DD_STAGES * DD_STAGE_BYTES) + wi * DD_STAGES;
+    pass.phase = 0;
+    if (g.lane == 0) {
+        for (int i = 0; i < DD_STAGES; ++i) dd_mbar_init(pass.bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    dd_cosine_track(g, V, w / V.T, w % V.T, det_count, pass);
+}
+
+static int g_gate_impl = 0;     // 1 = TMA-staged (default), 0 = direct loads (A/B baseline)
 
 __global__ void __launch_bounds__(32)
 k_match(const DDView V, const double* __restrict__ det_tlwh, const int* __restrict__ det_count,
@@ -149,15 +269,29 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
     k_prep<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_tlwh, det_feat, det_count);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
-    k_gate_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
+    k_gate<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[2], st);
-    k_match<<<V.S, 32, smem, st>>>(V, det_tlwh, det_count, out_det_track_id);
+    if (g_gate_impl == 1) {
+        const size_t gsm = (size_t)DD_WARPS * DD_STAGES * DD_STAGE_BYTES + DD_WARPS * DD_STAGES * 8;
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(k_cosine_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess)
+                return DD_ERR_CUDA;
+            attr_set = true;
+        }
+        k_cosine_tma<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, gsm, st>>>(V, det_count);
+    } else {
+        k_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
+    }
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[3], st);
-    k_apply<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_conf, det_label);
+    k_match<<<V.S, 32, smem, st>>>(V, det_tlwh, det_count, out_det_track_id);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[4], st);
+    k_apply<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_conf, det_label);
+    DD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[5], st);
     return DD_OK;
 }
 
@@ -171,12 +305,17 @@ int dd_tracker_update(void* state, const dd_tracker_config* cfg, const double* d
 int dd_tracker_update_profiled(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
                                const float* det_conf, const int32_t* det_label, const float* det_feat,
                                const int32_t* det_count, int32_t* out_det_track_id, void* stream,
-                               void* const* host_events5) {
-    if (!host_events5) return DD_ERR_INVALID;
-    cudaEvent_t ev[5];
-    for (int i = 0; i < 5; ++i) ev[i] = (cudaEvent_t)host_events5[i];
+                               void* const* host_events6) {
+    if (!host_events6) return DD_ERR_INVALID;
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; ++i) ev[i] = (cudaEvent_t)host_events6[i];
     return dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count,
                           out_det_track_id, (cudaStream_t)stream, ev);
+}
+
+int dd_tuning_set(int32_t key, int32_t value) {
+    if (key == 0 && (value == 0 || value == 1)) { g_gate_impl = value; return DD_OK; }
+    return DD_ERR_INVALID;
 }
 
 int dd_event_create(void** host_out) {

@@ -2,7 +2,8 @@
 //
 //   dd_prep_det        (stream, det)    Detection.to_xyah + feature normalisation
 //   dd_predict_track   (stream, track)  Track.predict
-//   dd_gate_cosine     (stream, track)  gating_distance + gallery min cosine distance for gated pairs
+//   dd_gate_track      (stream, track)  gating_distance -> gate bitmask + stream descriptor
+//   dd_cosine_track    (stream, track)  gallery min cosine distance for the gate-passing pairs
 //   dd_match_stream    (stream)         matching cascade + IoU stage + track lifecycle
 //   dd_apply_det       (stream, det)    Kalman update / initiate + gallery append + label vote
 //   dd_countline       (stream)         count-line crossing + per-label counters
@@ -80,17 +81,16 @@ DD_HD void dd_predict_track(const G& g, const DDView& V, int s, int t) {
 // row, up to DD_CH candidates share one pass over the gallery.
 // ------------------------------------------------------------------------------------------------
 #define DD_CH 4          // candidates sharing one pass over the gallery
-#define DD_ROWS 8        // gallery rows in flight per pass step (8 x 512 B = 4 KB of loads per warp)
+#define DD_ROWS 8        // gallery rows per pipeline step (8 x 512 B = 4 KB); fold size = DD_ROWS x NC
 
-// Cross-lane sum of N = DD_ROWS * NC per-lane partials v[r * NC + c] by a transposing butterfly
-// (N-1 + log2(32/N) shuffles instead of 5 N), folded into a running maximum over rows per candidate.
-// WarpG: after the butterfly lane L owns the total of value index idx(L) = top log2(N) bits of L, so its
+// Cross-lane sum of N = ROWS * NC per-lane partials v[r * NC + c] by a transposing butterfly
+// (N - 1 + log2(32 / N) shuffles instead of 5 N), folded into a running maximum over rows per candidate.
+// WarpG: after the butterfly lane L owns the total of value index idx(L) = L >> log2(32 / N), so its
 // candidate is idx(L) % NC; the running maximum lives in acc[0] and dd_fold_finish combines lanes.
 // HostG: one lane owns everything, acc[c] is the maximum for candidate c.
 #if defined(__CUDACC__)
-template <int NC>
-__device__ __forceinline__ void dd_fold_max(const WarpG& g, float (&v)[DD_ROWS * NC], float (&acc)[NC]) {
-    constexpr int N = DD_ROWS * NC;
+template <int NC, int N>
+__device__ __forceinline__ void dd_fold_max(const WarpG& g, float (&v)[N], float (&acc)[NC]) {
     int n = N, o = 16;
 #pragma unroll
     for (; n > 1; n >>= 1, o >>= 1) {
@@ -107,30 +107,33 @@ __device__ __forceinline__ void dd_fold_max(const WarpG& g, float (&v)[DD_ROWS *
     for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
     acc[0] = v[0] > acc[0] ? v[0] : acc[0];
 }
-template <int NC>
+template <int NC, int N>
 __device__ __forceinline__ void dd_fold_finish(const WarpG& g, float (&acc)[NC], float (&best)[NC]) {
-    constexpr int N = DD_ROWS * NC;
-    constexpr int SH = N >= 32 ? 0 : (N == 16 ? 1 : (N == 8 ? 2 : 3));     // idx(L) = L >> SH
+    constexpr int SH = N >= 32 ? 0 : (N == 16 ? 1 : (N == 8 ? 2 : (N == 4 ? 3 : 4)));   // idx(L) = L >> SH
     const int mine = (g.lane >> SH) % NC;
 #pragma unroll
     for (int c = 0; c < NC; ++c) best[c] = g.fmax(mine == c ? acc[0] : -3.0e38f);
 }
 #endif
-template <int NC>
-inline void dd_fold_max(const HostG&, float (&v)[DD_ROWS * NC], float (&acc)[NC]) {
-    for (int r = 0; r < DD_ROWS; ++r)
+template <int NC, int N>
+inline void dd_fold_max(const HostG&, float (&v)[N], float (&acc)[NC]) {
+    for (int r = 0; r < N / NC; ++r)
         for (int c = 0; c < NC; ++c) acc[c] = v[r * NC + c] > acc[c] ? v[r * NC + c] : acc[c];
 }
-template <int NC>
+template <int NC, int N>
 inline void dd_fold_finish(const HostG&, float (&acc)[NC], float (&best)[NC]) {
     for (int c = 0; c < NC; ++c) best[c] = acc[c];
 }
 
 // max over the gallery rows of row . q[c] for NC query vectors; rows are unit vectors, each lane owns
-// float4 chunk(s) of the 128-d row.  Rows past glen re-read the last row (duplicates do not change a max).
+// float4 chunk(s) of the 128-d row; DD_ROWS rows (4 KB) are loaded back to back before any arithmetic.
+// Rows past glen re-read the last row (duplicates do not change a max).  This is the direct-load
+// variant (host emulation, and the A/B baseline of the TMA-staged pass in dd_tracker.cu).
 template <class G, int NC>
 DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
                           const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
+    constexpr int ROWS = DD_ROWS;
+    constexpr int DD_FOLD = DD_ROWS * NC;
     constexpr int KP = (DD_FEAT_DIM / 4) / G::NL;          // float4 chunks per lane (1 on a warp)
     float4 q[NC][KP];
     for (int c = 0; c < NC; ++c) {
@@ -139,20 +142,20 @@ DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
     }
     float acc[NC];
     for (int c = 0; c < NC; ++c) acc[c] = -3.0e38f;
-    for (int g0 = 0; g0 < glen; g0 += DD_ROWS) {
-        float v[DD_ROWS * NC];
+    for (int g0 = 0; g0 < glen; g0 += ROWS) {
+        float v[DD_FOLD];
 #pragma unroll
-        for (int i = 0; i < DD_ROWS * NC; ++i) v[i] = 0.f;
+        for (int i = 0; i < DD_FOLD; ++i) v[i] = 0.f;
         int kk = 0;
         for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
-            float4 a[DD_ROWS];
+            float4 a[ROWS];
 #pragma unroll
-            for (int r = 0; r < DD_ROWS; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
                 const int row = dd_imin(g0 + r, glen - 1);
                 a[r] = gal4[(size_t)row * (DD_FEAT_DIM / 4) + k];
             }
 #pragma unroll
-            for (int r = 0; r < DD_ROWS; ++r)
+            for (int r = 0; r < ROWS; ++r)
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     float p = v[r * NC + c];
@@ -163,18 +166,37 @@ DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
                     v[r * NC + c] = p;
                 }
         }
-        dd_fold_max<NC>(g, v, acc);
+        dd_fold_max<NC, DD_FOLD>(g, v, acc);
     }
     float b[NC];
-    dd_fold_finish<NC>(g, acc, b);
+    dd_fold_finish<NC, DD_FOLD>(g, acc, b);
     for (int c = 0; c < NC; ++c) best[c] = b[c];
 }
 
 template <class G>
-DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* det_count) {
-    if (t >= V.n_tracks[s]) return;
-    const size_t slot = (size_t)s * V.T + V.order[(size_t)s * V.T + t];
-    if (V.state[slot] != DD_STATE_CONFIRMED) return;
+struct DDDirectPass {
+    template <int NC>
+    DD_HD void run(const G& g, const float4* gal4, int glen, const float4* const (&qp)[DD_CH],
+                   float (&best)[DD_CH]) {
+        dd_cosine_pass<G, NC>(g, gal4, glen, qp, best);
+    }
+};
+
+// Gate of one track index (every t < Tmax is visited so that inactive entries get an empty descriptor):
+// f64 projection + 4x4 Cholesky per lane (redundant), lanes sweep the detections, ballot -> gate words.
+template <class G>
+DD_HD void dd_gate_track(const G& g, const DDView& V, int s, int t, const int* det_count) {
+    int* desc = V.cdesc + ((size_t)s * V.T + t) * 2;
+    bool active = t < V.n_tracks[s];
+    size_t slot = 0;
+    if (active) {
+        slot = (size_t)s * V.T + V.order[(size_t)s * V.T + t];
+        active = V.state[slot] == DD_STATE_CONFIRMED;
+    }
+    if (!active) {
+        if (g.lane == 0) { desc[0] = 0; desc[1] = 0; }
+        return;
+    }
     int nd = det_count[s];
     if (nd > V.D) nd = V.D;
     const double* mean = V.mean + slot * 8;
@@ -182,8 +204,7 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
     dd_kf_project_cov(mean, V.cov + slot * 64, S);
     dd_chol<4>(S, L, rinv);
     const double pm[4] = {mean[0], mean[1], mean[2], mean[3]};
-    const int glen = V.gal_len[slot];
-    const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
+    int ncand = 0;
     for (int base = 0; base < nd; base += 32) {
         unsigned word = 0;
         const int lim = dd_imin(base + 32, nd);
@@ -193,6 +214,32 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
         }
         word = g.bor(word);
         if (g.lane == 0) V.gate[slot * V.DW + (base >> 5)] = word;
+#if defined(__CUDA_ARCH__)
+        ncand += __popc(word);
+#else
+        ncand += __builtin_popcount(word);
+#endif
+    }
+    if (g.lane == 0) {
+        desc[0] = (int)(slot - (size_t)s * V.T) | (V.gal_len[slot] << 16);
+        desc[1] = ncand;
+    }
+}
+
+// Appearance cost of one track index for its gate-passing detections: one descriptor load decides
+// whether anything is streamed; the gallery is then read once per group of <= DD_CH candidates.
+template <class G, class Pass>
+DD_HD void dd_cosine_track(const G& g, const DDView& V, int s, int t, const int* det_count, Pass& pass) {
+    const int* desc = V.cdesc + ((size_t)s * V.T + t) * 2;
+    if (desc[1] <= 0) return;
+    const int d0 = desc[0];
+    const size_t slot = (size_t)s * V.T + (d0 & 0xffff);
+    const int glen = d0 >> 16;
+    int nd = det_count[s];
+    if (nd > V.D) nd = V.D;
+    const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
+    for (int base = 0; base < nd; base += 32) {
+        unsigned word = V.gate[slot * V.DW + (base >> 5)];
         while (word) {
             int cj[DD_CH];
             int nc = 0;
@@ -208,11 +255,11 @@ DD_HD void dd_gate_cosine(const G& g, const DDView& V, int s, int t, const int* 
             if (glen <= 0) {
                 for (int c = 0; c < DD_CH; ++c) best[c] = -3.0e38f;
             } else if (nc == 1) {
-                dd_cosine_pass<G, 1>(g, gal4, glen, qp, best);
+                pass.template run<1>(g, gal4, glen, qp, best);
             } else if (nc == 2) {
-                dd_cosine_pass<G, 2>(g, gal4, glen, qp, best);
+                pass.template run<2>(g, gal4, glen, qp, best);
             } else {
-                dd_cosine_pass<G, 4>(g, gal4, glen, qp, best);
+                pass.template run<4>(g, gal4, glen, qp, best);
             }
             if (g.lane == 0)
                 for (int c = 0; c < nc; ++c) V.cost[slot * V.D + cj[c]] = dd_subf(1.0f, best[c]);

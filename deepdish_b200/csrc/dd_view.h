@@ -23,6 +23,7 @@ struct DDView {
     double* det_xyah;
     float* det_featn;
     int *det_slot, *det_kind;
+    int* cdesc;
     int label_rank[DD_MAX_LABELS];
 };
 
@@ -67,6 +68,7 @@ static inline int dd_layout_compute(const dd_tracker_config* c, dd_tracker_layou
     DD_PUT(det_featn, 4 * S * D * F);
     DD_PUT(det_slot, 4 * S * D);
     DD_PUT(det_kind, 4 * S * D);
+    DD_PUT(cdesc, 4 * S * T * 2);
 #undef DD_PUT
     L->total_bytes = off;
     return DD_OK;
@@ -98,6 +100,7 @@ static inline int dd_make_view(void* blob, const dd_tracker_config* c, DDView* v
     v->gate = (unsigned*)(b + L.gate); v->cost = (float*)(b + L.cost);
     v->det_xyah = (double*)(b + L.det_xyah); v->det_featn = (float*)(b + L.det_featn);
     v->det_slot = (int*)(b + L.det_slot); v->det_kind = (int*)(b + L.det_kind);
+    v->cdesc = (int*)(b + L.cdesc);
     for (int i = 0; i < DD_MAX_LABELS; ++i) v->label_rank[i] = i < c->n_labels ? c->label_rank[i] : 0;
     return DD_OK;
 }

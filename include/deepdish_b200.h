@@ -100,6 +100,8 @@ typedef struct dd_tracker_layout {
     uint64_t det_featn;     /* f32 [S,Dmax,128]   unit-normalised detection features                */
     uint64_t det_slot;      /* i32 [S,Dmax]       slot the detection was applied to                 */
     uint64_t det_kind;      /* i32 [S,Dmax]       0 none, 1 Kalman update, 2 new track              */
+    uint64_t cdesc;         /* i32 [S,Tmax,2]     per track index: slot | gallery rows << 16, #gate-passing
+                                                  detections (0 = nothing to stream)                        */
 } dd_tracker_layout;
 
 /* Host-only arithmetic: fills `host_out`.  No CUDA call. */
@@ -124,14 +126,17 @@ int dd_tracker_update(void* state, const dd_tracker_config* host_cfg,
                       const float* det_feat, const int32_t* det_count,
                       int32_t* out_det_track_id, void* stream);
 
-/* dd_tracker_update that also records five caller-supplied CUDA events on `stream`: before the
- * detection prep kernel and after each of prep / gate+cosine / match / apply (no synchronisation), so a
- * benchmark can time each kernel inside its own timed region.  host_events5: host array of 5 events
+/* dd_tracker_update that also records six caller-supplied CUDA events on `stream`: before the
+ * detection prep kernel and after each of prep / gate / cosine / match / apply (no synchronisation), so a
+ * benchmark can time each kernel inside its own timed region.  host_events6: host array of 6 events
  * made by dd_event_create. */
 int dd_tracker_update_profiled(void* state, const dd_tracker_config* host_cfg,
                                const double* det_tlwh, const float* det_conf, const int32_t* det_label,
                                const float* det_feat, const int32_t* det_count,
-                               int32_t* out_det_track_id, void* stream, void* const* host_events5);
+                               int32_t* out_det_track_id, void* stream, void* const* host_events6);
+/* Process-wide tuning knob for A/B measurements: key 0 = gallery pass of the gate+cosine kernel
+ * (1 = TMA-staged through shared memory, default; 0 = direct register loads). */
+int dd_tuning_set(int32_t key, int32_t value);
 int dd_event_create(void** host_out);
 int dd_event_destroy(void* ev);
 int dd_event_elapsed_ms(void* start, void* end, float* host_ms);   /* both events must have completed */
