@@ -231,8 +231,7 @@ class BatchedTracker:
         for i, c in enumerate(self.chunks):
             p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
             out = self.partial_counts[par, i].data_ptr() if reduce else None
-            _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream,
-                                                out, self._sp(c)), "dd_tracker_tick")
+            self._tick_call(c, p, out, self._sp(c))
         self._mark()
         if reduce:
             self._sum_partials(par)
@@ -240,6 +239,10 @@ class BatchedTracker:
         if join:
             self.join()
         return self.det_track_id
+
+    def _tick_call(self, c, p, out, sp):
+        _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream, out, sp),
+                   "dd_tracker_tick")
 
     def _sum_partials(self, par):
         """caller's stream: wait for the chunks' partial counters of this tick, sum them."""
@@ -278,11 +281,9 @@ class BatchedTracker:
                     dst.copy_(s[c.lo:c.hi], non_blocking=True)
                 t, cf, lb, ft, ct = c.staging
                 ids = self.det_track_id[c.lo:c.hi]
-                _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, t.data_ptr(), cf.data_ptr(), lb.data_ptr(),
-                                                    ft.data_ptr(), ct.data_ptr(), ids.data_ptr(),
-                                                    self._line_ptr(c), self.line_per_stream,
-                                                    self.partial_counts[par, i].data_ptr(),
-                                                    ctypes.c_void_p(st.cuda_stream)), "dd_tracker_tick")
+                self._tick_call(c, (t.data_ptr(), cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
+                                    ids.data_ptr()), self.partial_counts[par, i].data_ptr(),
+                                ctypes.c_void_p(st.cuda_stream))
                 if out_ids_host is not None:
                     out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
         self._mark()

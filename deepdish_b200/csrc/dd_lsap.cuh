@@ -59,6 +59,40 @@ DD_HD int dd_lsap_solve(const G& g, int nr, int nc, const CostFn& cost, DDLsapSc
     for (int j = g.lane; j < nc; j += G::NL) { s.v[j] = 0.0; s.row4col[j] = -1; s.path[j] = -1; }
     g.sync();
     for (int cur = 0; cur < nr; ++cur) {
+        // ---- fast path: the first scan of scipy's search, without materialising its work arrays.
+        // With spc = +inf everywhere and minVal = 0 the scan gives spc[j] = (0 + c(cur,j)) - u[cur] - v[j]
+        // for every column in list order it = nc-1-j.  If the winner is an unassigned column it is the sink,
+        // the path is (cur -> sink), the dual update is u[cur] += minVal and v[sink] -= (minVal - minVal),
+        // and nothing else of the search state survives the row.  Otherwise fall through to the full search.
+        {
+            const double ui = s.u[cur];
+            DDKey best;
+            best.val = DD_INF;
+            best.pref = -0x7fffffff;
+            bool have = false;
+            for (int it = g.lane; it < nc; it += G::NL) {
+                const int j = nc - 1 - it;
+                DDKey k;
+                k.val = dd_sub(dd_sub(dd_add(0.0, cost(cur, j)), ui), s.v[j]);
+                k.pref = (s.row4col[j] == -1) ? (it + 1) : -it;
+                if (!(k.val < DD_INF)) { k.val = DD_INF; }          // r < inf fails in scipy: spc stays inf
+                if (!have || dd_key_better(k, best)) { best = k; have = true; }
+            }
+            best = g.best(best);
+            if (!(best.val < DD_INF)) return -1;
+            if (best.pref > 0) {
+                const int sink = nc - 1 - (best.pref - 1);
+                g.sync();
+                if (g.lane == 0) {
+                    s.u[cur] = dd_add(ui, best.val);
+                    s.v[sink] = dd_sub(s.v[sink], dd_sub(best.val, best.val));
+                    s.row4col[sink] = (short)cur;
+                    s.col4row[cur] = (short)sink;
+                }
+                g.sync();
+                continue;
+            }
+        }
         for (int j = g.lane; j < nc; j += G::NL) {
             s.remaining[j] = (short)(nc - 1 - j);
             s.SC[j] = 0;

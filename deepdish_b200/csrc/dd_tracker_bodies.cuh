@@ -279,9 +279,11 @@ struct DDMatchSmem {
     short *tabA, *tabB, *tabC;
     int tab_cap;
     double* tbox;      // [T][5]  x, y, x2, y2, area of the IoU-stage rows (Track.to_tlwh, track.py:84-97)
+    unsigned* gate_sm; // [T][DW] gate words of the live tracks, by track index
 };
 
-DD_HD size_t dd_match_smem_bytes(int T, int D) {
+DD_HD size_t dd_match_smem_bytes(int T, int D);
+DD_HD size_t dd_match_smem_base_bytes(int T, int D) {
     const int n = T > D ? T : D;
     size_t b = dd_lsap_scratch_bytes(n);
     b += (size_t)T * 2 * 6 + (size_t)D * 2 * 2 + (size_t)n * 2 * 2;
@@ -291,6 +293,9 @@ DD_HD size_t dd_match_smem_bytes(int T, int D) {
     b = (b + 15) & ~(size_t)15;
     b += (size_t)T * 5 * 8;
     return (b + 15) & ~(size_t)15;
+}
+DD_HD size_t dd_match_smem_bytes(int T, int D) {
+    return dd_match_smem_base_bytes(T, D) + (size_t)T * ((D + 31) / 32) * 4;
 }
 
 DD_HD void dd_match_carve(char* mem, int T, int D, DDMatchSmem& m) {
@@ -316,20 +321,21 @@ DD_HD void dd_match_carve(char* mem, int T, int D, DDMatchSmem& m) {
     m.tabC = (short*)p; p += m.tab_cap * 2;
     p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     m.tbox = (double*)p;
+    m.gate_sm = (unsigned*)(mem + dd_match_smem_base_bytes(T, D));
 }
 
 // cost functors: (r, c) are positions in the rows[] / cols[] lists of the current sub-problem.
 struct DDCosineCost {      // tracker.py:97-105 + linear_assignment.py:57
-    const unsigned* gate;  // stream base [T, DW]
-    const float* cost;     // stream base [T, D]
+    const unsigned* gate;  // shared memory [T, DW], indexed by TRACK INDEX
+    const float* cost;     // stream base [T, D] in global memory, indexed by slot (read only where gated in)
     const short *trk_slot, *rows, *cols;
     int D, DW;
     double thr, clip;
     DD_HD double raw(int r, int c) const {
-        const int slot = trk_slot[rows[r]];
+        const int t = rows[r];
         const int d = cols[c];
-        const bool pass = (gate[slot * DW + (d >> 5)] >> (d & 31)) & 1u;
-        return pass ? (double)cost[slot * D + d] : DD_INFTY_COST;
+        const bool pass = (gate[t * DW + (d >> 5)] >> (d & 31)) & 1u;
+        return pass ? (double)cost[trk_slot[t] * D + d] : DD_INFTY_COST;
     }
     DD_HD double operator()(int r, int c) const {
         const double v = raw(r, c);
@@ -468,8 +474,13 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
 
     // ---- matching cascade (linear_assignment.py:121-139)
     {
+        for (int e = g.lane; e < nT * V.DW; e += G::NL) {      // stage the gate words (by track index)
+            const int t = e / V.DW, w = e - t * V.DW;
+            m.gate_sm[e] = m.trk_state[t] == DD_STATE_CONFIRMED ? V.gate[(sT + m.trk_slot[t]) * V.DW + w] : 0u;
+        }
+        g.sync();
         DDCosineCost cc;
-        cc.gate = V.gate + sT * V.DW; cc.cost = V.cost + sT * V.D;
+        cc.gate = m.gate_sm; cc.cost = V.cost + sT * V.D;
         cc.trk_slot = m.trk_slot; cc.rows = m.rows; cc.D = V.D; cc.DW = V.DW;
         cc.thr = V.thr_cos; cc.clip = dd_add(V.thr_cos, 1e-5);
         const int depth = dd_imin(V.max_age, max_tsu);
