@@ -141,6 +141,103 @@ k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const 
                  max_overlap, out_keep + (size_t)f * nmax, out_nkeep + f, smem);
 }
 
+// ---- SSD-MobileNet: one CTA per frame -------------------------------------------------------------
+//   phase A  tiles of DD_SSD_TILE anchors staged in shared memory (coalesced loads of the [na, ncls] score
+//            rows), 4 threads per anchor find the best non-background class, boxes are decoded (expf);
+//   phase B  bitonic sort of (score desc, anchor asc) keys;
+//   phase C  warp 0: greedy IoU NMS in score order until max_det boxes are selected;
+//   phase D  thread 0: the reference's own post-processing on the <= 10 selected boxes (dd_ssd_post).
+#define DD_SSD_TILE 64
+__global__ void __launch_bounds__(256)
+k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_scores,
+             const float* __restrict__ anchors, DDSsdParams P, const int* __restrict__ class_to_label,
+             int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_score,
+             int* __restrict__ out_label, int* __restrict__ out_count) {
+    extern __shared__ __align__(16) char smem[];
+    const int frame = blockIdx.x;
+    const int na = P.na, ncls = P.ncls;
+    const int NP = dd_next_pow2(na);
+    unsigned long long* keys = (unsigned long long*)smem;               // [NP]
+    float* dec = (float*)(keys + NP);                                   // [na][4]
+    int* bcls = (int*)(dec + (size_t)na * 4);                           // [na]
+    float* tile = (float*)(bcls + na);                                  // [DD_SSD_TILE][ncls]
+    __shared__ float sel_box[DD_SSD_MAXDET * 4];
+    __shared__ int sel_cls[DD_SSD_MAXDET];
+    __shared__ float sel_score[DD_SSD_MAXDET];
+    __shared__ int n_sel;
+    const float* fs = raw_scores + (size_t)frame * na * ncls;
+    const float* fb = raw_boxes + (size_t)frame * na * 4;
+    BlockG g;
+    for (int a0 = 0; a0 < na; a0 += DD_SSD_TILE) {
+        const int rows = min(DD_SSD_TILE, na - a0);
+        for (int i = threadIdx.x; i < rows * ncls; i += blockDim.x) tile[i] = fs[(size_t)a0 * ncls + i];
+        __syncthreads();
+        const int r = threadIdx.x >> 2, q = threadIdx.x & 3;            // 4 threads per anchor row
+        float best = -3.0e38f;
+        int bi = 0x7fffffff;
+        if (r < rows) {
+            for (int c = 1 + q; c < ncls; c += 4) {                     // skip background column 0
+                const float v = tile[r * ncls + c];
+                if (v > best) { best = v; bi = c - 1; }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {                              // first maximum wins across the 4 lanes
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (r < rows && q == 0) {
+            const int a = a0 + r;
+            dd_ssd_decode_box(fb + (size_t)a * 4, anchors + (size_t)a * 4, P, dec + (size_t)a * 4);
+            bcls[a] = bi;
+            keys[a] = best >= P.score_thr ? (((unsigned long long)(~dd_f32_key(best))) << 32) | (unsigned)a : ~0ull;
+        }
+        __syncthreads();
+    }
+    for (int i = na + threadIdx.x; i < NP; i += blockDim.x) keys[i] = ~0ull;
+    __syncthreads();
+    dd_bitonic_sort(g, keys, NP);
+    if (threadIdx.x < 32) {                                             // greedy NMS, one warp
+        const int lane = threadIdx.x;
+        int ns = 0;
+        for (int i = 0; i < na && ns < P.max_det; ++i) {
+            const unsigned long long k = keys[i];
+            if (k == ~0ull) break;
+            const int a = (int)(k & 0xffffffffu);
+            bool sup = false;
+            if (lane < ns) sup = dd_ssd_iou(sel_box + lane * 4, dec + (size_t)a * 4) > P.iou_thr;
+            if (__any_sync(0xffffffffu, sup)) continue;
+            if (lane == 0) {
+                for (int q = 0; q < 4; ++q) sel_box[ns * 4 + q] = dec[(size_t)a * 4 + q];
+                sel_cls[ns] = bcls[a];
+                union { unsigned u; float f; } cv;
+                const unsigned kk = ~(unsigned)(k >> 32);
+                cv.u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
+                sel_score[ns] = cv.f;
+            }
+            ++ns;
+            __syncwarp();
+        }
+        if (lane == 0) n_sel = ns;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t o = (size_t)frame * ncap;
+        double tl[DD_SSD_MAXDET * 4];
+        float sc[DD_SSD_MAXDET];
+        int lb[DD_SSD_MAXDET];
+        int n = dd_ssd_post(sel_box, sel_cls, sel_score, n_sel, P, class_to_label, tl, sc, lb);
+        if (n > ncap) n = ncap;
+        for (int i = 0; i < n; ++i) {
+            for (int q = 0; q < 4; ++q) out_tlwh[(o + i) * 4 + q] = tl[i * 4 + q];
+            out_score[o + i] = sc[i];
+            out_label[o + i] = lb[i];
+        }
+        out_count[frame] = n;
+    }
+}
+
 extern "C" {
 
 int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int32_t b, int32_t nmax,
@@ -188,6 +285,31 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
     const size_t osm = (size_t)dd_next_pow2(ncap) * 8 + (size_t)ncap * (32 + 4 + 4);
     if (osm > 48 * 1024 && cudaFuncSetAttribute(k_yolo_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm) != cudaSuccess) return DD_ERR_CUDA;
     k_yolo_order<<<b, 256, osm, st>>>(ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
+    DD_CHECK_LAUNCH();
+    return DD_OK;
+}
+
+int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* anchors, int32_t b,
+                  int32_t na, int32_t ncls, const int32_t* class_to_label, float conf_thr, double nms_iou,
+                  int32_t img_w, int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap,
+                  double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count, void* stream) {
+    if (!raw_boxes || !raw_scores || !anchors || !class_to_label || !out_tlwh || !out_score || !out_label || !out_count)
+        return DD_ERR_INVALID;
+    if (b < 0 || na <= 0 || na > 8192 || ncls < 2 || ncls > 1024 || ncap < 10) return DD_ERR_INVALID;
+    if (b == 0) return DD_OK;
+    DDSsdParams P;
+    P.na = na; P.ncls = ncls; P.max_det = 10; P.score_thr = 1e-8f; P.iou_thr = 0.6f;
+    P.sy = 10.f; P.sx = 10.f; P.sh = 5.f; P.sw = 5.f;
+    P.conf_thr = conf_thr; P.nms_iou = nms_iou;
+    P.img_w = img_w; P.img_h = img_h; P.frame_w = frame_w; P.frame_h = frame_h;
+    P.max_area = 0.9 * frame_w * frame_h;
+    const size_t smem = (size_t)dd_next_pow2(na) * 8 + (size_t)na * 20 + (size_t)DD_SSD_TILE * ncls * 4;
+    if (smem > 200 * 1024) return DD_ERR_CAPACITY;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_ssd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DD_ERR_CUDA;
+    k_ssd_decode<<<b, 256, smem, (cudaStream_t)stream>>>(raw_boxes, raw_scores, anchors, P, class_to_label, ncap,
+                                                        out_tlwh, out_score, out_label, out_count);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }

@@ -5,6 +5,7 @@
 //   dd_order_frame      one CTA per frame: put the appended candidates back into anchor order
 #pragma once
 #include "dd_common.cuh"
+#include "dd_lsap.cuh"
 #include "../../include/deepdish_b200.h"
 
 // ---- order-preserving f32 <-> u32 key (ascending key == ascending float) ---------------------
@@ -172,4 +173,151 @@ DD_HD bool dd_yolo_row(const Row& row, const DDYoloParams& p, const unsigned cha
     *out_score = best;
     *out_class = bi;
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SSD-MobileNet: TFLite_Detection_PostProcess (third-party op, restated from its published algorithm,
+// fast-NMS mode; PARITY UNPINNED -- see oracle/detect.py) followed by the reference's own
+// post-processing (tools/ssd_mobilenet.py:100-150,59-98,198-213) and the box filter
+// (deepdish.py:946-955).
+// ------------------------------------------------------------------------------------------------
+struct DDSsdParams {
+    int na, ncls;              // anchors (1917), classes incl. background column 0 (91)
+    int max_det;               // 10
+    float score_thr, iou_thr;  // 1e-8, 0.6 (op attributes)
+    float sy, sx, sh, sw;      // box coder scales 10, 10, 5, 5
+    float conf_thr;            // ssd_mobilenet.py:100 confidence 0.5 (also score_threshold :207)
+    double nms_iou;            // ssd_mobilenet.py:100 iou_threshold 0.5
+    int img_w, img_h, frame_w, frame_h;
+    double max_area;
+};
+#define DD_SSD_MAXDET 16
+
+#if defined(__CUDA_ARCH__)
+DD_D float dd_expf(float x) { return expf(x); }
+#else
+inline float dd_expf(float x) { return expf(x); }
+#endif
+
+// DecodeCenterSizeBoxes for one anchor: raw (ty,tx,th,tw), anchor (yc,xc,h,w) -> (ymin,xmin,ymax,xmax) f32.
+DD_HD void dd_ssd_decode_box(const float* raw, const float* an, const DDSsdParams& p, float* out) {
+    const float yc = dd_addf(dd_mulf(dd_divf(raw[0], p.sy), an[2]), an[0]);
+    const float xc = dd_addf(dd_mulf(dd_divf(raw[1], p.sx), an[3]), an[1]);
+    const float hh = dd_mulf(dd_mulf(0.5f, dd_expf(dd_divf(raw[2], p.sh))), an[2]);
+    const float hw = dd_mulf(dd_mulf(0.5f, dd_expf(dd_divf(raw[3], p.sw))), an[3]);
+    out[0] = dd_subf(yc, hh); out[1] = dd_subf(xc, hw); out[2] = dd_addf(yc, hh); out[3] = dd_addf(xc, hw);
+}
+
+// ComputeIntersectionOverUnion (f32).
+DD_HD float dd_ssd_iou(const float* a, const float* b) {
+    const float aa = dd_mulf(dd_subf(a[2], a[0]), dd_subf(a[3], a[1]));
+    const float ab = dd_mulf(dd_subf(b[2], b[0]), dd_subf(b[3], b[1]));
+    if (aa <= 0.f || ab <= 0.f) return 0.f;
+    const float ih = fmaxf(dd_subf(fminf(a[2], b[2]), fmaxf(a[0], b[0])), 0.f);
+    const float iw = fmaxf(dd_subf(fminf(a[3], b[3]), fmaxf(a[1], b[1])), 0.f);
+    const float inter = dd_mulf(ih, iw);
+    return dd_divf(inter, dd_subf(dd_addf(aa, ab), inter));
+}
+
+// Everything after the op's greedy selection, serial (<= max_det boxes):
+//   sel_box [n][4] (ymin,xmin,ymax,xmax normalised f32), sel_cls [n] (0-based, background removed),
+//   sel_score [n] in descending score order.  class_to_label[c] = output label id or -1 (label unknown
+//   or not wanted).  Writes <= n rows (tlwh integer-valued f64 after the box filter, score, label) in
+//   the reference's output order; returns the count.
+DD_HD int dd_ssd_post(const float* sel_box, const int* sel_cls, const float* sel_score, int n,
+                      const DDSsdParams& p, const int* class_to_label, double* out_tlwh,
+                      float* out_score, int* out_label) {
+    double bx[DD_SSD_MAXDET][4];
+    int cls[DD_SSD_MAXDET];
+    float sc[DD_SSD_MAXDET];
+    int m = 0;
+    // NaN scrub (:111-116).  Reference quirk kept: np.where on the [n,4] box array yields (rows, cols) and
+    // BOTH index lists are used to zero scores, so a NaN in column k also zeroes score[k].
+    unsigned zero = 0;
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k)
+            if (sel_box[i * 4 + k] != sel_box[i * 4 + k]) zero |= (1u << i) | (1u << k);
+    for (int i = 0; i < n; ++i) {                       // confidence filter (:119)
+        float s = sel_score[i];
+        if (((zero >> i) & 1u) || s != s) s = 0.f;
+        if (!(s >= p.conf_thr)) continue;
+        // reorder [1,0,3,2] * [w,h,w,h] -> f64 (xmin, ymin, xmax, ymax)  (:121-127)
+        bx[m][0] = dd_mul((double)sel_box[i * 4 + 1], (double)p.img_w);
+        bx[m][1] = dd_mul((double)sel_box[i * 4 + 0], (double)p.img_h);
+        bx[m][2] = dd_mul((double)sel_box[i * 4 + 3], (double)p.img_w);
+        bx[m][3] = dd_mul((double)sel_box[i * 4 + 2], (double)p.img_h);
+        cls[m] = sel_cls[i];
+        sc[m] = s;
+        ++m;
+    }
+    // class iteration order = CPython set(labels) order (:61): emulate the small-int set
+    short tabA[64], tabB[64];
+    short *R = tabA, *Rt = tabB;
+    int mask = 7, fill = 0;
+    for (int i = 0; i < 8; ++i) R[i] = 0;
+    for (int i = 0; i < m; ++i) {
+        bool dup = false;
+        for (int k = 0; k < i; ++k) dup = dup || cls[k] == cls[i];
+        if (!dup) dd_set_add(R, Rt, mask, fill, cls[i]);
+    }
+    int n_out = 0;
+    bool any_nan = false;
+    double cand[DD_SSD_MAXDET][4];
+    float cand_s[DD_SSD_MAXDET];
+    int cand_l[DD_SSD_MAXDET];
+    int nc = 0;
+    for (int slot = 0; slot <= mask; ++slot) {
+        if (!R[slot]) continue;
+        const int c = R[slot] - 1;
+        int idx[DD_SSD_MAXDET];
+        int k = 0;
+        for (int i = 0; i < m; ++i)
+            if (cls[i] == c) idx[k++] = i;               // already in descending score order (stable)
+        bool dead[DD_SSD_MAXDET];
+        for (int i = 0; i < k; ++i) dead[i] = false;
+        for (int a = 0; a < k; ++a) {                    // per-class greedy NMS, IoU with +1 px (:59-98)
+            if (dead[a]) continue;
+            const double* A = bx[idx[a]];
+            const double wa = dd_sub(A[2], A[0]), ha = dd_sub(A[3], A[1]);
+            const double area_a = dd_mul(wa, ha);
+            for (int b = a + 1; b < k; ++b) {
+                if (dead[b]) continue;
+                const double* B = bx[idx[b]];
+                const double wb = dd_sub(B[2], B[0]), hb = dd_sub(B[3], B[1]);
+                const double xx1 = dd_max(A[0], B[0]), yy1 = dd_max(A[1], B[1]);
+                const double xx2 = dd_min(dd_add(A[0], wa), dd_add(B[0], wb));
+                const double yy2 = dd_min(dd_add(A[1], ha), dd_add(B[1], hb));
+                const double w1 = dd_max(0.0, dd_add(dd_sub(xx2, xx1), 1.0));
+                const double h1 = dd_max(0.0, dd_add(dd_sub(yy2, yy1), 1.0));
+                const double inter = dd_mul(w1, h1);
+                const double ovr = dd_div(inter, dd_sub(dd_add(area_a, dd_mul(wb, hb)), inter));
+                if (!(ovr <= p.nms_iou)) dead[b] = true;
+            }
+            // label map (+1) / wanted filter / tlwh (:143-147, :207-212)
+            const int lab = class_to_label[c];
+            if (lab < 0 || !(sc[idx[a]] >= p.conf_thr)) continue;
+            cand[nc][0] = A[0]; cand[nc][1] = A[1]; cand[nc][2] = wa; cand[nc][3] = ha;
+            for (int q = 0; q < 4; ++q) any_nan = any_nan || (cand[nc][q] != cand[nc][q]);
+            cand_s[nc] = sc[idx[a]];
+            cand_l[nc] = lab;
+            ++nc;
+        }
+    }
+    if (any_nan) return 0;                               // deepdish.py:947-949
+    for (int i = 0; i < nc; ++i) {                       // box filter (deepdish.py:950-955)
+        const double fx = cand[i][0] < 0.0 ? 0.0 : (cand[i][0] > p.frame_w ? (double)p.frame_w : cand[i][0]);
+        const double fy = cand[i][1] < 0.0 ? 0.0 : (cand[i][1] > p.frame_h ? (double)p.frame_h : cand[i][1]);
+        const int ix = (int)fx, iy = (int)fy;
+        const double mw = (double)(p.frame_w - ix), mh = (double)(p.frame_h - iy);
+        const double fw = cand[i][2] < 0.0 ? 0.0 : (cand[i][2] > mw ? mw : cand[i][2]);
+        const double fh = cand[i][3] < 0.0 ? 0.0 : (cand[i][3] > mh ? mh : cand[i][3]);
+        const int iw = (int)fw, ih = (int)fh;
+        if ((double)((long long)iw * ih) > p.max_area) continue;
+        out_tlwh[n_out * 4 + 0] = ix; out_tlwh[n_out * 4 + 1] = iy;
+        out_tlwh[n_out * 4 + 2] = iw; out_tlwh[n_out * 4 + 3] = ih;
+        out_score[n_out] = cand_s[i];
+        out_label[n_out] = cand_l[i];
+        ++n_out;
+    }
+    return n_out;
 }

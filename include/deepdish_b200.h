@@ -227,6 +227,20 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
                    float* out_score, int32_t* out_class, int32_t* out_anchor, int32_t* out_count,
                    int32_t* out_flags, void* stream);
 
+/* SSD-MobileNet post-processing for b frames: the TFLite custom op TFLite_Detection_PostProcess
+ * (1917-anchor centre-size decode, best non-background class per anchor, greedy IoU NMS at 0.6, <= 10
+ * boxes; third-party, restated -- see DESIGN.md "parity unpinned") followed by SSDMobileNet.predict /
+ * nms_boxes / SSD_MOBILENET.detect_image (tools/ssd_mobilenet.py:100-150, 59-98, 198-213) and the box
+ * filter (deepdish.py:946-955).
+ *   raw_boxes f32 [b,na,4] (ty,tx,th,tw), raw_scores f32 [b,na,ncls] (column 0 = background),
+ *   anchors f32 [na,4] (ycenter,xcenter,h,w), class_to_label i32 [ncls-1]: output label id of 0-based
+ *   class c (the reference's labels[c+1]) or -1 when that label is not wanted.
+ *   out_tlwh f64 [b,ncap,4], out_score f32 [b,ncap], out_label i32 [b,ncap], out_count i32 [b]; ncap >= 10. */
+int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* anchors, int32_t b,
+                  int32_t na, int32_t ncls, const int32_t* class_to_label, float conf_thr, double nms_iou,
+                  int32_t img_w, int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap,
+                  double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,4 +126,50 @@ int ddh_intersection(const double* seg, int n, int32_t* out) {
     return 0;
 }
 
+// SSD: the post-processing of the op's outputs (device function dd_ssd_post) on host arrays.
+int ddh_ssd_post(const float* sel_box, const int32_t* sel_cls, const float* sel_score, int n,
+                 const int32_t* class_to_label, float conf_thr, double nms_iou, int img_w, int img_h,
+                 int frame_w, int frame_h, double* out_tlwh, float* out_score, int32_t* out_label) {
+    DDSsdParams P;
+    P.na = 0; P.ncls = 0; P.max_det = 10; P.score_thr = 1e-8f; P.iou_thr = 0.6f;
+    P.sy = 10.f; P.sx = 10.f; P.sh = 5.f; P.sw = 5.f;
+    P.conf_thr = conf_thr; P.nms_iou = nms_iou;
+    P.img_w = img_w; P.img_h = img_h; P.frame_w = frame_w; P.frame_h = frame_h;
+    P.max_area = 0.9 * frame_w * frame_h;
+    return dd_ssd_post(sel_box, sel_cls, sel_score, n, P, class_to_label, out_tlwh, out_score, out_label);
+}
+
+// NMS device body on host arrays (one frame).
+int ddh_nms(const double* boxes, const float* scores, int n, double max_overlap, int32_t* keep) {
+    HostG g;
+    std::vector<char> smem(dd_nms_smem_bytes(n > 0 ? n : 1) + 64);
+    int nk = 0;
+    dd_nms_frame(g, boxes, scores, n, n > 0 ? n : 1, max_overlap, keep, &nk, smem.data());
+    return nk;
+}
+
+// YOLO row decode + box filter device body on host arrays: head [na, 5+nc] f32.
+int ddh_yolo_rows(const float* head, int na, int nc, const uint8_t* wanted, float thr, int img_w, int img_h,
+                  int frame_w, int frame_h, double* out_tlwh, float* out_score, int32_t* out_class,
+                  int32_t* out_anchor, int32_t* out_nan) {
+    DDYoloParams P;
+    P.nc = nc; P.thr = thr; P.img_w = (float)img_w; P.img_h = (float)img_h;
+    P.frame_w = frame_w; P.frame_h = frame_h; P.max_area = 0.9 * frame_w * frame_h;
+    struct Row { const float* p; float operator()(int k) const { return p[k]; } };
+    int n = 0;
+    *out_nan = 0;
+    for (int a = 0; a < na; ++a) {
+        Row row{head + (size_t)a * (5 + nc)};
+        bool isnan = false;
+        double tl[4]; float sc; int cl;
+        const bool ok = dd_yolo_row(row, P, wanted, tl, &sc, &cl, &isnan);
+        if (isnan) *out_nan = 1;
+        if (!ok) continue;
+        for (int q = 0; q < 4; ++q) out_tlwh[n * 4 + q] = tl[q];
+        out_score[n] = sc; out_class[n] = cl; out_anchor[n] = a;
+        ++n;
+    }
+    return n;
+}
+
 }  // extern "C"

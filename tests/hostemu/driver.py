@@ -75,3 +75,38 @@ def intersection(segs):
     out = np.zeros(len(segs), dtype=np.int32)
     emu().ddh_intersection(_p(segs), len(segs), _p(out))
     return out
+
+
+def ssd_post(sel_box, sel_cls, sel_score, class_to_label, conf_thr=0.5, nms_iou=0.5, img=(640, 480), frame=(640, 480)):
+    sel_box = np.ascontiguousarray(sel_box, np.float32).reshape(-1, 4)
+    n = len(sel_box)
+    sel_cls = np.ascontiguousarray(sel_cls, np.int32)
+    sel_score = np.ascontiguousarray(sel_score, np.float32)
+    c2l = np.ascontiguousarray(class_to_label, np.int32)
+    tl = np.zeros((16, 4)); sc = np.zeros(16, np.float32); lb = np.zeros(16, np.int32)
+    emu().ddh_ssd_post.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_float, ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
+    k = emu().ddh_ssd_post(_p(sel_box), _p(sel_cls), _p(sel_score), n, _p(c2l), conf_thr, nms_iou, img[0], img[1],
+                           frame[0], frame[1], _p(tl), _p(sc), _p(lb))
+    return tl[:k], sc[:k], lb[:k]
+
+
+def nms(boxes, scores, max_overlap):
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+    scores = np.ascontiguousarray(scores, np.float32)
+    keep = np.zeros(max(len(boxes), 1), np.int32)
+    emu().ddh_nms.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    k = emu().ddh_nms(_p(boxes), _p(scores), len(boxes), max_overlap, _p(keep))
+    return keep[:k].tolist()
+
+
+def yolo_rows(head, wanted_mask, thr, img, frame):
+    head = np.ascontiguousarray(head, np.float32)
+    na, rw = head.shape
+    wanted_mask = np.ascontiguousarray(wanted_mask, np.uint8)
+    tl = np.zeros((na, 4)); sc = np.zeros(na, np.float32); cl = np.zeros(na, np.int32); an = np.zeros(na, np.int32)
+    nan = np.zeros(1, np.int32)
+    emu().ddh_yolo_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_float] + \
+        [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
+    k = emu().ddh_yolo_rows(_p(head), na, rw - 5, _p(wanted_mask), thr, img[0], img[1], frame[0], frame[1],
+                            _p(tl), _p(sc), _p(cl), _p(an), _p(nan))
+    return tl[:k], sc[:k], cl[:k], an[:k], int(nan[0])

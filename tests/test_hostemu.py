@@ -74,3 +74,38 @@ def test_trajectory_parity_host_emulation():
             if f > 5:
                 checked += compare_costs(orc.trk[s], pre, emu.v, s)
     assert checked > 500 and int(emu.v["err"].sum()) == 0
+
+
+def test_detection_bodies_vs_reference_fixtures():
+    """NMS, YOLO row decode + box filter and the SSD post-processing device functions (host emulation)
+    against the fixtures produced by the unmodified reference."""
+    from tests import goldens
+    g = goldens.load("nms.npz")
+    for i in range(len(g["counts"])):
+        n = int(g["counts"][i])
+        assert hd.nms(g["boxes"][i, :n], g["scores"][i, :n], float(g["thr"][i])) == list(g["keep"][i, :g["nkeep"][i]])
+    g = goldens.load("yolo.npz")
+    names, wanted = list(g["names"]), list(g["wanted"])
+    mask = np.array([1 if n in wanted else 0 for n in names], np.uint8)
+    for f in range(g["head"].shape[0]):
+        tl, sc, cl, an, nan = hd.yolo_rows(g["head"][f], mask, 0.25, (640, 480), (640, 480))
+        fidx = g["fidx%d" % f]
+        assert nan == 0 and len(tl) == len(fidx)
+        np.testing.assert_array_equal(tl, g["fbox%d" % f].reshape(-1, 4).astype(float))
+        np.testing.assert_array_equal(sc, g["score%d" % f][fidx])
+        np.testing.assert_array_equal(cl, g["cls%d" % f][fidx])
+    g = goldens.load("ssd_post.npz")
+    names, wanted = list(g["names"]), list(g["wanted"])
+    c2l = np.array([(c + 1) if (c + 1 < len(names) and names[c + 1] in wanted) else -1 for c in range(len(names) - 1)], np.int32)
+    total = 0
+    for c in range(len(g["op_boxes"])):
+        tl, sc, lb = hd.ssd_post(g["op_boxes"][c], g["op_classes"][c].astype(np.int32), g["op_scores"][c], c2l)
+        exp = g["tlwh%d" % c]
+        # the fixture holds detect_image's float boxes; the device function also applies the box filter
+        from oracle import detect as odet
+        ib, kept = odet.box_filter([tuple(r) for r in exp], 640, 480)
+        np.testing.assert_array_equal(tl, ib.astype(float).reshape(-1, 4))
+        np.testing.assert_array_equal(sc, g["score%d" % c][kept])
+        np.testing.assert_array_equal(lb, g["lab%d" % c][kept])
+        total += len(tl)
+    assert total > 100
