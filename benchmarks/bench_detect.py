@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Detector post-processing micro-benchmarks (BASELINE.json configs[1] "C2" and the SSD half of C5).
+
+    python benchmarks/bench_detect.py [--frames 64] [--iters 20]
+
+Prints one JSON line per kernel group: frames/s, achieved algorithmic GB/s and the fraction of the
+measured HBM peak.  Inputs are resident in HBM; several input copies are rotated so that every timed
+iteration reads data that is not in L2 (64 frames x 8.568 MB = 548 MB per copy > 126 MB L2 anyway).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from deepdish_b200 import ops  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def synth_head(frames, na, nc, gen, hot=0.01):
+    h = torch.empty((frames, na, 5 + nc), device="cuda")
+    h[..., 0:2] = 0.05 + 0.85 * torch.rand((frames, na, 2), device="cuda", generator=gen)
+    h[..., 2:4] = 0.01 + 0.19 * torch.rand((frames, na, 2), device="cuda", generator=gen)
+    h[..., 4] = torch.rand((frames, na), device="cuda", generator=gen) ** 6
+    h[..., 5:] = torch.rand((frames, na, nc), device="cuda", generator=gen) ** 4
+    m = torch.rand((frames, na), device="cuda", generator=gen) < hot
+    h[..., 4][m] = 0.5 + 0.5 * torch.rand(int(m.sum()), device="cuda", generator=gen)
+    idx = m.nonzero()
+    cls = torch.randint(0, 6, (len(idx),), device="cuda", generator=gen)
+    h[idx[:, 0], idx[:, 1], 5 + cls] = 0.5 + 0.5 * torch.rand(len(idx), device="cuda", generator=gen)
+    return h
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=20)
+    args = ap.parse_args()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    B, NA, NC = args.frames, 25200, 80
+    pk = peak()
+    mask = torch.zeros(NC, dtype=torch.uint8, device="cuda")
+    mask[:8] = 1
+    heads = [synth_head(B, NA, NC, gen) for _ in range(3)]
+    out = {}
+
+    def run_yolo(i):
+        out["y"] = ops.yolo_decode(heads[i % 3], mask, 0.25, (640, 480), (640, 480), ncap=1024)
+
+    ms = timed(run_yolo, args.iters)
+    nbytes = B * NA * (5 + NC) * 4
+    cand = float(out["y"]["count"].float().mean())
+    print(json.dumps({"kernel": "k_yolo_decode+k_yolo_order (f32 head)", "frames": B, "ms": ms, "frames_per_s": B / ms * 1e3,
+                      "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_measured_hbm": nbytes / ms / 1e6 / pk,
+                      "candidates_per_frame": cand}))
+
+    def run_yolo_nms(i):
+        y = ops.yolo_decode(heads[i % 3], mask, 0.25, (640, 480), (640, 480), ncap=1024)
+        out["k"] = ops.nms(y["tlwh"], y["score"], y["count"], 0.6)
+
+    ms2 = timed(run_yolo_nms, args.iters)
+    print(json.dumps({"kernel": "C2: yolo decode + box filter + NMS", "frames": B, "ms": ms2, "frames_per_s": B / ms2 * 1e3,
+                      "algorithmic_GBps": nbytes / ms2 / 1e6, "frac_of_measured_hbm": nbytes / ms2 / 1e6 / pk,
+                      "kept_per_frame": float(out["k"][1].float().mean())}))
+    y = out["y"]
+
+    def run_nms(i):
+        ops.nms(y["tlwh"], y["score"], y["count"], 0.6)
+
+    ms3 = timed(run_nms, args.iters)
+    print(json.dumps({"kernel": "k_nms alone", "frames": B, "ms": ms3, "candidates_per_frame": cand}))
+    del heads
+    q = [torch.randint(0, 256, (B, NA, 5 + NC), dtype=torch.uint8, device="cuda", generator=gen) for _ in range(3)]
+    for t in q:
+        t[..., 4] = (t[..., 4].float() * 0.3).to(torch.uint8)
+
+    def run_u8(i):
+        out["u"] = ops.yolo_decode(q[i % 3], mask, 0.6, (640, 480), (640, 480), ncap=4096, quant=(1 / 255.0, 0))
+
+    ms4 = timed(run_u8, args.iters)
+    nb8 = B * NA * (5 + NC)
+    print(json.dumps({"kernel": "k_yolo_decode (u8 head)", "frames": B, "ms": ms4, "frames_per_s": B / ms4 * 1e3,
+                      "algorithmic_GBps": nb8 / ms4 / 1e6, "frac_of_measured_hbm": nb8 / ms4 / 1e6 / pk}))
+    del q
+    # SSD: 2048 frames (C5: the SSD share of 16384 streams over 8 GPUs)
+    Bs, A, C = 2048, 1917, 91
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_free_anchors import ssd_anchors
+    anchors = torch.from_numpy(ssd_anchors()).cuda()
+    rb = [torch.randn((Bs, A, 4), device="cuda", generator=gen) * 0.8 for _ in range(2)]
+    sc = [torch.rand((Bs, A, C), device="cuda", generator=gen) ** 8 for _ in range(2)]
+    c2l = torch.arange(1, C, dtype=torch.int32, device="cuda")
+
+    def run_ssd(i):
+        out["s"] = ops.ssd_decode(rb[i % 2], sc[i % 2], anchors, c2l, 0.5, 0.5)
+
+    ms5 = timed(run_ssd, max(5, args.iters // 2))
+    nbs = Bs * A * (4 + C) * 4
+    print(json.dumps({"kernel": "k_ssd_decode", "frames": Bs, "ms": ms5, "frames_per_s": Bs / ms5 * 1e3,
+                      "algorithmic_GBps": nbs / ms5 / 1e6, "frac_of_measured_hbm": nbs / ms5 / 1e6 / pk}))
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,13 @@ inline int dd_ctz(unsigned w) { return __builtin_ctz(w); }
 DD_HD int dd_imin(int a, int b) { return a < b ? a : b; }
 DD_HD int dd_imax(int a, int b) { return a > b ? a : b; }
 
+// __syncwarp for code that only the first warp of a CTA executes (no-op on the host emulation)
+#if defined(__CUDA_ARCH__)
+DD_D void dd_first_warp_sync() { __syncwarp(); }
+#else
+inline void dd_first_warp_sync() {}
+#endif
+
 // (value, preference) pair used by the LSAP column scan: lower value wins, ties -> higher pref.
 struct DDKey {
     double val;

@@ -11,6 +11,7 @@
 //   k_nms          one CTA per frame: sort by score, N x N/64 suppression bitmask, serial scan.
 #include <cuda_runtime.h>
 #include "dd_detect_bodies.cuh"
+#include "dd_tma.cuh"
 
 #define DD_CHECK_LAUNCH()                                         \
     do {                                                          \
@@ -45,12 +46,18 @@ k_yolo_decode(const void* __restrict__ head, float scale, int zero_point, int na
     const size_t row_bytes = (size_t)rw * esz;
     const char* src = (const char*)head + ((size_t)frame * na + row0) * row_bytes;
     const size_t bytes = (size_t)rows * row_bytes;
+    __shared__ unsigned long long bar;
     if ((((uintptr_t)src) & 15) == 0 && (bytes & 15) == 0) {
-        const int4* s4 = (const int4*)src;
-        int4* d4 = (int4*)smem;
-        const int n4 = (int)(bytes >> 4);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n4; i += DD_YOLO_ROWS) d4[i] = __ldg(s4 + i);
+        // one bulk asynchronous copy (TMA engine) brings the whole tile; no registers are tied up by
+        // loads in flight and every resident CTA keeps its full tile outstanding
+        if (threadIdx.x == 0) {
+            dd_mbar_init(&bar, 1);
+            dd_mbar_fence_init();
+            dd_mbar_expect_tx(&bar, (unsigned)bytes);
+            dd_bulk_g2s(smem, src, (unsigned)bytes, &bar);
+        }
+        __syncthreads();                 // barrier initialised before anyone polls it
+        dd_mbar_wait(&bar, 0);
     } else if (U8) {
         for (int i = threadIdx.x; i < (int)bytes; i += DD_YOLO_ROWS) smem[i] = src[i];
     } else {
@@ -131,7 +138,7 @@ k_yolo_order(int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_sc
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ counts,
       int nmax, double max_overlap, int* __restrict__ out_keep, int* __restrict__ out_nkeep) {
     extern __shared__ __align__(16) char smem[];
@@ -144,11 +151,13 @@ k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const 
 // ---- SSD-MobileNet: one CTA per frame -------------------------------------------------------------
 //   phase A  tiles of DD_SSD_TILE anchors staged in shared memory (coalesced loads of the [na, ncls] score
 //            rows), 4 threads per anchor find the best non-background class, boxes are decoded (expf);
-//   phase B  bitonic sort of (score desc, anchor asc) keys;
-//   phase C  warp 0: greedy IoU NMS in score order until max_det boxes are selected;
-//   phase D  thread 0: the reference's own post-processing on the <= 10 selected boxes (dd_ssd_post).
+//   phase B  greedy NMS as <= max_det rounds of {block-wide arg-max over the live candidates, eager
+//            suppression of every live candidate with IoU > 0.6 against the pick} -- the same selection as
+//            the op's sort + scan (a candidate dies iff an earlier-ranked pick overlaps it), without a sort;
+//   phase C  thread 0: the reference's own post-processing on the <= 10 selected boxes (dd_ssd_post).
 #define DD_SSD_TILE 64
-__global__ void __launch_bounds__(256)
+#define DD_SSD_THREADS 256
+__global__ void __launch_bounds__(DD_SSD_THREADS)
 k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_scores,
              const float* __restrict__ anchors, DDSsdParams P, const int* __restrict__ class_to_label,
              int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_score,
@@ -156,21 +165,19 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
     extern __shared__ __align__(16) char smem[];
     const int frame = blockIdx.x;
     const int na = P.na, ncls = P.ncls;
-    const int NP = dd_next_pow2(na);
-    unsigned long long* keys = (unsigned long long*)smem;               // [NP]
-    float* dec = (float*)(keys + NP);                                   // [na][4]
+    unsigned long long* keys = (unsigned long long*)smem;               // [na]  live candidate keys (~0 = dead)
+    float* dec = (float*)(keys + na);                                   // [na][4]
     int* bcls = (int*)(dec + (size_t)na * 4);                           // [na]
     float* tile = (float*)(bcls + na);                                  // [DD_SSD_TILE][ncls]
     __shared__ float sel_box[DD_SSD_MAXDET * 4];
     __shared__ int sel_cls[DD_SSD_MAXDET];
     __shared__ float sel_score[DD_SSD_MAXDET];
-    __shared__ int n_sel;
+    __shared__ unsigned long long wmin[DD_SSD_THREADS / 32];
     const float* fs = raw_scores + (size_t)frame * na * ncls;
     const float* fb = raw_boxes + (size_t)frame * na * 4;
-    BlockG g;
     for (int a0 = 0; a0 < na; a0 += DD_SSD_TILE) {
         const int rows = min(DD_SSD_TILE, na - a0);
-        for (int i = threadIdx.x; i < rows * ncls; i += blockDim.x) tile[i] = fs[(size_t)a0 * ncls + i];
+        for (int i = threadIdx.x; i < rows * ncls; i += DD_SSD_THREADS) tile[i] = fs[(size_t)a0 * ncls + i];
         __syncthreads();
         const int r = threadIdx.x >> 2, q = threadIdx.x & 3;            // 4 threads per anchor row
         float best = -3.0e38f;
@@ -195,39 +202,40 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
         }
         __syncthreads();
     }
-    for (int i = na + threadIdx.x; i < NP; i += blockDim.x) keys[i] = ~0ull;
-    __syncthreads();
-    dd_bitonic_sort(g, keys, NP);
-    if (threadIdx.x < 32) {                                             // greedy NMS, one warp
-        const int lane = threadIdx.x;
-        int ns = 0;
-        for (int i = 0; i < na && ns < P.max_det; ++i) {
-            const unsigned long long k = keys[i];
-            if (k == ~0ull) break;
-            const int a = (int)(k & 0xffffffffu);
-            bool sup = false;
-            if (lane < ns) sup = dd_ssd_iou(sel_box + lane * 4, dec + (size_t)a * 4) > P.iou_thr;
-            if (__any_sync(0xffffffffu, sup)) continue;
-            if (lane == 0) {
-                for (int q = 0; q < 4; ++q) sel_box[ns * 4 + q] = dec[(size_t)a * 4 + q];
-                sel_cls[ns] = bcls[a];
-                union { unsigned u; float f; } cv;
-                const unsigned kk = ~(unsigned)(k >> 32);
-                cv.u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
-                sel_score[ns] = cv.f;
-            }
-            ++ns;
-            __syncwarp();
+    int ns = 0;
+    for (; ns < P.max_det; ++ns) {
+        unsigned long long mk = ~0ull;                                  // smallest key = best live candidate
+        for (int a = threadIdx.x; a < na; a += DD_SSD_THREADS) mk = min(mk, keys[a]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+        if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = mk;
+        __syncthreads();
+        mk = wmin[0];
+#pragma unroll
+        for (int w = 1; w < DD_SSD_THREADS / 32; ++w) mk = min(mk, wmin[w]);
+        if (mk == ~0ull) break;                                         // uniform: no live candidate left
+        const int pick = (int)(mk & 0xffffffffu);
+        const float pb[4] = {dec[pick * 4], dec[pick * 4 + 1], dec[pick * 4 + 2], dec[pick * 4 + 3]};
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < 4; ++q) sel_box[ns * 4 + q] = pb[q];
+            sel_cls[ns] = bcls[pick];
+            union { unsigned u; float f; } cv;
+            const unsigned kk = ~(unsigned)(mk >> 32);
+            cv.u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
+            sel_score[ns] = cv.f;
         }
-        if (lane == 0) n_sel = ns;
+        for (int a = threadIdx.x; a < na; a += DD_SSD_THREADS) {
+            if (keys[a] == ~0ull) continue;
+            if (a == pick || dd_ssd_iou(pb, dec + (size_t)a * 4) > P.iou_thr) keys[a] = ~0ull;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
         const size_t o = (size_t)frame * ncap;
         double tl[DD_SSD_MAXDET * 4];
         float sc[DD_SSD_MAXDET];
         int lb[DD_SSD_MAXDET];
-        int n = dd_ssd_post(sel_box, sel_cls, sel_score, n_sel, P, class_to_label, tl, sc, lb);
+        int n = dd_ssd_post(sel_box, sel_cls, sel_score, ns, P, class_to_label, tl, sc, lb);
         if (n > ncap) n = ncap;
         for (int i = 0; i < n; ++i) {
             for (int q = 0; q < 4; ++q) out_tlwh[(o + i) * 4 + q] = tl[i * 4 + q];
@@ -249,7 +257,7 @@ int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int3
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DD_ERR_CUDA;
-    k_nms<<<b, 256, smem, (cudaStream_t)stream>>>(boxes, scores, counts, nmax, max_overlap, out_keep, out_nkeep);
+    k_nms<<<b, 512, smem, (cudaStream_t)stream>>>(boxes, scores, counts, nmax, max_overlap, out_keep, out_nkeep);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
@@ -303,12 +311,12 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
     P.conf_thr = conf_thr; P.nms_iou = nms_iou;
     P.img_w = img_w; P.img_h = img_h; P.frame_w = frame_w; P.frame_h = frame_h;
     P.max_area = 0.9 * frame_w * frame_h;
-    const size_t smem = (size_t)dd_next_pow2(na) * 8 + (size_t)na * 20 + (size_t)DD_SSD_TILE * ncls * 4;
+    const size_t smem = (size_t)na * 8 + (size_t)na * 20 + (size_t)DD_SSD_TILE * ncls * 4;
     if (smem > 200 * 1024) return DD_ERR_CAPACITY;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_ssd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DD_ERR_CUDA;
-    k_ssd_decode<<<b, 256, smem, (cudaStream_t)stream>>>(raw_boxes, raw_scores, anchors, P, class_to_label, ncap,
+    k_ssd_decode<<<b, DD_SSD_THREADS, smem, (cudaStream_t)stream>>>(raw_boxes, raw_scores, anchors, P, class_to_label, ncap,
                                                         out_tlwh, out_score, out_label, out_count);
     DD_CHECK_LAUNCH();
     return DD_OK;

@@ -93,6 +93,11 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
     }
     for (int w = g.lane; w < nw; w += g.nl) m.remv[w] = 0;
     g.sync();
+    // exact decision of fl(inter / area_j) > max_overlap without a division in the common cases:
+    // disjoint boxes (inter = 0) never suppress; otherwise compare inter against max_overlap * area_j with a
+    // 2^-40 relative guard band and fall back to the division only inside the band.
+    const bool fast = max_overlap >= 0.0;     // disjoint pairs never suppress only for thresholds >= 0
+    const double lo_f = max_overlap * (1.0 - 9.094947017729282e-13), hi_f = max_overlap * (1.0 + 9.094947017729282e-13);
     for (int e = g.lane; e < n * nw; e += g.nl) {
         const int i = e / nw, w = e - i * nw;
         unsigned long long bits = 0;
@@ -100,16 +105,27 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
             const double ax1 = m.x1[i], ay1 = m.y1[i], ax2 = m.x2[i], ay2 = m.y2[i];
             const int j1 = dd_imin(n, w * 64 + 64);
             for (int j = dd_imax(i + 1, w * 64); j < j1; ++j) {
-                const double iw = dd_max(0.0, dd_add(dd_sub(dd_min(ax2, m.x2[j]), dd_max(ax1, m.x1[j])), 1.0));
-                const double ih = dd_max(0.0, dd_add(dd_sub(dd_min(ay2, m.y2[j]), dd_max(ay1, m.y1[j])), 1.0));
-                if (dd_div(dd_mul(iw, ih), m.area[j]) > max_overlap) bits |= 1ull << (j - w * 64);
+                double iw = dd_add(dd_sub(dd_min(ax2, m.x2[j]), dd_max(ax1, m.x1[j])), 1.0);
+                if (fast && !(iw > 0.0)) continue;
+                double ih = dd_add(dd_sub(dd_min(ay2, m.y2[j]), dd_max(ay1, m.y1[j])), 1.0);
+                if (fast && !(ih > 0.0)) continue;
+                iw = dd_max(0.0, iw); ih = dd_max(0.0, ih);
+                const double inter = dd_mul(iw, ih), aj = m.area[j];
+                bool sup;
+                if (fast && aj > 0.0 && inter > hi_f * aj) sup = true;
+                else if (fast && aj > 0.0 && inter < lo_f * aj) sup = false;
+                else sup = dd_div(inter, aj) > max_overlap;
+                if (sup) bits |= 1ull << (j - w * 64);
             }
         }
         m.mask[e] = bits;
     }
     g.sync();
-    // scan: jump from survivor to survivor (first zero bit of remv at or after the cursor)
-    if (g.lane == 0) {
+    // scan: jump from survivor to survivor (first zero bit of remv at or after the cursor); the lanes of
+    // the first warp share the OR of the picked row into remv.
+    if (g.lane < 32) {
+        const int lane = g.lane;
+        const int nscan = g.nl < 32 ? g.nl : 32;
         int nk = 0;
         int i = 0;
         while (i < n) {
@@ -121,11 +137,13 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
             i = (i & ~63) + __builtin_ctzll(word);
 #endif
             if (i >= n) break;
-            keep[nk++] = (int)(m.keys[i] & 0xffffffffu);
-            for (int w = i >> 6; w < nw; ++w) m.remv[w] |= m.mask[(size_t)i * nw + w];
+            if (lane == 0) keep[nk] = (int)(m.keys[i] & 0xffffffffu);
+            ++nk;
+            for (int w = (i >> 6) + lane; w < nw; w += nscan) m.remv[w] |= m.mask[(size_t)i * nw + w];
+            dd_first_warp_sync();
             ++i;
         }
-        *nkeep = nk;
+        if (lane == 0) *nkeep = nk;
     }
 }
 

@@ -10,6 +10,7 @@
 //   k_countline    one warp per stream                    4 warps / CTA
 #include <cuda_runtime.h>
 #include "dd_tracker_bodies.cuh"
+#include "dd_tma.cuh"
 
 #define DD_WARPS 4
 
@@ -59,25 +60,6 @@ k_cosine(const DDView V, const int* __restrict__ det_count) {
 // DD_STAGES x 4 KB outstanding at ~70 registers/thread and the SM holds several such warps.
 #define DD_STAGES 4
 #define DD_STAGE_BYTES (DD_ROWS * DD_FEAT_DIM * 4)
-
-__device__ __forceinline__ unsigned dd_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void dd_mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dd_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void dd_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dd_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void dd_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(dd_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void dd_mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok = 0;
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(dd_smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
 
 struct DDTmaPass {
     float4* ring;                 // [DD_STAGES][DD_ROWS][32] float4, this warp's
