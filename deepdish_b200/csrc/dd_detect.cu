@@ -138,7 +138,7 @@ k_yolo_order(int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_sc
     }
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ counts,
       int nmax, double max_overlap, int* __restrict__ out_keep, int* __restrict__ out_nkeep) {
     extern __shared__ __align__(16) char smem[];
@@ -149,8 +149,8 @@ k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const 
 }
 
 // ---- SSD-MobileNet: one CTA per frame -------------------------------------------------------------
-//   phase A  tiles of DD_SSD_TILE anchors staged in shared memory (coalesced loads of the [na, ncls] score
-//            rows), 4 threads per anchor find the best non-background class, boxes are decoded (expf);
+//   phase A  4 threads per anchor scan its [ncls] score row (adjacent rows -> coalesced), best
+//            non-background class, box decode (expf);
 //   phase B  greedy NMS as <= max_det rounds of {block-wide arg-max over the live candidates, eager
 //            suppression of every live candidate with IoU > 0.6 against the pick} -- the same selection as
 //            the op's sort + scan (a candidate dies iff an earlier-ranked pick overlaps it), without a sort;
@@ -168,40 +168,41 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
     unsigned long long* keys = (unsigned long long*)smem;               // [na]  live candidate keys (~0 = dead)
     float* dec = (float*)(keys + na);                                   // [na][4]
     int* bcls = (int*)(dec + (size_t)na * 4);                           // [na]
-    float* tile = (float*)(bcls + na);                                  // [DD_SSD_TILE][ncls]
     __shared__ float sel_box[DD_SSD_MAXDET * 4];
     __shared__ int sel_cls[DD_SSD_MAXDET];
     __shared__ float sel_score[DD_SSD_MAXDET];
     __shared__ unsigned long long wmin[DD_SSD_THREADS / 32];
     const float* fs = raw_scores + (size_t)frame * na * ncls;
     const float* fb = raw_boxes + (size_t)frame * na * 4;
-    for (int a0 = 0; a0 < na; a0 += DD_SSD_TILE) {
-        const int rows = min(DD_SSD_TILE, na - a0);
-        for (int i = threadIdx.x; i < rows * ncls; i += DD_SSD_THREADS) tile[i] = fs[(size_t)a0 * ncls + i];
-        __syncthreads();
-        const int r = threadIdx.x >> 2, q = threadIdx.x & 3;            // 4 threads per anchor row
-        float best = -3.0e38f;
-        int bi = 0x7fffffff;
-        if (r < rows) {
-            for (int c = 1 + q; c < ncls; c += 4) {                     // skip background column 0
-                const float v = tile[r * ncls + c];
-                if (v > best) { best = v; bi = c - 1; }
+    // phase A: 4 threads per anchor read its score row straight from global memory (a warp covers 8
+    // adjacent rows = 2912 contiguous bytes; no staging, no barriers, all loads independent)
+    {
+        const int q = threadIdx.x & 3;
+        for (int a = threadIdx.x >> 2; a < ((na + 63) & ~63); a += DD_SSD_THREADS / 4) {
+            float best = -3.0e38f;
+            int bi = 0x7fffffff;
+            if (a < na) {
+                const float* row = fs + (size_t)a * ncls;
+#pragma unroll 4
+                for (int c = 1 + q; c < ncls; c += 4) {                 // skip background column 0
+                    const float v = __ldg(row + c);
+                    if (v > best) { best = v; bi = c - 1; }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {                          // first maximum wins across the 4 lanes
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (a < na && q == 0) {
+                dd_ssd_decode_box(fb + (size_t)a * 4, anchors + (size_t)a * 4, P, dec + (size_t)a * 4);
+                bcls[a] = bi;
+                keys[a] = best >= P.score_thr ? (((unsigned long long)(~dd_f32_key(best))) << 32) | (unsigned)a : ~0ull;
             }
         }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {                              // first maximum wins across the 4 lanes
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (r < rows && q == 0) {
-            const int a = a0 + r;
-            dd_ssd_decode_box(fb + (size_t)a * 4, anchors + (size_t)a * 4, P, dec + (size_t)a * 4);
-            bcls[a] = bi;
-            keys[a] = best >= P.score_thr ? (((unsigned long long)(~dd_f32_key(best))) << 32) | (unsigned)a : ~0ull;
-        }
-        __syncthreads();
     }
+    __syncthreads();
     int ns = 0;
     for (; ns < P.max_det; ++ns) {
         unsigned long long mk = ~0ull;                                  // smallest key = best live candidate
@@ -257,7 +258,7 @@ int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int3
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DD_ERR_CUDA;
-    k_nms<<<b, 512, smem, (cudaStream_t)stream>>>(boxes, scores, counts, nmax, max_overlap, out_keep, out_nkeep);
+    k_nms<<<b, 1024, smem, (cudaStream_t)stream>>>(boxes, scores, counts, nmax, max_overlap, out_keep, out_nkeep);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
@@ -311,7 +312,7 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
     P.conf_thr = conf_thr; P.nms_iou = nms_iou;
     P.img_w = img_w; P.img_h = img_h; P.frame_w = frame_w; P.frame_h = frame_h;
     P.max_area = 0.9 * frame_w * frame_h;
-    const size_t smem = (size_t)na * 8 + (size_t)na * 20 + (size_t)DD_SSD_TILE * ncls * 4;
+    const size_t smem = (size_t)na * 8 + (size_t)na * 20;
     if (smem > 200 * 1024) return DD_ERR_CAPACITY;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_ssd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

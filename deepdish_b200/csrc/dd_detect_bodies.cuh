@@ -59,6 +59,27 @@ DD_HD void dd_nms_carve(char* mem, int nmax, DDNmsSmem& m) {
     m.y1 = m.x1 + nmax; m.x2 = m.y1 + nmax; m.y2 = m.x2 + nmax; m.area = m.y2 + nmax;
 }
 
+// Does box A (the higher-ranked pick) suppress box J:  fl(inter / area_J) > max_overlap, +1 px convention
+// (preprocessing.py:59-71), all f64.  Exact without a division in the common cases: disjoint boxes never
+// suppress (for thresholds >= 0); otherwise inter is compared against max_overlap * area_J with a 2^-40
+// relative guard band and only inside the band the division decides.
+DD_HD bool dd_nms_suppresses(double ax1, double ay1, double ax2, double ay2, double jx1, double jy1, double jx2,
+                             double jy2, double aj, double max_overlap, bool fast) {
+    double iw = dd_add(dd_sub(dd_min(ax2, jx2), dd_max(ax1, jx1)), 1.0);
+    if (fast && !(iw > 0.0)) return false;
+    double ih = dd_add(dd_sub(dd_min(ay2, jy2), dd_max(ay1, jy1)), 1.0);
+    if (fast && !(ih > 0.0)) return false;
+    iw = dd_max(0.0, iw);
+    ih = dd_max(0.0, ih);
+    const double inter = dd_mul(iw, ih);
+    if (fast && aj > 0.0) {
+        const double t = max_overlap * aj;
+        if (inter > t * (1.0 + 9.094947017729282e-13)) return true;
+        if (inter < t * (1.0 - 9.094947017729282e-13)) return false;
+    }
+    return dd_div(inter, aj) > max_overlap;
+}
+
 // deep_sort/preprocessing.py:6-73.  boxes f64 [n,4] tlwh, scores f32 [n].  keep[] receives the
 // original indices in pick order (descending score); returns their number through *nkeep.
 //   sort     : descending score (ties: lower index first -- the reference's np.argsort is unstable, so
@@ -93,33 +114,43 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
     }
     for (int w = g.lane; w < nw; w += g.nl) m.remv[w] = 0;
     g.sync();
-    // exact decision of fl(inter / area_j) > max_overlap without a division in the common cases:
-    // disjoint boxes (inter = 0) never suppress; otherwise compare inter against max_overlap * area_j with a
-    // 2^-40 relative guard band and fall back to the division only inside the band.
-    const bool fast = max_overlap >= 0.0;     // disjoint pairs never suppress only for thresholds >= 0
-    const double lo_f = max_overlap * (1.0 - 9.094947017729282e-13), hi_f = max_overlap * (1.0 + 9.094947017729282e-13);
+    const bool fast = max_overlap >= 0.0;
+#if defined(__CUDA_ARCH__)
+    // one warp per (row i, 64-bit word w) item: lanes test 32 candidates j at a time, ballots give the bits
+    {
+        const int wid = g.lane >> 5, ln = g.lane & 31, nwarp = g.nl >> 5;
+        for (int e = wid; e < n * nw; e += nwarp) {
+            const int i = e / nw, w = e - i * nw;
+            unsigned long long bits = 0;
+            if (w * 64 + 63 > i) {
+                const double ax1 = m.x1[i], ay1 = m.y1[i], ax2 = m.x2[i], ay2 = m.y2[i];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = w * 64 + h * 32 + ln;
+                    bool sup = false;
+                    if (j > i && j < n)
+                        sup = dd_nms_suppresses(ax1, ay1, ax2, ay2, m.x1[j], m.y1[j], m.x2[j], m.y2[j], m.area[j],
+                                                max_overlap, fast);
+                    bits |= (unsigned long long)__ballot_sync(0xffffffffu, sup) << (32 * h);
+                }
+            }
+            if (ln == 0) m.mask[e] = bits;
+        }
+    }
+#else
     for (int e = g.lane; e < n * nw; e += g.nl) {
         const int i = e / nw, w = e - i * nw;
         unsigned long long bits = 0;
         if (w * 64 + 63 > i) {
-            const double ax1 = m.x1[i], ay1 = m.y1[i], ax2 = m.x2[i], ay2 = m.y2[i];
             const int j1 = dd_imin(n, w * 64 + 64);
-            for (int j = dd_imax(i + 1, w * 64); j < j1; ++j) {
-                double iw = dd_add(dd_sub(dd_min(ax2, m.x2[j]), dd_max(ax1, m.x1[j])), 1.0);
-                if (fast && !(iw > 0.0)) continue;
-                double ih = dd_add(dd_sub(dd_min(ay2, m.y2[j]), dd_max(ay1, m.y1[j])), 1.0);
-                if (fast && !(ih > 0.0)) continue;
-                iw = dd_max(0.0, iw); ih = dd_max(0.0, ih);
-                const double inter = dd_mul(iw, ih), aj = m.area[j];
-                bool sup;
-                if (fast && aj > 0.0 && inter > hi_f * aj) sup = true;
-                else if (fast && aj > 0.0 && inter < lo_f * aj) sup = false;
-                else sup = dd_div(inter, aj) > max_overlap;
-                if (sup) bits |= 1ull << (j - w * 64);
-            }
+            for (int j = dd_imax(i + 1, w * 64); j < j1; ++j)
+                if (dd_nms_suppresses(m.x1[i], m.y1[i], m.x2[i], m.y2[i], m.x1[j], m.y1[j], m.x2[j], m.y2[j],
+                                      m.area[j], max_overlap, fast))
+                    bits |= 1ull << (j - w * 64);
         }
         m.mask[e] = bits;
     }
+#endif
     g.sync();
     // scan: jump from survivor to survivor (first zero bit of remv at or after the cursor); the lanes of
     // the first warp share the OR of the picked row into remv.
