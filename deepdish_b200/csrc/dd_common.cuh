@@ -54,6 +54,11 @@ DD_D int dd_ctz(unsigned w) { return __ffs((int)w) - 1; }
 #else
 inline int dd_ctz(unsigned w) { return __builtin_ctz(w); }
 #endif
+#if defined(__CUDA_ARCH__)
+DD_D int dd_popc(unsigned w) { return __popc(w); }
+#else
+inline int dd_popc(unsigned w) { return __builtin_popcount(w); }
+#endif
 DD_HD int dd_imin(int a, int b) { return a < b ? a : b; }
 DD_HD int dd_imax(int a, int b) { return a > b ? a : b; }
 
@@ -125,6 +130,30 @@ struct WarpG {
         return r;
     }
     __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
+};
+
+// ---------------------------------------------------------------------------------------- SubG<W>
+// W adjacent lanes of a warp (W = 8: four independent work items per warp for the small per-track /
+// per-detection kernels).  Every collective names only the group's own lanes, so groups of one warp
+// may diverge (different item kinds, early exits) without deadlocking each other.
+template <int W>
+struct SubG {
+    static constexpr int NL = W;
+    int lane;          // lane within the group
+    unsigned mask;     // the group's lanes within the warp
+    __device__ explicit SubG() {
+        const int wl = threadIdx.x & 31;
+        lane = wl & (W - 1);
+        mask = ((W == 32) ? 0xffffffffu : ((1u << W) - 1u)) << (wl & ~(W - 1));
+    }
+    __device__ void sync() const { __syncwarp(mask); }
+    __device__ float sum(float v) const {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+        return v;
+    }
+    __device__ unsigned bor(unsigned v) const { return __reduce_or_sync(mask, v); }
+    __device__ int imax(int v) const { return __reduce_max_sync(mask, v); }
 };
 
 // ---------------------------------------------------------------------------------------- BlockG

@@ -20,27 +20,31 @@
         if (e__ != cudaSuccess) return DD_ERR_CUDA;               \
     } while (0)
 
+// Small per-item kernels: DD_SUB lanes per item, 32 / DD_SUB items per warp (SubG).
+#define DD_SUB 8
+#define DD_ITEMS_PER_CTA (DD_WARPS * 32 / DD_SUB)
+
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_prep(const DDView V, const double* __restrict__ det_tlwh, const float* __restrict__ det_feat,
        const int* __restrict__ det_count) {
-    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (w >= V.S * V.D) return;
-    WarpG g;
+    SubG<DD_SUB> g;
     dd_prep_det(g, V, w / V.D, w % V.D, det_tlwh, det_feat, det_count);
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32) k_predict(const DDView V) {
-    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (w >= V.S * V.T) return;
-    WarpG g;
+    SubG<DD_SUB> g;
     dd_predict_track(g, V, w / V.T, w % V.T);
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_gate(const DDView V, const int* __restrict__ det_count) {
-    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (w >= V.S * V.T) return;
-    WarpG g;
+    SubG<DD_SUB> g;
     dd_gate_track(g, V, w / V.T, w % V.T, det_count);
 }
 
@@ -154,11 +158,11 @@ k_match(const DDView V, const double* __restrict__ det_tlwh, const int* __restri
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_apply(const DDView V, const float* __restrict__ det_conf, const int* __restrict__ det_label) {
-    __shared__ double scratch[DD_WARPS][64];
-    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    __shared__ double scratch[DD_ITEMS_PER_CTA][64];
+    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (w >= V.S * V.D) return;
-    WarpG g;
-    dd_apply_det(g, V, w / V.D, w % V.D, det_conf, det_label, scratch[threadIdx.x >> 5]);
+    SubG<DD_SUB> g;
+    dd_apply_det(g, V, w / V.D, w % V.D, det_conf, det_label, scratch[threadIdx.x / DD_SUB]);
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
@@ -199,6 +203,7 @@ k_status(const int* __restrict__ err, int S, int* __restrict__ out) {
 }
 
 static inline int warps_to_blocks(long long n_warps) { return (int)((n_warps + DD_WARPS - 1) / DD_WARPS); }
+static inline int items_to_blocks(long long n) { return (int)((n + DD_ITEMS_PER_CTA - 1) / DD_ITEMS_PER_CTA); }
 
 extern "C" {
 
@@ -228,7 +233,7 @@ int dd_tracker_predict(void* state, const dd_tracker_config* cfg, void* stream) 
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
-    k_predict<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, (cudaStream_t)stream>>>(V);
+    k_predict<<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, (cudaStream_t)stream>>>(V);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
@@ -241,17 +246,17 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
     if (!det_tlwh || !det_conf || !det_label || !det_feat || !det_count) return DD_ERR_INVALID;
-    const size_t smem = dd_match_smem_bytes(V.T, V.D);
+    const size_t smem = dd_match_smem_bytes(V.T, V.D, V.tab_cap);
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) return DD_ERR_INVALID;
         if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return DD_ERR_CUDA;
     }
     if (ev) cudaEventRecord(ev[0], st);
-    k_prep<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_tlwh, det_feat, det_count);
+    k_prep<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_tlwh, det_feat, det_count);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
-    k_gate<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
+    k_gate<<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[2], st);
     if (g_gate_impl == 1) {
@@ -271,7 +276,7 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
     k_match<<<V.S, 32, smem, st>>>(V, det_tlwh, det_count, out_det_track_id);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[4], st);
-    k_apply<<<warps_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_conf, det_label);
+    k_apply<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_conf, det_label);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[5], st);
     return DD_OK;
@@ -335,7 +340,7 @@ int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det
     if (rc != DD_OK) return rc;
     if (!line) return DD_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    k_predict<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V);
+    k_predict<<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V);
     DD_CHECK_LAUNCH();
     rc = dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, st, nullptr);
     if (rc != DD_OK) return rc;

@@ -280,25 +280,26 @@ struct DDMatchSmem {
     int tab_cap;
     double* tbox;      // [T][5]  x, y, x2, y2, area of the IoU-stage rows (Track.to_tlwh, track.py:84-97)
     unsigned* gate_sm; // [T][DW] gate words of the live tracks, by track index
+    float* cval;       // [T][DD_CVAL] cost of the first DD_CVAL gate-passing detections of each track
 };
 
-DD_HD size_t dd_match_smem_bytes(int T, int D);
-DD_HD size_t dd_match_smem_base_bytes(int T, int D) {
+DD_HD size_t dd_match_smem_base_bytes(int T, int D, int tab_cap) {
     const int n = T > D ? T : D;
     size_t b = dd_lsap_scratch_bytes(n);
     b += (size_t)T * 2 * 6 + (size_t)D * 2 * 2 + (size_t)n * 2 * 2;
     b += (size_t)T * 2;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)dd_set_table_slots(T) * 2 * 3;
+    b += (size_t)tab_cap * 2 * 3;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)T * 5 * 8;
     return (b + 15) & ~(size_t)15;
 }
-DD_HD size_t dd_match_smem_bytes(int T, int D) {
-    return dd_match_smem_base_bytes(T, D) + (size_t)T * ((D + 31) / 32) * 4;
+#define DD_CVAL 4       // gate-passing costs per track kept in shared memory (the rest is read from global)
+DD_HD size_t dd_match_smem_bytes(int T, int D, int tab_cap) {
+    return dd_match_smem_base_bytes(T, D, tab_cap) + (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4;
 }
 
-DD_HD void dd_match_carve(char* mem, int T, int D, DDMatchSmem& m) {
+DD_HD void dd_match_carve(char* mem, int T, int D, int tab_cap, DDMatchSmem& m) {
     const int n = T > D ? T : D;
     dd_lsap_carve(mem, n, m.ls);
     char* p = mem + dd_lsap_scratch_bytes(n);
@@ -315,27 +316,33 @@ DD_HD void dd_match_carve(char* mem, int T, int D, DDMatchSmem& m) {
     m.trk_state = (unsigned char*)p; p += T;
     m.flag = (unsigned char*)p; p += T;
     p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    m.tab_cap = dd_set_table_slots(T);
+    m.tab_cap = tab_cap;
     m.tabA = (short*)p; p += m.tab_cap * 2;
     m.tabB = (short*)p; p += m.tab_cap * 2;
     m.tabC = (short*)p; p += m.tab_cap * 2;
     p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     m.tbox = (double*)p;
-    m.gate_sm = (unsigned*)(mem + dd_match_smem_base_bytes(T, D));
+    m.gate_sm = (unsigned*)(mem + dd_match_smem_base_bytes(T, D, tab_cap));
+    m.cval = (float*)(m.gate_sm + (size_t)T * ((D + 31) / 32));
 }
 
 // cost functors: (r, c) are positions in the rows[] / cols[] lists of the current sub-problem.
 struct DDCosineCost {      // tracker.py:97-105 + linear_assignment.py:57
     const unsigned* gate;  // shared memory [T, DW], indexed by TRACK INDEX
-    const float* cost;     // stream base [T, D] in global memory, indexed by slot (read only where gated in)
+    const float* cval;     // shared memory [T, DD_CVAL]: costs of the first gate-passing detections
+    const float* cost;     // stream base [T, D] in global memory, indexed by slot (overflow of cval only)
     const short *trk_slot, *rows, *cols;
     int D, DW;
     double thr, clip;
     DD_HD double raw(int r, int c) const {
         const int t = rows[r];
         const int d = cols[c];
-        const bool pass = (gate[t * DW + (d >> 5)] >> (d & 31)) & 1u;
-        return pass ? (double)cost[trk_slot[t] * D + d] : DD_INFTY_COST;
+        const unsigned* gw = gate + t * DW;
+        const unsigned word = gw[d >> 5];
+        if (!((word >> (d & 31)) & 1u)) return DD_INFTY_COST;
+        int k = dd_popc(word & ((1u << (d & 31)) - 1u));          // rank of d among the track's set bits
+        for (int w = 0; w < (d >> 5); ++w) k += dd_popc(gw[w]);
+        return (double)(k < DD_CVAL ? cval[t * DD_CVAL + k] : cost[trk_slot[t] * D + d]);
     }
     DD_HD double operator()(int r, int c) const {
         const double v = raw(r, c);
@@ -429,7 +436,7 @@ template <class G>
 DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det_tlwh,
                            const int* det_count, int* out_det_track_id, char* smem) {
     DDMatchSmem m;
-    dd_match_carve(smem, V.T, V.D, m);
+    dd_match_carve(smem, V.T, V.D, V.tab_cap, m);
     const size_t sT = (size_t)s * V.T, sD = (size_t)s * V.D;
     int nd = det_count[s];
     if (nd > V.D) {
@@ -479,13 +486,36 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
             m.gate_sm[e] = m.trk_state[t] == DD_STATE_CONFIRMED ? V.gate[(sT + m.trk_slot[t]) * V.DW + w] : 0u;
         }
         g.sync();
+        for (int e = g.lane; e < nT * DD_CVAL; e += G::NL) {   // stage the first gate-passing costs per track
+            const int t = e / DD_CVAL, k = e - t * DD_CVAL;
+            int seen = 0, d = -1;
+            for (int w = 0; w < V.DW && d < 0; ++w) {
+                unsigned word = m.gate_sm[t * V.DW + w];
+                const int pc = dd_popc(word);
+                if (seen + pc <= k) { seen += pc; continue; }
+                for (int q = seen; q < k; ++q) word &= word - 1;
+                d = w * 32 + dd_ctz(word);
+            }
+            if (d >= 0) m.cval[e] = V.cost[(sT + m.trk_slot[t]) * V.D + d];
+        }
+        g.sync();
         DDCosineCost cc;
-        cc.gate = m.gate_sm; cc.cost = V.cost + sT * V.D;
+        cc.gate = m.gate_sm; cc.cval = m.cval; cc.cost = V.cost + sT * V.D;
         cc.trk_slot = m.trk_slot; cc.rows = m.rows; cc.D = V.D; cc.DW = V.DW;
         cc.thr = V.thr_cos; cc.clip = dd_add(V.thr_cos, 1e-5);
         const int depth = dd_imin(V.max_age, max_tsu);
         for (int level = 0; level < depth; ++level) {
             if (nund == 0) break;
+            {   // jump to the next occupied level (levels without tracks are skipped by the reference too)
+                int nxt = 0x7fffffff;
+                for (int k = g.lane; k < nconf; k += G::NL) {
+                    const int ts = m.trk_tsu[m.lista[k]];
+                    if (ts >= 1 + level && ts < nxt) nxt = ts;
+                }
+                nxt = g.imin(nxt);
+                if (nxt > depth) break;
+                level = nxt - 1;
+            }
             int nr = 0;
             for (int base = 0; base < nconf; base += G::NL) {
                 const int k = base + g.lane;

@@ -2,9 +2,11 @@
 #pragma once
 #include "../../include/deepdish_b200.h"
 #include "dd_common.cuh"
+#include "dd_lsap.cuh"
 
 struct DDView {
     int S, T, D, B, C, DW;           // streams, slots, det capacity, budget, labels, gate words / row
+    int tab_cap;                     // slots of each CPython-set emulation table (dd_set_table_slots(T))
     int max_age, n_init;
     double thr_cos, thr_iou;
     int lbl_motorbike, lbl_bicycle;
@@ -82,6 +84,7 @@ static inline int dd_make_view(void* blob, const dd_tracker_config* c, DDView* v
     char* b = (char*)blob;
     v->S = c->n_streams; v->T = c->max_tracks; v->D = c->max_dets; v->B = c->budget;
     v->C = c->n_labels; v->DW = (c->max_dets + 31) / 32;
+    v->tab_cap = dd_set_table_slots(c->max_tracks);
     v->max_age = c->max_age; v->n_init = c->n_init;
     v->thr_cos = c->max_cosine_distance; v->thr_iou = c->max_iou_distance;
     v->lbl_motorbike = c->label_motorbike; v->lbl_bicycle = c->label_bicycle;

@@ -51,7 +51,7 @@ int ddh_tracker_update(void* state, const dd_tracker_config* cfg, const double* 
         for (int t = 0; t < V.T; ++t) dd_gate_track(g, V, s, t, det_count);
     for (int s = 0; s < V.S; ++s)
         for (int t = 0; t < V.T; ++t) { DDDirectPass<HostG> pass; dd_cosine_track(g, V, s, t, det_count, pass); }
-    std::vector<char> smem(dd_match_smem_bytes(V.T, V.D) + 16);
+    std::vector<char> smem(dd_match_smem_bytes(V.T, V.D, V.tab_cap) + 16);
     for (int s = 0; s < V.S; ++s)
         dd_match_stream(g, V, s, det_tlwh, det_count, out_det_track_id, smem.data());
     double scratch[64];
