@@ -130,3 +130,10 @@ def test_stream_chunks_pipelined_and_step_host():
     for s in range(S):
         compare_stream(orc.trk[s], orc.cnt[s], v, s, LABELS3)
     bt.check()
+
+
+def test_c4_like_crowd_200_dets():
+    """BASELINE config 3 shape (crowd: ~200 dets/frame, up to 256+ tracks, budget 100) on a few streams:
+    multi-word gate masks, transposed and non-transposed LSAPs up to ~200 x 200, CTA-sized shared memory."""
+    bt, orc = _run(3, 190, 224, 384, 45, 60, seed=17, check_every=5)
+    assert max(len(t.tracks) for t in orc.trk) > 200
