@@ -247,6 +247,38 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
     }
 }
 
+// Kept candidates (NMS pick order) -> the tracker's padded detection batch for a range of streams:
+// deepdish.py:996-998 (boxesA1 = boxesA0[indices], ...) + the Detection list of :1014 as SoA.
+__global__ void __launch_bounds__(128)
+k_gather_kept(const double* __restrict__ cand_tlwh, const float* __restrict__ cand_score,
+              const int* __restrict__ cand_label, const int* __restrict__ label_map, int n_map, int ncap,
+              const int* __restrict__ keep, const int* __restrict__ nkeep, int nmax, int dmax,
+              double* __restrict__ det_tlwh, float* __restrict__ det_conf, int* __restrict__ det_label,
+              int* __restrict__ det_count, int* __restrict__ out_flags) {
+    const int f = blockIdx.x;
+    int n = nkeep[f];
+    if (n > dmax) {
+        n = dmax;
+        if (threadIdx.x == 0) atomicOr(out_flags + f, DD_FLAG_DET_OVERFLOW);
+    }
+    for (int k = threadIdx.x; k < dmax; k += blockDim.x) {
+        const size_t o = (size_t)f * dmax + k;
+        if (k < n) {
+            const size_t c = (size_t)f * ncap + keep[(size_t)f * nmax + k];
+            det_tlwh[o * 4 + 0] = cand_tlwh[c * 4 + 0]; det_tlwh[o * 4 + 1] = cand_tlwh[c * 4 + 1];
+            det_tlwh[o * 4 + 2] = cand_tlwh[c * 4 + 2]; det_tlwh[o * 4 + 3] = cand_tlwh[c * 4 + 3];
+            det_conf[o] = cand_score[c];
+            const int l = cand_label[c];
+            det_label[o] = (label_map && l >= 0 && l < n_map) ? label_map[l] : l;
+        } else {
+            det_tlwh[o * 4 + 0] = 0.0; det_tlwh[o * 4 + 1] = 0.0; det_tlwh[o * 4 + 2] = 0.0; det_tlwh[o * 4 + 3] = 0.0;
+            det_conf[o] = 0.f;
+            det_label[o] = 0;
+        }
+    }
+    if (threadIdx.x == 0) det_count[f] = n;
+}
+
 extern "C" {
 
 int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int32_t b, int32_t nmax,
@@ -319,6 +351,22 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
         return DD_ERR_CUDA;
     k_ssd_decode<<<b, DD_SSD_THREADS, smem, (cudaStream_t)stream>>>(raw_boxes, raw_scores, anchors, P, class_to_label, ncap,
                                                         out_tlwh, out_score, out_label, out_count);
+    DD_CHECK_LAUNCH();
+    return DD_OK;
+}
+
+int dd_gather_detections(const double* cand_tlwh, const float* cand_score, const int32_t* cand_label,
+                         const int32_t* label_map, int32_t n_map, int32_t ncap, const int32_t* keep,
+                         const int32_t* nkeep, int32_t nmax, int32_t b, int32_t dmax, double* det_tlwh,
+                         float* det_conf, int32_t* det_label, int32_t* det_count, int32_t* out_flags,
+                         void* stream) {
+    if (!cand_tlwh || !cand_score || !cand_label || !keep || !nkeep || !det_tlwh || !det_conf || !det_label ||
+        !det_count || !out_flags || b < 0 || dmax <= 0 || ncap <= 0 || nmax <= 0)
+        return DD_ERR_INVALID;
+    if (b == 0) return DD_OK;
+    k_gather_kept<<<b, 128, 0, (cudaStream_t)stream>>>(cand_tlwh, cand_score, cand_label, label_map, n_map, ncap, keep,
+                                                      nkeep, nmax, dmax, det_tlwh, det_conf, det_label, det_count,
+                                                      out_flags);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }

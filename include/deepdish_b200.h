@@ -241,6 +241,18 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
                   int32_t img_w, int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap,
                   double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count, void* stream);
 
+/* The step between NMS and the tracker (deepdish.py:996-998,1014): gather the kept candidates, in NMS pick
+ * order, into the tracker's padded detection batch for b streams.
+ *   cand_* [b,ncap] candidate arrays (dd_yolo_decode / dd_ssd_decode outputs), keep i32 [b,nmax] + nkeep i32 [b]
+ *   from dd_nms; label_map i32 [n_map] (may be NULL): detector class / label id -> tracker label id.
+ *   Writes det_tlwh f64 [b,dmax,4], det_conf f32 [b,dmax], det_label i32 [b,dmax], det_count i32 [b];
+ *   nkeep > dmax sets DD_FLAG_DET_OVERFLOW in out_flags[b] (never silently truncated). */
+int dd_gather_detections(const double* cand_tlwh, const float* cand_score, const int32_t* cand_label,
+                         const int32_t* label_map, int32_t n_map, int32_t ncap, const int32_t* keep,
+                         const int32_t* nkeep, int32_t nmax, int32_t b, int32_t dmax, double* det_tlwh,
+                         float* det_conf, int32_t* det_label, int32_t* det_count, int32_t* out_flags,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif
