@@ -135,6 +135,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -301,7 +310,7 @@ def gpu_arm(args):
             "gpu_launches": K * 8 * P,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_cosine", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic("k_cosine"), "peak_source": peak_src,
                          "bytes_per_launch": gc_bytes, "ms_per_launch": gc_ms,
                          "tick_bytes": tick_bytes, "tick_frac": tick_bytes / (ms_all / K * 1e-3) / 1e9 / peak},
             "stage_ms": {"pass": "same K ticks, n_chunks=1, CUDA events between kernels", "prep": stage[0],

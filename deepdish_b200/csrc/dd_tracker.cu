@@ -151,7 +151,7 @@ static int g_gate_impl = 0;     // 1 = TMA-staged (default), 0 = direct loads (A
 __global__ void __launch_bounds__(32)
 k_match(const DDView V, const double* __restrict__ det_tlwh, const int* __restrict__ det_count,
         int* out_det_track_id) {
-    extern __shared__ __align__(16) char smem[];
+    extern __shared__ __align__(128) char smem[];
     WarpG g;
     dd_match_stream(g, V, blockIdx.x, det_tlwh, det_count, out_det_track_id, smem);
 }
