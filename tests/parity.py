@@ -14,8 +14,12 @@ class OracleStreams:
         kw = dict(lsap=od.lsap_port, set_order=od.cpython_set_difference_order) if port else {}
         self.trk = [od.Trkr(od.Metric("cosine", max_cos, budget), max_iou, max_age, n_init, **kw)
                     for _ in range(n_streams)]
-        line = oc.default_line(640, 480) if line is None else np.asarray(line, float).reshape(2, 2)
-        self.cnt = [oc.LineCounter(line, self.labels) for _ in range(n_streams)]
+        if line is None:
+            lines = [oc.default_line(640, 480)] * n_streams
+        else:
+            line = np.asarray(line, float)
+            lines = [line.reshape(2, 2)] * n_streams if line.size == 4 else [l.reshape(2, 2) for l in line]
+        self.cnt = [oc.LineCounter(l, self.labels) for l in lines]
         self.det_ids = None
 
     def step(self, batch, streams=None):

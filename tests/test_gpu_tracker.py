@@ -137,3 +137,63 @@ def test_c4_like_crowd_200_dets():
     multi-word gate masks, transposed and non-transposed LSAPs up to ~200 x 200, CTA-sized shared memory."""
     bt, orc = _run(3, 190, 224, 384, 45, 60, seed=17, check_every=5)
     assert max(len(t.tracks) for t in orc.trk) > 200
+
+
+def test_label_vote_motorbike_bicycle_rule_and_per_stream_lines():
+    """track.py:154-188: Dirichlet vote with the motorbike / bicycle special case (30 % label noise makes
+    the vote matter), counters keyed by the voted label; one count-line per stream (vertical, horizontal,
+    diagonal) -- counters bit-exact."""
+    from deepdish_b200.batched import BatchedTracker
+    labels = ["motorbike", "bicycle", "person"]
+    S = 6
+    lines = np.array([[320, 0, 320, 480], [0, 240, 640, 240], [0, 0, 640, 480], [100, 0, 500, 480],
+                      [640, 100, 0, 300], [320, 480, 320, 0]], dtype=np.float64)
+    bt = BatchedTracker(S, labels, max_tracks=64, max_dets=24, budget=40, max_age=25, line=lines, n_chunks=2)
+    orc = OracleStreams(S, labels, budget=40, max_age=25, line=lines)
+    sc = Scene(S, 16, 24, n_labels=3, seed=41, label_noise=0.3)
+    for f in range(140):
+        b = sc.step()
+        ids = orc.step(b)
+        got = bt.step(b.to("cuda")).cpu().numpy()
+        for s in range(S):
+            assert list(got[s, :int(b.count[s])]) == ids[s], (f, s)
+        if f % 10 == 9:
+            v = bt.host_view()
+            for s in range(S):
+                compare_stream(orc.trk[s], orc.cnt[s], v, s, labels)
+    tot = bt.reduce_counts().cpu().numpy()
+    assert tot[:, 2].sum() > 20 and (tot[:, 2] > 0).sum() >= 2         # several labels were counted
+    bt.check()
+
+
+@pytest.mark.parametrize("n_init,max_age", [(1, 1), (2, 4), (5, 12)])
+def test_n_init_and_max_age_variants(n_init, max_age):
+    from deepdish_b200.batched import BatchedTracker
+    from oracle import deepsort as od, countline as oc
+    S = 3
+    bt = BatchedTracker(S, LABELS3, max_tracks=96, max_dets=24, budget=10, max_age=max_age, n_init=n_init)
+    trk = [od.Trkr(od.Metric("cosine", 0.2, 10), 0.7, max_age, n_init) for _ in range(S)]
+    cnt = [oc.LineCounter(oc.default_line(640, 480), LABELS3) for _ in range(S)]
+    sc = Scene(S, 14, 24, n_labels=3, seed=50 + n_init, miss_prob=0.2)
+    for f in range(70):
+        b = sc.step()
+        if 30 <= f < 30 + max_age + 3:
+            b.count[1] = 0                         # stream 1 goes blind: every track ages out, ids restart later
+        got = bt.step(b.to("cuda")).cpu().numpy()
+        for s in range(S):
+            tlwh, conf, lab, feat = b.stream(s)
+            dets = [od.Det(tlwh[i], LABELS3[lab[i]], conf[i], feat[i]) for i in range(len(conf))]
+            trk[s].trace = {}
+            trk[s].predict(); trk[s].update(dets); cnt[s].step(trk[s])
+            exp = [-1] * len(dets)
+            for tid, d in trk[s].trace["match_ids"]:
+                exp[d] = tid
+            nxt = trk[s]._next_id - len(trk[s].trace["unmatched_detections"])
+            for k, d in enumerate(trk[s].trace["unmatched_detections"]):
+                exp[d] = nxt + k
+            assert list(got[s, :len(dets)]) == exp, (f, s)
+        if f % 7 == 0:
+            v = bt.host_view()
+            for s in range(S):
+                compare_stream(trk[s], cnt[s], v, s, LABELS3)
+    bt.check()
