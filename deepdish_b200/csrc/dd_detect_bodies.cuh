@@ -39,24 +39,35 @@ DD_HD int dd_next_pow2(int n) {
     return p;
 }
 
-// Shared-memory plan of dd_nms_frame for up to n candidates.
+// Shared-memory plan of dd_nms_frame for up to nmax candidates.
+#define DD_NMS_BATCH 32          // survivors-so-far whose suppression rows are evaluated together
 struct DDNmsSmem {
-    unsigned long long* keys;   // [P]
-    unsigned long long* mask;   // [n * nw]
-    unsigned long long* remv;   // [nw]
-    double *x1, *y1, *x2, *y2, *area;   // [n] in sorted order
+    unsigned long long* ukeys;  // [nmax] unsorted (score desc, index asc) keys
+    unsigned long long* keys;   // [nmax] sorted
+    unsigned* remv;             // [nh]   removed bits by rank (32 per word)
+    unsigned* rows;             // [DD_NMS_BATCH][nh] suppression rows of the current batch
+    int* batch;                 // [DD_NMS_BATCH + 2] ranks of the batch, then {count, next cursor}
+    double *x1, *y1, *x2, *y2, *area;   // [nmax] in rank order
+    int *ix1, *iy1, *ix2, *iy2;         // [nmax] integer copies (valid when every box is integer-valued)
+    int* allint;                        // [1]
 };
 DD_HD size_t dd_nms_smem_bytes(int nmax) {
-    const int P = dd_next_pow2(nmax), nw = (nmax + 63) / 64;
-    return (size_t)P * 8 + (size_t)nmax * nw * 8 + (size_t)nw * 8 + (size_t)nmax * 5 * 8;
+    const int nh = (nmax + 31) / 32;
+    return (size_t)nmax * 16 + (size_t)nh * 4 * (1 + DD_NMS_BATCH) + (DD_NMS_BATCH + 2) * 4 + 16 +
+           (size_t)nmax * 5 * 8 + (size_t)nmax * 16 + 16;
 }
 DD_HD void dd_nms_carve(char* mem, int nmax, DDNmsSmem& m) {
-    const int P = dd_next_pow2(nmax), nw = (nmax + 63) / 64;
-    m.keys = (unsigned long long*)mem;
-    m.mask = m.keys + P;
-    m.remv = m.mask + (size_t)nmax * nw;
-    m.x1 = (double*)(m.remv + nw);
+    const int nh = (nmax + 31) / 32;
+    m.ukeys = (unsigned long long*)mem;
+    m.keys = m.ukeys + nmax;
+    m.x1 = (double*)(m.keys + nmax);
     m.y1 = m.x1 + nmax; m.x2 = m.y1 + nmax; m.y2 = m.x2 + nmax; m.area = m.y2 + nmax;
+    m.ix1 = (int*)(m.area + nmax);
+    m.iy1 = m.ix1 + nmax; m.ix2 = m.iy1 + nmax; m.iy2 = m.ix2 + nmax;
+    m.remv = (unsigned*)(m.iy2 + nmax);
+    m.rows = m.remv + nh;
+    m.batch = (int*)(m.rows + (size_t)DD_NMS_BATCH * nh);
+    m.allint = m.batch + DD_NMS_BATCH + 2;
 }
 
 // Does box A (the higher-ranked pick) suppress box J:  fl(inter / area_J) > max_overlap, +1 px convention
@@ -82,11 +93,15 @@ DD_HD bool dd_nms_suppresses(double ax1, double ay1, double ax2, double ay2, dou
 
 // deep_sort/preprocessing.py:6-73.  boxes f64 [n,4] tlwh, scores f32 [n].  keep[] receives the
 // original indices in pick order (descending score); returns their number through *nkeep.
-//   sort     : descending score (ties: lower index first -- the reference's np.argsort is unstable, so
-//              callers keep scores unique);
-//   bitmask  : bit j of row i = candidate j (ranked after i) has inter(i,j) / area(j) > max_overlap,
-//              with the +1 pixel convention, all in f64 like boxes.astype(float);
-//   scan     : serial over ranks, a candidate survives unless an earlier survivor set its bit.
+//   rank     : descending score (ties: lower index first -- the reference's np.argsort is unstable, so
+//              callers keep scores unique) by counting smaller keys (n^2 / 32 warp ops);
+//   greedy   : the reference keeps a candidate unless an earlier survivor suppresses it
+//              (inter(i,j) / area(j) > max_overlap, +1 pixel convention, f64 like boxes.astype(float)).  Only
+//              survivors' suppression rows are ever needed, so they are built lazily: take the next <= 32
+//              candidates that are still alive, build their rows over all later candidates in parallel
+//              (one warp per 32 candidates, ballots give the bits; integer-valued boxes -- the pipeline's
+//              case -- are tested for disjointness in int32 first), then scan the batch serially with the
+//              removed bits held in the scanning warp's registers.
 template <class G>
 DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, int n, int nmax,
                         double max_overlap, int* keep, int* nkeep, char* smem) {
@@ -97,85 +112,144 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
     }
     DDNmsSmem m;
     dd_nms_carve(smem, nmax, m);
-    const int P = dd_next_pow2(n), nw = (n + 63) / 64;
-    for (int i = g.lane; i < P; i += g.nl) {
-        unsigned long long k = ~0ull;
-        if (i < n) k = ((unsigned long long)(~dd_f32_key(scores[i])) << 32) | (unsigned)i;
-        m.keys[i] = k;
-    }
+    const int nh = (n + 31) / 32;
+    for (int i = g.lane; i < n; i += g.nl)
+        m.ukeys[i] = ((unsigned long long)(~dd_f32_key(scores[i])) << 32) | (unsigned)i;
+    for (int w = g.lane; w < nh; w += g.nl) m.remv[w] = 0u;
+    if (g.lane == 0) { *m.allint = 1; m.batch[DD_NMS_BATCH + 1] = 0; }
     g.sync();
-    dd_bitonic_sort(g, m.keys, P);
-    for (int r = g.lane; r < n; r += g.nl) {
-        const int i = (int)(m.keys[r] & 0xffffffffu);
-        const double x = boxes[i * 4 + 0], y = boxes[i * 4 + 1], w = boxes[i * 4 + 2], h = boxes[i * 4 + 3];
+    for (int i = g.lane; i < n; i += g.nl) {                 // rank = number of smaller keys (keys are distinct)
+        const unsigned long long k = m.ukeys[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += m.ukeys[j] < k;
+        m.keys[r] = k;
+        const int o = (int)(k & 0xffffffffu);
+        const double x = boxes[o * 4 + 0], y = boxes[o * 4 + 1], w = boxes[o * 4 + 2], h = boxes[o * 4 + 3];
         const double xx2 = dd_add(w, x), yy2 = dd_add(h, y);
         m.x1[r] = x; m.y1[r] = y; m.x2[r] = xx2; m.y2[r] = yy2;
         m.area[r] = dd_mul(dd_add(dd_sub(xx2, x), 1.0), dd_add(dd_sub(yy2, y), 1.0));
+        // |coords| < 2^20 keeps every int32 intermediate of the disjointness test exact
+        const bool isint = x == (double)(int)x && y == (double)(int)y && xx2 == (double)(int)xx2 && yy2 == (double)(int)yy2 &&
+                           fabs(x) < 1048576.0 && fabs(y) < 1048576.0 && fabs(xx2) < 1048576.0 && fabs(yy2) < 1048576.0;
+        if (isint) { m.ix1[r] = (int)x; m.iy1[r] = (int)y; m.ix2[r] = (int)xx2; m.iy2[r] = (int)yy2; }
+        else *m.allint = 0;
     }
-    for (int w = g.lane; w < nw; w += g.nl) m.remv[w] = 0;
     g.sync();
     const bool fast = max_overlap >= 0.0;
+    const bool ints = fast && *m.allint != 0;
+    int nk = 0;
 #if defined(__CUDA_ARCH__)
-    // one warp per (row i, 64-bit word w) item: lanes test 32 candidates j at a time, ballots give the bits
-    {
-        const int wid = g.lane >> 5, ln = g.lane & 31, nwarp = g.nl >> 5;
-        for (int e = wid; e < n * nw; e += nwarp) {
-            const int i = e / nw, w = e - i * nw;
-            unsigned long long bits = 0;
-            if (w * 64 + 63 > i) {
-                const double ax1 = m.x1[i], ay1 = m.y1[i], ax2 = m.x2[i], ay2 = m.y2[i];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = w * 64 + h * 32 + ln;
-                    bool sup = false;
-                    if (j > i && j < n)
-                        sup = dd_nms_suppresses(ax1, ay1, ax2, ay2, m.x1[j], m.y1[j], m.x2[j], m.y2[j], m.area[j],
-                                                max_overlap, fast);
-                    bits |= (unsigned long long)__ballot_sync(0xffffffffu, sup) << (32 * h);
+    // first warp: removed bits live in registers (lane w owns ranks 32w..32w+31) when they fit
+    const bool regpath = nh <= 32;
+    unsigned remv_reg = 0u;
+    int cursor_reg = 0;
+#endif
+    while (true) {
+        // ---- next batch: up to DD_NMS_BATCH ranks >= cursor whose removed bit is clear (first warp)
+        if (g.lane < 32) {
+            int nb = 0;
+#if defined(__CUDA_ARCH__)
+            int cursor = regpath ? cursor_reg : m.batch[DD_NMS_BATCH + 1];
+            while (nb < DD_NMS_BATCH && cursor < n) {
+                const int r = cursor + g.lane;
+                const unsigned word = regpath ? __shfl_sync(0xffffffffu, remv_reg, (r >> 5) & 31)
+                                              : (r < n ? m.remv[r >> 5] : 0u);
+                const bool alive = r < n && !((word >> (r & 31)) & 1u);
+                const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                const int pos = nb + __popc(bal & ((1u << g.lane) - 1u));
+                if (alive && pos < DD_NMS_BATCH) m.batch[pos] = r;
+                const int tot = __popc(bal);
+                if (nb + tot > DD_NMS_BATCH) {              // batch full inside this window: resume after its last rank
+                    const int last = __fns(bal, 0, DD_NMS_BATCH - nb);      // bit of the (BATCH-nb)-th set bit
+                    cursor += last + 1;
+                    nb = DD_NMS_BATCH;
+                } else {
+                    nb += tot;
+                    cursor += 32;
                 }
             }
-            if (ln == 0) m.mask[e] = bits;
-        }
-    }
+            cursor_reg = cursor;
 #else
-    for (int e = g.lane; e < n * nw; e += g.nl) {
-        const int i = e / nw, w = e - i * nw;
-        unsigned long long bits = 0;
-        if (w * 64 + 63 > i) {
-            const int j1 = dd_imin(n, w * 64 + 64);
-            for (int j = dd_imax(i + 1, w * 64); j < j1; ++j)
+            int cursor = m.batch[DD_NMS_BATCH + 1];
+            while (nb < DD_NMS_BATCH && cursor < n) {
+                if (!((m.remv[cursor >> 5] >> (cursor & 31)) & 1u)) m.batch[nb++] = cursor;
+                ++cursor;
+            }
+#endif
+            dd_first_warp_sync();
+            if (g.lane == 0) { m.batch[DD_NMS_BATCH] = nb; m.batch[DD_NMS_BATCH + 1] = cursor < n ? cursor : n; }
+        }
+        g.sync();
+        const int nb = m.batch[DD_NMS_BATCH];
+        if (nb == 0) break;
+        // ---- suppression rows of the batch over the later candidates
+#if defined(__CUDA_ARCH__)
+        {
+            const int wid = g.lane >> 5, ln = g.lane & 31, nwarp = g.nl >> 5;
+            for (int e = wid; e < nb * nh; e += nwarp) {
+                const int b = e / nh, hw = e - b * nh;
+                const int i = m.batch[b];
+                unsigned bits = 0;
+                if (hw >= (i >> 5)) {                        // warp-uniform
+                    const int j = hw * 32 + ln;
+                    bool sup = false;
+                    if (j > i && j < n) {
+                        bool test = true;
+                        if (ints)
+                            test = (min(m.ix2[i], m.ix2[j]) - max(m.ix1[i], m.ix1[j]) + 1 > 0) &&
+                                   (min(m.iy2[i], m.iy2[j]) - max(m.iy1[i], m.iy1[j]) + 1 > 0);
+                        if (test)
+                            sup = dd_nms_suppresses(m.x1[i], m.y1[i], m.x2[i], m.y2[i], m.x1[j], m.y1[j], m.x2[j],
+                                                    m.y2[j], m.area[j], max_overlap, fast);
+                    }
+                    bits = __ballot_sync(0xffffffffu, sup);
+                }
+                if (ln == 0) m.rows[b * nh + hw] = bits;
+            }
+        }
+#else
+        for (int e = g.lane; e < nb * nh; e += g.nl) {
+            const int b = e / nh, hw = e - b * nh;
+            const int i = m.batch[b];
+            unsigned bits = 0;
+            for (int j = dd_imax(i + 1, hw * 32); j < dd_imin(n, hw * 32 + 32); ++j)
                 if (dd_nms_suppresses(m.x1[i], m.y1[i], m.x2[i], m.y2[i], m.x1[j], m.y1[j], m.x2[j], m.y2[j],
                                       m.area[j], max_overlap, fast))
-                    bits |= 1ull << (j - w * 64);
+                    bits |= 1u << (j - hw * 32);
+            m.rows[e] = bits;
         }
-        m.mask[e] = bits;
-    }
 #endif
-    g.sync();
-    // scan: jump from survivor to survivor (first zero bit of remv at or after the cursor); the lanes of
-    // the first warp share the OR of the picked row into remv.
-    if (g.lane < 32) {
-        const int lane = g.lane;
-        const int nscan = g.nl < 32 ? g.nl : 32;
-        int nk = 0;
-        int i = 0;
-        while (i < n) {
-            const unsigned long long word = ~m.remv[i >> 6] & (~0ull << (i & 63));
-            if (!word) { i = ((i >> 6) + 1) << 6; continue; }
+        g.sync();
+        // ---- serial scan of the batch (first warp)
+        if (g.lane < 32) {
 #if defined(__CUDA_ARCH__)
-            i = (i & ~63) + (__ffsll((long long)word) - 1);
-#else
-            i = (i & ~63) + __builtin_ctzll(word);
+            if (regpath) {
+                const int mine = g.lane < nb ? m.batch[g.lane] : 0;
+                for (int b = 0; b < nb; ++b) {
+                    const int i = __shfl_sync(0xffffffffu, mine, b);
+                    const unsigned word = __shfl_sync(0xffffffffu, remv_reg, i >> 5);
+                    if ((word >> (i & 31)) & 1u) continue;                 // suppressed inside the batch
+                    if (g.lane == 0) keep[nk] = (int)(m.keys[i] & 0xffffffffu);
+                    ++nk;
+                    if (g.lane >= (i >> 5) && g.lane < nh) remv_reg |= m.rows[b * nh + g.lane];
+                }
+            } else
 #endif
-            if (i >= n) break;
-            if (lane == 0) keep[nk] = (int)(m.keys[i] & 0xffffffffu);
-            ++nk;
-            for (int w = (i >> 6) + lane; w < nw; w += nscan) m.remv[w] |= m.mask[(size_t)i * nw + w];
-            dd_first_warp_sync();
-            ++i;
+            {
+                const int nscan = g.nl < 32 ? g.nl : 32;
+                for (int b = 0; b < nb; ++b) {
+                    const int i = m.batch[b];
+                    if ((m.remv[i >> 5] >> (i & 31)) & 1u) continue;       // suppressed inside the batch
+                    if (g.lane == 0) keep[nk] = (int)(m.keys[i] & 0xffffffffu);
+                    ++nk;
+                    for (int w = (i >> 5) + g.lane; w < nh; w += nscan) m.remv[w] |= m.rows[b * nh + w];
+                    dd_first_warp_sync();
+                }
+            }
         }
-        if (lane == 0) *nkeep = nk;
+        g.sync();
     }
+    if (g.lane == 0) *nkeep = nk;
 }
 
 // ------------------------------------------------------------------------------------------------
