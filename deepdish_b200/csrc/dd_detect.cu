@@ -74,7 +74,15 @@ k_yolo_decode(const void* __restrict__ head, float scale, int zero_point, int na
     bool isnan = false, ok;
     if (U8) {
         RowU8 row{(const unsigned char*)smem + (size_t)r * rw, scale, (float)zero_point};
-        ok = dd_yolo_row(row, P, wanted, tlwh, &score, &cls, &isnan);
+        // conf = dequant(cls) * dequant(obj) is linear in the class byte: its maximum over all bytes is at
+        // byte 0 or 255, so a row whose objectness cannot reach the threshold even then is dropped after
+        // reading one byte (the products are evaluated with the very same f32 operations as the full scan)
+        const float obj = row(4);
+        const float hi0 = dd_mulf(dd_mulf(dd_subf(0.f, (float)zero_point), scale), obj);
+        const float hi1 = dd_mulf(dd_mulf(dd_subf(255.f, (float)zero_point), scale), obj);
+        ok = false;
+        if (hi0 >= P.thr || hi1 >= P.thr || hi0 != hi0 || hi1 != hi1)
+            ok = dd_yolo_row(row, P, wanted, tlwh, &score, &cls, &isnan);
     } else {
         RowF32 row{(const float*)smem + (size_t)r * rw};
         ok = dd_yolo_row(row, P, wanted, tlwh, &score, &cls, &isnan);
@@ -95,7 +103,7 @@ k_yolo_decode(const void* __restrict__ head, float scale, int zero_point, int na
 }
 
 // Re-order the unordered appends of one frame by anchor index.  Shared: keys[P] + payload copy.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_yolo_order(int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_score,
              int* __restrict__ out_class, int* __restrict__ out_anchor, int* __restrict__ out_count,
              int* __restrict__ out_flags) {
@@ -112,29 +120,29 @@ k_yolo_order(int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_sc
     }
     if (threadIdx.x == 0) out_count[frame] = n;
     if (n <= 1) return;
-    const int P = dd_next_pow2(n);
-    unsigned long long* keys = (unsigned long long*)smem;
-    double* tl = (double*)(keys + P);
+    // rank of a candidate = number of candidates with a smaller anchor index (anchors are distinct)
+    int* an = (int*)smem;
+    double* tl = (double*)(an + ((n + 1) & ~1));
     float* sc = (float*)(tl + (size_t)n * 4);
     int* cl = (int*)(sc + n);
     const size_t base = (size_t)frame * ncap;
-    for (int i = threadIdx.x; i < P; i += blockDim.x)
-        keys[i] = i < n ? (((unsigned long long)(unsigned)out_anchor[base + i]) << 32) | (unsigned)i : ~0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        an[i] = out_anchor[base + i];
         tl[i * 4 + 0] = out_tlwh[(base + i) * 4 + 0]; tl[i * 4 + 1] = out_tlwh[(base + i) * 4 + 1];
         tl[i * 4 + 2] = out_tlwh[(base + i) * 4 + 2]; tl[i * 4 + 3] = out_tlwh[(base + i) * 4 + 3];
         sc[i] = out_score[base + i];
         cl[i] = out_class[base + i];
     }
     __syncthreads();
-    dd_bitonic_sort(g, keys, P);
-    for (int r = threadIdx.x; r < n; r += blockDim.x) {
-        const int i = (int)(keys[r] & 0xffffffffu);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int a = an[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += an[j] < a;
         out_tlwh[(base + r) * 4 + 0] = tl[i * 4 + 0]; out_tlwh[(base + r) * 4 + 1] = tl[i * 4 + 1];
         out_tlwh[(base + r) * 4 + 2] = tl[i * 4 + 2]; out_tlwh[(base + r) * 4 + 3] = tl[i * 4 + 3];
         out_score[base + r] = sc[i];
         out_class[base + r] = cl[i];
-        out_anchor[base + r] = (int)(keys[r] >> 32);
+        out_anchor[base + r] = a;
     }
 }
 
@@ -323,9 +331,9 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
         k_yolo_decode<false><<<grid, DD_YOLO_ROWS, smem, st>>>(head, scale, zero_point, na, P, wanted, ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
     }
     DD_CHECK_LAUNCH();
-    const size_t osm = (size_t)dd_next_pow2(ncap) * 8 + (size_t)ncap * (32 + 4 + 4);
+    const size_t osm = (size_t)(ncap + 2) * 4 + (size_t)ncap * (32 + 4 + 4);
     if (osm > 48 * 1024 && cudaFuncSetAttribute(k_yolo_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm) != cudaSuccess) return DD_ERR_CUDA;
-    k_yolo_order<<<b, 256, osm, st>>>(ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
+    k_yolo_order<<<b, 512, osm, st>>>(ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
