@@ -19,7 +19,8 @@
         if (e__ != cudaSuccess) return DD_ERR_CUDA;               \
     } while (0)
 
-#define DD_YOLO_ROWS 128
+#define DD_YOLO_ROWS 128        // anchor rows per CTA, f32 head (43.5 KB tile)
+#define DD_YOLO_ROWS_U8 512     // u8 head: same tile bytes, 4x the rows
 
 struct RowF32 {
     const float* p;
@@ -31,16 +32,16 @@ struct RowU8 {
     __device__ float operator()(int k) const { return dd_mulf(dd_subf((float)p[k], zp), scale); }
 };
 
-template <bool U8>
-__global__ void __launch_bounds__(DD_YOLO_ROWS)
+template <bool U8, int ROWS>
+__global__ void __launch_bounds__(ROWS)
 k_yolo_decode(const void* __restrict__ head, float scale, int zero_point, int na, DDYoloParams P,
               const unsigned char* __restrict__ wanted, int ncap, double* __restrict__ out_tlwh,
               float* __restrict__ out_score, int* __restrict__ out_class, int* __restrict__ out_anchor,
               int* __restrict__ out_count, int* __restrict__ out_flags) {
     extern __shared__ __align__(16) char smem[];
     const int frame = blockIdx.y;
-    const int row0 = blockIdx.x * DD_YOLO_ROWS;
-    const int rows = min(DD_YOLO_ROWS, na - row0);
+    const int row0 = blockIdx.x * ROWS;
+    const int rows = min(ROWS, na - row0);
     const int rw = 5 + P.nc;
     const size_t esz = U8 ? 1 : 4;
     const size_t row_bytes = (size_t)rw * esz;
@@ -59,11 +60,11 @@ k_yolo_decode(const void* __restrict__ head, float scale, int zero_point, int na
         __syncthreads();                 // barrier initialised before anyone polls it
         dd_mbar_wait(&bar, 0);
     } else if (U8) {
-        for (int i = threadIdx.x; i < (int)bytes; i += DD_YOLO_ROWS) smem[i] = src[i];
+        for (int i = threadIdx.x; i < (int)bytes; i += ROWS) smem[i] = src[i];
     } else {
         const float* sf = (const float*)src;
         float* df = (float*)smem;
-        for (int i = threadIdx.x; i < rows * rw; i += DD_YOLO_ROWS) df[i] = sf[i];
+        for (int i = threadIdx.x; i < rows * rw; i += ROWS) df[i] = sf[i];
     }
     __syncthreads();
     const int r = threadIdx.x;
@@ -319,16 +320,17 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
     P.nc = nc; P.thr = score_thr; P.img_w = (float)img_w; P.img_h = (float)img_h;
     P.frame_w = frame_w; P.frame_h = frame_h;
     P.max_area = 0.9 * frame_w * frame_h;                  // deepdish.py:953, left to right
-    const int tiles = (na + DD_YOLO_ROWS - 1) / DD_YOLO_ROWS;
-    const size_t smem = (size_t)DD_YOLO_ROWS * (5 + nc) * (head_is_u8 ? 1 : 4);
+    const int rows_per_cta = head_is_u8 ? DD_YOLO_ROWS_U8 : DD_YOLO_ROWS;
+    const int tiles = (na + rows_per_cta - 1) / rows_per_cta;
+    const size_t smem = (size_t)rows_per_cta * (5 + nc) * (head_is_u8 ? 1 : 4);
     if (smem > 227 * 1024) return DD_ERR_INVALID;
     dim3 grid(tiles, b);
     if (head_is_u8) {
-        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_yolo_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DD_ERR_CUDA;
-        k_yolo_decode<true><<<grid, DD_YOLO_ROWS, smem, st>>>(head, scale, zero_point, na, P, wanted, ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_yolo_decode<true, DD_YOLO_ROWS_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DD_ERR_CUDA;
+        k_yolo_decode<true, DD_YOLO_ROWS_U8><<<grid, DD_YOLO_ROWS_U8, smem, st>>>(head, scale, zero_point, na, P, wanted, ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
     } else {
-        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_yolo_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DD_ERR_CUDA;
-        k_yolo_decode<false><<<grid, DD_YOLO_ROWS, smem, st>>>(head, scale, zero_point, na, P, wanted, ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(k_yolo_decode<false, DD_YOLO_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DD_ERR_CUDA;
+        k_yolo_decode<false, DD_YOLO_ROWS><<<grid, DD_YOLO_ROWS, smem, st>>>(head, scale, zero_point, na, P, wanted, ncap, out_tlwh, out_score, out_class, out_anchor, out_count, out_flags);
     }
     DD_CHECK_LAUNCH();
     const size_t osm = (size_t)(ncap + 2) * 4 + (size_t)ncap * (32 + 4 + 4);

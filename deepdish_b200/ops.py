@@ -156,13 +156,17 @@ def segments_intersect(seg):
 
 
 # ------------------------------------------------------------------------------------- detection
-def nms(boxes, scores, counts, max_overlap):
+def nms(boxes, scores, counts, max_overlap, out=None):
     """preprocessing.non_max_suppression for b frames (preprocessing.py:6-73).
-    boxes f64 [b,nmax,4] tlwh, scores f32 [b,nmax], counts i32 [b] -> keep i32 [b,nmax], nkeep i32 [b]."""
+    boxes f64 [b,nmax,4] tlwh, scores f32 [b,nmax], counts i32 [b] -> keep i32 [b,nmax], nkeep i32 [b].
+    out = (keep, nkeep) reuses caller buffers (entries past nkeep are then left untouched)."""
     _need_cuda(boxes)
     b, nmax = scores.shape
-    keep = torch.full((b, nmax), -1, dtype=torch.int32, device=boxes.device)
-    nkeep = torch.zeros((b,), dtype=torch.int32, device=boxes.device)
+    if out is None:
+        keep = torch.full((b, nmax), -1, dtype=torch.int32, device=boxes.device)
+        nkeep = torch.zeros((b,), dtype=torch.int32, device=boxes.device)
+    else:
+        keep, nkeep = out
     _lib.check(_lib.lib().dd_nms(boxes.data_ptr(), scores.data_ptr(), counts.data_ptr(), b, nmax,
                                  float(max_overlap), keep.data_ptr(), nkeep.data_ptr(), _stream(boxes.device)),
                "dd_nms")
@@ -170,7 +174,7 @@ def nms(boxes, scores, counts, max_overlap):
 
 
 def yolo_decode(head, wanted_mask, score_thr=0.25, img_size=(640, 480), frame_size=(640, 480), ncap=1024,
-                quant=None):
+                quant=None, out=None):
     """YOLOv5 head decode + box filter for b frames (tools/yolov5.py:115-146, deepdish.py:946-955).
     head f32 [b,na,5+nc] (or u8 with quant=(scale, zero_point)); wanted_mask u8 [nc].
     Returns dict(tlwh f64 [b,ncap,4], score f32, cls i32, anchor i32, count i32 [b], flags i32 [b])."""
@@ -178,12 +182,13 @@ def yolo_decode(head, wanted_mask, score_thr=0.25, img_size=(640, 480), frame_si
     b, na, rw = head.shape
     nc = rw - 5
     dev = head.device
-    out = dict(tlwh=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
-               score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
-               cls=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
-               anchor=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
-               count=torch.zeros((b,), dtype=torch.int32, device=dev),
-               flags=torch.zeros((b,), dtype=torch.int32, device=dev))
+    if out is None:      # pass the previous result back as `out` to reuse its buffers (rows past count are stale)
+        out = dict(tlwh=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
+                   score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
+                   cls=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
+                   anchor=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
+                   count=torch.zeros((b,), dtype=torch.int32, device=dev),
+                   flags=torch.zeros((b,), dtype=torch.int32, device=dev))
     is_u8 = head.dtype == torch.uint8
     if is_u8 and quant is None:
         raise ValueError("u8 head needs quant=(scale, zero_point)")

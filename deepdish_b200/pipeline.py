@@ -44,7 +44,8 @@ class YoloFrontEnd(_FrontEnd):
         self.map = self._label_map(self.class_names, device)
 
     def candidates(self, head):
-        out = ops.yolo_decode(head, self.mask, self.thr, self.img_size, self.frame_size, self.ncap, self.quant)
+        self._out = out = ops.yolo_decode(head, self.mask, self.thr, self.img_size, self.frame_size, self.ncap,
+                                          self.quant, out=getattr(self, "_out", None))
         return out["tlwh"], out["score"], out["cls"], out["count"], out["flags"]
 
 
@@ -93,7 +94,8 @@ class DetectTrackPipeline:
         self.flags.zero_()
         for fe, h in zip(self.frontends, heads):
             tlwh, score, label, count, flags = fe.candidates(h)
-            keep, nkeep = ops.nms(tlwh, score, count, fe.nms_max_overlap)
+            fe._keep = ops.nms(tlwh, score, count, fe.nms_max_overlap, out=getattr(fe, "_keep", None))
+            keep, nkeep = fe._keep
             self.flags[fe.lo:fe.hi] |= flags
             n = fe.hi - fe.lo
             _lib.check(self.lib.dd_gather_detections(
