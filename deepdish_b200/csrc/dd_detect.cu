@@ -159,12 +159,15 @@ k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const 
 
 // ---- SSD-MobileNet: one CTA per frame -------------------------------------------------------------
 //   phase A  4 threads per anchor scan its [ncls] score row (adjacent rows -> coalesced), best
-//            non-background class, box decode (expf);
-//   phase B  greedy NMS as <= max_det rounds of {block-wide arg-max over the live candidates, eager
-//            suppression of every live candidate with IoU > 0.6 against the pick} -- the same selection as
-//            the op's sort + scan (a candidate dies iff an earlier-ranked pick overlaps it), without a sort;
+//            non-background class.  Only anchors whose best score reaches the reference's confidence
+//            threshold are kept (compacted into shared memory and decoded, expf): the op processes
+//            candidates in descending score and a candidate can only be suppressed by a higher-scored
+//            pick, so every op selection below the confidence threshold comes after all the ones above it
+//            and is dropped by tools/ssd_mobilenet.py:119 anyway -- the result is identical;
+//   phase B  greedy NMS as <= max_det rounds of {arg-max over the live candidates, eager suppression of
+//            every live candidate with IoU > 0.6 against the pick} -- the same selection as the op's
+//            sort + scan, without a sort;
 //   phase C  thread 0: the reference's own post-processing on the <= 10 selected boxes (dd_ssd_post).
-#define DD_SSD_TILE 64
 #define DD_SSD_THREADS 256
 __global__ void __launch_bounds__(DD_SSD_THREADS)
 k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_scores,
@@ -175,16 +178,18 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
     const int frame = blockIdx.x;
     const int na = P.na, ncls = P.ncls;
     unsigned long long* keys = (unsigned long long*)smem;               // [na]  live candidate keys (~0 = dead)
-    float* dec = (float*)(keys + na);                                   // [na][4]
+    float* dec = (float*)(keys + na);                                   // [na][4] decoded boxes of the candidates
     int* bcls = (int*)(dec + (size_t)na * 4);                           // [na]
     __shared__ float sel_box[DD_SSD_MAXDET * 4];
     __shared__ int sel_cls[DD_SSD_MAXDET];
     __shared__ float sel_score[DD_SSD_MAXDET];
     __shared__ unsigned long long wmin[DD_SSD_THREADS / 32];
+    __shared__ int n_cand;
     const float* fs = raw_scores + (size_t)frame * na * ncls;
     const float* fb = raw_boxes + (size_t)frame * na * 4;
-    // phase A: 4 threads per anchor read its score row straight from global memory (a warp covers 8
-    // adjacent rows = 2912 contiguous bytes; no staging, no barriers, all loads independent)
+    if (threadIdx.x == 0) n_cand = 0;
+    __syncthreads();
+    const float keep_thr = fmaxf(P.score_thr, P.conf_thr);
     {
         const int q = threadIdx.x & 3;
         for (int a = threadIdx.x >> 2; a < ((na + 63) & ~63); a += DD_SSD_THREADS / 4) {
@@ -192,7 +197,7 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
             int bi = 0x7fffffff;
             if (a < na) {
                 const float* row = fs + (size_t)a * ncls;
-#pragma unroll 4
+#pragma unroll 8
                 for (int c = 1 + q; c < ncls; c += 4) {                 // skip background column 0
                     const float v = __ldg(row + c);
                     if (v > best) { best = v; bi = c - 1; }
@@ -204,39 +209,50 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
-            if (a < na && q == 0) {
-                dd_ssd_decode_box(fb + (size_t)a * 4, anchors + (size_t)a * 4, P, dec + (size_t)a * 4);
-                bcls[a] = bi;
-                keys[a] = best >= P.score_thr ? (((unsigned long long)(~dd_f32_key(best))) << 32) | (unsigned)a : ~0ull;
+            if (a < na && q == 0 && best >= keep_thr) {
+                const int k = atomicAdd(&n_cand, 1);
+                dd_ssd_decode_box(fb + (size_t)a * 4, anchors + (size_t)a * 4, P, dec + (size_t)k * 4);
+                bcls[k] = bi;
+                keys[k] = (((unsigned long long)(~dd_f32_key(best))) << 32) | (unsigned)a;
             }
         }
     }
     __syncthreads();
+    const int nc = n_cand;
     int ns = 0;
     for (; ns < P.max_det; ++ns) {
         unsigned long long mk = ~0ull;                                  // smallest key = best live candidate
-        for (int a = threadIdx.x; a < na; a += DD_SSD_THREADS) mk = min(mk, keys[a]);
+        int mi = -1;
+        for (int k = threadIdx.x; k < nc; k += DD_SSD_THREADS)
+            if (keys[k] < mk) { mk = keys[k]; mi = k; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mk = min(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, mk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (ok < mk) { mk = ok; mi = oi; }
+        }
         if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = mk;
         __syncthreads();
-        mk = wmin[0];
+        unsigned long long bk = wmin[0];
 #pragma unroll
-        for (int w = 1; w < DD_SSD_THREADS / 32; ++w) mk = min(mk, wmin[w]);
-        if (mk == ~0ull) break;                                         // uniform: no live candidate left
-        const int pick = (int)(mk & 0xffffffffu);
+        for (int w = 1; w < DD_SSD_THREADS / 32; ++w) bk = min(bk, wmin[w]);
+        if (bk == ~0ull) break;                                         // uniform: no live candidate left
+        __shared__ int pick_slot;
+        if (mk == bk && (threadIdx.x & 31) == 0) pick_slot = mi;        // keys are distinct: exactly one warp
+        __syncthreads();
+        const int pick = pick_slot;
         const float pb[4] = {dec[pick * 4], dec[pick * 4 + 1], dec[pick * 4 + 2], dec[pick * 4 + 3]};
         if (threadIdx.x == 0) {
             for (int q = 0; q < 4; ++q) sel_box[ns * 4 + q] = pb[q];
             sel_cls[ns] = bcls[pick];
             union { unsigned u; float f; } cv;
-            const unsigned kk = ~(unsigned)(mk >> 32);
+            const unsigned kk = ~(unsigned)(bk >> 32);
             cv.u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
             sel_score[ns] = cv.f;
         }
-        for (int a = threadIdx.x; a < na; a += DD_SSD_THREADS) {
-            if (keys[a] == ~0ull) continue;
-            if (a == pick || dd_ssd_iou(pb, dec + (size_t)a * 4) > P.iou_thr) keys[a] = ~0ull;
+        for (int k = threadIdx.x; k < nc; k += DD_SSD_THREADS) {
+            if (keys[k] == ~0ull) continue;
+            if (k == pick || dd_ssd_iou(pb, dec + (size_t)k * 4) > P.iou_thr) keys[k] = ~0ull;
         }
         __syncthreads();
     }
