@@ -60,7 +60,7 @@ def main():
         cls = torch.tensor([0, 1, 2, 5], device=dev)[torch.randint(0, 4, (n, args.objects), device=dev, generator=gen)]
         h[fi, rows, 5 + cls] = 1.0
     rb = 0.3 * torch.randn((SS, 1917, 4), device=dev, generator=gen)
-    sc = torch.rand((SS, 1917, 91), device=dev, generator=gen) ** 10
+    sc = 0.3 * torch.rand((SS, 1917, 91), device=dev, generator=gen) ** 4         # background: below the 0.5 threshold
     hot = torch.rand((SS, 1917), device=dev, generator=gen).argsort(dim=1)[:, :12]
     fi = torch.arange(SS, device=dev)[:, None].expand_as(hot)
     sc[fi, hot, 1 + torch.tensor([0, 1, 2, 5], device=dev)[torch.randint(0, 4, (SS, 12), device=dev, generator=gen)]] = \

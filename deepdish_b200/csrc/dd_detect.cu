@@ -158,67 +158,109 @@ k_nms(const double* __restrict__ boxes, const float* __restrict__ scores, const 
 }
 
 // ---- SSD-MobileNet: one CTA per frame -------------------------------------------------------------
-//   phase A  4 threads per anchor scan its [ncls] score row (adjacent rows -> coalesced), best
-//            non-background class.  Only anchors whose best score reaches the reference's confidence
-//            threshold are kept (compacted into shared memory and decoded, expf): the op processes
-//            candidates in descending score and a candidate can only be suppressed by a higher-scored
-//            pick, so every op selection below the confidence threshold comes after all the ones above it
-//            and is dropped by tools/ssd_mobilenet.py:119 anyway -- the result is identical;
+//   phase A  the [na, ncls] score rows stream through a 3-stage shared-memory ring of 64-row tiles filled by
+//            TMA bulk copies (cp.async.bulk + one mbarrier per stage; rows are only 4-byte aligned, so each
+//            copy starts at the 16-byte boundary below its tile and the row addressing absorbs the offset);
+//            4 threads per anchor find the best non-background class.  Only anchors whose best score reaches
+//            the reference's confidence threshold are kept (compacted into shared memory and decoded, expf):
+//            the op processes candidates in descending score and a candidate can only be suppressed by a
+//            higher-scored pick, so every op selection below the confidence threshold comes after all the
+//            ones above it and is dropped by tools/ssd_mobilenet.py:119 anyway -- the result is identical;
 //   phase B  greedy NMS as <= max_det rounds of {arg-max over the live candidates, eager suppression of
 //            every live candidate with IoU > 0.6 against the pick} -- the same selection as the op's
 //            sort + scan, without a sort;
 //   phase C  thread 0: the reference's own post-processing on the <= 10 selected boxes (dd_ssd_post).
 #define DD_SSD_THREADS 256
+#define DD_SSD_TILE 64           // anchor rows per stage (= DD_SSD_THREADS / 4)
+#define DD_SSD_STAGES 3
+#define DD_SSD_CAND 1024         // candidates above the confidence threshold kept per frame
+
+__device__ __forceinline__ size_t dd_ssd_stage_bytes(int ncls) { return ((size_t)DD_SSD_TILE * ncls * 4 + 16 + 15) & ~(size_t)15; }
+
 __global__ void __launch_bounds__(DD_SSD_THREADS)
-k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_scores,
+k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_scores, size_t scores_bytes,
              const float* __restrict__ anchors, DDSsdParams P, const int* __restrict__ class_to_label,
              int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_score,
-             int* __restrict__ out_label, int* __restrict__ out_count) {
-    extern __shared__ __align__(16) char smem[];
+             int* __restrict__ out_label, int* __restrict__ out_count, int* __restrict__ out_flags) {
+    extern __shared__ __align__(128) char smem[];
     const int frame = blockIdx.x;
     const int na = P.na, ncls = P.ncls;
-    unsigned long long* keys = (unsigned long long*)smem;               // [na]  live candidate keys (~0 = dead)
-    float* dec = (float*)(keys + na);                                   // [na][4] decoded boxes of the candidates
-    int* bcls = (int*)(dec + (size_t)na * 4);                           // [na]
+    const size_t stage_bytes = dd_ssd_stage_bytes(ncls);
+    unsigned long long* keys = (unsigned long long*)(smem + DD_SSD_STAGES * stage_bytes);   // [DD_SSD_CAND]
+    float* dec = (float*)(keys + DD_SSD_CAND);                                              // [DD_SSD_CAND][4]
+    int* bcls = (int*)(dec + (size_t)DD_SSD_CAND * 4);                                      // [DD_SSD_CAND]
     __shared__ float sel_box[DD_SSD_MAXDET * 4];
     __shared__ int sel_cls[DD_SSD_MAXDET];
     __shared__ float sel_score[DD_SSD_MAXDET];
     __shared__ unsigned long long wmin[DD_SSD_THREADS / 32];
-    __shared__ int n_cand;
-    const float* fs = raw_scores + (size_t)frame * na * ncls;
+    __shared__ unsigned long long bars[DD_SSD_STAGES];
+    __shared__ int n_cand, pick_slot;
+    const char* all_scores = (const char*)raw_scores;
+    const size_t frame_off = (size_t)frame * na * ncls * 4;
     const float* fb = raw_boxes + (size_t)frame * na * 4;
-    if (threadIdx.x == 0) n_cand = 0;
+    const int ntiles = (na + DD_SSD_TILE - 1) / DD_SSD_TILE;
+
+    auto issue = [&](int t) {            // thread 0: bulk copy of tile t into stage t % STAGES
+        const size_t off = frame_off + (size_t)t * DD_SSD_TILE * ncls * 4;
+        const size_t lo = off & ~(size_t)15;                             // 16-byte boundary below the tile
+        const int rows = min(DD_SSD_TILE, na - t * DD_SSD_TILE);
+        size_t hi = (off + (size_t)rows * ncls * 4 + 15) & ~(size_t)15;
+        if (hi > scores_bytes) hi = scores_bytes & ~(size_t)15;          // never read past the buffer
+        const int st = t % DD_SSD_STAGES;
+        dd_mbar_expect_tx(&bars[st], (unsigned)(hi - lo));
+        dd_bulk_g2s(smem + st * stage_bytes, all_scores + lo, (unsigned)(hi - lo), &bars[st]);
+    };
+    if (threadIdx.x == 0) {
+        n_cand = 0;
+        for (int i = 0; i < DD_SSD_STAGES; ++i) dd_mbar_init(&bars[i], 1);
+        dd_mbar_fence_init();
+    }
     __syncthreads();
+    if (threadIdx.x == 0)
+        for (int t = 0; t < DD_SSD_STAGES - 1 && t < ntiles; ++t) issue(t);
     const float keep_thr = fmaxf(P.score_thr, P.conf_thr);
-    {
-        const int q = threadIdx.x & 3;
-        for (int a = threadIdx.x >> 2; a < ((na + 63) & ~63); a += DD_SSD_THREADS / 4) {
-            float best = -3.0e38f;
-            int bi = 0x7fffffff;
-            if (a < na) {
-                const float* row = fs + (size_t)a * ncls;
-#pragma unroll 8
-                for (int c = 1 + q; c < ncls; c += 4) {                 // skip background column 0
-                    const float v = __ldg(row + c);
-                    if (v > best) { best = v; bi = c - 1; }
-                }
+    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;                // 4 threads per anchor row
+    for (int t = 0; t < ntiles; ++t) {
+        if (threadIdx.x == 0 && t + DD_SSD_STAGES - 1 < ntiles) issue(t + DD_SSD_STAGES - 1);
+        const int st = t % DD_SSD_STAGES;
+        dd_mbar_wait(&bars[st], (unsigned)((t / DD_SSD_STAGES) & 1));
+        const size_t off = frame_off + (size_t)t * DD_SSD_TILE * ncls * 4;
+        const float* tile = (const float*)(smem + st * stage_bytes + (off & 15));
+        const int a = t * DD_SSD_TILE + r;
+        float best = -3.0e38f;
+        int bi = 0x7fffffff;
+        if (a < na) {
+            const float* row = tile + r * ncls;
+            // the last bytes of the very last tile may lie beyond a clamped copy: they are read from global
+            const bool tail = frame_off + ((size_t)(a + 1) * ncls) * 4 > (scores_bytes & ~(size_t)15);
+            if (tail) row = (const float*)(all_scores + frame_off) + (size_t)a * ncls;
+#pragma unroll 4
+            for (int c = 1 + q; c < ncls; c += 4) {                     // skip background column 0
+                const float v = row[c];
+                if (v > best) { best = v; bi = c - 1; }
             }
+        }
 #pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {                          // first maximum wins across the 4 lanes
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (a < na && q == 0 && best >= keep_thr) {
-                const int k = atomicAdd(&n_cand, 1);
+        for (int o = 1; o <= 2; o <<= 1) {                              // first maximum wins across the 4 lanes
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (a < na && q == 0 && best >= keep_thr) {
+            const int k = atomicAdd(&n_cand, 1);
+            if (k < DD_SSD_CAND) {
                 dd_ssd_decode_box(fb + (size_t)a * 4, anchors + (size_t)a * 4, P, dec + (size_t)k * 4);
                 bcls[k] = bi;
                 keys[k] = (((unsigned long long)(~dd_f32_key(best))) << 32) | (unsigned)a;
             }
         }
+        __syncthreads();                                                // stage st may be refilled next iteration
     }
-    __syncthreads();
-    const int nc = n_cand;
+    int nc = n_cand;
+    if (nc > DD_SSD_CAND) {                                             // never silently truncated
+        nc = DD_SSD_CAND;
+        if (threadIdx.x == 0) atomicOr(out_flags + frame, DD_FLAG_DET_OVERFLOW);
+    }
     int ns = 0;
     for (; ns < P.max_det; ++ns) {
         unsigned long long mk = ~0ull;                                  // smallest key = best live candidate
@@ -237,13 +279,12 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
 #pragma unroll
         for (int w = 1; w < DD_SSD_THREADS / 32; ++w) bk = min(bk, wmin[w]);
         if (bk == ~0ull) break;                                         // uniform: no live candidate left
-        __shared__ int pick_slot;
         if (mk == bk && (threadIdx.x & 31) == 0) pick_slot = mi;        // keys are distinct: exactly one warp
         __syncthreads();
         const int pick = pick_slot;
         const float pb[4] = {dec[pick * 4], dec[pick * 4 + 1], dec[pick * 4 + 2], dec[pick * 4 + 3]};
         if (threadIdx.x == 0) {
-            for (int q = 0; q < 4; ++q) sel_box[ns * 4 + q] = pb[q];
+            for (int k = 0; k < 4; ++k) sel_box[ns * 4 + k] = pb[k];
             sel_cls[ns] = bcls[pick];
             union { unsigned u; float f; } cv;
             const unsigned kk = ~(unsigned)(bk >> 32);
@@ -264,7 +305,7 @@ k_ssd_decode(const float* __restrict__ raw_boxes, const float* __restrict__ raw_
         int n = dd_ssd_post(sel_box, sel_cls, sel_score, ns, P, class_to_label, tl, sc, lb);
         if (n > ncap) n = ncap;
         for (int i = 0; i < n; ++i) {
-            for (int q = 0; q < 4; ++q) out_tlwh[(o + i) * 4 + q] = tl[i * 4 + q];
+            for (int k = 0; k < 4; ++k) out_tlwh[(o + i) * 4 + k] = tl[i * 4 + k];
             out_score[o + i] = sc[i];
             out_label[o + i] = lb[i];
         }
@@ -359,9 +400,12 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
 int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* anchors, int32_t b,
                   int32_t na, int32_t ncls, const int32_t* class_to_label, float conf_thr, double nms_iou,
                   int32_t img_w, int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap,
-                  double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count, void* stream) {
-    if (!raw_boxes || !raw_scores || !anchors || !class_to_label || !out_tlwh || !out_score || !out_label || !out_count)
+                  double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count,
+                  int32_t* out_flags, void* stream) {
+    if (!raw_boxes || !raw_scores || !anchors || !class_to_label || !out_tlwh || !out_score || !out_label ||
+        !out_count || !out_flags)
         return DD_ERR_INVALID;
+    if (((uintptr_t)raw_scores & 15) != 0) return DD_ERR_INVALID;      /* bulk copies need a 16-byte aligned base */
     if (b < 0 || na <= 0 || na > 8192 || ncls < 2 || ncls > 1024 || ncap < 10) return DD_ERR_INVALID;
     if (b == 0) return DD_OK;
     DDSsdParams P;
@@ -370,13 +414,17 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
     P.conf_thr = conf_thr; P.nms_iou = nms_iou;
     P.img_w = img_w; P.img_h = img_h; P.frame_w = frame_w; P.frame_h = frame_h;
     P.max_area = 0.9 * frame_w * frame_h;
-    const size_t smem = (size_t)na * 8 + (size_t)na * 20;
+    const size_t stage = ((size_t)DD_SSD_TILE * ncls * 4 + 16 + 15) & ~(size_t)15;
+    const size_t smem = DD_SSD_STAGES * stage + (size_t)DD_SSD_CAND * (8 + 16 + 4);
     if (smem > 200 * 1024) return DD_ERR_CAPACITY;
+    if (cudaMemsetAsync(out_flags, 0, sizeof(int) * b, (cudaStream_t)stream) != cudaSuccess) return DD_ERR_CUDA;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_ssd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DD_ERR_CUDA;
-    k_ssd_decode<<<b, DD_SSD_THREADS, smem, (cudaStream_t)stream>>>(raw_boxes, raw_scores, anchors, P, class_to_label, ncap,
-                                                        out_tlwh, out_score, out_label, out_count);
+    k_ssd_decode<<<b, DD_SSD_THREADS, smem, (cudaStream_t)stream>>>(raw_boxes, raw_scores,
+                                                                   (size_t)b * na * ncls * 4, anchors, P,
+                                                                   class_to_label, ncap, out_tlwh, out_score,
+                                                                   out_label, out_count, out_flags);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }

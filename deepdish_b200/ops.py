@@ -205,23 +205,25 @@ def yolo_decode(head, wanted_mask, score_thr=0.25, img_size=(640, 480), frame_si
 
 
 def ssd_decode(raw_boxes, raw_scores, anchors, class_to_label, conf_thr=0.5, nms_iou=0.5, img_size=(640, 480),
-               frame_size=(640, 480), ncap=16):
+               frame_size=(640, 480), ncap=16, out=None):
     """SSD-MobileNet post-processing for b frames (TFLite_Detection_PostProcess restated +
     tools/ssd_mobilenet.py:59-150,198-213 + deepdish.py:946-955).  raw_boxes f32 [b,na,4], raw_scores f32
     [b,na,ncls], anchors f32 [na,4], class_to_label i32 [ncls-1].
-    Returns dict(tlwh f64 [b,ncap,4], score f32, label i32, count i32 [b])."""
+    Returns dict(tlwh f64 [b,ncap,4], score f32, label i32, count i32 [b], flags i32 [b])."""
     _need_cuda(raw_boxes)
     b, na, _ = raw_boxes.shape
     ncls = raw_scores.shape[2]
     dev = raw_boxes.device
-    out = dict(tlwh=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
-               score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
-               label=torch.full((b, ncap), -1, dtype=torch.int32, device=dev),
-               count=torch.zeros((b,), dtype=torch.int32, device=dev))
+    if out is None:
+        out = dict(tlwh=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
+                   score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
+                   label=torch.full((b, ncap), -1, dtype=torch.int32, device=dev),
+                   count=torch.zeros((b,), dtype=torch.int32, device=dev),
+                   flags=torch.zeros((b,), dtype=torch.int32, device=dev))
     _lib.check(_lib.lib().dd_ssd_decode(raw_boxes.data_ptr(), raw_scores.data_ptr(), anchors.data_ptr(), b, na, ncls,
                                         class_to_label.data_ptr(), float(conf_thr), float(nms_iou),
                                         int(img_size[0]), int(img_size[1]), int(frame_size[0]), int(frame_size[1]),
                                         ncap, out["tlwh"].data_ptr(), out["score"].data_ptr(),
-                                        out["label"].data_ptr(), out["count"].data_ptr(), _stream(dev)),
-               "dd_ssd_decode")
+                                        out["label"].data_ptr(), out["count"].data_ptr(), out["flags"].data_ptr(),
+                                        _stream(dev)), "dd_ssd_decode")
     return out

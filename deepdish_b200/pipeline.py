@@ -67,10 +67,9 @@ class SsdFrontEnd(_FrontEnd):
 
     def candidates(self, heads):
         raw_boxes, raw_scores = heads
-        out = ops.ssd_decode(raw_boxes, raw_scores, self.anchors, self.c2l, self.thr, self.iou, self.img_size,
-                             self.frame_size, self.ncap)
-        flags = torch.zeros_like(out["count"])
-        return out["tlwh"], out["score"], out["label"], out["count"], flags
+        self._out = out = ops.ssd_decode(raw_boxes, raw_scores, self.anchors, self.c2l, self.thr, self.iou,
+                                         self.img_size, self.frame_size, self.ncap, out=getattr(self, "_out", None))
+        return out["tlwh"], out["score"], out["label"], out["count"], out["flags"]
 
 
 class DetectTrackPipeline:

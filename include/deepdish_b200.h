@@ -235,11 +235,14 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
  *   raw_boxes f32 [b,na,4] (ty,tx,th,tw), raw_scores f32 [b,na,ncls] (column 0 = background),
  *   anchors f32 [na,4] (ycenter,xcenter,h,w), class_to_label i32 [ncls-1]: output label id of 0-based
  *   class c (the reference's labels[c+1]) or -1 when that label is not wanted.
- *   out_tlwh f64 [b,ncap,4], out_score f32 [b,ncap], out_label i32 [b,ncap], out_count i32 [b]; ncap >= 10. */
+ *   out_tlwh f64 [b,ncap,4], out_score f32 [b,ncap], out_label i32 [b,ncap], out_count i32 [b]; ncap >= 10;
+ *   out_flags i32 [b]: DD_FLAG_DET_OVERFLOW when more than 1024 anchors of a frame reach conf_thr.
+ *   raw_scores must be 16-byte aligned (TMA bulk copies). */
 int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* anchors, int32_t b,
                   int32_t na, int32_t ncls, const int32_t* class_to_label, float conf_thr, double nms_iou,
                   int32_t img_w, int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap,
-                  double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count, void* stream);
+                  double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count,
+                  int32_t* out_flags, void* stream);
 
 /* The step between NMS and the tracker (deepdish.py:996-998,1014): gather the kept candidates, in NMS pick
  * order, into the tracker's padded detection batch for b streams.
