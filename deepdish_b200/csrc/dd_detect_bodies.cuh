@@ -282,6 +282,12 @@ DD_HD bool dd_yolo_row(const Row& row, const DDYoloParams& p, const unsigned cha
     const float x1 = dd_mulf(dd_subf(cx, hx), p.img_w), y1 = dd_mulf(dd_subf(cy, hy), p.img_h);
     const float x2 = dd_mulf(dd_addf(cx, hx), p.img_w), y2 = dd_mulf(dd_addf(cy, hy), p.img_h);
     const float bw = dd_subf(x2, x1), bh = dd_subf(y2, y1);       // yolov5.py:141-142
+    if (p.frame_w <= 0) {            // adapter mode: detect_image's own output, no box filter
+        out_tlwh[0] = x1; out_tlwh[1] = y1; out_tlwh[2] = bw; out_tlwh[3] = bh;
+        *out_score = best;
+        *out_class = bi;
+        return true;
+    }
     *out_nan = (x1 != x1) || (y1 != y1) || (bw != bw) || (bh != bh);
     // deepdish.py:950-951: int(np.clip(...)) truncates toward zero
     const float fx = x1 < 0.f ? 0.f : (x1 > (float)p.frame_w ? (float)p.frame_w : x1);
@@ -425,6 +431,14 @@ DD_HD int dd_ssd_post(const float* sel_box, const int* sel_cls, const float* sel
             cand_l[nc] = lab;
             ++nc;
         }
+    }
+    if (p.frame_w <= 0) {                                // adapter mode: detect_image's own output
+        for (int i = 0; i < nc; ++i) {
+            for (int q = 0; q < 4; ++q) out_tlwh[i * 4 + q] = cand[i][q];
+            out_score[i] = cand_s[i];
+            out_label[i] = cand_l[i];
+        }
+        return nc;
     }
     if (any_nan) return 0;                               // deepdish.py:947-949
     for (int i = 0; i < nc; ++i) {                       // box filter (deepdish.py:950-955)

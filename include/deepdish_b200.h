@@ -217,7 +217,8 @@ int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int3
  * (deepdish.py:946-955) for b frames:
  *   head: f32 [b,na,5+nc], or u8 with (scale, zero_point) when head_is_u8 != 0 (yolov5.py:115-118);
  *   wanted u8 [nc] (1 = label in wanted_labels); img_w/img_h = PIL image size (yolov5.py:98,131);
- *   frame_w/frame_h = camera viewport of the box filter (deepdish.py:945).
+ *   frame_w/frame_h = camera viewport of the box filter (deepdish.py:945); frame_w <= 0 skips the box
+ *   filter and emits detect_image's own float boxes (adapter mode, tools/yolov5.py:137-146).
  *   Candidates are emitted in ascending anchor order, at most ncap per frame (more -> DD_FLAG_DET_OVERFLOW
  *   in out_flags[b]):  out_tlwh f64 [b,ncap,4] integer-valued boxes after the filter, out_score f32,
  *   out_class i32, out_anchor i32, out_count i32 [b]. */
@@ -237,7 +238,8 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
  *   class c (the reference's labels[c+1]) or -1 when that label is not wanted.
  *   out_tlwh f64 [b,ncap,4], out_score f32 [b,ncap], out_label i32 [b,ncap], out_count i32 [b]; ncap >= 10;
  *   out_flags i32 [b]: DD_FLAG_DET_OVERFLOW when more than 1024 anchors of a frame reach conf_thr.
- *   raw_scores must be 16-byte aligned (TMA bulk copies). */
+ *   raw_scores must be 16-byte aligned (TMA bulk copies).  frame_w <= 0 skips the box filter (adapter mode:
+ *   the float boxes SSD_MOBILENET.detect_image returns). */
 int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* anchors, int32_t b,
                   int32_t na, int32_t ncls, const int32_t* class_to_label, float conf_thr, double nms_iou,
                   int32_t img_w, int32_t img_h, int32_t frame_w, int32_t frame_h, int32_t ncap,

@@ -98,3 +98,38 @@ def test_per_function_api():
     assert got == exp
     assert linear_assignment.INFTY_COST == 1e5
     assert Detection([1, 2, 3, 4], "person", 0.5, np.zeros(128)).to_xyah().tolist() == [2.5, 4.0, 0.75, 4.0]
+
+
+def test_detector_adapter_facades_vs_reference_fixture():
+    """tools.yolov5.YOLOV5 / tools.ssd_mobilenet.SSD_MOBILENET mirrors: detect_image's own output (float
+    boxes, label names, scores, order) against what the unmodified reference adapters returned."""
+    from PIL import Image
+    from deepdish_b200.tools.yolov5 import YOLOV5
+    from deepdish_b200.tools.ssd_mobilenet import SSD_MOBILENET
+    from oracle import detect as odet
+    g = goldens.load("yolo.npz")
+    names, wanted = list(g["names"]), list(g["wanted"])
+    img = Image.new("RGB", (640, 480))
+    for f in range(g["head"].shape[0]):
+        det = YOLOV5(wanted_labels=wanted, labels=names, head_fn=lambda im, f=f: g["head"][f:f + 1])
+        boxes, labels, scores = det.detect_image(img)
+        np.testing.assert_array_equal(np.array(boxes, np.float32).reshape(-1, 4), g["tlwh%d" % f])
+        assert [names.index(l) for l in labels] == list(g["cls%d" % f])
+        np.testing.assert_array_equal(np.array(scores, np.float32), g["score%d" % f])
+    # SSD: the op's decode is unpinned (third party); feed heads whose decoded top boxes are known via the oracle
+    rng = np.random.default_rng(2)
+    anchors = odet.ssd_anchors()
+    names = ["???"] + ["c%02d" % i for i in range(1, 91)]
+    names[1], names[3] = "person", "car"
+    rb = rng.normal(0, 0.5, (4, 1917, 4)).astype(np.float32)
+    sc = rng.beta(0.4, 12, (4, 1917, 91)).astype(np.float32)
+    for b in range(4):
+        sc[b, rng.choice(1917, 10, replace=False), 1 + rng.choice([0, 2], 10)] = rng.uniform(0.55, 1, 10).astype(np.float32)
+    det = SSD_MOBILENET(wanted_labels=["person", "car"], labels=names, anchors=anchors)
+    got = det.detect_heads(rb, sc, (640, 480))
+    for b in range(4):
+        ob, oc, os_, _ = odet.tflite_detection_postprocess(rb[b], sc[b], anchors)
+        tlwh, labels, scores = odet.ssd_postprocess(ob, oc, os_, 640, 480, names, ["person", "car"])
+        assert got[b][1] == labels
+        np.testing.assert_array_equal(np.array(got[b][2], np.float32), scores)
+        np.testing.assert_allclose(np.array(got[b][0]).reshape(-1, 4), tlwh, rtol=1e-5, atol=1e-3)
