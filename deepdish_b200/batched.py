@@ -337,6 +337,27 @@ class BatchedTracker:
             raise ValueError("cost matrix is infeasible")
 
     # ------------------------------------------------------------------------------------------
+    def state_dict(self):
+        """Checkpoint of the whole tracker state (the reference never saves tracker
+        state; only its counters survive a restart).  Host copies of every chunk's blob + the tick counter."""
+        self.join()
+        torch.cuda.synchronize(self.device)
+        return {"blobs": [c.blob.cpu() for c in self.chunks], "tick": self._tick,
+                "shape": (self.n_streams, self.max_tracks, self.max_dets, self.budget, len(self.labels),
+                          len(self.chunks)), "total_counts": self.total_counts.cpu()}
+
+    def load_state_dict(self, sd):
+        shape = (self.n_streams, self.max_tracks, self.max_dets, self.budget, len(self.labels), len(self.chunks))
+        if tuple(sd["shape"]) != shape:
+            raise ValueError("checkpoint shape %s does not match tracker %s" % (tuple(sd["shape"]), shape))
+        self.join()
+        for c, b in zip(self.chunks, sd["blobs"]):
+            c.blob.copy_(b.to(self.device))
+        self.total_counts.copy_(sd["total_counts"].to(self.device))
+        self._tick = int(sd["tick"])
+        self._sum_done = [None, None]
+        torch.cuda.synchronize(self.device)
+
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
         names = names or [n for n in self.v.keys() if n not in ("gal", "cost", "gate", "det_featn")]

@@ -197,3 +197,24 @@ def test_n_init_and_max_age_variants(n_init, max_age):
             for s in range(S):
                 compare_stream(trk[s], cnt[s], v, s, LABELS3)
     bt.check()
+
+
+def test_checkpoint_resume_is_bit_identical():
+    from deepdish_b200.batched import BatchedTracker
+    S = 5
+    kw = dict(max_tracks=64, max_dets=24, budget=20, max_age=20, n_chunks=2)
+    a = BatchedTracker(S, LABELS3, **kw)
+    sc = Scene(S, 14, 24, n_labels=3, seed=77)
+    frames = [sc.step().to("cuda") for _ in range(45)]
+    for b in frames[:25]:
+        a.step(b)
+    sd = a.state_dict()
+    ids_a = [a.step(b).clone() for b in frames[25:]]
+    b2 = BatchedTracker(S, LABELS3, **kw)
+    b2.load_state_dict(sd)
+    for k, b in enumerate(frames[25:]):
+        assert torch.equal(b2.step(b), ids_a[k])
+    va, vb = a.host_view(), b2.host_view()
+    for name in ("n_tracks", "order", "track_id", "state", "mean", "cov", "counts", "next_id"):
+        np.testing.assert_array_equal(va[name], vb[name])
+    assert torch.equal(a.reduce_counts(), b2.reduce_counts())
