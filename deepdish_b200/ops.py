@@ -227,3 +227,42 @@ def ssd_decode(raw_boxes, raw_scores, anchors, class_to_label, conf_thr=0.5, nms
                                         out["label"].data_ptr(), out["count"].data_ptr(), out["flags"].data_ptr(),
                                         _stream(dev)), "dd_ssd_decode")
     return out
+
+
+# ------------------------------------------------------------------------------------- encoder input
+def extract_patches(frames, boxes, counts=None, patch_shape=(128, 64), boxes_are_int=True, out=None):
+    """extract_image_patch for every box of b frames (tools/generate_detections.py:40-84, 198-205).
+    frames u8 [b,H,W,3], boxes f64 [b,dmax,4] tlwh, counts i32 [b] or None.
+    Returns (patches u8 [b,dmax,ph,pw,3], valid i32 [b,dmax]); out = (patches, valid) reuses buffers."""
+    _need_cuda(frames)
+    if frames.dtype != torch.uint8 or boxes.dtype != torch.float64:
+        raise ValueError("frames must be uint8 and boxes float64")
+    b, H, W, ch = frames.shape
+    if ch != 3:
+        raise ValueError("frames must be [b,H,W,3]")
+    dmax = boxes.shape[1]
+    ph, pw = int(patch_shape[0]), int(patch_shape[1])
+    if out is None:
+        patches = torch.zeros((b, dmax, ph, pw, 3), dtype=torch.uint8, device=frames.device)
+        valid = torch.zeros((b, dmax), dtype=torch.int32, device=frames.device)
+    else:
+        patches, valid = out
+    _lib.check(_lib.lib().dd_extract_patches(frames.data_ptr(), b, H, W, boxes.data_ptr(),
+                                             counts.data_ptr() if counts is not None else None, dmax,
+                                             1 if boxes_are_int else 0, ph, pw, patches.data_ptr(),
+                                             valid.data_ptr(), _stream(frames.device)), "dd_extract_patches")
+    return patches, valid
+
+
+def dummy_encode(patches, out=None):
+    """DummyImageEncoder.__call__ (tools/generate_detections.py:86-105): u8 [...,16,8,3] -> f32 [...,128]."""
+    _need_cuda(patches)
+    if patches.dtype != torch.uint8 or tuple(patches.shape[-3:]) != (16, 8, 3):
+        raise ValueError("patches must be uint8 [...,16,8,3]")
+    lead = tuple(patches.shape[:-3])
+    n = int(np.prod(lead)) if lead else 1
+    if out is None:
+        out = torch.empty(lead + (128,), dtype=torch.float32, device=patches.device)
+    _lib.check(_lib.lib().dd_dummy_encode(patches.data_ptr(), n, out.data_ptr(), _stream(patches.device)),
+               "dd_dummy_encode")
+    return out

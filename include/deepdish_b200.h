@@ -258,6 +258,26 @@ int dd_gather_detections(const double* cand_tlwh, const float* cand_score, const
                          float* det_conf, int32_t* det_label, int32_t* det_count, int32_t* out_flags,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Re-ID encoder input (the step between NMS and the tracker's feature input).
+ * ---------------------------------------------------------------------------------------------- */
+/* extract_image_patch (tools/generate_detections.py:40-84) for every detection box of b frames, as the
+ * encoder loop calls it (generate_detections.py:198-205): aspect-corrected crop, clip to the frame, 8-bit
+ * bilinear cv2.resize to (patch_h, patch_w) -- OpenCV's fixed-point arithmetic, bit-exact.
+ *   frames u8 [b,img_h,img_w,3]; boxes f64 [b,dmax,4] tlwh; counts i32 [b] boxes present per frame (NULL = dmax);
+ *   boxes_are_int != 0: numpy int64 box semantics (what deepdish.py:993-1008 passes: the aspect correction
+ *   truncates toward zero at each item assignment), 0: float box semantics (one truncation at astype(int));
+ *   out_patches u8 [b,dmax,patch_h,patch_w,3]; out_valid i32 [b,dmax]: 0 where the reference returns None
+ *   (empty or fully outside box; the patch is zero-filled -- the reference substitutes np.random noise) and
+ *   for slots >= counts (patch left untouched).  patch_w must be a multiple of 4 and <= 512. */
+int dd_extract_patches(const uint8_t* frames, int32_t b, int32_t img_h, int32_t img_w, const double* boxes,
+                       const int32_t* counts, int32_t dmax, int32_t boxes_are_int, int32_t patch_h,
+                       int32_t patch_w, uint8_t* out_patches, int32_t* out_valid, void* stream);
+
+/* DummyImageEncoder.__call__ (tools/generate_detections.py:86-105), the reference's arithmetic stand-in for the
+ * MARS CNN: patches u8 [n,16,8,3] -> out_feat f32 [n,128] (channel mean - 128, L2-normalised; bit-exact). */
+int dd_dummy_encode(const uint8_t* patches, int32_t n, float* out_feat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,9 +255,58 @@ def golden_ssd_post(R):
     print("ssd_post.npz", sum(len(res["lab%d" % c]) for c in range(cases)))
 
 
+def golden_patches(R):
+    """tools/generate_detections.py:40-84 (the unmodified reference function, cv2.resize inside), :86-116
+    (DummyImageEncoder) and :180-211 (create_box_encoder)."""
+    import importlib
+    gd = importlib.import_module("tools.generate_detections")
+    rng = np.random.default_rng(5)
+    H, W, N, NF = 240, 320, 24, 12
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    img[50:150, 100:200] = (rng.integers(0, 256, (100, 100, 1)) // 2 + np.arange(100)[None, :, None]).astype(np.uint8)
+    boxes = np.stack([rng.integers(-20, W, N), rng.integers(-20, H, N), rng.integers(1, 90, N),
+                      rng.integers(1, 160, N)], 1).astype(np.int64)
+    boxes[0] = [W - 10, H - 10, 30, 60]     # mostly outside
+    boxes[1] = [W + 60, 100, 20, 40]        # fully outside -> None
+    boxes[2] = [10, 10, 1, 2]
+    boxes[3] = [40, 20, 128, 256]           # taller than the frame: clipped, then 2:1-ish downscale
+    boxes[4] = [5, 5, 300, 230]             # strong horizontal downscale
+
+    def run(bs, shape):
+        out = np.zeros((len(bs),) + shape + (3,), np.uint8)
+        valid = np.zeros(len(bs), np.int32)
+        for i, b in enumerate(bs):
+            p = gd.extract_image_patch(img, b.copy(), shape)
+            if p is not None:
+                out[i], valid[i] = p, 1
+        return out, valid
+
+    patches, valid = run(boxes, (128, 64))
+    # float boxes take the other arithmetic path of the same function (no truncation before astype(int))
+    fboxes = boxes[:NF].astype(np.float64) + rng.uniform(-0.9, 0.9, (NF, 4))
+    fboxes[:, 2:] = np.maximum(fboxes[:, 2:], 1.0)
+    fpatches, fvalid = run(fboxes, (128, 64))
+    # the reference's own arithmetic encoder: create_box_encoder('dummy') = extract_image_patch at 16x8 +
+    # DummyImageEncoder; valid boxes only (a failed patch is replaced by np.random noise there)
+    dpatches, dvalid = run(boxes, (16, 8))
+    dboxes = boxes[dvalid == 1]
+    dpatches = dpatches[dvalid == 1]
+    dfeat = gd.create_box_encoder("dummy")(img, list(dboxes))
+    flat = np.zeros((3, 16, 8, 3), np.uint8); flat[0] = 128; flat[1] = 7; flat[2, 3, 2] = (255, 0, 1)
+    dflat = gd.DummyImageEncoder()(flat)
+    np.savez_compressed(os.path.join(OUT, "patches.npz"), image=img, boxes=boxes, patches=patches, valid=valid,
+                        fboxes=fboxes, fpatches=fpatches, fvalid=fvalid, dboxes=dboxes, dpatches=dpatches,
+                        dfeat=dfeat, flat=flat, dflat=dflat)
+    print("patches.npz valid", int(valid.sum()), "of", len(valid), "float", int(fvalid.sum()), "dummy", len(dboxes))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = refload.load()
+    if os.environ.get("DD_GOLDEN_ONLY") == "patches":
+        golden_patches(R)
+        return
+    golden_patches(R)
     golden_kalman(R)
     golden_metric_iou(R)
     golden_nms(R)
