@@ -175,9 +175,10 @@ def gpu_arm(args):
         cpu = cpu_reference(steps=60, warm=0, preroll=100)
 
     P = args.chunks
-    if args.gate_impl is not None:
-        from deepdish_b200 import _lib
-        _lib.check(_lib.lib().dd_tuning_set(0, args.gate_impl), "dd_tuning_set")
+    from deepdish_b200 import _lib
+    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs)):
+        if val is not None:
+            _lib.check(_lib.lib().dd_tuning_set(key, val), "dd_tuning_set")
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
                         n_chunks=P)
     scene = Scene(S, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=1234 + rank, device=dev)
@@ -345,7 +346,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gate-impl", type=int, default=None, help="A/B knob: 1 TMA-staged gallery pass, 0 direct loads")
+    ap.add_argument("--gate-impl", type=int, default=None, help="A/B knob: gallery kernel 2 persistent work list (default), 0 full grid, 1 TMA ring")
+    ap.add_argument("--cosine-ctas", type=int, default=None, help="A/B knob: CTAs per SM of the persistent gallery kernel")
+    ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
+    ap.add_argument("--prio", type=int, default=None, help="A/B knob: 1 = small kernels at high priority, 0 = equal")
     ap.add_argument("--chunks", type=int, default=4, help="stream chunks pipelined on separate CUDA streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

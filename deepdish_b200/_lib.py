@@ -27,7 +27,7 @@ class TrackerConfig(ctypes.Structure):
 LAYOUT_FIELDS = ["n_tracks", "next_id", "n_deleted", "err", "order", "deleted", "counts", "mean", "cov",
                  "track_id", "hits", "age", "tsu", "state", "gal_len", "gal_pos", "gal", "lab_cnt",
                  "lab_sum", "path_n", "path_last", "path_crossed", "gate", "cost", "det_xyah",
-                 "det_featn", "det_slot", "det_kind", "cdesc"]
+                 "det_featn", "det_slot", "det_kind", "cdesc", "work", "work_ctl", "galh", "det_feath"]
 
 
 class TrackerLayout(ctypes.Structure):
@@ -49,6 +49,8 @@ def field_specs(cfg):
         "path_last": (d, (S, T, 2)), "path_crossed": (i, (S, T)), "gate": (i, (S, T, DW)),
         "cost": (f, (S, T, D)), "det_xyah": (d, (S, D, 4)), "det_featn": (f, (S, D, 128)),
         "det_slot": (i, (S, D)), "det_kind": (i, (S, D)), "cdesc": (i, (S, T, 2)),
+        "work": (i, (S * T,)), "work_ctl": (i, (64,)),
+        "galh": ("float16", (S, T, B, 128)), "det_feath": ("float16", (S, D, 128)),
     }
 
 
@@ -93,13 +95,14 @@ def lib():
         "dd_tracker_predict": [_vp, cfgp, _vp],
         "dd_tracker_update": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
         "dd_tracker_update_profiled": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       ctypes.POINTER(_vp)],
+                                       ctypes.POINTER(_vp), _vp, _vp],
         "dd_tuning_set": [_i32, _i32],
         "dd_event_create": [ctypes.POINTER(_vp)],
         "dd_event_destroy": [_vp],
         "dd_event_elapsed_ms": [_vp, _vp, ctypes.POINTER(ctypes.c_float)],
         "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
         "dd_tracker_tick": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+        "dd_tracker_tick_chained": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
         "dd_tracker_count_reduce": [_vp, cfgp, _vp, _vp],
         "dd_tracker_status": [_vp, cfgp, ctypes.POINTER(_i32), _vp],
         "dd_kalman_initiate": [_vp, _vp, _vp, _i32, _vp],

@@ -21,7 +21,7 @@ import torch
 from . import _lib
 
 _DT = {"int32": torch.int32, "int64": torch.int64, "float32": torch.float32,
-       "float64": torch.float64}
+       "float64": torch.float64, "float16": torch.float16}
 
 
 class _Chunk:
@@ -48,6 +48,8 @@ class _Chunk:
             self.v[name] = self.blob[off:off + n].view(_DT[dt]).view(shape)
         self.done = torch.cuda.Event()
         self.staging = None
+        self.turn_done = None     # C-ABI event: this chunk's gallery kernel of the latest tick has finished
+        self.turn_wait = None     # the previous chunk's turn_done
 
 
 class _CatView:
@@ -109,6 +111,14 @@ class BatchedTracker:
         self.total_counts = torch.zeros((C, 4), dtype=torch.int64, device=self.device)
         self._tick = 0
         self._sum_done = [None, None]
+        self.chain_gallery = n_chunks > 1
+        if n_chunks > 1:          # chunks take turns on the HBM-bound gallery kernel (dd_tracker_tick_chained)
+            for c in self.chunks:
+                h = ctypes.c_void_p()
+                _lib.check(self.lib.dd_event_create(ctypes.byref(h)), "dd_event_create")
+                c.turn_done = h
+            for i, c in enumerate(self.chunks):
+                c.turn_wait = self.chunks[i - 1].turn_done
         torch.cuda.synchronize(self.device)
         for c in self.chunks:
             _lib.check(self.lib.dd_tracker_init(c.state, c.cfgp, self._sp(c)), "dd_tracker_init")
@@ -192,7 +202,7 @@ class BatchedTracker:
             raise RuntimeError("update_profiled needs n_chunks=1")
         c = self.chunks[0]
         p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
-        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events6),
+        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events6, None, None),
                    "dd_tracker_update_profiled")
         return self.det_track_id
 
@@ -241,8 +251,12 @@ class BatchedTracker:
         return self.det_track_id
 
     def _tick_call(self, c, p, out, sp):
-        _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream, out, sp),
-                   "dd_tracker_tick")
+        if self.chain_gallery:
+            _lib.check(self.lib.dd_tracker_tick_chained(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream,
+                                                        out, c.turn_wait, c.turn_done, sp), "dd_tracker_tick_chained")
+        else:
+            _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream, out,
+                                                sp), "dd_tracker_tick")
 
     def _sum_partials(self, par):
         """caller's stream: wait for the chunks' partial counters of this tick, sum them."""
@@ -360,7 +374,7 @@ class BatchedTracker:
 
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
-        names = names or [n for n in self.v.keys() if n not in ("gal", "cost", "gate", "det_featn")]
+        names = names or [n for n in self.v.keys() if n not in ("gal", "galh", "cost", "gate", "det_featn", "det_feath")]
         out = {}
         for n in names:
             t = self.v[n]

@@ -13,6 +13,9 @@
 #include "dd_tma.cuh"
 
 #define DD_WARPS 4
+#ifndef DD_COSINE_MIN_CTAS
+#define DD_COSINE_MIN_CTAS 5
+#endif
 
 #define DD_CHECK_LAUNCH()                                         \
     do {                                                          \
@@ -28,6 +31,10 @@ __global__ void __launch_bounds__(DD_WARPS * 32)
 k_prep(const DDView V, const double* __restrict__ det_tlwh, const float* __restrict__ det_feat,
        const int* __restrict__ det_count) {
     const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {      // new tick: empty work list, claim cursor at 0
+        V.work_ctl[0] = 0;
+        V.work_ctl[32] = 0;
+    }
     if (w >= V.S * V.D) return;
     SubG<DD_SUB> g;
     dd_prep_det(g, V, w / V.D, w % V.D, det_tlwh, det_feat, det_count);
@@ -42,10 +49,25 @@ __global__ void __launch_bounds__(DD_WARPS * 32) k_predict(const DDView V) {
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_gate(const DDView V, const int* __restrict__ det_count) {
-    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
-    if (w >= V.S * V.T) return;
+    // gate, then append the track indices that have something to stream to the work list of the gallery
+    // kernel: one atomicAdd per CTA (16 track indices), entries of a CTA stay in ascending order.
+    __shared__ int s_has[DD_ITEMS_PER_CTA];
+    __shared__ int s_base;
+    const int item = threadIdx.x / DD_SUB;
+    const int w = blockIdx.x * DD_ITEMS_PER_CTA + item;
     SubG<DD_SUB> g;
-    dd_gate_track(g, V, w / V.T, w % V.T, det_count);
+    int has = 0;
+    if (w < V.S * V.T) has = dd_gate_track(g, V, w / V.T, w % V.T, det_count) > 0 ? 1 : 0;
+    if (g.lane == 0) s_has[item] = has;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int h = threadIdx.x < DD_ITEMS_PER_CTA ? s_has[threadIdx.x] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, h != 0);
+        if (threadIdx.x == 0) s_base = m ? atomicAdd(V.work_ctl, __popc(m)) : 0;
+        if (threadIdx.x < DD_ITEMS_PER_CTA) s_has[threadIdx.x] = __popc(m & ((1u << threadIdx.x) - 1u));
+    }
+    __syncthreads();
+    if (has && g.lane == 0) V.work[s_base + s_has[item]] = w;
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32, 7)
@@ -55,6 +77,234 @@ k_cosine(const DDView V, const int* __restrict__ det_count) {
     WarpG g;
     DDDirectPass<WarpG> pass;
     dd_cosine_track(g, V, w / V.T, w % V.T, det_count, pass);
+}
+
+// Persistent form of the gallery kernel: a fixed grid (a few CTAs per SM, leaving registers and warp slots
+// free so that the latency-bound kernels of OTHER stream chunks can run beside it), each warp claims track
+// indices from the work list k_gate built until it is empty.  No idle warps (45 % of the track indices have
+// nothing to stream), no CTA churn, a balanced tail; the pass itself is software-pipelined.
+template <bool CS>
+__global__ void __launch_bounds__(DD_WARPS * 32, DD_COSINE_MIN_CTAS)
+k_cosine_work(const DDView V, const int* __restrict__ det_count) {
+    WarpG g;
+    const int n = V.work_ctl[0];
+    DDPipelinedPass<CS> pass;
+    for (;;) {
+        int i = 0;
+        if (g.lane == 0) i = atomicAdd(V.work_ctl + 32, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const int w = V.work[i];
+        dd_cosine_track(g, V, w / V.T, w % V.T, det_count, pass);
+    }
+}
+
+
+// ---- half-precision pre-pass + exact re-check ("k_cosine_h") ---------------------------------------------
+// The gallery kernel is bound by HBM bytes, so it streams the round-to-nearest HALF copy of the gallery
+// (galh, 256 B per row instead of 512) and uses it only to decide which rows can hold the exact maximum:
+//   a(r, n) = tensor-core dot (mma.sync m16n8k16, f16 inputs, f32 accumulate) of half row r and half query n,
+//   e(r, n) = the f32 value the exact pass computes (4 FMAs per lane + the 16-8-4-2-1 butterfly).
+// |a - e| <= E := 1.1e-3 for unit vectors (2^-10 from rounding both operands to half, Cauchy-Schwarz; 1e-4 of
+// slack for the tensor-core accumulation and 1e-5 for the f32 pass itself).  With m = max_r a(r, n) the row
+// r* that maximises e satisfies a(r*, n) >= m - 2E, so the exact maximum is the maximum of e over the rows with
+// a >= m - 2E -- typically one or two rows, read from the f32 gallery and evaluated with exactly the
+// arithmetic of the exact pass.  The cost matrix is therefore bit-identical, whatever the data; only the number
+// of re-checked rows (speed) depends on it.
+// Fragment trick: a dot product does not care about the order of its terms, so each thread feeds the mma with
+// the eight consecutive halves it loaded with one 16-byte load (lane = 4 g + t reads bytes 16 t + 64 j of row
+// g and row g + 8, j = 0..3) and takes the B operand from the same bytes of query g: fully sectored loads, no
+// shared-memory transposition.  Up to 8 gate-passing detections share one pass over the gallery.
+#define DD_H_WINDOW 2.2e-3f
+
+__device__ __forceinline__ void dd_mma_f16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3,
+                                           unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct DDHalfSmem {          // per warp
+    float* approx;           // [rows_pad][8]  a(r, n); overwritten with e(r, n) for the re-checked entries
+    unsigned short* cand;    // [rows_pad * 8] re-check list, entry = row << 3 | n
+    float* thr;              // [8]            m - 2E per query
+    int* cj;                 // [8]            detection index of each query column
+};
+__host__ __device__ inline int dd_half_rows_pad(int B) { return (B + 15) & ~15; }
+__host__ __device__ inline size_t dd_half_smem_per_warp(int B) {
+    return (size_t)dd_half_rows_pad(B) * 8 * 6 + 64;
+}
+
+// one track index: all its gate-passing detections, 8 at a time
+__device__ __forceinline__ void dd_cosine_track_half(const WarpG& g, const DDView& V, int s, int t,
+                                                     const int* __restrict__ det_count, const DDHalfSmem& sm) {
+    const int* desc = V.cdesc + ((size_t)s * V.T + t) * 2;
+    if (desc[1] <= 0) return;
+    const int d0 = desc[0];
+    const size_t slot = (size_t)s * V.T + (d0 & 0xffff);
+    const int glen = d0 >> 16;
+    int nd = det_count[s];
+    if (nd > V.D) nd = V.D;
+    const int gq = g.lane >> 2, tq = g.lane & 3;
+    const uint4* galh = (const uint4*)(V.galh + slot * (size_t)V.B * DD_FEAT_DIM);       // 16 uint4 per row
+    const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
+    const int last = glen - 1;
+    int base = 0;
+    unsigned word = nd > 0 ? V.gate[slot * V.DW] : 0u;
+    for (;;) {
+        // ---- next group of <= 8 gate-passing detections
+        int nq = 0;
+        while (nq < 8) {
+            if (!word) {
+                base += 32;
+                if (base >= nd) break;
+                word = V.gate[slot * V.DW + (base >> 5)];
+                continue;
+            }
+            if (g.lane == 0) sm.cj[nq] = base + dd_ctz(word);
+            ++nq;
+            word &= word - 1;
+        }
+        if (nq == 0) break;
+        __syncwarp();
+        const int myq = gq < nq ? sm.cj[gq] : 0;       // detection whose half row feeds column gq
+        if (glen <= 0) {
+            if (g.lane < nq) V.cost[slot * V.D + sm.cj[g.lane]] = dd_subf(1.0f, -3.0e38f);
+            __syncwarp();
+            continue;
+        }
+        uint4 qb[4];
+        {
+            const uint4* qh = (const uint4*)(V.det_feath + ((size_t)s * V.D + myq) * DD_FEAT_DIM);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qb[j] = gq < nq ? qh[tq + 4 * j] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---- stream the half gallery, 16 rows per step, two steps in flight
+        const int nsteps = (glen + 15) >> 4;
+        uint4 ga[2][4], gb[2][4];
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+            const uint4* r0 = galh + (size_t)dd_imin(st * 16 + gq, last) * 16 + tq;
+            const uint4* r1 = galh + (size_t)dd_imin(st * 16 + gq + 8, last) * 16 + tq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ga[st][j] = r0[4 * j]; gb[st][j] = r1[4 * j]; }
+        }
+        float mx0 = -3.0e38f, mx1 = -3.0e38f;
+        for (int step = 0; step < nsteps; step += 2) {
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+                const int cur = step + st;
+                if (cur >= nsteps) break;
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dd_mma_f16(c, ga[st][j].x, gb[st][j].x, ga[st][j].y, gb[st][j].y, qb[j].x, qb[j].y);
+                    dd_mma_f16(c, ga[st][j].z, gb[st][j].z, ga[st][j].w, gb[st][j].w, qb[j].z, qb[j].w);
+                }
+                const int nxt = cur + 2;
+                if (nxt < nsteps) {
+                    const uint4* r0 = galh + (size_t)dd_imin(nxt * 16 + gq, last) * 16 + tq;
+                    const uint4* r1 = galh + (size_t)dd_imin(nxt * 16 + gq + 8, last) * 16 + tq;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { ga[st][j] = r0[4 * j]; gb[st][j] = r1[4 * j]; }
+                }
+                const int ra = cur * 16 + gq, rb = ra + 8;
+                if (ra >= glen) { c[0] = -3.0e38f; c[1] = -3.0e38f; }      // padding rows never win
+                if (rb >= glen) { c[2] = -3.0e38f; c[3] = -3.0e38f; }
+                *(float2*)(sm.approx + ra * 8 + 2 * tq) = make_float2(c[0], c[1]);
+                *(float2*)(sm.approx + rb * 8 + 2 * tq) = make_float2(c[2], c[3]);
+                mx0 = fmaxf(mx0, fmaxf(c[0], c[2]));
+                mx1 = fmaxf(mx1, fmaxf(c[1], c[3]));
+            }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+        }
+        if (gq == 0) { sm.thr[2 * tq] = mx0 - DD_H_WINDOW; sm.thr[2 * tq + 1] = mx1 - DD_H_WINDOW; }
+        __syncwarp();
+        // ---- re-check list: every (row, query) whose approximate dot is within the window of the maximum
+        int ncand = 0;
+        const int total = nsteps * 16 * 8;
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + g.lane;
+            const int n = i & 7;
+            const bool p = n < nq && sm.approx[i] >= sm.thr[n];
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (p) sm.cand[ncand + __popc(m & ((1u << g.lane) - 1u))] = (unsigned short)i;
+            ncand += __popc(m);
+        }
+        __syncwarp();
+        // ---- exact values of the listed entries, 4 per round: the exact pass's arithmetic, bit for bit
+        for (int c0 = 0; c0 < ncand; c0 += 4) {
+            float v[4];
+            float4 a[4], q[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = sm.cand[dd_imin(c0 + k, ncand - 1)];
+                const int d = sm.cj[e & 7];
+                a[k] = gal4[(size_t)(e >> 3) * (DD_FEAT_DIM / 4) + g.lane];
+                q[k] = ((const float4*)(V.det_featn + ((size_t)s * V.D + d) * DD_FEAT_DIM))[g.lane];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float p = dd_fmaf(a[k].x, q[k].x, 0.f);
+                p = dd_fmaf(a[k].y, q[k].y, p);
+                p = dd_fmaf(a[k].z, q[k].z, p);
+                p = dd_fmaf(a[k].w, q[k].w, p);
+                v[k] = p;
+            }
+            int n = 4, o = 16;                          // transposing butterfly, as dd_fold_max
+#pragma unroll
+            for (; n > 1; n >>= 1, o >>= 1) {
+                const bool up = (g.lane & o) != 0;
+                const int half = n >> 1;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const float send = up ? v[i] : v[i + half];
+                    const float keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+#pragma unroll
+            for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+            const int k = g.lane >> 3;                  // lane L owns the total of entry c0 + (L >> 3)
+            if ((g.lane & 7) == 0 && c0 + k < ncand) sm.approx[sm.cand[c0 + k]] = v[0];
+        }
+        __syncwarp();
+        if (g.lane < nq) {                              // exact maximum per query over its re-checked rows
+            float best = -3.0e38f;
+            for (int i = 0; i < ncand; ++i) {
+                const int e = sm.cand[i];
+                if ((e & 7) == g.lane) best = fmaxf(best, sm.approx[e]);
+            }
+            V.cost[slot * V.D + sm.cj[g.lane]] = dd_subf(1.0f, best);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(DD_WARPS * 32, 4)
+k_cosine_h(const DDView V, const int* __restrict__ det_count) {
+    extern __shared__ __align__(16) char smem[];
+    WarpG g;
+    const int rows_pad = dd_half_rows_pad(V.B);
+    char* mine = smem + (size_t)(threadIdx.x >> 5) * dd_half_smem_per_warp(V.B);
+    DDHalfSmem sm;
+    sm.approx = (float*)mine;
+    sm.cand = (unsigned short*)(mine + (size_t)rows_pad * 8 * 4);
+    sm.thr = (float*)(mine + (size_t)rows_pad * 8 * 6);
+    sm.cj = (int*)(mine + (size_t)rows_pad * 8 * 6 + 32);
+    const int n = V.work_ctl[0];
+    for (;;) {
+        int i = 0;
+        if (g.lane == 0) i = atomicAdd(V.work_ctl + 32, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const int w = V.work[i];
+        dd_cosine_track_half(g, V, w / V.T, w % V.T, det_count, sm);
+    }
 }
 
 // ---- TMA-staged gallery pass ---------------------------------------------------------------------
@@ -146,7 +396,37 @@ k_cosine_tma(const DDView V, const int* __restrict__ det_count) {
     dd_cosine_track(g, V, w / V.T, w % V.T, det_count, pass);
 }
 
-static int g_gate_impl = 0;     // 1 = TMA-staged (default), 0 = direct loads (A/B baseline)
+static int g_gate_impl = 3;     // gallery kernel: 2 = persistent work-list kernel (default), 0 = one warp per
+                                // track index over the whole grid, 1 = TMA-staged ring (A/B baselines)
+static int g_cosine_ctas_per_sm = 4;   // persistent grid = SMs x this
+static int g_gallery_streaming = 0;    // 1: gallery loads are ld.global.cs (evict-first), 0: default policy
+static int g_small_priority = 1;       // 1: launch the latency-bound kernels at the highest stream priority
+
+static int dd_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// launch config carrying a per-kernel priority (cudaLaunchAttributePriority): the small latency-bound kernels
+// of one stream chunk must not queue behind the not-yet-dispatched CTAs of another chunk's gallery kernel.
+struct DDLaunch {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    DDLaunch(unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool high) {
+        static int lo = 0, hi = 0, have = 0;
+        if (!have) { cudaDeviceGetStreamPriorityRange(&lo, &hi); have = 1; }
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        attr[0].id = cudaLaunchAttributePriority;
+        attr[0].val.priority = (high && g_small_priority) ? hi : lo;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+};
 
 __global__ void __launch_bounds__(32)
 k_match(const DDView V, const double* __restrict__ det_tlwh, const int* __restrict__ det_count,
@@ -220,7 +500,9 @@ int dd_tracker_init(void* state, const dd_tracker_config* cfg, void* stream) {
     dd_tracker_layout L;
     dd_layout_compute(cfg, &L);
     cudaStream_t st = (cudaStream_t)stream;
-    // everything except the gallery is zeroed; the gallery is only ever read below gal_len
+    // everything except the gallery and its half copy (adjacent in the blob) is zeroed; both are only ever read
+    // below gal_len
+    if (L.galh != dd_align256(L.gal + 4ull * V.S * V.T * V.B * DD_FEAT_DIM) || L.lab_cnt < L.galh) return DD_ERR_INVALID;
     if (cudaMemsetAsync(state, 0, L.gal, st) != cudaSuccess) return DD_ERR_CUDA;
     if (cudaMemsetAsync((char*)state + L.lab_cnt, 0, L.total_bytes - L.lab_cnt, st) != cudaSuccess)
         return DD_ERR_CUDA;
@@ -241,7 +523,7 @@ int dd_tracker_predict(void* state, const dd_tracker_config* cfg, void* stream) 
 static int dd_update_impl(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
                           const float* det_conf, const int32_t* det_label, const float* det_feat,
                           const int32_t* det_count, int32_t* out_det_track_id, cudaStream_t st,
-                          cudaEvent_t* ev) {
+                          cudaEvent_t* ev, cudaEvent_t gallery_wait = nullptr, cudaEvent_t gallery_done = nullptr) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
@@ -253,12 +535,19 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
             return DD_ERR_CUDA;
     }
     if (ev) cudaEventRecord(ev[0], st);
-    k_prep<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_tlwh, det_feat, det_count);
-    DD_CHECK_LAUNCH();
+    {
+        DDLaunch L(items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_prep, V, det_tlwh, det_feat, det_count) != cudaSuccess) return DD_ERR_CUDA;
+    }
     if (ev) cudaEventRecord(ev[1], st);
-    k_gate<<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
-    DD_CHECK_LAUNCH();
+    {
+        DDLaunch L(items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_gate, V, det_count) != cudaSuccess) return DD_ERR_CUDA;
+    }
     if (ev) cudaEventRecord(ev[2], st);
+    // stream chunks take turns on the HBM-bound gallery kernel: one at a time at full bandwidth, while the
+    // latency-bound kernels of the other chunks run beside it in the SM resources its fixed grid leaves free
+    if (gallery_wait && cudaStreamWaitEvent(st, gallery_wait, 0) != cudaSuccess) return DD_ERR_CUDA;
     if (g_gate_impl == 1) {
         const size_t gsm = (size_t)DD_WARPS * DD_STAGES * DD_STAGE_BYTES + DD_WARPS * DD_STAGES * 8;
         static bool attr_set = false;
@@ -268,16 +557,39 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
             attr_set = true;
         }
         k_cosine_tma<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, gsm, st>>>(V, det_count);
-    } else {
+    } else if (g_gate_impl == 3 && dd_half_smem_per_warp(V.B) * DD_WARPS <= 100 * 1024) {
+        long long grid = (long long)dd_sm_count() * g_cosine_ctas_per_sm;
+        const long long need = warps_to_blocks((long long)V.S * V.T);
+        if (grid > need) grid = need;
+        const size_t hsm = dd_half_smem_per_warp(V.B) * DD_WARPS;
+        if (hsm > 48 * 1024 &&
+            cudaFuncSetAttribute(k_cosine_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm) != cudaSuccess)
+            return DD_ERR_CUDA;
+        DDLaunch L((unsigned)grid, DD_WARPS * 32, hsm, st, false);
+        if (cudaLaunchKernelEx(&L.cfg, k_cosine_h, V, det_count) != cudaSuccess) return DD_ERR_CUDA;
+    } else if (g_gate_impl == 0) {
         k_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
+    } else {
+        long long grid = (long long)dd_sm_count() * g_cosine_ctas_per_sm;
+        const long long need = warps_to_blocks((long long)V.S * V.T);
+        if (grid > need) grid = need;
+        DDLaunch L((unsigned)grid, DD_WARPS * 32, 0, st, false);
+        const cudaError_t le = g_gallery_streaming ? cudaLaunchKernelEx(&L.cfg, k_cosine_work<true>, V, det_count)
+                                                   : cudaLaunchKernelEx(&L.cfg, k_cosine_work<false>, V, det_count);
+        if (le != cudaSuccess) return DD_ERR_CUDA;
     }
     DD_CHECK_LAUNCH();
+    if (gallery_done && cudaEventRecord(gallery_done, st) != cudaSuccess) return DD_ERR_CUDA;
     if (ev) cudaEventRecord(ev[3], st);
-    k_match<<<V.S, 32, smem, st>>>(V, det_tlwh, det_count, out_det_track_id);
-    DD_CHECK_LAUNCH();
+    {
+        DDLaunch L(V.S, 32, smem, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_match, V, det_tlwh, det_count, out_det_track_id) != cudaSuccess) return DD_ERR_CUDA;
+    }
     if (ev) cudaEventRecord(ev[4], st);
-    k_apply<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, det_conf, det_label);
-    DD_CHECK_LAUNCH();
+    {
+        DDLaunch L(items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_apply, V, det_conf, det_label) != cudaSuccess) return DD_ERR_CUDA;
+    }
     if (ev) cudaEventRecord(ev[5], st);
     return DD_OK;
 }
@@ -292,16 +604,20 @@ int dd_tracker_update(void* state, const dd_tracker_config* cfg, const double* d
 int dd_tracker_update_profiled(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
                                const float* det_conf, const int32_t* det_label, const float* det_feat,
                                const int32_t* det_count, int32_t* out_det_track_id, void* stream,
-                               void* const* host_events6) {
+                               void* const* host_events6, void* gallery_wait, void* gallery_done) {
     if (!host_events6) return DD_ERR_INVALID;
     cudaEvent_t ev[6];
     for (int i = 0; i < 6; ++i) ev[i] = (cudaEvent_t)host_events6[i];
     return dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count,
-                          out_det_track_id, (cudaStream_t)stream, ev);
+                          out_det_track_id, (cudaStream_t)stream, ev, (cudaEvent_t)gallery_wait,
+                          (cudaEvent_t)gallery_done);
 }
 
 int dd_tuning_set(int32_t key, int32_t value) {
-    if (key == 0 && (value == 0 || value == 1)) { g_gate_impl = value; return DD_OK; }
+    if (key == 0 && value >= 0 && value <= 3) { g_gate_impl = value; return DD_OK; }
+    if (key == 1 && value >= 1 && value <= 16) { g_cosine_ctas_per_sm = value; return DD_OK; }
+    if (key == 2 && (value == 0 || value == 1)) { g_small_priority = value; return DD_OK; }
+    if (key == 3 && (value == 0 || value == 1)) { g_gallery_streaming = value; return DD_OK; }
     return DD_ERR_INVALID;
 }
 
@@ -331,26 +647,41 @@ int dd_tracker_countline(void* state, const dd_tracker_config* cfg, const double
     return DD_OK;
 }
 
-int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
-                    const float* det_conf, const int32_t* det_label, const float* det_feat,
-                    const int32_t* det_count, int32_t* out_det_track_id, const double* line,
-                    int line_per_stream, int64_t* out_counts, void* stream) {
+int dd_tracker_tick_chained(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                            const float* det_conf, const int32_t* det_label, const float* det_feat,
+                            const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                            int line_per_stream, int64_t* out_counts, void* gallery_wait, void* gallery_done,
+                            void* stream) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
     if (!line) return DD_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    k_predict<<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V);
-    DD_CHECK_LAUNCH();
-    rc = dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, st, nullptr);
+    {
+        DDLaunch L(items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_predict, V) != cudaSuccess) return DD_ERR_CUDA;
+    }
+    rc = dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, st, nullptr,
+                        (cudaEvent_t)gallery_wait, (cudaEvent_t)gallery_done);
     if (rc != DD_OK) return rc;
-    k_countline<<<warps_to_blocks(V.S), DD_WARPS * 32, 0, st>>>(V, line, line_per_stream);
-    DD_CHECK_LAUNCH();
+    {
+        DDLaunch L(warps_to_blocks(V.S), DD_WARPS * 32, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_countline, V, line, line_per_stream) != cudaSuccess) return DD_ERR_CUDA;
+    }
     if (out_counts) {
-        k_count_reduce<<<V.C * 4, 256, 0, st>>>(V.counts, V.S, V.C * 4, (long long*)out_counts);
-        DD_CHECK_LAUNCH();
+        DDLaunch L(V.C * 4, 256, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_count_reduce, (const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts) != cudaSuccess)
+            return DD_ERR_CUDA;
     }
     return DD_OK;
+}
+
+int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                    const float* det_conf, const int32_t* det_label, const float* det_feat,
+                    const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                    int line_per_stream, int64_t* out_counts, void* stream) {
+    return dd_tracker_tick_chained(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id,
+                                   line, line_per_stream, out_counts, nullptr, nullptr, stream);
 }
 
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* cfg, int64_t* out_counts, void* stream) {

@@ -11,13 +11,26 @@
 #include "dd_view.h"
 #include "dd_kalman.cuh"
 #include "dd_lsap.cuh"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 #define DD_INFTY_COST 1e5          // deep_sort/linear_assignment.py:8
 
 #if defined(__CUDA_ARCH__)
+// half copies of unit vectors for the gallery kernel's pre-pass (device only; the host emulation runs the
+// exact pass and never reads them)
+DD_D void dd_store_half4(unsigned short* dst, const float4& x) {
+    const __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&lo);
+    u.y = *reinterpret_cast<const unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(dst) = u;
+}
 DD_D void dd_atomic_add_ll(long long* p, long long v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 DD_D void dd_atomic_or(int* p, int v) { atomicOr(p, v); }
 #else
+inline void dd_store_half4(unsigned short*, const float4&) {}
 inline void dd_atomic_add_ll(long long* p, long long v) { *p += v; }
 inline void dd_atomic_or(int* p, int v) { *p |= v; }
 #endif
@@ -54,6 +67,7 @@ DD_HD void dd_prep_det(const G& g, const DDView& V, int s, int d, const double* 
         x.x = dd_divf(x.x, nrm); x.y = dd_divf(x.y, nrm);
         x.z = dd_divf(x.z, nrm); x.w = dd_divf(x.w, nrm);
         o4[k] = x;
+        dd_store_half4(V.det_feath + sd * DD_FEAT_DIM + 4 * k, x);
     }
 }
 
@@ -82,6 +96,11 @@ DD_HD void dd_predict_track(const G& g, const DDView& V, int s, int t) {
 // ------------------------------------------------------------------------------------------------
 #define DD_CH 4          // candidates sharing one pass over the gallery
 #define DD_ROWS 8        // gallery rows per pipeline step (8 x 512 B = 4 KB); fold size = DD_ROWS x NC
+#ifndef DD_HR1
+#define DD_HR1 8         // pipelined pass: rows per half-buffer for 1 / 2 / 3-4 candidates
+#define DD_HR2 4
+#define DD_HR4 4
+#endif
 
 // Cross-lane sum of N = ROWS * NC per-lane partials v[r * NC + c] by a transposing butterfly
 // (N - 1 + log2(32 / N) shuffles instead of 5 N), folded into a running maximum over rows per candidate.
@@ -173,6 +192,73 @@ DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
     for (int c = 0; c < NC; ++c) best[c] = b[c];
 }
 
+#if defined(__CUDACC__)
+// The same pass, software-pipelined for a warp.  Two half-buffers of HR rows each: as soon as the FMAs of one
+// half are done its registers are re-loaded with the rows 2*HR further on, before the shuffle butterfly of that
+// half runs, so a warp keeps between HR and 2*HR rows (HR * 512 B each) in flight at all times.
+// Identical arithmetic: per-lane FMA order, the butterfly's pairing by lane offsets 16, 8, 4, 2, 1 (the same
+// summation tree for every fold width) and an order-free max -> identical bits.
+// CS = true: the gallery is read with ld.global.cs (evict-first in L1 and L2): 2.5 GB stream through a 126 MB L2
+// every tick and would otherwise evict the tracker state, gate words and costs the latency-bound kernels re-read.
+template <bool CS>
+__device__ __forceinline__ float4 dd_ld_gallery(const float4* p) { return CS ? __ldcs(p) : *p; }
+
+template <int NC, int HR, bool CS>
+__device__ __forceinline__ void dd_cosine_pass_pipelined(const WarpG& g, const float4* __restrict__ gal4, int glen,
+                                                         const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
+    constexpr int N = HR * NC;
+    float4 q[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) q[c] = qp[c][g.lane];
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = -3.0e38f;
+    const float4* base = gal4 + g.lane;
+    const int last = glen - 1;
+    float4 a[2][HR];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int r = 0; r < HR; ++r) a[h][r] = dd_ld_gallery<CS>(base + (size_t)dd_imin(h * HR + r, last) * (DD_FEAT_DIM / 4));
+    for (int g0 = 0; g0 < glen; g0 += 2 * HR) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && g0 + HR >= glen) break;          // second half entirely past the end
+            float v[N];
+#pragma unroll
+            for (int r = 0; r < HR; ++r)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float p = dd_fmaf(a[h][r].x, q[c].x, 0.f);
+                    p = dd_fmaf(a[h][r].y, q[c].y, p);
+                    p = dd_fmaf(a[h][r].z, q[c].z, p);
+                    p = dd_fmaf(a[h][r].w, q[c].w, p);
+                    v[r * NC + c] = p;
+                }
+            const int nxt = g0 + 2 * HR + h * HR;
+            if (nxt < glen) {
+#pragma unroll
+                for (int r = 0; r < HR; ++r) a[h][r] = dd_ld_gallery<CS>(base + (size_t)dd_imin(nxt + r, last) * (DD_FEAT_DIM / 4));
+            }
+            dd_fold_max<NC, N>(g, v, acc);
+        }
+    }
+    float b[NC];
+    dd_fold_finish<NC, N>(g, acc, b);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) best[c] = b[c];
+}
+
+template <bool CS>
+struct DDPipelinedPass {
+    template <int NC>
+    __device__ __forceinline__ void run(const WarpG& g, const float4* gal4, int glen,
+                                        const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
+        dd_cosine_pass_pipelined<NC, (NC == 1 ? DD_HR1 : (NC == 2 ? DD_HR2 : DD_HR4)), CS>(g, gal4, glen, qp, best);
+    }
+};
+#endif
+
 template <class G>
 struct DDDirectPass {
     template <int NC>
@@ -185,7 +271,7 @@ struct DDDirectPass {
 // Gate of one track index (every t < Tmax is visited so that inactive entries get an empty descriptor):
 // f64 projection + 4x4 Cholesky per lane (redundant), lanes sweep the detections, ballot -> gate words.
 template <class G>
-DD_HD void dd_gate_track(const G& g, const DDView& V, int s, int t, const int* det_count) {
+DD_HD int dd_gate_track(const G& g, const DDView& V, int s, int t, const int* det_count) {
     int* desc = V.cdesc + ((size_t)s * V.T + t) * 2;
     bool active = t < V.n_tracks[s];
     size_t slot = 0;
@@ -195,7 +281,7 @@ DD_HD void dd_gate_track(const G& g, const DDView& V, int s, int t, const int* d
     }
     if (!active) {
         if (g.lane == 0) { desc[0] = 0; desc[1] = 0; }
-        return;
+        return 0;
     }
     int nd = det_count[s];
     if (nd > V.D) nd = V.D;
@@ -224,6 +310,7 @@ DD_HD void dd_gate_track(const G& g, const DDView& V, int s, int t, const int* d
         desc[0] = (int)(slot - (size_t)s * V.T) | (V.gal_len[slot] << 16);
         desc[1] = ncand;
     }
+    return ncand;       // > 0: the track index goes on the gallery kernel's work list
 }
 
 // Appearance cost of one track index for its gate-passing detections: one descriptor load decides
@@ -281,6 +368,7 @@ struct DDMatchSmem {
     double* tbox;      // [T][5]  x, y, x2, y2, area of the IoU-stage rows (Track.to_tlwh, track.py:84-97)
     unsigned* gate_sm; // [T][DW] gate words of the live tracks, by track index
     float* cval;       // [T][DD_CVAL] cost of the first DD_CVAL gate-passing detections of each track
+    double* dbox;      // [D][4]  this stream's detection boxes (the IoU-stage scan reads them per column)
 };
 
 DD_HD size_t dd_match_smem_base_bytes(int T, int D, int tab_cap) {
@@ -296,7 +384,8 @@ DD_HD size_t dd_match_smem_base_bytes(int T, int D, int tab_cap) {
 }
 #define DD_CVAL 4       // gate-passing costs per track kept in shared memory (the rest is read from global)
 DD_HD size_t dd_match_smem_bytes(int T, int D, int tab_cap) {
-    return dd_match_smem_base_bytes(T, D, tab_cap) + (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4;
+    return dd_match_smem_base_bytes(T, D, tab_cap) + (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4 +
+           (size_t)D * 32 + 16;
 }
 
 DD_HD void dd_match_carve(char* mem, int T, int D, int tab_cap, DDMatchSmem& m) {
@@ -324,6 +413,7 @@ DD_HD void dd_match_carve(char* mem, int T, int D, int tab_cap, DDMatchSmem& m) 
     m.tbox = (double*)p;
     m.gate_sm = (unsigned*)(mem + dd_match_smem_base_bytes(T, D, tab_cap));
     m.cval = (float*)(m.gate_sm + (size_t)T * ((D + 31) / 32));
+    m.dbox = (double*)(((uintptr_t)(m.cval + (size_t)T * DD_CVAL) + 15) & ~(uintptr_t)15);
 }
 
 // cost functors: (r, c) are positions in the rows[] / cols[] lists of the current sub-problem.
@@ -352,7 +442,7 @@ struct DDCosineCost {      // tracker.py:97-105 + linear_assignment.py:57
 
 struct DDIouCost {         // iou_matching.py:7-81 + linear_assignment.py:57
     const double* tbox;    // [nr][5] per row: x, y, x2, y2, area (INFTY rows: area < 0)
-    const double* det_tlwh;// stream base [D, 4]
+    const double* det_tlwh;// stream's boxes [D, 4] (shared-memory copy)
     const short* cols;
     double thr, clip;
     DD_HD double raw(int r, int c) const {
@@ -458,6 +548,7 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
         m.trk_det[t] = -1;
     }
     for (int d = g.lane; d < nd; d += G::NL) m.undA[d] = (short)d;
+    for (int e = g.lane; e < nd * 4; e += G::NL) m.dbox[e] = det_tlwh[sD * 4 + e];
     g.sync();
     short *und = m.undA, *und_next = m.undB;
     int nund = nd;
@@ -605,7 +696,7 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
         }
         g.sync();
         DDIouCost ic;
-        ic.tbox = m.tbox; ic.det_tlwh = det_tlwh + sD * 4; ic.cols = und;
+        ic.tbox = m.tbox; ic.det_tlwh = m.dbox; ic.cols = und;
         ic.thr = V.thr_iou; ic.clip = dd_add(V.thr_iou, 1e-5);
         if (dd_min_cost_matching(g, ic, V.thr_iou, m, nr, und, und_next, nund) != 0) infeasible = 1;
     }
@@ -724,7 +815,12 @@ DD_HD void dd_apply_det(const G& g, const DDView& V, int s, int d, const float* 
     const int len = V.gal_len[slot];
     const float4* src = (const float4*)(V.det_featn + sd * DD_FEAT_DIM);
     float4* dst = (float4*)(V.gal + (slot * (size_t)V.B + pos) * DD_FEAT_DIM);
-    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) dst[k] = src[k];
+    unsigned short* dsth = V.galh + (slot * (size_t)V.B + pos) * DD_FEAT_DIM;
+    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) {
+        const float4 x = src[k];
+        dst[k] = x;
+        dd_store_half4(dsth + 4 * k, x);
+    }
     g.sync();
     if (g.lane == 0) {
         V.gal_pos[slot] = (pos + 1 == V.B) ? 0 : pos + 1;

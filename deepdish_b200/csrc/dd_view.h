@@ -26,6 +26,8 @@ struct DDView {
     float* det_featn;
     int *det_slot, *det_kind;
     int* cdesc;
+    int *work, *work_ctl;
+    unsigned short *galh, *det_feath;
     int label_rank[DD_MAX_LABELS];
 };
 
@@ -59,6 +61,7 @@ static inline int dd_layout_compute(const dd_tracker_config* c, dd_tracker_layou
     DD_PUT(gal_len, 4 * S * T);
     DD_PUT(gal_pos, 4 * S * T);
     DD_PUT(gal, 4 * S * T * B * F);
+    DD_PUT(galh, 2 * S * T * B * F);
     DD_PUT(lab_cnt, 4 * S * T * C);
     DD_PUT(lab_sum, 8 * S * T * C);
     DD_PUT(path_n, 4 * S * T);
@@ -71,6 +74,9 @@ static inline int dd_layout_compute(const dd_tracker_config* c, dd_tracker_layou
     DD_PUT(det_slot, 4 * S * D);
     DD_PUT(det_kind, 4 * S * D);
     DD_PUT(cdesc, 4 * S * T * 2);
+    DD_PUT(work, 4 * S * T);
+    DD_PUT(work_ctl, 4 * 64);
+    DD_PUT(det_feath, 2 * S * D * F);
 #undef DD_PUT
     L->total_bytes = off;
     return DD_OK;
@@ -104,6 +110,8 @@ static inline int dd_make_view(void* blob, const dd_tracker_config* c, DDView* v
     v->det_xyah = (double*)(b + L.det_xyah); v->det_featn = (float*)(b + L.det_featn);
     v->det_slot = (int*)(b + L.det_slot); v->det_kind = (int*)(b + L.det_kind);
     v->cdesc = (int*)(b + L.cdesc);
+    v->galh = (unsigned short*)(b + L.galh); v->det_feath = (unsigned short*)(b + L.det_feath);
+    v->work = (int*)(b + L.work); v->work_ctl = (int*)(b + L.work_ctl);
     for (int i = 0; i < DD_MAX_LABELS; ++i) v->label_rank[i] = i < c->n_labels ? c->label_rank[i] : 0;
     return DD_OK;
 }

@@ -102,6 +102,13 @@ typedef struct dd_tracker_layout {
     uint64_t det_kind;      /* i32 [S,Dmax]       0 none, 1 Kalman update, 2 new track              */
     uint64_t cdesc;         /* i32 [S,Tmax,2]     per track index: slot | gallery rows << 16, #gate-passing
                                                   detections (0 = nothing to stream)                        */
+    uint64_t work;          /* i32 [S*Tmax]       work list of the gallery kernel: s * Tmax + track index of
+                                                  every track with a gate-passing detection (any order)     */
+    uint64_t work_ctl;      /* i32 [64]           [0] = entries in `work`, [32] = claim cursor              */
+    uint64_t galh;          /* f16 [S,Tmax,budget,128]  round-to-nearest half copy of `gal` (same ring positions):
+                                                  what the gallery kernel streams; `gal` rows are re-read only
+                                                  for the few rows that can hold the exact maximum           */
+    uint64_t det_feath;     /* f16 [S,Dmax,128]   half copy of det_featn                                     */
 } dd_tracker_layout;
 
 /* Host-only arithmetic: fills `host_out`.  No CUDA call. */
@@ -129,13 +136,18 @@ int dd_tracker_update(void* state, const dd_tracker_config* host_cfg,
 /* dd_tracker_update that also records six caller-supplied CUDA events on `stream`: before the
  * detection prep kernel and after each of prep / gate / cosine / match / apply (no synchronisation), so a
  * benchmark can time each kernel inside its own timed region.  host_events6: host array of 6 events
- * made by dd_event_create. */
+ * made by dd_event_create.  gallery_wait / gallery_done (may be NULL): as in dd_tracker_tick_chained. */
 int dd_tracker_update_profiled(void* state, const dd_tracker_config* host_cfg,
                                const double* det_tlwh, const float* det_conf, const int32_t* det_label,
                                const float* det_feat, const int32_t* det_count,
-                               int32_t* out_det_track_id, void* stream, void* const* host_events6);
-/* Process-wide tuning knob for A/B measurements: key 0 = gallery pass of the gate+cosine kernel
- * (1 = TMA-staged through shared memory, default; 0 = direct register loads). */
+                               int32_t* out_det_track_id, void* stream, void* const* host_events6,
+                               void* gallery_wait, void* gallery_done);
+/* Process-wide tuning knobs for A/B measurements.
+ *   key 0: gallery kernel -- 2 = persistent work-list kernel with a software-pipelined pass (default),
+ *          0 = one warp per track index over the whole grid, 1 = TMA-staged ring through shared memory;
+ *   key 1: CTAs per SM of the persistent gallery kernel (1..16, default 4);
+ *   key 2: 1 = launch the latency-bound kernels at the highest priority (default), 0 = all equal;
+ *   key 3: 1 = gallery loads use ld.global.cs (evict-first in L2), 0 = default cache policy (default). */
 int dd_tuning_set(int32_t key, int32_t value);
 int dd_event_create(void** host_out);
 int dd_event_destroy(void* ev);
@@ -152,6 +164,15 @@ int dd_tracker_tick(void* state, const dd_tracker_config* host_cfg, const double
                     const float* det_conf, const int32_t* det_label, const float* det_feat,
                     const int32_t* det_count, int32_t* out_det_track_id, const double* line,
                     int line_per_stream, int64_t* out_counts, void* stream);
+
+/* dd_tracker_tick for one of several stream chunks that share the GPU, each on its own CUDA stream: the chunk
+ * waits for `gallery_wait` (a dd_event_create event, may be NULL) before its HBM-bound gallery kernel and records
+ * `gallery_done` (may be NULL) after it, so the chunks take turns on that kernel while everything else overlaps. */
+int dd_tracker_tick_chained(void* state, const dd_tracker_config* host_cfg, const double* det_tlwh,
+                            const float* det_conf, const int32_t* det_label, const float* det_feat,
+                            const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                            int line_per_stream, int64_t* out_counts, void* gallery_wait, void* gallery_done,
+                            void* stream);
 
 /* Sum the per-stream counters into out_counts i64 [C,4] (the tensor handed to the NCCL all-reduce). */
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int64_t* out_counts,
