@@ -180,7 +180,7 @@ def gpu_arm(args):
         if val is not None:
             _lib.check(_lib.lib().dd_tuning_set(key, val), "dd_tuning_set")
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
-                        n_chunks=P)
+                        n_chunks=P, chain_gallery=bool(args.chain))
     scene = Scene(S, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=1234 + rank, device=dev)
     pre = [scene.step() for _ in range(PREROLL)]
     for b in pre:
@@ -227,12 +227,14 @@ def gpu_arm(args):
     bt.check()
 
     # ---- end-to-end through the public API with pinned host buffers (same tracker, next K ticks)
-    host = [b.to("cpu").pin() for b in e2e_dev]
+    # the host batch is ragged, like the reference's per-stream lists of Detection objects: one pinned blob per
+    # stream chunk holding only the detections that exist (BatchedTracker.pack_host)
+    host = [bt.pack_host(b) for b in e2e_dev]
     del e2e_dev
     ids_host = torch.empty((S, DMAX), dtype=torch.int32).pin_memory()
     cnt_host = torch.empty((len(LABELS), 4), dtype=torch.int64).pin_memory()
     for hb in host[:W]:
-        bt.step_host(hb, ids_host)
+        bt.step_host_packed(hb, ids_host)
     bt.join()
     torch.cuda.synchronize()
     if world > 1:
@@ -241,7 +243,7 @@ def gpu_arm(args):
     tw0 = time.perf_counter()
     es.record()
     for hb in host[W:]:
-        cnt = bt.step_host(hb, ids_host)
+        cnt = bt.step_host_packed(hb, ids_host)
         cnt = bt.all_reduce_counts(reduced=True)
         cnt_host.copy_(cnt, non_blocking=True)
     bt.join()
@@ -250,7 +252,7 @@ def gpu_arm(args):
     e2e_wall_ms = 1e3 * (time.perf_counter() - tw0)
     e2e_ms = max(es.elapsed_time(ee), e2e_wall_ms)
     bt.check()
-    h2d = host[0].nbytes()
+    h2d = sum(bt.packed_nbytes(hb) for hb in host[W:]) // K
     d2h = ids_host.numel() * 4 + cnt_host.numel() * 8
     del host
 
@@ -348,6 +350,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gate-impl", type=int, default=None, help="A/B knob: gallery kernel 2 persistent work list (default), 0 full grid, 1 TMA ring")
     ap.add_argument("--cosine-ctas", type=int, default=None, help="A/B knob: CTAs per SM of the persistent gallery kernel")
+    ap.add_argument("--chain", type=int, default=0, help="A/B knob: chunks take turns on the gallery kernel")
     ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
     ap.add_argument("--prio", type=int, default=None, help="A/B knob: 1 = small kernels at high priority, 0 = equal")
     ap.add_argument("--chunks", type=int, default=4, help="stream chunks pipelined on separate CUDA streams")

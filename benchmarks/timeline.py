@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chunks", type=int, default=4)
     ap.add_argument("--ticks", type=int, default=3)
-    ap.add_argument("--chain", type=int, default=1)
+    ap.add_argument("--chain", type=int, default=0)
     ap.add_argument("--cosine-ctas", type=int, default=None)
     ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
     ap.add_argument("--prio", type=int, default=None)

@@ -76,7 +76,7 @@ class _CatView:
 class BatchedTracker:
     def __init__(self, n_streams, labels, max_tracks=128, max_dets=64, budget=100,
                  max_cosine_distance=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
-                 line=None, frame_size=(640, 480), device="cuda", n_chunks=1):
+                 line=None, frame_size=(640, 480), device="cuda", n_chunks=1, chain_gallery=False):
         self.lib = _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -111,7 +111,7 @@ class BatchedTracker:
         self.total_counts = torch.zeros((C, 4), dtype=torch.int64, device=self.device)
         self._tick = 0
         self._sum_done = [None, None]
-        self.chain_gallery = n_chunks > 1
+        self.chain_gallery = bool(chain_gallery) and n_chunks > 1
         if n_chunks > 1:          # chunks take turns on the HBM-bound gallery kernel (dd_tracker_tick_chained)
             for c in self.chunks:
                 h = ctypes.c_void_p()
@@ -285,19 +285,93 @@ class BatchedTracker:
             n = c.hi - c.lo
             st = c.stream if multi else self._cur()
             with torch.cuda.stream(st):
-                if c.staging is None:
-                    c.staging = (torch.empty((n, D, 4), dtype=torch.float64, device=self.device),
-                                 torch.empty((n, D), dtype=torch.float32, device=self.device),
-                                 torch.empty((n, D), dtype=torch.int32, device=self.device),
-                                 torch.empty((n, D, 128), dtype=torch.float32, device=self.device),
-                                 torch.empty((n,), dtype=torch.int32, device=self.device))
-                for dst, s in zip(c.staging, src):
+                for dst, s in zip(self._staging(c), src):
                     dst.copy_(s[c.lo:c.hi], non_blocking=True)
                 t, cf, lb, ft, ct = c.staging
                 ids = self.det_track_id[c.lo:c.hi]
                 self._tick_call(c, (t.data_ptr(), cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
                                     ids.data_ptr()), self.partial_counts[par, i].data_ptr(),
                                 ctypes.c_void_p(st.cuda_stream))
+                if out_ids_host is not None:
+                    out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
+        self._mark()
+        self._sum_partials(par)
+        self._tick += 1
+        return self.total_counts
+
+    # ------------------------------------------------------------------------------------------
+    def _staging(self, c):
+        if c.staging is None:
+            n, D = c.hi - c.lo, self.max_dets
+            c.staging = (torch.empty((n, D, 4), dtype=torch.float64, device=self.device),
+                         torch.empty((n, D), dtype=torch.float32, device=self.device),
+                         torch.empty((n, D), dtype=torch.int32, device=self.device),
+                         torch.empty((n, D, 128), dtype=torch.float32, device=self.device),
+                         torch.empty((n,), dtype=torch.int32, device=self.device))
+        return c.staging
+
+    def pack_host(self, batch):
+        """Ragged host form of a padded batch (the batched equivalent of the reference's per-stream list of
+        Detection objects, deepdish.py:1014): per chunk ONE pinned byte blob
+        ``[i32 offsets[n+1] | f64 tlwh[N,4] | f32 conf[N] | i32 label[N] | f32 feat[N,128]]`` holding only the
+        detections that exist, so a tick uploads one copy per chunk and no padding."""
+        import numpy as np
+        cnt = batch.count.cpu().numpy().astype(np.int64)
+        tlwh, conf = batch.tlwh.cpu().numpy(), batch.conf.cpu().numpy()
+        label, feat = batch.label.cpu().numpy(), batch.feat.cpu().numpy()
+        if int(cnt.max(initial=0)) > self.max_dets:
+            raise RuntimeError("detection capacity exceeded (max_dets=%d)" % self.max_dets)
+        out = []
+        for c in self.chunks:
+            k = cnt[c.lo:c.hi]
+            offs = np.zeros(len(k) + 1, dtype=np.int32)
+            offs[1:] = np.cumsum(k)
+            N = int(offs[-1])
+            sel = np.arange(self.max_dets)[None, :] < k[:, None]
+            o_tlwh = (4 * len(offs) + 15) // 16 * 16
+            o_conf = o_tlwh + 32 * N
+            o_label = o_conf + 4 * N
+            o_feat = (o_label + 4 * N + 15) // 16 * 16
+            total = o_feat + 512 * N
+            blob = torch.empty(max(total, 16), dtype=torch.uint8).pin_memory()
+            b = blob.numpy()
+            b[:4 * len(offs)].view(np.int32)[:] = offs
+            b[o_tlwh:o_conf].view(np.float64)[:] = tlwh[c.lo:c.hi][sel].reshape(-1)
+            b[o_conf:o_label].view(np.float32)[:] = conf[c.lo:c.hi][sel]
+            b[o_label:o_label + 4 * N].view(np.int32)[:] = label[c.lo:c.hi][sel]
+            b[o_feat:total].view(np.float32)[:] = feat[c.lo:c.hi][sel].reshape(-1)
+            out.append((blob, total, (o_tlwh, o_conf, o_label, o_feat)))
+        return out
+
+    @staticmethod
+    def packed_nbytes(packed):
+        return sum(p[1] for p in packed)
+
+    def step_host_packed(self, packed, out_ids_host=None):
+        """End-to-end tick from a ragged pinned host batch (``pack_host``): per chunk, on the chunk's stream, ONE
+        H2D copy, the unpack kernel, the tick with its partial count reduction and (optionally) the D2H copy of
+        the det->track ids.  Returns total_counts (device, summed on the caller's stream)."""
+        par = self._tick & 1
+        multi = len(self.chunks) > 1
+        if multi and self._sum_done[par] is not None:
+            for c in self.chunks:
+                c.stream.wait_event(self._sum_done[par])
+        for i, (c, (blob, total, offs)) in enumerate(zip(self.chunks, packed)):
+            n = c.hi - c.lo
+            st = c.stream if multi else self._cur()
+            with torch.cuda.stream(st):
+                if getattr(c, "blob_dev", None) is None:
+                    c.blob_dev = torch.empty(4 * (n + 1) + 64 + n * self.max_dets * (32 + 4 + 4 + 512),
+                                             dtype=torch.uint8, device=self.device)
+                c.blob_dev[:total].copy_(blob[:total], non_blocking=True)
+                t, cf, lb, ft, ct = self._staging(c)
+                sp = ctypes.c_void_p(st.cuda_stream)
+                _lib.check(self.lib.dd_unpack_detections(c.blob_dev.data_ptr(), n, self.max_dets, *offs, t.data_ptr(),
+                                                         cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
+                                                         sp), "dd_unpack_detections")
+                ids = self.det_track_id[c.lo:c.hi]
+                self._tick_call(c, (t.data_ptr(), cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
+                                    ids.data_ptr()), self.partial_counts[par, i].data_ptr(), sp)
                 if out_ids_host is not None:
                     out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
         self._mark()

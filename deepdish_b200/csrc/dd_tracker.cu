@@ -400,7 +400,7 @@ static int g_gate_impl = 3;     // gallery kernel: 2 = persistent work-list kern
                                 // track index over the whole grid, 1 = TMA-staged ring (A/B baselines)
 static int g_cosine_ctas_per_sm = 4;   // persistent grid = SMs x this
 static int g_gallery_streaming = 0;    // 1: gallery loads are ld.global.cs (evict-first), 0: default policy
-static int g_small_priority = 1;       // 1: launch the latency-bound kernels at the highest stream priority
+static int g_small_priority = 0;       // 1: launch the latency-bound kernels at the highest stream priority
 
 static int dd_sm_count() {
     static int n = 0;
@@ -480,6 +480,27 @@ k_status(const int* __restrict__ err, int S, int* __restrict__ out) {
     for (int s = threadIdx.x; s < S; s += blockDim.x) acc |= err[s];
     acc = __reduce_or_sync(0xffffffffu, acc);
     if ((threadIdx.x & 31) == 0 && acc) atomicOr(out, acc);
+}
+
+// Ragged host batch -> the padded arrays of the tick.  One warp per detection (512 B feature + box + conf + label).
+__global__ void __launch_bounds__(DD_WARPS * 32)
+k_unpack(const unsigned char* __restrict__ blob, int S, int dmax, long long off_tlwh, long long off_conf,
+         long long off_label, long long off_feat, double* __restrict__ det_tlwh, float* __restrict__ det_conf,
+         int* __restrict__ det_label, float* __restrict__ det_feat, int* __restrict__ det_count) {
+    const int* offs = (const int*)blob;                           // [S + 1]
+    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= S * dmax) return;
+    const int s = w / dmax, d = w - s * dmax;
+    const int o0 = offs[s];
+    const int n = offs[s + 1] - o0;
+    if (d == 0 && lane == 0) det_count[s] = n;                    // n > dmax: the tick raises DD_FLAG_DET_OVERFLOW
+    if (d >= n) return;
+    const size_t src = (size_t)o0 + d, dst = (size_t)s * dmax + d;
+    ((float4*)(det_feat + dst * DD_FEAT_DIM))[lane] = ((const float4*)(blob + off_feat) + src * (DD_FEAT_DIM / 4))[lane];
+    if (lane < 4) det_tlwh[dst * 4 + lane] = ((const double*)(blob + off_tlwh))[src * 4 + lane];
+    if (lane == 4) det_conf[dst] = ((const float*)(blob + off_conf))[src];
+    if (lane == 5) det_label[dst] = ((const int*)(blob + off_label))[src];
 }
 
 static inline int warps_to_blocks(long long n_warps) { return (int)((n_warps + DD_WARPS - 1) / DD_WARPS); }
@@ -682,6 +703,19 @@ int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det
                     int line_per_stream, int64_t* out_counts, void* stream) {
     return dd_tracker_tick_chained(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id,
                                    line, line_per_stream, out_counts, nullptr, nullptr, stream);
+}
+
+int dd_unpack_detections(const void* blob, int32_t n_streams, int32_t max_dets, int64_t off_tlwh, int64_t off_conf,
+                         int64_t off_label, int64_t off_feat, double* det_tlwh, float* det_conf,
+                         int32_t* det_label, float* det_feat, int32_t* det_count, void* stream) {
+    if (!blob || !det_tlwh || !det_conf || !det_label || !det_feat || !det_count) return DD_ERR_INVALID;
+    if (n_streams <= 0 || max_dets <= 0) return DD_ERR_INVALID;
+    if ((off_tlwh & 7) || (off_conf & 3) || (off_label & 3) || (off_feat & 15) || ((uintptr_t)blob & 15)) return DD_ERR_INVALID;
+    k_unpack<<<warps_to_blocks((long long)n_streams * max_dets), DD_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const unsigned char*)blob, n_streams, max_dets, off_tlwh, off_conf, off_label, off_feat, det_tlwh, det_conf,
+        det_label, det_feat, det_count);
+    DD_CHECK_LAUNCH();
+    return DD_OK;
 }
 
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* cfg, int64_t* out_counts, void* stream) {

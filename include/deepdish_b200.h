@@ -143,10 +143,11 @@ int dd_tracker_update_profiled(void* state, const dd_tracker_config* host_cfg,
                                int32_t* out_det_track_id, void* stream, void* const* host_events6,
                                void* gallery_wait, void* gallery_done);
 /* Process-wide tuning knobs for A/B measurements.
- *   key 0: gallery kernel -- 2 = persistent work-list kernel with a software-pipelined pass (default),
- *          0 = one warp per track index over the whole grid, 1 = TMA-staged ring through shared memory;
+ *   key 0: gallery kernel -- 3 = half-precision pre-pass on tensor cores + exact re-check of the rows that can
+ *          hold the maximum (default; bit-identical costs), 2 = persistent work-list kernel with a
+ *          software-pipelined exact pass, 0 = one warp per track index over the whole grid, 1 = TMA-staged ring;
  *   key 1: CTAs per SM of the persistent gallery kernel (1..16, default 4);
- *   key 2: 1 = launch the latency-bound kernels at the highest priority (default), 0 = all equal;
+ *   key 2: 1 = launch the latency-bound kernels at the highest priority, 0 = all equal (default);
  *   key 3: 1 = gallery loads use ld.global.cs (evict-first in L2), 0 = default cache policy (default). */
 int dd_tuning_set(int32_t key, int32_t value);
 int dd_event_create(void** host_out);
@@ -173,6 +174,17 @@ int dd_tracker_tick_chained(void* state, const dd_tracker_config* host_cfg, cons
                             const int32_t* det_count, int32_t* out_det_track_id, const double* line,
                             int line_per_stream, int64_t* out_counts, void* gallery_wait, void* gallery_done,
                             void* stream);
+
+/* Ragged detection batch -> the padded arrays dd_tracker_tick consumes.  The reference hands Tracker.update a
+ * Python list of Detection objects per stream (deepdish.py:1014); its batched equivalent is one contiguous blob
+ * (what a host uploads with a single copy):  i32 offsets[S+1] (stream s owns entries offsets[s]..offsets[s+1]),
+ * then at the given byte offsets f64 tlwh[N][4], f32 conf[N], i32 label[N], f32 feat[N][128], N = offsets[S].
+ * Writes det_count[s] and the first det_count[s] rows of each padded array (rows beyond are left untouched;
+ * a stream with more than max_dets entries gets det_count > max_dets, which the tick reports as
+ * DD_FLAG_DET_OVERFLOW).  blob and off_feat must be 16-byte aligned. */
+int dd_unpack_detections(const void* blob, int32_t n_streams, int32_t max_dets, int64_t off_tlwh, int64_t off_conf,
+                         int64_t off_label, int64_t off_feat, double* det_tlwh, float* det_conf,
+                         int32_t* det_label, float* det_feat, int32_t* det_count, void* stream);
 
 /* Sum the per-stream counters into out_counts i64 [C,4] (the tensor handed to the NCCL all-reduce). */
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int64_t* out_counts,

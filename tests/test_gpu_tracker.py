@@ -112,10 +112,15 @@ def test_stream_chunks_pipelined_and_step_host():
     for f in range(60):
         b = sc.step()
         ids = orc.step(b)
-        if f % 2 == 0:
+        if f % 3 == 0:
             bt.step(b.to("cuda"), join=False, reduce=True)
             bt.join()
             got = bt.det_track_id.cpu().numpy()
+        elif f % 3 == 1:              # ragged pinned host batch: one H2D copy per chunk + unpack kernel
+            bt.step_host_packed(bt.pack_host(b), ids_host)
+            bt.join()
+            torch.cuda.synchronize()
+            got = ids_host.numpy().copy()
         else:
             bt.step_host(b.pin(), ids_host)
             bt.join()
