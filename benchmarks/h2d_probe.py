@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Host-to-device bandwidth of one pinned buffer split over k concurrent CUDA streams (what bounds bench.py's e2e)."""
+import torch
+
+def main():
+    n = 26_600_000
+    h = torch.randint(0, 255, (n,), dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for k in (1, 2, 3, 4, 6, 8, 12):
+        streams = [torch.cuda.Stream() for _ in range(k)]
+        step = (n + k - 1) // k
+        def go():
+            ev = torch.cuda.current_stream().record_event()
+            for i, st in enumerate(streams):
+                st.wait_event(ev)
+                with torch.cuda.stream(st):
+                    d[i * step:(i + 1) * step].copy_(h[i * step:(i + 1) * step], non_blocking=True)
+                torch.cuda.current_stream().wait_event(st.record_event())
+        for _ in range(3):
+            go()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(20):
+            go()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 20
+        print("H2D 26.6 MB over %2d streams: %.4f ms  %.1f GB/s" % (k, ms, n / ms / 1e6))
+
+if __name__ == "__main__":
+    main()

@@ -348,9 +348,11 @@ class BatchedTracker:
         return sum(p[1] for p in packed)
 
     def step_host_packed(self, packed, out_ids_host=None):
-        """End-to-end tick from a ragged pinned host batch (``pack_host``): per chunk, on the chunk's stream, ONE
-        H2D copy, the unpack kernel, the tick with its partial count reduction and (optionally) the D2H copy of
-        the det->track ids.  Returns total_counts (device, summed on the caller's stream)."""
+        """End-to-end tick from a ragged pinned host batch (``pack_host``).  Per chunk: ONE H2D copy on the chunk's
+        own copy stream into a double-buffered device blob -- so the upload of tick k + 1 runs under the kernels of
+        tick k --, then on the chunk's compute stream the unpack kernel, the tick with its partial count reduction
+        and (optionally) the D2H copy of the det->track ids.  The pinned blobs must stay alive until their copy has
+        run.  Returns total_counts (device, summed on the caller's stream)."""
         par = self._tick & 1
         multi = len(self.chunks) > 1
         if multi and self._sum_done[par] is not None:
@@ -359,16 +361,25 @@ class BatchedTracker:
         for i, (c, (blob, total, offs)) in enumerate(zip(self.chunks, packed)):
             n = c.hi - c.lo
             st = c.stream if multi else self._cur()
+            if getattr(c, "copy_stream", None) is None:
+                c.copy_stream = torch.cuda.Stream(device=self.device)
+                cap = 4 * (n + 1) + 64 + n * self.max_dets * (32 + 4 + 4 + 512)
+                c.blob_dev = [torch.empty(cap, dtype=torch.uint8, device=self.device) for _ in range(2)]
+                c.unpacked = [None, None]
+            dev_blob = c.blob_dev[par]
+            if c.unpacked[par] is not None:               # the unpack kernel of tick k - 2 has read this buffer
+                c.copy_stream.wait_event(c.unpacked[par])
+            with torch.cuda.stream(c.copy_stream):
+                dev_blob[:total].copy_(blob[:total], non_blocking=True)
+                copied = c.copy_stream.record_event()
             with torch.cuda.stream(st):
-                if getattr(c, "blob_dev", None) is None:
-                    c.blob_dev = torch.empty(4 * (n + 1) + 64 + n * self.max_dets * (32 + 4 + 4 + 512),
-                                             dtype=torch.uint8, device=self.device)
-                c.blob_dev[:total].copy_(blob[:total], non_blocking=True)
+                st.wait_event(copied)
                 t, cf, lb, ft, ct = self._staging(c)
                 sp = ctypes.c_void_p(st.cuda_stream)
-                _lib.check(self.lib.dd_unpack_detections(c.blob_dev.data_ptr(), n, self.max_dets, *offs, t.data_ptr(),
+                _lib.check(self.lib.dd_unpack_detections(dev_blob.data_ptr(), n, self.max_dets, *offs, t.data_ptr(),
                                                          cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
                                                          sp), "dd_unpack_detections")
+                c.unpacked[par] = st.record_event()
                 ids = self.det_track_id[c.lo:c.hi]
                 self._tick_call(c, (t.data_ptr(), cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
                                     ids.data_ptr()), self.partial_counts[par, i].data_ptr(), sp)
