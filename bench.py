@@ -314,7 +314,7 @@ def gpu_arm(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K,
                     "host_enqueue_ms_per_step": e2e_enq_ms / K},
             "host_enqueue_ms_per_step": enq_ms / K,
-            "gpu_launches": K * 8 * P,
+            "gpu_launches": K * 7 * P,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_cosine", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic("k_cosine"), "peak_source": peak_src,

@@ -1,13 +1,14 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tracker.py -x -q -k "chunks" 2>&1 | tail -2
-for cfg in "--chunks 1" "--chunks 2" "--chunks 4"; do
+python -m pytest tests/test_gpu_tracker.py tests/test_gpu_golden.py tests/test_gpu_pipeline.py tests/test_gpu_api.py -x -q 2>&1 | tail -2
+for cfg in "--chunks 1" "--chunks 2" "--chunks 3"; do
   n=$(echo $cfg | tr -d ' -')
   python bench.py --steps 30 --warmup 5 --no-cpu-baseline $cfg > gpurun_out/b_$n.json 2> gpurun_out/b_$n.err
   python - <<PY
 import json
 for l in open("gpurun_out/b_$n.json"):
     if l.startswith("{"):
-        d=json.loads(l); s=d["stage_ms"]; print("$cfg", round(d["value"]), "enq", d["host_enqueue_ms_per_step"], "e2e", d["e2e"])
+        d=json.loads(l); s=d["stage_ms"]; print("$cfg", round(d["value"]), "e2e", round(d["e2e"]["value"]), {k: round(v,4) for k,v in s.items() if k!="pass"})
 PY
   tail -2 gpurun_out/b_$n.err
 done
+cd benchmarks; python timeline.py --chunks 2 --ticks 3 --chain 0 | tail -7

@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(DD_WARPS * 32) k_predict(const DDView V) {
     dd_predict_track(g, V, w / V.T, w % V.T);
 }
 
+// PREDICT = true: Tracker.predict of the same track index first (the fused tick): the 8 lanes that gate a track
+// have just written its predicted mean / covariance, so the state is read back from L1 instead of HBM and one
+// launch disappears.
+template <bool PREDICT>
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_gate(const DDView V, const int* __restrict__ det_count) {
     // gate, then append the track indices that have something to stream to the work list of the gallery
@@ -57,7 +61,13 @@ k_gate(const DDView V, const int* __restrict__ det_count) {
     const int w = blockIdx.x * DD_ITEMS_PER_CTA + item;
     SubG<DD_SUB> g;
     int has = 0;
-    if (w < V.S * V.T) has = dd_gate_track(g, V, w / V.T, w % V.T, det_count) > 0 ? 1 : 0;
+    if (w < V.S * V.T) {
+        if (PREDICT) {
+            dd_predict_track(g, V, w / V.T, w % V.T);
+            g.sync();
+        }
+        has = dd_gate_track(g, V, w / V.T, w % V.T, det_count) > 0 ? 1 : 0;
+    }
     if (g.lane == 0) s_has[item] = has;
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -544,7 +554,8 @@ int dd_tracker_predict(void* state, const dd_tracker_config* cfg, void* stream) 
 static int dd_update_impl(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
                           const float* det_conf, const int32_t* det_label, const float* det_feat,
                           const int32_t* det_count, int32_t* out_det_track_id, cudaStream_t st,
-                          cudaEvent_t* ev, cudaEvent_t gallery_wait = nullptr, cudaEvent_t gallery_done = nullptr) {
+                          cudaEvent_t* ev, cudaEvent_t gallery_wait = nullptr, cudaEvent_t gallery_done = nullptr,
+                          bool with_predict = false) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
@@ -563,7 +574,9 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
     if (ev) cudaEventRecord(ev[1], st);
     {
         DDLaunch L(items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st, true);
-        if (cudaLaunchKernelEx(&L.cfg, k_gate, V, det_count) != cudaSuccess) return DD_ERR_CUDA;
+        const cudaError_t le = with_predict ? cudaLaunchKernelEx(&L.cfg, k_gate<true>, V, det_count)
+                                            : cudaLaunchKernelEx(&L.cfg, k_gate<false>, V, det_count);
+        if (le != cudaSuccess) return DD_ERR_CUDA;
     }
     if (ev) cudaEventRecord(ev[2], st);
     // stream chunks take turns on the HBM-bound gallery kernel: one at a time at full bandwidth, while the
@@ -678,12 +691,8 @@ int dd_tracker_tick_chained(void* state, const dd_tracker_config* cfg, const dou
     if (rc != DD_OK) return rc;
     if (!line) return DD_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    {
-        DDLaunch L(items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st, true);
-        if (cudaLaunchKernelEx(&L.cfg, k_predict, V) != cudaSuccess) return DD_ERR_CUDA;
-    }
     rc = dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, st, nullptr,
-                        (cudaEvent_t)gallery_wait, (cudaEvent_t)gallery_done);
+                        (cudaEvent_t)gallery_wait, (cudaEvent_t)gallery_done, /*with_predict=*/true);
     if (rc != DD_OK) return rc;
     {
         DDLaunch L(warps_to_blocks(V.S), DD_WARPS * 32, 0, st, true);
