@@ -1,14 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tracker.py tests/test_gpu_golden.py tests/test_gpu_pipeline.py tests/test_gpu_api.py -x -q 2>&1 | tail -2
-for cfg in "--chunks 1" "--chunks 2" "--chunks 3"; do
-  n=$(echo $cfg | tr -d ' -')
-  python bench.py --steps 30 --warmup 5 --no-cpu-baseline $cfg > gpurun_out/b_$n.json 2> gpurun_out/b_$n.err
-  python - <<PY
-import json
-for l in open("gpurun_out/b_$n.json"):
-    if l.startswith("{"):
-        d=json.loads(l); s=d["stage_ms"]; print("$cfg", round(d["value"]), "e2e", round(d["e2e"]["value"]), {k: round(v,4) for k,v in s.items() if k!="pass"})
-PY
-  tail -2 gpurun_out/b_$n.err
-done
-cd benchmarks; python timeline.py --chunks 2 --ticks 3 --chain 0 | tail -7
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py > gpurun_out/bench_r1g.json 2> gpurun_out/bench_r1g.err; tail -2 gpurun_out/bench_r1g.err; cat gpurun_out/bench_r1g.json
+python bench.py --workload c4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4_r1g.json 2> gpurun_out/bench_c4_r1g.err; tail -3 gpurun_out/bench_c4_r1g.err; cat gpurun_out/bench_c4_r1g.json
+python bench.py --workload c4 --steps 10 --warmup 3 --no-cpu-baseline --gate-impl 0 --chunks 1 > gpurun_out/bench_c4_g0.json 2> gpurun_out/bench_c4_g0.err; tail -3 gpurun_out/bench_c4_g0.err; cat gpurun_out/bench_c4_g0.json
