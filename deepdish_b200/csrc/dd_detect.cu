@@ -345,6 +345,84 @@ k_gather_kept(const double* __restrict__ cand_tlwh, const float* __restrict__ ca
     if (threadIdx.x == 0) det_count[f] = n;
 }
 
+
+// ---- TFLite object-detector adapter (tools/tflite_object_detector.py:234-295 + tools/tflite.py:26-41) -------------
+// One warp per frame.  The detections that pass the score threshold (:254) and the deny / allow lists (:276-288)
+// are ranked by a STABLE descending sort on the score (:270-273: ties keep the op's order) -- rank = #(higher score)
+// + #(equal score, lower index) --, cut at max_results (:291-293), filtered by wanted_labels (tflite.py:31-35) and
+// emitted in rank order as [left, top, right-left, bottom-top] with int() truncation of the float32 products
+// (:256-260).
+__global__ void __launch_bounds__(128)
+k_tflite_post(const float* __restrict__ boxes, const float* __restrict__ classes, const float* __restrict__ scores,
+              const int* __restrict__ count, int b, int n, float img_w, float img_h, float score_thr,
+              const unsigned char* __restrict__ list_ok, const unsigned char* __restrict__ wanted, int n_labels,
+              int max_results, int ncap, double* __restrict__ out_tlwh, float* __restrict__ out_score,
+              int* __restrict__ out_label, int* __restrict__ out_count, int* __restrict__ out_flags) {
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= b) return;
+    const float* sc = scores + (size_t)f * n;
+    const float* cl = classes + (size_t)f * n;
+    int cnt = count[f];
+    if (cnt > n) cnt = n;
+    int flags = 0, emitted = 0;
+    // pass 1 is implicit: "alive" = passes threshold and lists; rank among alive entries
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int i = i0 + lane;
+        bool alive = false;
+        float si = 0.f;
+        int li = -1;
+        if (i < cnt) {
+            si = sc[i];
+            li = (int)cl[i];
+            if (si >= score_thr) {
+                if (li < 0 || li >= n_labels) flags |= DD_FLAG_DET_OVERFLOW;       // IndexError in the reference
+                else alive = list_ok[li] != 0;
+            }
+        }
+        int rank = 0;
+        if (alive) {
+            for (int j = 0; j < cnt; ++j) {
+                const float sj = sc[j];
+                if (!(sj >= score_thr)) continue;
+                const int lj = (int)cl[j];
+                if (lj < 0 || lj >= n_labels || !list_ok[lj]) continue;
+                rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+            }
+            if (max_results > 0 && rank >= max_results) alive = false;
+        }
+        if (alive && wanted[li]) {
+            // output position = number of emitted entries with a smaller rank: count them the same way
+            int pos = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const float sj = sc[j];
+                if (!(sj >= score_thr)) continue;
+                const int lj = (int)cl[j];
+                if (lj < 0 || lj >= n_labels || !list_ok[lj] || !wanted[lj]) continue;
+                pos += (sj > si || (sj == si && j < i)) ? 1 : 0;
+            }
+            if (pos < ncap) {
+                const float* bx = boxes + ((size_t)f * n + i) * 4;
+                const int top = (int)dd_mulf(bx[0], img_h), left = (int)dd_mulf(bx[1], img_w);
+                const int bottom = (int)dd_mulf(bx[2], img_h), right = (int)dd_mulf(bx[3], img_w);
+                double* o = out_tlwh + ((size_t)f * ncap + pos) * 4;
+                o[0] = left; o[1] = top; o[2] = right - left; o[3] = bottom - top;
+                out_score[(size_t)f * ncap + pos] = si;
+                out_label[(size_t)f * ncap + pos] = li;
+            } else {
+                flags |= DD_FLAG_DET_OVERFLOW;
+            }
+            emitted += 1;
+        }
+    }
+    emitted = __reduce_add_sync(0xffffffffu, emitted);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0) {
+        out_count[f] = emitted < ncap ? emitted : ncap;
+        out_flags[f] = flags;
+    }
+}
+
 extern "C" {
 
 int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int32_t b, int32_t nmax,
@@ -441,6 +519,24 @@ int dd_gather_detections(const double* cand_tlwh, const float* cand_score, const
     k_gather_kept<<<b, 128, 0, (cudaStream_t)stream>>>(cand_tlwh, cand_score, cand_label, label_map, n_map, ncap, keep,
                                                       nkeep, nmax, dmax, det_tlwh, det_conf, det_label, det_count,
                                                       out_flags);
+    DD_CHECK_LAUNCH();
+    return DD_OK;
+}
+
+int dd_tflite_postprocess(const float* op_boxes, const float* op_classes, const float* op_scores,
+                          const int32_t* op_count, int32_t b, int32_t n, int32_t img_w, int32_t img_h,
+                          float score_thr, const uint8_t* list_ok, const uint8_t* wanted, int32_t n_labels,
+                          int32_t max_results, int32_t ncap, double* out_tlwh, float* out_score, int32_t* out_label,
+                          int32_t* out_count, int32_t* out_flags, void* stream) {
+    if (!op_boxes || !op_classes || !op_scores || !op_count || !list_ok || !wanted || !out_tlwh || !out_score ||
+        !out_label || !out_count || !out_flags)
+        return DD_ERR_INVALID;
+    if (b < 0 || n <= 0 || n_labels <= 0 || ncap <= 0) return DD_ERR_INVALID;
+    if (b == 0) return DD_OK;
+    k_tflite_post<<<(b + 3) / 4, 128, 0, (cudaStream_t)stream>>>(op_boxes, op_classes, op_scores, op_count, b, n,
+                                                               (float)img_w, (float)img_h, score_thr, list_ok, wanted,
+                                                               n_labels, max_results, ncap, out_tlwh, out_score,
+                                                               out_label, out_count, out_flags);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }

@@ -229,6 +229,30 @@ def ssd_decode(raw_boxes, raw_scores, anchors, class_to_label, conf_thr=0.5, nms
     return out
 
 
+def tflite_postprocess(op_boxes, op_classes, op_scores, op_count, list_ok, wanted, score_thr=0.5, img_size=(640, 480),
+                       max_results=-1, ncap=None):
+    """TFLite object-detector adapter for b frames (tools/tflite_object_detector.py:234-295, tools/tflite.py:26-41).
+    op_boxes f32 [b,n,4], op_classes f32 [b,n], op_scores f32 [b,n], op_count i32 [b]; list_ok / wanted u8 [n_labels].
+    Returns dict(tlwh f64 [b,ncap,4], score f32, label i32, count i32 [b], flags i32 [b])."""
+    _need_cuda(op_boxes)
+    b, n, _ = op_boxes.shape
+    ncap = n if ncap is None else ncap
+    dev = op_boxes.device
+    out = dict(tlwh=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
+               score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
+               label=torch.full((b, ncap), -1, dtype=torch.int32, device=dev),
+               count=torch.zeros((b,), dtype=torch.int32, device=dev),
+               flags=torch.zeros((b,), dtype=torch.int32, device=dev))
+    _lib.check(_lib.lib().dd_tflite_postprocess(op_boxes.data_ptr(), op_classes.data_ptr(), op_scores.data_ptr(),
+                                                op_count.data_ptr(), b, n, int(img_size[0]), int(img_size[1]),
+                                                float(score_thr), list_ok.data_ptr(), wanted.data_ptr(),
+                                                list_ok.shape[0], int(max_results), ncap, out["tlwh"].data_ptr(),
+                                                out["score"].data_ptr(), out["label"].data_ptr(),
+                                                out["count"].data_ptr(), out["flags"].data_ptr(), _stream(dev)),
+               "dd_tflite_postprocess")
+    return out
+
+
 # ------------------------------------------------------------------------------------- encoder input
 def extract_patches(frames, boxes, counts=None, patch_shape=(128, 64), boxes_are_int=True, out=None):
     """extract_image_patch for every box of b frames (tools/generate_detections.py:40-84, 198-205).

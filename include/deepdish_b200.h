@@ -279,6 +279,20 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
                   double* out_tlwh, float* out_score, int32_t* out_label, int32_t* out_count,
                   int32_t* out_flags, void* stream);
 
+/* TFLite object-detector adapter for b frames: ObjectDetector._postprocess (tools/tflite_object_detector.py:234-295)
+ * followed by TFLITE.detect_image (tools/tflite.py:26-41), on the outputs of the model's own detection post-process op:
+ *   op_boxes f32 [b,n,4] (ymin,xmin,ymax,xmax normalised), op_classes f32 [b,n], op_scores f32 [b,n], op_count i32 [b];
+ *   list_ok u8 [n_labels]: 1 where the label passes label_deny_list / label_allow_list; wanted u8 [n_labels]: 1 where
+ *   the label is in wanted_labels; max_results <= 0 = unlimited.  Output in the reference's order (stable descending
+ *   score): out_tlwh f64 [b,ncap,4] = [left, top, right-left, bottom-top] (integers), out_score f32, out_label i32
+ *   (class id), out_count i32 [b]; out_flags i32 [b]: DD_FLAG_DET_OVERFLOW when more than ncap detections survive
+ *   or a class id is outside the label list (IndexError in the reference). */
+int dd_tflite_postprocess(const float* op_boxes, const float* op_classes, const float* op_scores,
+                          const int32_t* op_count, int32_t b, int32_t n, int32_t img_w, int32_t img_h,
+                          float score_thr, const uint8_t* list_ok, const uint8_t* wanted, int32_t n_labels,
+                          int32_t max_results, int32_t ncap, double* out_tlwh, float* out_score, int32_t* out_label,
+                          int32_t* out_count, int32_t* out_flags, void* stream);
+
 /* The step between NMS and the tracker (deepdish.py:996-998,1014): gather the kept candidates, in NMS pick
  * order, into the tracker's padded detection batch for b streams.
  *   cand_* [b,ncap] candidate arrays (dd_yolo_decode / dd_ssd_decode outputs), keep i32 [b,nmax] + nkeep i32 [b]

@@ -235,3 +235,34 @@ def ssd_postprocess(op_boxes, op_classes, op_scores, img_w, img_h, label_names, 
             out_b.append([bb[i][0], bb[i][1], bb[i][2] - bb[i][0], bb[i][3] - bb[i][1]])
             out_l.append(names[i]); out_s.append(ss[i])
     return np.array(out_b, dtype=float).reshape(-1, 4), out_l, np.array(out_s, np.float32)
+
+
+def tflite_adapter_postprocess(op_boxes, op_classes, op_scores, count, img_w, img_h, label_list, wanted,
+                               score_thr=0.5, allow=None, deny=None, max_results=-1):
+    """tools/tflite_object_detector.py:234-295 (ObjectDetector._postprocess) followed by
+    tools/tflite.py:26-41 (TFLITE.detect_image): the outputs of the model's detection post-process op (boxes
+    (ymin,xmin,ymax,xmax) normalised, class ids, scores, count) -> (boxes [left, top, w, h] ints, label names,
+    scores).  score >= threshold (:254); int() truncation of float32 products (:256-260); STABLE descending sort
+    by score (:270-273); deny / allow lists (:276-288); max_results (:291-293); then the adapter keeps the
+    detections whose label is wanted (tflite.py:31-40)."""
+    res = []
+    for i in range(int(count)):
+        if op_scores[i] >= score_thr:
+            y0, x0, y1, x1 = (np.float32(v) for v in op_boxes[i])
+            rect = (int(x0 * np.float32(img_w)), int(y0 * np.float32(img_h)), int(x1 * np.float32(img_w)),
+                    int(y1 * np.float32(img_h)))                                   # left, top, right, bottom
+            res.append((rect, label_list[int(op_classes[i])], op_scores[i]))
+    res = sorted(res, key=lambda d: d[2], reverse=True)
+    if deny is not None:
+        res = [d for d in res if d[1] not in deny]
+    if allow is not None:
+        res = [d for d in res if d[1] in allow]
+    if max_results > 0:
+        res = res[:min(len(res), max_results)]
+    boxes, labels, scores = [], [], []
+    for (l, t, r, b), lab, sc in res:
+        if lab in wanted:
+            boxes.append([l, t, r - l, b - t])
+            labels.append(lab)
+            scores.append(sc)
+    return boxes, labels, scores

@@ -255,6 +255,57 @@ def golden_ssd_post(R):
     print("ssd_post.npz", sum(len(res["lab%d" % c]) for c in range(cases)))
 
 
+def golden_tflite_adapter(R):
+    """tools/tflite.py TFLITE.detect_image over tools/tflite_object_detector.py ObjectDetector._postprocess, both
+    unmodified; the interpreter, the model metadata and the camera image are the only stand-ins."""
+    import importlib
+    import sys
+    import types
+    from PIL import Image
+    if "tflite_support" not in sys.modules:
+        ts = types.ModuleType("tflite_support")
+        ts.metadata = types.ModuleType("tflite_support.metadata")
+        sys.modules["tflite_support"] = ts
+        sys.modules["tflite_support.metadata"] = ts.metadata
+    tod = importlib.import_module("tools.tflite_object_detector")
+    tfl = importlib.import_module("tools.tflite")
+    rng = np.random.default_rng(8)
+    label_list = ["person", "bicycle", "car", "motorcycle", "bus", "truck", "dog", "chair"]
+    wanted = ["person", "car", "bus", "dog"]
+    N, cases = 25, 48
+    ob = np.zeros((cases, N, 4), np.float32); ocl = np.zeros((cases, N), np.float32)
+    osc = np.zeros((cases, N), np.float32); cnt = np.zeros(cases, np.int32)
+    opts, res = [], {}
+    img = Image.new("RGB", (640, 480))
+    for c in range(cases):
+        y0 = rng.uniform(-0.05, 0.8, N); x0 = rng.uniform(-0.05, 0.8, N)
+        ob[c] = np.stack([y0, x0, y0 + rng.uniform(0.02, 0.4, N), x0 + rng.uniform(0.02, 0.3, N)], 1)
+        ocl[c] = rng.integers(0, len(label_list), N).astype(np.float32)
+        sc = rng.uniform(0.1, 1.0, N).astype(np.float32)
+        sc[rng.integers(0, N, 6)] = sc[rng.integers(0, N, 6)]          # tied scores: the sort must be stable
+        osc[c] = sc
+        cnt[c] = rng.integers(0, N + 1)
+        o = dict(score_threshold=[0.5, 0.3, 0.0][c % 3], max_results=[-1, 5, 12][c % 3 if c % 4 else 0],
+                 label_deny_list=[None, ["chair", "dog"]][c % 2], label_allow_list=[None, None, ["person", "car", "bus"]][c % 3])
+        opts.append((o["score_threshold"], o["max_results"], c % 2, 1 if c % 3 == 2 else 0))
+        det = object.__new__(tod.ObjectDetector)
+        det._options = tod.ObjectDetectorOptions(**o)
+        det._label_list = label_list
+        det._input_size = (320, 320)
+        det.detect = (lambda d, b, k, s, n: (lambda image: d._postprocess(b, k, s, n, image.shape[1], image.shape[0])))(
+            det, ob[c], ocl[c], osc[c], int(cnt[c]))
+        ad = object.__new__(tfl.TFLITE)
+        ad.detector, ad.wanted_labels = det, wanted
+        boxes, labels, scores = ad.detect_image(img)
+        res["tlwh%d" % c] = np.array(boxes, np.int64).reshape(-1, 4)
+        res["lab%d" % c] = np.array([label_list.index(l) for l in labels], np.int32)
+        res["score%d" % c] = np.array(scores, np.float32)
+    np.savez_compressed(os.path.join(OUT, "tflite_adapter.npz"), op_boxes=ob, op_classes=ocl, op_scores=osc, count=cnt,
+                        opts=np.array(opts, np.float64), names=np.array(label_list), wanted=np.array(wanted),
+                        deny=np.array(["chair", "dog"]), allow=np.array(["person", "car", "bus"]), **res)
+    print("tflite_adapter.npz", sum(len(res["lab%d" % c]) for c in range(cases)))
+
+
 def golden_patches(R):
     """tools/generate_detections.py:40-84 (the unmodified reference function, cv2.resize inside), :86-116
     (DummyImageEncoder) and :180-211 (create_box_encoder)."""
@@ -306,6 +357,10 @@ def main():
     if os.environ.get("DD_GOLDEN_ONLY") == "patches":
         golden_patches(R)
         return
+    if os.environ.get("DD_GOLDEN_ONLY") == "tflite":
+        golden_tflite_adapter(R)
+        return
+    golden_tflite_adapter(R)
     golden_patches(R)
     golden_kalman(R)
     golden_metric_iou(R)

@@ -121,3 +121,32 @@ def test_ssd_decode_vs_oracle():
         exact += int(np.array_equal(o["tlwh"][b, :n], ib.astype(float)))
         total += n
     assert total > 100 and exact >= B - 2
+
+
+def test_tflite_adapter_golden_batched_and_facade():
+    """TFLITE adapter (tools/tflite.py + tflite_object_detector._postprocess) against the reference's own outputs."""
+    from deepdish_b200.tools.tflite import TFLITE, ObjectDetectorOptions
+    from tests import goldens
+    g = goldens.load("tflite_adapter.npz")
+    names, wanted = list(g["names"]), list(g["wanted"])
+    total = 0
+    for c in range(len(g["count"])):
+        thr, maxr, use_deny, use_allow = g["opts"][c]
+        opt = ObjectDetectorOptions(score_threshold=float(thr), max_results=int(maxr),
+                                    label_deny_list=list(g["deny"]) if use_deny else None,
+                                    label_allow_list=list(g["allow"]) if use_allow else None)
+        ad = TFLITE(wanted_labels=wanted, label_list=names, options=opt,
+                    outputs_fn=lambda img, c=c: (g["op_boxes"][c], g["op_classes"][c], g["op_scores"][c], g["count"][c]))
+        boxes, labels, scores = ad.detect_image(np.zeros((480, 640, 3), np.uint8))
+        np.testing.assert_array_equal(np.array(boxes, np.int64).reshape(-1, 4), g["tlwh%d" % c])
+        assert [names.index(l) for l in labels] == list(g["lab%d" % c])
+        np.testing.assert_array_equal(np.array(scores, np.float32), g["score%d" % c])
+        total += len(labels)
+    assert total > 100
+    # batched call: every third case shares the same options
+    ad = TFLITE(wanted_labels=wanted, label_list=names, options=ObjectDetectorOptions(score_threshold=0.5))
+    sel = [c for c in range(len(g["count"])) if tuple(g["opts"][c]) == (0.5, -1.0, 0.0, 0.0)]
+    res = ad.detect_outputs(g["op_boxes"][sel], g["op_classes"][sel], g["op_scores"][sel], g["count"][sel], (640, 480))
+    for c, (boxes, labels, scores) in zip(sel, res):
+        np.testing.assert_array_equal(np.array(boxes, np.int64).reshape(-1, 4), g["tlwh%d" % c])
+    assert len(sel) >= 4
