@@ -190,7 +190,7 @@ def gpu_arm(args):
 
     P = args.chunks
     from deepdish_b200 import _lib
-    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs)):
+    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs), (4, args.pdl)):
         if val is not None:
             _lib.check(_lib.lib().dd_tuning_set(key, val), "dd_tuning_set")
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--cosine-ctas", type=int, default=None, help="A/B knob: CTAs per SM of the persistent gallery kernel")
     ap.add_argument("--chain", type=int, default=0, help="A/B knob: chunks take turns on the gallery kernel")
     ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
+    ap.add_argument("--pdl", type=int, default=None, help="A/B knob: programmatic dependent launch on / off")
     ap.add_argument("--prio", type=int, default=None, help="A/B knob: 1 = small kernels at high priority, 0 = equal")
     ap.add_argument("--chunks", type=int, default=2, help="stream chunks pipelined on separate CUDA streams")
     args = ap.parse_args()
