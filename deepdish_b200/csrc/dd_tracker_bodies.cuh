@@ -795,41 +795,55 @@ DD_HD void dd_apply_det(const G& g, const DDView& V, int s, int d, const float* 
     if (kind == 0) return;
     const size_t slot = (size_t)s * V.T + V.det_slot[sd];
     const double* z = V.det_xyah + sd * 4;
+    // everything the tail needs is loaded before the Kalman arithmetic (independent of it; the compiler cannot
+    // hoist these loads over the state stores itself): the feature chunks, the ring position, label and confidence
+    constexpr int KP = (DD_FEAT_DIM / 4 + G::NL - 1) / G::NL;
+    float4 x[KP];
+    {
+        const float4* src = (const float4*)(V.det_featn + sd * DD_FEAT_DIM);
+        int kk = 0;
+        for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) x[kk] = src[k];
+    }
+    int pos = V.gal_pos[slot];
+    int len = V.gal_len[slot];
+    int lbl = det_label[sd];
+    const double conf = (double)det_conf[sd];
+    if (lbl < 0) lbl = 0;
+    if (lbl >= V.C) lbl = V.C - 1;
+    int lcnt = 0;
+    double lsum = 0.0;
     if (kind == 1) {
+        lcnt = V.lab_cnt[slot * V.C + lbl];
+        lsum = V.lab_sum[slot * V.C + lbl];
         dd_kf_update(g, V.mean + slot * 8, V.cov + slot * 64, z, scratch);
     } else {
         dd_kf_initiate(g, z, V.mean + slot * 8, V.cov + slot * 64);
         for (int c = g.lane; c < V.C; c += G::NL) {
+            if (c == lbl) continue;                      // written below with the first vote
             V.lab_cnt[slot * V.C + c] = 0;
             V.lab_sum[slot * V.C + c] = 0.0;
         }
         if (g.lane == 0) {
-            V.gal_len[slot] = 0;
-            V.gal_pos[slot] = 0;
             V.path_n[slot] = 0;
             V.path_crossed[slot] = 0;
         }
-        g.sync();
+        pos = 0;
+        len = 0;
     }
-    const int pos = V.gal_pos[slot];
-    const int len = V.gal_len[slot];
-    const float4* src = (const float4*)(V.det_featn + sd * DD_FEAT_DIM);
     float4* dst = (float4*)(V.gal + (slot * (size_t)V.B + pos) * DD_FEAT_DIM);
     unsigned short* dsth = V.galh + (slot * (size_t)V.B + pos) * DD_FEAT_DIM;
-    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) {
-        const float4 x = src[k];
-        dst[k] = x;
-        dd_store_half4(dsth + 4 * k, x);
+    {
+        int kk = 0;
+        for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
+            dst[k] = x[kk];
+            dd_store_half4(dsth + 4 * k, x[kk]);
+        }
     }
-    g.sync();
     if (g.lane == 0) {
         V.gal_pos[slot] = (pos + 1 == V.B) ? 0 : pos + 1;
         V.gal_len[slot] = len < V.B ? len + 1 : V.B;
-        int lbl = det_label[sd];
-        if (lbl < 0) lbl = 0;
-        if (lbl >= V.C) lbl = V.C - 1;
-        V.lab_cnt[slot * V.C + lbl] += 1;
-        V.lab_sum[slot * V.C + lbl] = dd_add(V.lab_sum[slot * V.C + lbl], (double)det_conf[sd]);
+        V.lab_cnt[slot * V.C + lbl] = lcnt + 1;
+        V.lab_sum[slot * V.C + lbl] = dd_add(lsum, conf);
     }
 }
 
