@@ -459,7 +459,7 @@ class BatchedTracker:
 
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
-        names = names or [n for n in self.v.keys() if n not in ("gal", "galh", "cost", "gate", "det_featn", "det_feath")]
+        names = names or [n for n in self.v.keys() if n not in ("gal", "galh", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl")]
         out = {}
         for n in names:
             t = self.v[n]
