@@ -176,6 +176,17 @@ def gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not args.no_affinity:
+        # one rank per GPU: run (and allocate the pinned host batches) on the CPUs next to this rank's GPU, so the
+        # uploads of 8 ranks do not all cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = sorted(os.sched_getaffinity(0))
+        except Exception as e:            # no NVML / not permitted: leave the scheduler alone
+            numa = "unavailable: %r" % (e,)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from deepdish_b200.batched import BatchedTracker
@@ -190,7 +201,7 @@ def gpu_arm(args):
 
     P = args.chunks
     from deepdish_b200 import _lib
-    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs), (4, args.pdl)):
+    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs), (4, args.pdl), (5, args.match_cta)):
         if val is not None:
             _lib.check(_lib.lib().dd_tuning_set(key, val), "dd_tuning_set")
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
@@ -343,7 +354,7 @@ def gpu_arm(args):
                        "l2": "inputs larger than L2: %.2f GB of galleries streamed per tick" % (512 * G / 1e9)},
             "e2e": {"value": S * world * K / (e2e_all * 1e-3), "unit": "stream-frames/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K,
-                    "host_enqueue_ms_per_step": e2e_enq_ms / K},
+                    "host_enqueue_ms_per_step": e2e_enq_ms / K, "rank0_cpu_affinity": numa},
             "host_enqueue_ms_per_step": enq_ms / K,
             "gpu_launches": K * 7 * P,
             "clocks": clocks,
@@ -380,11 +391,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="multi-GPU: do not pin each rank to its GPU's CPUs")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"], help="c3 = the metric's configuration (default)")
     ap.add_argument("--gate-impl", type=int, default=None, help="A/B knob: gallery kernel 3 half pre-pass + exact re-check (default), 2 exact persistent work list, 0 exact full grid, 1 exact TMA ring")
     ap.add_argument("--cosine-ctas", type=int, default=None, help="A/B knob: CTAs per SM of the persistent gallery kernel")
     ap.add_argument("--chain", type=int, default=0, help="A/B knob: chunks take turns on the gallery kernel")
     ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
+    ap.add_argument("--match-cta", type=int, default=None, help="A/B knob: 1 = four warps per stream in k_match, 0 = one")
     ap.add_argument("--pdl", type=int, default=None, help="A/B knob: programmatic dependent launch on / off")
     ap.add_argument("--prio", type=int, default=None, help="A/B knob: 1 = small kernels at high priority, 0 = equal")
     ap.add_argument("--chunks", type=int, default=2, help="stream chunks pipelined on separate CUDA streams")

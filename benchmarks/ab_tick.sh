@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tracker.py tests/test_gpu_golden.py tests/test_gpu_pipeline.py tests/test_gpu_api.py -x -q 2>&1 | tail -2
-for cfg in "--chunks 1" "--chunks 2"; do
+for cfg in "--workload c4 --steps 10 --chunks 2 --match-cta 2" "--workload c4 --steps 10 --chunks 1 --match-cta 2" "--workload c4 --steps 10 --chunks 4 --match-cta 1"; do
   n=$(echo $cfg | tr -d ' -')
   python bench.py --steps 30 --warmup 5 --no-cpu-baseline $cfg > gpurun_out/b_$n.json 2> gpurun_out/b_$n.err
   python - <<PY

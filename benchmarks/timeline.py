@@ -28,11 +28,12 @@ def main():
     ap.add_argument("--chain", type=int, default=0)
     ap.add_argument("--cosine-ctas", type=int, default=None)
     ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
+    ap.add_argument("--match-cta", type=int, default=None, help="A/B knob: 1 = four warps per stream in k_match, 0 = one")
     ap.add_argument("--pdl", type=int, default=None, help="A/B knob: programmatic dependent launch on / off")
     ap.add_argument("--prio", type=int, default=None)
     ap.add_argument("--gate-impl", type=int, default=None)
     args = ap.parse_args()
-    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs), (4, args.pdl)):
+    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs), (4, args.pdl), (5, args.match_cta)):
         if val is not None:
             _lib.check(_lib.lib().dd_tuning_set(key, val), "dd_tuning_set")
     dev = torch.device("cuda", 0)

@@ -156,6 +156,76 @@ struct SubG {
     __device__ int imax(int v) const { return __reduce_max_sync(mask, v); }
 };
 
+// ---------------------------------------------------------------------------------------- CtaG<NW>
+// NW warps of one CTA cooperating on one unit of work (the per-stream matching of crowded scenes, where the
+// column scans of the assignment solver are hundreds of entries wide).  Same interface as WarpG; every
+// collective is a warp-level step, one shared-memory slot per warp and ONE __syncthreads: the slots are
+// double-buffered (a thread can only reach the collective after next once everybody has left this one).
+// All threads of the CTA must execute the same sequence of collectives.
+template <int NW>
+struct CtaG {
+    static constexpr int NL = NW * 32;
+    int lane;                  // thread index in the CTA
+    mutable int phase;         // which half of the scratch the next collective uses
+    int* scr_i;                // [2][NW] ints
+    double* scr_d;             // [2][NW] doubles
+    __device__ CtaG(void* scratch) : lane(threadIdx.x), phase(0) {
+        scr_d = (double*)scratch;
+        scr_i = (int*)(scr_d + 2 * NW);
+    }
+    static constexpr int scratch_bytes() { return 2 * NW * 8 + 2 * NW * 4 * 2; }
+    __device__ void sync() const { __syncthreads(); }
+    __device__ int* slot_i() const { int* p = scr_i + phase * NW; return p; }
+    __device__ int imax(int v) const {
+        int* sl = slot_i();
+        const int w = __reduce_max_sync(0xffffffffu, v);
+        if ((lane & 31) == 0) sl[lane >> 5] = w;
+        __syncthreads();
+        int r = sl[0];
+#pragma unroll
+        for (int k = 1; k < NW; ++k) r = r > sl[k] ? r : sl[k];
+        phase ^= 1;
+        return r;
+    }
+    __device__ int imin(int v) const { return -imax(-v); }
+    __device__ bool all(bool p) const { return imax(p ? 0 : 1) == 0; }
+    __device__ bool any(bool p) const { return imax(p ? 1 : 0) != 0; }
+    __device__ int scan_excl(bool p, int& total) const {
+        int* sl = slot_i();
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if ((lane & 31) == 0) sl[lane >> 5] = __popc(m);
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int c = sl[k];
+            before += (k < (lane >> 5)) ? c : 0;
+            tot += c;
+        }
+        phase ^= 1;
+        total = tot;
+        return before + __popc(m & ((1u << (lane & 31)) - 1u));
+    }
+    __device__ DDKey best(DDKey k) const {
+        WarpG wg;
+        const DDKey w = wg.best(k);
+        double* sd = scr_d + phase * NW;
+        int* si = scr_i + 2 * NW + phase * NW;
+        if ((lane & 31) == 0) { sd[lane >> 5] = w.val; si[lane >> 5] = w.pref; }
+        __syncthreads();
+        DDKey r;
+        r.val = sd[0]; r.pref = si[0];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) {
+            DDKey c;
+            c.val = sd[q]; c.pref = si[q];
+            if (dd_key_better(c, r)) r = c;
+        }
+        phase ^= 1;
+        return r;
+    }
+};
+
 // ---------------------------------------------------------------------------------------- BlockG
 // Whole CTA; collectives go through a small shared-memory scratch supplied by the kernel.
 struct BlockG {

@@ -425,6 +425,7 @@ static int g_gate_impl = 3;     // gallery kernel: 2 = persistent work-list kern
                                 // track index over the whole grid, 1 = TMA-staged ring (A/B baselines)
 static int g_cosine_ctas_per_sm = 4;   // persistent grid = SMs x this
 static int g_gallery_streaming = 0;    // 1: gallery loads are ld.global.cs (evict-first), 0: default policy
+static int g_match_cta = -1;           // matching kernel: -1 = by problem size, 0 = one warp per stream, 1 = 4 warps
 static int g_small_priority = 0;       // 1: launch the latency-bound kernels at the highest stream priority
 
 static int dd_sm_count() {
@@ -463,6 +464,18 @@ k_match(const DDView V, const double* __restrict__ det_tlwh, const int* __restri
     extern __shared__ __align__(128) char smem[];
     WarpG g;
     dd_match_stream(g, V, blockIdx.x, det_tlwh, det_count, out_det_track_id, smem);
+}
+
+// Crowded scenes (C4: ~260 tracks x ~180 detections per stream): the same matching body run by 4 (or 8) warps of
+// one CTA per stream, so every column scan, list compaction and staging loop is 4x (8x) wider.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_match_cta(const DDView V, const double* __restrict__ det_tlwh, const int* __restrict__ det_count,
+            int* out_det_track_id) {
+    extern __shared__ __align__(128) char smem[];
+    dd_pdl_sync();
+    CtaG<NW> g(smem);
+    dd_match_stream(g, V, blockIdx.x, det_tlwh, det_count, out_det_track_id, smem + 256);
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
@@ -637,7 +650,18 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
     DD_CHECK_LAUNCH();
     if (gallery_done && cudaEventRecord(gallery_done, st) != cudaSuccess) return DD_ERR_CUDA;
     if (ev) cudaEventRecord(ev[3], st);
-    {
+    const int wide = g_match_cta >= 0 ? g_match_cta : ((V.T > 160 || V.D > 160) ? 1 : 0);
+    if (wide && smem + 256 <= 227 * 1024) {
+        const size_t wsm = smem + 256;
+        if (wsm > 48 * 1024 &&
+            (cudaFuncSetAttribute(k_match_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm) != cudaSuccess ||
+             cudaFuncSetAttribute(k_match_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm) != cudaSuccess))
+            return DD_ERR_CUDA;
+        DDLaunch L(V.S, (wide == 2 ? 8 : 4) * 32, wsm, st, true);
+        const cudaError_t le = wide == 2 ? cudaLaunchKernelEx(&L.cfg, k_match_cta<8>, V, det_tlwh, det_count, out_det_track_id)
+                                         : cudaLaunchKernelEx(&L.cfg, k_match_cta<4>, V, det_tlwh, det_count, out_det_track_id);
+        if (le != cudaSuccess) return DD_ERR_CUDA;
+    } else {
         DDLaunch L(V.S, 32, smem, st, true);
         if (cudaLaunchKernelEx(&L.cfg, k_match, V, det_tlwh, det_count, out_det_track_id) != cudaSuccess) return DD_ERR_CUDA;
     }
@@ -675,6 +699,7 @@ int dd_tuning_set(int32_t key, int32_t value) {
     if (key == 2 && (value == 0 || value == 1)) { g_small_priority = value; return DD_OK; }
     if (key == 3 && (value == 0 || value == 1)) { g_gallery_streaming = value; return DD_OK; }
     if (key == 4 && (value == 0 || value == 1)) { g_pdl = value; return DD_OK; }
+    if (key == 5 && value >= -1 && value <= 2) { g_match_cta = value; return DD_OK; }
     return DD_ERR_INVALID;
 }
 

@@ -149,7 +149,9 @@ int dd_tracker_update_profiled(void* state, const dd_tracker_config* host_cfg,
  *   key 1: CTAs per SM of the persistent gallery kernel (1..16, default 4);
  *   key 2: 1 = launch the latency-bound kernels at the highest priority, 0 = all equal (default);
  *   key 3: 1 = gallery loads use ld.global.cs (evict-first in L2), 0 = default cache policy (default);
- *   key 4: 1 = programmatic dependent launch between the kernels of a tick, 0 = plain stream order (default). */
+ *   key 4: 1 = programmatic dependent launch between the kernels of a tick, 0 = plain stream order (default);
+ *   key 5: matching kernel -- -1 = chosen by problem size (default: 4 warps per stream when max_tracks or max_dets > 160),
+ *          0 = one warp per stream, 1 = four warps per stream, 2 = eight. */
 int dd_tuning_set(int32_t key, int32_t value);
 int dd_event_create(void** host_out);
 int dd_event_destroy(void* ev);

@@ -223,3 +223,21 @@ def test_checkpoint_resume_is_bit_identical():
     for name in ("n_tracks", "order", "track_id", "state", "mean", "cov", "counts", "next_id"):
         np.testing.assert_array_equal(va[name], vb[name])
     assert torch.equal(a.reduce_counts(), b2.reduce_counts())
+
+
+@pytest.mark.parametrize("shape", ["crowd", "c3", "small_budget"])
+def test_four_warp_matching_kernel(shape):
+    """k_match_cta (4 warps per stream, picked automatically for crowded scenes) forced on for several shapes: the
+    same oracle parity as the one-warp kernel."""
+    from deepdish_b200 import _lib
+    _lib.check(_lib.lib().dd_tuning_set(5, 1), "dd_tuning_set")
+    try:
+        if shape == "crowd":
+            bt, orc = _run(3, 190, 224, 384, 40, 60, seed=18, check_every=5)
+            assert max(len(t.tracks) for t in orc.trk) > 200
+        elif shape == "c3":
+            _run(12, 50, 64, 128, 70, 60, seed=6, check_every=10)
+        else:
+            _run(4, 12, 16, 48, 100, 3, seed=10, budget=5, check_every=4)
+    finally:
+        _lib.check(_lib.lib().dd_tuning_set(5, -1), "dd_tuning_set")
