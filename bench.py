@@ -248,6 +248,8 @@ def gpu_arm(args):
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms = start.elapsed_time(end)
+    cd = bt.v["cdesc"][..., 1]
+    cand_per_track = float(cd.sum()) / max(1, int((cd > 0).sum()))      # gate-passing detections per streamed track
     g1 = int(bt.gallery_vectors().sum())
     conf1 = int(((bt.v["state"] == 2).sum()))
     bt.check()
@@ -350,7 +352,7 @@ def gpu_arm(args):
             "dtype": "f64 (Kalman/gating/IoU/LSAP/count-line) + f32 (cosine)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": S, "max_tracks": TMAX, "max_dets": DMAX,
                        "preroll_ticks": PREROLL, "stream_chunks": P, "gallery_vectors_per_stream": G / S,
-                       "confirmed_tracks_per_stream": TC / S, "dets_per_frame": Dn / S,
+                       "confirmed_tracks_per_stream": TC / S, "dets_per_frame": Dn / S, "gate_passing_dets_per_streamed_track": cand_per_track,
                        "l2": "inputs larger than L2: %.2f GB of galleries streamed per tick" % (512 * G / 1e9)},
             "e2e": {"value": S * world * K / (e2e_all * 1e-3), "unit": "stream-frames/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K,
