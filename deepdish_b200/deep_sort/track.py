@@ -33,6 +33,9 @@ class Track:
         self._max_age = max_age
         # label statistics mirrored from the device state: {label: (count, sum of confidences)}
         self._label_stats = None
+        # detections applied on the host since the last device call (Track.update called from outside the
+        # tracker, e.g. FrameRecords.process_tracking): Tracker._flush writes them back to the device state
+        self._pending = []
 
     def to_tlwh(self):
         """track.py:84-97."""
@@ -67,6 +70,7 @@ class Track:
         if self._label_stats is not None:
             c, s = self._label_stats.get(detection.label, (0, 0.0))
             self._label_stats[detection.label] = (c + 1, s + detection.confidence)
+        self._pending.append(detection)
 
     def _stats(self):
         if self._label_stats is not None:

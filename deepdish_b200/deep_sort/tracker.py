@@ -22,11 +22,90 @@ class Tracker:
         self.max_age = max_age
         self.n_init = n_init
         self.kf = kalman_filter.KalmanFilter()
-        self.tracks = []
+        self._tracks = []
+        self._device_ids = []                  # track ids of the device's live list, in its order
+        self._late_features = []               # (track_id, unit feature) to enter the gallery after the next matching
         self.deleted_tracks = []
         self._labels = []                      # label vocabulary in first-seen order
         self._bt = None
         self._cap = metric.budget if metric.budget is not None else self.UNBOUNDED_GALLERY
+
+    # -- host edits written back to the device ------------------------------------------------
+    @property
+    def tracks(self):
+        return self._tracks
+
+    @tracks.setter
+    def tracks(self, value):
+        """``tracker.tracks = [...]`` (deepdish.py:1047): tracks missing from the new list are dropped from the
+        device's live list at the next device call."""
+        self._tracks = list(value)
+
+    def _flush(self):
+        """Write host-side edits back before the device runs again: tracks dropped from ``tracks`` leave the live
+        list (their slots become free), and tracks updated through ``Track.update(kf, detection)`` outside the tracker
+        (framerecords.py:157-160) get their Kalman state, hits, time_since_update, state and label votes stored.
+        Their features join the gallery after the NEXT matching, exactly when the reference's partial_fit would
+        move them from ``track.features`` to ``metric.samples`` (tracker.py:84-93)."""
+        if self._bt is None:
+            return
+        v = self._bt.chunks[0].v
+        keep = {t.track_id for t in self._tracks}
+        if any(tid not in keep for tid in self._device_ids):
+            n = int(v["n_tracks"][0])
+            order = v["order"][0, :n].cpu().numpy()
+            ids = v["track_id"][0].cpu().numpy()
+            live = [int(s) for s in order if int(ids[s]) in keep]
+            for s in order:
+                if int(ids[s]) not in keep:
+                    v["state"][0, int(s)] = 0                                   # DD_STATE_FREE
+            if live:
+                v["order"][0, :len(live)] = torch.as_tensor(live, dtype=torch.int32, device=v["order"].device)
+            v["n_tracks"][0] = len(live)
+            self._device_ids = [int(ids[s]) for s in live]
+        for t in self._tracks:
+            if not t._pending:
+                continue
+            s = t._slot
+            dev = v["mean"].device
+            v["mean"][0, s] = torch.as_tensor(np.asarray(t.mean, np.float64), device=dev)
+            v["cov"][0, s] = torch.as_tensor(np.asarray(t.covariance, np.float64), device=dev)
+            v["hits"][0, s], v["tsu"][0, s], v["state"][0, s] = int(t.hits), int(t.time_since_update), int(t.state)
+            for d in t._pending:
+                c = self._label_id(d.label)
+                v["lab_cnt"][0, s, c] += 1
+                v["lab_sum"][0, s, c] += float(d.confidence)
+                f = np.asarray(d.feature, np.float32)
+                self._late_features.append((t.track_id, f / np.float32(np.sqrt(np.sum(f * f, dtype=np.float32)))))
+            t._pending = []
+
+    def _apply_late_features(self, matched_ids):
+        """Ring surgery after a matching: a late feature goes in BEFORE the feature the update just appended for the
+        same track (the order partial_fit would produce), or at the end if the track was not matched."""
+        if not self._late_features:
+            return
+        v = self._bt.chunks[0].v
+        B = self._bt.cfg.budget
+        slot_of = {t.track_id: t._slot for t in self._tracks}
+        for tid, f in self._late_features:
+            if tid not in slot_of:
+                continue
+            s = slot_of[tid]
+            pos, ln = int(v["gal_pos"][0, s]), int(v["gal_len"][0, s])
+            ft = torch.as_tensor(f, device=v["gal"].device)
+            if tid in matched_ids and ln > 0:
+                last = (pos - 1) % B
+                newest = v["gal"][0, s, last].clone()
+                v["gal"][0, s, last] = ft
+                v["galh"][0, s, last] = ft.half()
+                v["gal"][0, s, pos] = newest
+                v["galh"][0, s, pos] = newest.half()
+            else:
+                v["gal"][0, s, pos] = ft
+                v["galh"][0, s, pos] = ft.half()
+            v["gal_pos"][0, s] = (pos + 1) % B
+            v["gal_len"][0, s] = min(ln + 1, B)
+        self._late_features = []
 
     # -- device state -----------------------------------------------------------------------
     def _ensure(self):
@@ -59,7 +138,7 @@ class Tracker:
         bt = self._bt
         v = bt.host_view(["n_tracks", "n_deleted", "order", "deleted", "mean", "cov", "track_id", "hits", "age",
                           "tsu", "state", "lab_cnt", "lab_sum", "gal_len", "gal_pos"])
-        old = {t.track_id: t for t in self.tracks}
+        old = {t.track_id: t for t in self._tracks + self.deleted_tracks}
 
         def make(slot):
             tid = int(v["track_id"][0, slot])
@@ -73,7 +152,8 @@ class Tracker:
                               for c in range(len(self._labels)) if v["lab_cnt"][0, slot, c] > 0}
             return t
 
-        self.tracks = [make(s) for s in v["order"][0, :int(v["n_tracks"][0])]]
+        self._tracks = [make(s) for s in v["order"][0, :int(v["n_tracks"][0])]]
+        self._device_ids = [t.track_id for t in self._tracks]
         self.deleted_tracks = [make(s) for s in v["deleted"][0, :int(v["n_deleted"][0])]]
         if self.metric.budget is None and len(self.tracks) and \
                 int(v["gal_len"][0, [t._slot for t in self.tracks]].max()) >= self._cap:
@@ -86,12 +166,14 @@ class Tracker:
         """tracker.py:51-57."""
         if self._bt is None:
             return
+        self._flush()
         self._bt.predict()
         self._snapshot()
 
     def update(self, detections):
         """tracker.py:59-93."""
         bt = self._ensure()
+        self._flush()
         D = bt.cfg.max_dets
         n = len(detections)
         if n > D:
@@ -106,6 +188,7 @@ class Tracker:
         self.last_detection_track_ids = ids[0, :n].cpu().numpy()
         bt.check()
         self._snapshot()
+        self._apply_late_features({int(i) for i in self.last_detection_track_ids})
         by_id = {t.track_id: t for t in self.tracks + self.deleted_tracks}
         for i, d in enumerate(detections):              # host-side caches kept like track.py:75-80,147-151
             t = by_id.get(int(self.last_detection_track_ids[i]))

@@ -306,6 +306,89 @@ def golden_tflite_adapter(R):
     print("tflite_adapter.npz", sum(len(res["lab%d" % c]) for c in range(cases)))
 
 
+def golden_framerecords(R):
+    """deepdish/framerecords.py FrameRecords.process_boxes / process_detections / process_tracking (unmodified) driven
+    like deepdish.py:993-1047 on top of the unmodified reference Tracker: an annotated object the detector misses for
+    a while (process_tracking force-updates and confirms its track), an annotation overlapping a detection, an
+    annotation without a detection (fed to the tracker with score 1.0) and an annotation with an unknown label."""
+    import importlib
+    import json
+    fr = importlib.import_module("deepdish.framerecords")
+    nn, Det, Trk = R.deep_sort_nn_matching, R.deep_sort_detection.Detection, R.deep_sort_tracker.Tracker
+    rng = np.random.default_rng(21)
+    names = {0: "person", 1: "bicycle", 2: "car"}
+    F, NOBJ = 36, 6
+    pos = rng.uniform([60, 60], [520, 340], (NOBJ, 2))
+    vel = rng.normal(0, 3.0, (NOBJ, 2))
+    size = np.stack([rng.uniform(24, 40, NOBJ), rng.uniform(50, 90, NOBJ)], 1)
+    ident = rng.normal(size=(NOBJ + 1, 128))
+    ident /= np.linalg.norm(ident, axis=1, keepdims=True)
+    lab = rng.integers(0, 3, NOBJ)
+
+    def feat(o, f):
+        g = np.random.default_rng(1000 * f + o)
+        v = ident[o] + 0.02 * g.normal(size=128)
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    frec = fr.FrameRecords(names)
+    for n in names.values():
+        frec.add_annotation_label_info(n, frec.detector_labelname_to_id[n], "#000000")
+    frec.add_annotation_label_info("unicorn", None, "#ffffff")
+    annotations = []           # (frame, annot_track_id, label name, [x1, y1, x2, y2])
+    metric = nn.NearestNeighborDistanceMetric("cosine", 0.2, 50)
+    trk = Trk(metric, max_iou_distance=0.7, max_age=30, n_init=3)
+    frames = []
+    for f in range(F):
+        pos = pos + vel
+        boxes, labels, scores, owner = [], [], [], []
+        for o in range(NOBJ):
+            x, y = np.floor(pos[o] + rng.normal(0, 1, 2))
+            w, h = np.floor(size[o] + rng.normal(0, 1, 2))
+            tl = np.array([x, y, w, h], dtype=np.int64)
+            missed = (o == 0 and 12 <= f < 20) or rng.random() < 0.08
+            if o == 0 and f >= 8:                 # object 0 is annotated from frame 8 on (track 7); at frame 16 the
+                jx, jy = (70.0, 30.0) if f >= 16 else (0.0, 0.0)      # annotation jumps: the gate fails, the track is
+                annotations.append((f, 7, names[int(lab[0])],         # force-updated by process_tracking
+                                    [float(x) + 0.4 + jx, float(y) + 0.3 + jy, float(x + w) + 0.2 + jx, float(y + h) + 0.1 + jy]))
+            if o == 1 and 5 <= f < 15:            # a label the detector does not know, overlapping no detection
+                annotations.append((f, 9, "unicorn", [600.0, 440.0, 630.0, 470.0]))   # (an overlap would be a KeyError
+                                                                                      # at framerecords.py:116)
+            if not missed:
+                boxes.append(tl); labels.append(names[int(lab[o])]); scores.append(np.float32(0.5 + 0.45 * rng.random()))
+                owner.append(o)
+        if 22 <= f < 30:                          # annotated object nobody detects (track 11): enters with score 1.0
+            annotations.append((f, 11, "car", [300.0 + 2 * f, 200.0, 340.0 + 2 * f, 280.0]))
+        for a in [a for a in annotations if a[0] == f]:
+            frec.add_annotated_track(a[0], a[1], a[2], np.array(a[3]), False, False, True, 0)
+        order = np.argsort(scores)[::-1]
+        boxes = [boxes[i] for i in order]; labels = [labels[i] for i in order]; scores = [scores[i] for i in order]
+        owner = [owner[i] for i in order]
+        b2, l2, s2 = frec.process_boxes(f, np.array(boxes).reshape(-1, 4), labels, np.array(scores))
+        feats = []
+        for bx in b2:                             # the encoder's stand-in: identity of the nearest object centre
+            c = np.array([bx[0] + bx[2] / 2.0, bx[1] + bx[3] / 2.0])
+            d2 = ((pos + size / 2.0 - c) ** 2).sum(1)
+            o = int(np.argmin(d2)) if d2.min() < 40 ** 2 else NOBJ
+            feats.append(feat(o, f))
+        dets = [Det(bx, lb, sc, ft) for bx, lb, sc, ft in zip(b2, l2, s2, feats)]
+        dets = frec.process_detections(f, dets)
+        trk.predict()
+        trk.update(dets)
+        trk.tracks = frec.process_tracking(f, trk)
+        frames.append(dict(
+            boxes=[[int(v) for v in b] for b in boxes], labels=labels, scores=[float(s) for s in scores],
+            out_boxes=[[float(v) for v in b] for b in b2], out_labels=list(l2), out_scores=[float(s) for s in s2],
+            feats=[ft.tolist() for ft in feats],
+            track_ids=[t.track_id for t in trk.tracks], states=[int(t.state) for t in trk.tracks],
+            tsu=[int(t.time_since_update) for t in trk.tracks], hits=[int(t.hits) for t in trk.tracks],
+            means=[t.mean.tolist() for t in trk.tracks], next_id=int(trk._next_id)))
+    import gzip
+    with gzip.open(os.path.join(OUT, "framerecords.json.gz"), "wt") as fh:
+        json.dump(dict(names={str(k): v for k, v in names.items()}, annotations=annotations, frames=frames), fh)
+    forced = sum(1 for fr_ in frames for t, s in zip(fr_["tsu"], fr_["states"]) if t == 0 and s == 2)
+    print("framerecords.json.gz frames", len(frames), "tracks at end", len(frames[-1]["track_ids"]), "next_id", frames[-1]["next_id"])
+
+
 def golden_patches(R):
     """tools/generate_detections.py:40-84 (the unmodified reference function, cv2.resize inside), :86-116
     (DummyImageEncoder) and :180-211 (create_box_encoder)."""
@@ -357,10 +440,14 @@ def main():
     if os.environ.get("DD_GOLDEN_ONLY") == "patches":
         golden_patches(R)
         return
+    if os.environ.get("DD_GOLDEN_ONLY") == "framerecords":
+        golden_framerecords(R)
+        return
     if os.environ.get("DD_GOLDEN_ONLY") == "tflite":
         golden_tflite_adapter(R)
         return
     golden_tflite_adapter(R)
+    golden_framerecords(R)
     golden_patches(R)
     golden_kalman(R)
     golden_metric_iou(R)
