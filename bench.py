@@ -219,11 +219,12 @@ def gpu_arm(args):
     # ---- main timed region: K ticks, stream chunks pipelined, counts reduced (+ NCCL) every tick
     def tick(b):
         bt.step(b, join=False, reduce=True)
-        bt.all_reduce_counts(reduced=True)
+        bt.all_reduce_counts(reduced=True, async_op=True)     # NCCL on its own stream: ranks do not rendezvous per tick
 
     for b in frames[:W]:
         tick(b)
     bt.join()
+    bt.wait_counts()
     g0 = int(bt.gallery_vectors().sum())
     conf0 = int(((bt.v["state"] == 2).sum()))
     dets = sum(int(b.count.sum()) for b in frames[W:])
@@ -241,6 +242,7 @@ def gpu_arm(args):
         tick(b)
     enq_ms = 1e3 * (time.perf_counter() - t0)      # host time to enqueue the K ticks (no waiting)
     bt.join()
+    bt.wait_counts()                               # every count all-reduce of the timed ticks has completed
     end.record()
     if world > 1:
         dist.barrier()

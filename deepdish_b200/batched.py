@@ -406,14 +406,37 @@ class BatchedTracker:
         self._tick += 1
         return self.total_counts
 
-    def all_reduce_counts(self, reduced=False):
+    def all_reduce_counts(self, reduced=False, async_op=False):
         """[C,4] counters summed over streams and, over NCCL, ranks (the path's only collective).
-        reduced=True: total_counts already holds this tick's local sum (step(reduce=True) / step_host)."""
+        reduced=True: total_counts already holds this tick's local sum (step(reduce=True) / step_host).
+        async_op=True: the all-reduce runs on NCCL's own stream on a copy of the counters (two alternating buffers)
+        and the caller's stream is not made to wait, so ranks do not rendezvous every tick; the returned tensor is
+        valid after wait_counts()."""
         t = self.total_counts if reduced else self.reduce_counts()
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if not async_op:
+            if multi:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t
+        if not hasattr(self, "_ar_buf"):
+            self._ar_buf = [torch.zeros_like(self.total_counts) for _ in range(2)]
+            self._ar_work = [None, None]
+            self._ar_turn = 0
+        k = self._ar_turn
+        self._ar_turn ^= 1
+        if self._ar_work[k] is not None:
+            self._ar_work[k].wait()
+        self._ar_buf[k].copy_(t)
+        self._ar_work[k] = dist.all_reduce(self._ar_buf[k], op=dist.ReduceOp.SUM, async_op=True) if multi else None
+        return self._ar_buf[k]
+
+    def wait_counts(self):
+        """Make the caller's stream wait for every outstanding asynchronous count all-reduce."""
+        for k, w in enumerate(getattr(self, "_ar_work", [])):
+            if w is not None:
+                w.wait()
+                self._ar_work[k] = None
 
     def status(self):
         self.join()

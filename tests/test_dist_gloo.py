@@ -20,6 +20,17 @@ counts = torch.randint(0, 9, (S, C, 4), generator=g, dtype=torch.int64)
 local = counts[lo:hi].sum(0)
 dist.all_reduce(local, op=dist.ReduceOp.SUM)
 assert torch.equal(local, counts.sum(0)), (rank, local, counts.sum(0))
+# the asynchronous, double-buffered form bench.py uses per tick (BatchedTracker.all_reduce_counts(async_op=True))
+bufs, works = [torch.zeros_like(local) for _ in range(2)], [None, None]
+for k in range(5):
+    i = k & 1
+    if works[i] is not None:
+        works[i].wait()
+    bufs[i].copy_(counts[lo:hi].sum(0) * (k + 1))
+    works[i] = dist.all_reduce(bufs[i], op=dist.ReduceOp.SUM, async_op=True)
+for w in works:
+    w.wait()
+assert torch.equal(bufs[0], counts.sum(0) * 5) and torch.equal(bufs[1], counts.sum(0) * 4)
 spans = [None] * world
 dist.all_gather_object(spans, (lo, hi))
 assert spans[0][0] == 0 and spans[-1][1] == S and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
