@@ -49,10 +49,7 @@ def main():
     bt.join()
     torch.cuda.synchronize()
     evs = [[bt.new_events(6) for _ in bt.chunks] for _ in range(args.ticks)]
-    origin = bt.new_events(1)
     lib = bt.lib
-    cur = torch.cuda.current_stream(dev)
-    lib.dd_event_record = getattr(lib, "dd_event_record", None)
     o = torch.cuda.Event(enable_timing=True)
     o.record()
     bt._fork()
