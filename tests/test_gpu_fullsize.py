@@ -69,3 +69,49 @@ def test_c3_full_size_sampled_oracle_and_schedule_invariance():
     slots = va["order"][live]
     for name in ("track_id", "state", "hits", "age", "tsu", "gal_len", "gal_pos", "mean", "cov"):
         np.testing.assert_array_equal(va[name][rows, slots], vb[name][rows, slots], err_msg=name)   # bit for bit
+
+
+def test_c4_shard_size_matching_kernels_agree():
+    """BASELINE configs[3] at its 8-GPU shard size (512 streams x ~180 detections, ~260 tracks): the 4-warp matching
+    kernel (k_match_cta, the default at this size) and the one-warp kernel must produce bit-identical ids and track
+    tables for every stream and tick -- any shared-memory race among the four warps would show up here -- and a
+    sample of streams is replayed through the oracle."""
+    from deepdish_b200 import _lib
+    from deepdish_b200.batched import BatchedTracker
+    S4, NOBJ4, D4, T4, TICKS4 = 512, 200, 224, 384, 14
+    sc = Scene(S4, NOBJ4, D4, n_labels=3, seed=91, device="cuda")
+    frames = [sc.step() for _ in range(TICKS4)]
+    sample = [0, 255, 511]
+    orc = OracleStreams(len(sample), LABELS3, budget=BUDGET, max_age=MAX_AGE)
+    idx = torch.as_tensor(sample, device="cuda")
+    runs = []
+    for impl in (1, 0):
+        _lib.check(_lib.lib().dd_tuning_set(5, impl), "dd_tuning_set")
+        try:
+            bt = BatchedTracker(S4, LABELS3, max_tracks=T4, max_dets=D4, budget=BUDGET, max_age=MAX_AGE)
+            ids = []
+            for f, b in enumerate(frames):
+                got = bt.step(b).cpu().numpy().copy()
+                ids.append(got)
+                if impl == 1:
+                    hb = SceneBatch(*(getattr(b, k)[idx].cpu() for k in SceneBatch.__slots__))
+                    exp = orc.step(hb)
+                    for k, s in enumerate(sample):
+                        assert list(got[s, :int(hb.count[k])]) == exp[k], (f, s)
+            bt.check()
+            runs.append((ids, bt.host_view(["n_tracks", "order", "track_id", "state", "hits", "tsu", "next_id", "mean"])))
+            del bt
+            torch.cuda.empty_cache()
+        finally:
+            _lib.check(_lib.lib().dd_tuning_set(5, -1), "dd_tuning_set")
+    (ia, va), (ib, vb) = runs
+    for f in range(TICKS4):
+        np.testing.assert_array_equal(ia[f], ib[f], err_msg="tick %d" % f)
+    np.testing.assert_array_equal(va["n_tracks"], vb["n_tracks"])
+    np.testing.assert_array_equal(va["next_id"], vb["next_id"])
+    live = np.arange(T4)[None, :] < va["n_tracks"][:, None]
+    np.testing.assert_array_equal(va["order"][live], vb["order"][live])
+    rows, slots = np.repeat(np.arange(S4), va["n_tracks"]), va["order"][live]
+    for name in ("track_id", "state", "hits", "tsu", "mean"):
+        np.testing.assert_array_equal(va[name][rows, slots], vb[name][rows, slots], err_msg=name)
+    assert int(va["n_tracks"].max()) > 200
