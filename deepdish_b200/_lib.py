@@ -103,6 +103,8 @@ def lib():
         "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
         "dd_tracker_tick": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
         "dd_tracker_tick_chained": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+        "dd_tracker_tick_ragged": [_vp, cfgp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
         "dd_unpack_detections": [_vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                  _vp, _vp, _vp, _vp, _vp, _vp],
         "dd_tracker_count_reduce": [_vp, cfgp, _vp, _vp],

@@ -310,6 +310,15 @@ class BatchedTracker:
                          torch.empty((n,), dtype=torch.int32, device=self.device))
         return c.staging
 
+    def _staging_small(self, c):
+        if getattr(c, "staging_small", None) is None:
+            n, D = c.hi - c.lo, self.max_dets
+            c.staging_small = (torch.empty((n, D, 4), dtype=torch.float64, device=self.device),
+                               torch.empty((n, D), dtype=torch.float32, device=self.device),
+                               torch.empty((n, D), dtype=torch.int32, device=self.device),
+                               torch.empty((n,), dtype=torch.int32, device=self.device))
+        return c.staging_small
+
     def pack_host(self, batch):
         """Ragged host form of a padded batch (the batched equivalent of the reference's per-stream list of
         Detection objects, deepdish.py:1014): per chunk ONE pinned byte blob
@@ -350,8 +359,8 @@ class BatchedTracker:
     def step_host_packed(self, packed, out_ids_host=None):
         """End-to-end tick from a ragged pinned host batch (``pack_host``).  Per chunk: ONE H2D copy on the chunk's
         own copy stream into a double-buffered device blob -- so the upload of tick k + 1 runs under the kernels of
-        tick k --, then on the chunk's compute stream the unpack kernel, the tick with its partial count reduction
-        and (optionally) the D2H copy of the det->track ids.  The pinned blobs must stay alive until their copy has
+        tick k --, then on the chunk's compute stream the tick reading the blob directly (dd_tracker_tick_ragged)
+        with its partial count reduction and (optionally) the D2H copy of the det->track ids.  The pinned blobs must stay alive until their copy has
         run.  Returns total_counts (device, summed on the caller's stream)."""
         par = self._tick & 1
         multi = len(self.chunks) > 1
@@ -374,15 +383,17 @@ class BatchedTracker:
                 copied = c.copy_stream.record_event()
             with torch.cuda.stream(st):
                 st.wait_event(copied)
-                t, cf, lb, ft, ct = self._staging(c)
+                t, cf, lb, ct = self._staging_small(c)
                 sp = ctypes.c_void_p(st.cuda_stream)
-                _lib.check(self.lib.dd_unpack_detections(dev_blob.data_ptr(), n, self.max_dets, *offs, t.data_ptr(),
-                                                         cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
-                                                         sp), "dd_unpack_detections")
-                c.unpacked[par] = st.record_event()
                 ids = self.det_track_id[c.lo:c.hi]
-                self._tick_call(c, (t.data_ptr(), cf.data_ptr(), lb.data_ptr(), ft.data_ptr(), ct.data_ptr(),
-                                    ids.data_ptr()), self.partial_counts[par, i].data_ptr(), sp)
+                # the tick's first kernel reads the blob (features normalised straight from it); later kernels read
+                # box / confidence / label from the small padded arrays it fills, so the blob is free after the tick
+                _lib.check(self.lib.dd_tracker_tick_ragged(c.state, c.cfgp, dev_blob.data_ptr(), *offs, t.data_ptr(),
+                                                           cf.data_ptr(), lb.data_ptr(), ct.data_ptr(), ids.data_ptr(),
+                                                           self._line_ptr(c), self.line_per_stream,
+                                                           self.partial_counts[par, i].data_ptr(), sp),
+                           "dd_tracker_tick_ragged")
+                c.unpacked[par] = st.record_event()
                 if out_ids_host is not None:
                     out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
         self._mark()

@@ -62,6 +62,41 @@ __global__ void __launch_bounds__(DD_WARPS * 32) k_predict(const DDView V) {
 // PREDICT = true: Tracker.predict of the same track index first (the fused tick): the 8 lanes that gate a track
 // have just written its predicted mean / covariance, so the state is read back from L1 instead of HBM and one
 // launch disappears.
+// k_prep fed by a ragged blob (dd_unpack_detections' format): expands box / confidence / label / count into the
+// padded arrays the later kernels read and normalises the feature straight from the blob, so the 512-byte feature
+// rows are never copied to a padded staging buffer.
+struct DDRagged {
+    const unsigned char* blob;
+    long long off_tlwh, off_conf, off_label, off_feat;
+    double* det_tlwh;
+    float* det_conf;
+    int *det_label, *det_count;
+};
+
+__global__ void __launch_bounds__(DD_WARPS * 32)
+k_prep_ragged(const DDView V, const DDRagged R) {
+    dd_pdl_sync();
+    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {      // new tick: empty work list, claim cursor at 0
+        V.work_ctl[0] = 0;
+        V.work_ctl[32] = 0;
+    }
+    if (w >= V.S * V.D) return;
+    SubG<DD_SUB> g;
+    const int s = w / V.D, d = w - s * V.D;
+    const int* offs = (const int*)R.blob;
+    const int o0 = offs[s];
+    const int n = offs[s + 1] - o0;
+    if (d == 0 && g.lane == 0) R.det_count[s] = n;     // n > max_dets: the tick raises DD_FLAG_DET_OVERFLOW
+    if (d >= n) return;
+    const size_t src = (size_t)o0 + d, dst = (size_t)s * V.D + d;
+    const double* box = (const double*)(R.blob + R.off_tlwh) + src * 4;
+    if (g.lane < 4) R.det_tlwh[dst * 4 + g.lane] = box[g.lane];
+    if (g.lane == 4) R.det_conf[dst] = ((const float*)(R.blob + R.off_conf))[src];
+    if (g.lane == 5) R.det_label[dst] = ((const int*)(R.blob + R.off_label))[src];
+    dd_prep_det_at(g, V, s, d, box, (const float*)(R.blob + R.off_feat) + src * DD_FEAT_DIM);
+}
+
 template <bool PREDICT>
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_gate(const DDView V, const int* __restrict__ det_count) {
@@ -590,11 +625,11 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
                           const float* det_conf, const int32_t* det_label, const float* det_feat,
                           const int32_t* det_count, int32_t* out_det_track_id, cudaStream_t st,
                           cudaEvent_t* ev, cudaEvent_t gallery_wait = nullptr, cudaEvent_t gallery_done = nullptr,
-                          bool with_predict = false) {
+                          bool with_predict = false, const DDRagged* ragged = nullptr) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
-    if (!det_tlwh || !det_conf || !det_label || !det_feat || !det_count) return DD_ERR_INVALID;
+    if (!det_tlwh || !det_conf || !det_label || (!det_feat && !ragged) || !det_count) return DD_ERR_INVALID;
     const size_t smem = dd_match_smem_bytes(V.T, V.D, V.tab_cap);
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) return DD_ERR_INVALID;
@@ -604,7 +639,9 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const doubl
     if (ev) cudaEventRecord(ev[0], st);
     {
         DDLaunch L(items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st, true);
-        if (cudaLaunchKernelEx(&L.cfg, k_prep, V, det_tlwh, det_feat, det_count) != cudaSuccess) return DD_ERR_CUDA;
+        const cudaError_t le = ragged ? cudaLaunchKernelEx(&L.cfg, k_prep_ragged, V, *ragged)
+                                      : cudaLaunchKernelEx(&L.cfg, k_prep, V, det_tlwh, det_feat, det_count);
+        if (le != cudaSuccess) return DD_ERR_CUDA;
     }
     if (ev) cudaEventRecord(ev[1], st);
     {
@@ -760,6 +797,35 @@ int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det
                     int line_per_stream, int64_t* out_counts, void* stream) {
     return dd_tracker_tick_chained(state, cfg, det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id,
                                    line, line_per_stream, out_counts, nullptr, nullptr, stream);
+}
+
+int dd_tracker_tick_ragged(void* state, const dd_tracker_config* cfg, const void* blob, int64_t off_tlwh,
+                           int64_t off_conf, int64_t off_label, int64_t off_feat, double* det_tlwh, float* det_conf,
+                           int32_t* det_label, int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                           int line_per_stream, int64_t* out_counts, void* stream) {
+    DDView V;
+    int rc = dd_make_view(state, cfg, &V);
+    if (rc != DD_OK) return rc;
+    if (!line || !blob) return DD_ERR_INVALID;
+    if ((off_tlwh & 7) || (off_conf & 3) || (off_label & 3) || (off_feat & 15) || ((uintptr_t)blob & 15)) return DD_ERR_INVALID;
+    DDRagged R;
+    R.blob = (const unsigned char*)blob;
+    R.off_tlwh = off_tlwh; R.off_conf = off_conf; R.off_label = off_label; R.off_feat = off_feat;
+    R.det_tlwh = det_tlwh; R.det_conf = det_conf; R.det_label = det_label; R.det_count = det_count;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = dd_update_impl(state, cfg, det_tlwh, det_conf, det_label, nullptr, det_count, out_det_track_id, st, nullptr,
+                        nullptr, nullptr, /*with_predict=*/true, &R);
+    if (rc != DD_OK) return rc;
+    {
+        DDLaunch L(warps_to_blocks(V.S), DD_WARPS * 32, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_countline, V, line, line_per_stream) != cudaSuccess) return DD_ERR_CUDA;
+    }
+    if (out_counts) {
+        DDLaunch L(V.C * 4, 256, 0, st, true);
+        if (cudaLaunchKernelEx(&L.cfg, k_count_reduce, (const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts) != cudaSuccess)
+            return DD_ERR_CUDA;
+    }
+    return DD_OK;
 }
 
 int dd_unpack_detections(const void* blob, int32_t n_streams, int32_t max_dets, int64_t off_tlwh, int64_t off_conf,

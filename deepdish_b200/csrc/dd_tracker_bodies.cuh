@@ -38,22 +38,19 @@ inline void dd_atomic_or(int* p, int v) { *p |= v; }
 // ------------------------------------------------------------------------------------------------
 // Detection.to_xyah (deep_sort/detection.py:43-50) and b / |b| (deep_sort/nn_matching.py:53).
 // ------------------------------------------------------------------------------------------------
+// box = the detection's tlwh (4 doubles), feat = its raw 128-d feature row; results go to slot (s, d) of the scratch
 template <class G>
-DD_HD void dd_prep_det(const G& g, const DDView& V, int s, int d, const double* det_tlwh,
-                       const float* det_feat, const int* det_count) {
-    int nd = det_count[s];
-    if (nd > V.D) nd = V.D;
-    if (d >= nd) return;
+DD_HD void dd_prep_det_at(const G& g, const DDView& V, int s, int d, const double* box, const float* feat) {
     const size_t sd = (size_t)s * V.D + d;
     if (g.lane == 0) {
-        const double* b = det_tlwh + sd * 4;
+        const double* b = box;
         double* o = V.det_xyah + sd * 4;
         o[0] = dd_add(b[0], dd_div(b[2], 2.0));
         o[1] = dd_add(b[1], dd_div(b[3], 2.0));
         o[2] = dd_div(b[2], b[3]);
         o[3] = b[3];
     }
-    const float4* f4 = (const float4*)(det_feat + sd * DD_FEAT_DIM);
+    const float4* f4 = (const float4*)feat;
     float4* o4 = (float4*)(V.det_featn + sd * DD_FEAT_DIM);
     float ss = 0.f;
     for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL) {
@@ -69,6 +66,16 @@ DD_HD void dd_prep_det(const G& g, const DDView& V, int s, int d, const double* 
         o4[k] = x;
         dd_store_half4(V.det_feath + sd * DD_FEAT_DIM + 4 * k, x);
     }
+}
+
+template <class G>
+DD_HD void dd_prep_det(const G& g, const DDView& V, int s, int d, const double* det_tlwh,
+                       const float* det_feat, const int* det_count) {
+    int nd = det_count[s];
+    if (nd > V.D) nd = V.D;
+    if (d >= nd) return;
+    const size_t sd = (size_t)s * V.D + d;
+    dd_prep_det_at(g, V, s, d, det_tlwh + sd * 4, det_feat + sd * DD_FEAT_DIM);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -189,6 +189,15 @@ int dd_unpack_detections(const void* blob, int32_t n_streams, int32_t max_dets, 
                          int64_t off_label, int64_t off_feat, double* det_tlwh, float* det_conf,
                          int32_t* det_label, float* det_feat, int32_t* det_count, void* stream);
 
+/* dd_tracker_tick fed directly by a ragged blob (the format of dd_unpack_detections): the first kernel of the tick
+ * expands box / confidence / label / count into the caller's padded arrays det_tlwh f64 [S,Dmax,4], det_conf f32 [S,Dmax],
+ * det_label i32 [S,Dmax], det_count i32 [S] (read by the later kernels) and normalises the features straight from the
+ * blob -- no padded copy of the 512-byte feature rows. */
+int dd_tracker_tick_ragged(void* state, const dd_tracker_config* host_cfg, const void* blob, int64_t off_tlwh,
+                           int64_t off_conf, int64_t off_label, int64_t off_feat, double* det_tlwh, float* det_conf,
+                           int32_t* det_label, int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                           int line_per_stream, int64_t* out_counts, void* stream);
+
 /* Sum the per-stream counters into out_counts i64 [C,4] (the tensor handed to the NCCL all-reduce). */
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int64_t* out_counts,
                             void* stream);

@@ -241,3 +241,25 @@ def test_four_warp_matching_kernel(shape):
             _run(4, 12, 16, 48, 100, 3, seed=10, budget=5, check_every=4)
     finally:
         _lib.check(_lib.lib().dd_tuning_set(5, -1), "dd_tuning_set")
+
+
+def test_unpack_detections_entry():
+    """dd_unpack_detections (ragged blob -> padded arrays) on its own: equals the padded batch it was packed from."""
+    import ctypes
+    from deepdish_b200 import _lib
+    from deepdish_b200.batched import BatchedTracker
+    S, D = 9, 24
+    bt = BatchedTracker(S, LABELS3, max_tracks=32, max_dets=D, budget=10)
+    b = Scene(S, 16, D, n_labels=3, seed=5).step()
+    (blob, total, offs), = bt.pack_host(b)
+    dev = blob[:total].cuda()
+    t = torch.zeros((S, D, 4), dtype=torch.float64, device="cuda"); cf = torch.zeros((S, D), device="cuda")
+    lb = torch.zeros((S, D), dtype=torch.int32, device="cuda"); ft = torch.zeros((S, D, 128), device="cuda")
+    ct = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    _lib.check(bt.lib.dd_unpack_detections(dev.data_ptr(), S, D, *offs, t.data_ptr(), cf.data_ptr(), lb.data_ptr(),
+                                           ft.data_ptr(), ct.data_ptr(), ctypes.c_void_p(0)), "dd_unpack_detections")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ct.cpu().numpy(), b.count.numpy())
+    valid = (torch.arange(D)[None, :] < b.count[:, None]).numpy()
+    for got, exp in ((t, b.tlwh), (cf, b.conf), (lb, b.label), (ft, b.feat)):
+        np.testing.assert_array_equal(got.cpu().numpy()[valid], exp.numpy()[valid])
