@@ -39,6 +39,7 @@ static inline int dd_layout_compute(const dd_tracker_config* c, dd_tracker_layou
     if (c->feat_dim != DD_FEAT_DIM) return DD_ERR_INVALID;
     if (c->n_labels <= 0 || c->n_labels > DD_MAX_LABELS) return DD_ERR_INVALID;
     if (c->max_tracks > 1024 || c->max_dets > 1024) return DD_ERR_INVALID;
+    if (c->budget > 32767) return DD_ERR_INVALID;      /* the track descriptor packs the gallery length in 15 bits */
     if (c->max_age < 0 || c->n_init < 1) return DD_ERR_INVALID;
     const uint64_t S = c->n_streams, T = c->max_tracks, D = c->max_dets, B = c->budget,
                    C = c->n_labels, F = DD_FEAT_DIM, DW = (D + 31) / 32;
