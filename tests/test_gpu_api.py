@@ -13,7 +13,11 @@ pytestmark = pytest.mark.gpu
 
 def test_install_as_deep_sort_and_track_lifecycle():
     import deepdish_b200
-    deepdish_b200.install_as_deep_sort()
+    deepdish_b200.install_as_deep_sort(box_encoder=True, framerecords=True)
+    from tools import generate_detections as gdet
+    from deepdish.framerecords import FrameRecords
+    assert gdet.create_box_encoder("constant")(np.zeros((32, 32, 3), np.uint8), [np.array([2, 2, 8, 16])]).shape == (1, 128)
+    assert FrameRecords({0: "person"}).process_boxes(0, np.zeros((0, 4), np.int64), [], np.zeros(0)) == ([], [], [])
     from deep_sort import nn_matching, preprocessing
     from deep_sort.detection import Detection
     from deep_sort.tracker import Tracker
