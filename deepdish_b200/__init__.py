@@ -15,10 +15,6 @@ def install_as_deep_sort(box_encoder=False, framerecords=False):
     from . import _lib, deep_sort, tools
     from .tools import intersection
     _lib.lib()
-    if box_encoder:
-        from .tools import generate_detections
-        sys.modules["tools.generate_detections"] = generate_detections
-        tools.generate_detections = generate_detections
     if framerecords:
         import types
         from . import framerecords as fr
@@ -31,3 +27,7 @@ def install_as_deep_sort(box_encoder=False, framerecords=False):
         sys.modules["deep_sort." + name] = getattr(deep_sort, name)
     sys.modules.setdefault("tools", tools)
     sys.modules["tools.intersection"] = intersection
+    if box_encoder:
+        from .tools import generate_detections
+        sys.modules["tools.generate_detections"] = generate_detections
+        sys.modules["tools"].generate_detections = generate_detections
