@@ -115,3 +115,71 @@ def test_c4_shard_size_matching_kernels_agree():
     for name in ("track_id", "state", "hits", "tsu", "mean"):
         np.testing.assert_array_equal(va[name][rows, slots], vb[name][rows, slots], err_msg=name)
     assert int(va["n_tracks"].max()) > 200
+
+
+def test_c2_full_batch_nms_properties():
+    """BASELINE configs[1] at full size (YOLOv5s head [64, 25200, 85], decode + confidence / box filter + NMS): the
+    first 2 frames against the oracle, all 64 through size-independent properties of non_max_suppression
+    (preprocessing.py:6-73): keep-lists in strictly descending score order, no kept box covering another kept box of
+    lower score by more than max_bbox_overlap of the other's area, every dropped candidate covered by some kept box
+    of higher score, and idempotence (NMS of the kept boxes keeps them all, in order)."""
+    from oracle import detect as odet
+    from oracle.make_golden import synth_yolo_head
+    from deepdish_b200 import ops
+    from tests.test_gpu_detect import COCO
+    rng = np.random.default_rng(31)
+    head = synth_yolo_head(rng, 64, 25200, hot=0.01)
+    wanted = ["person", "bicycle", "car", "motorbike", "bus", "truck"]
+    mask = torch.tensor([1 if n in wanted else 0 for n in COCO], dtype=torch.uint8, device="cuda")
+    out = ops.yolo_decode(torch.from_numpy(head).cuda(), mask, 0.25, (640, 480), (640, 480), ncap=1024)
+    keep, nkeep = ops.nms(out["tlwh"], out["score"], out["count"], 0.6)
+    assert int(out["flags"].sum()) == 0
+    tl, sc, cn = out["tlwh"].cpu().numpy(), out["score"].cpu().numpy(), out["count"].cpu().numpy()
+    kp, nk = keep.cpu().numpy(), nkeep.cpu().numpy()
+    for f in range(2):
+        tlwh, cls, score, anchor = odet.yolo_decode(head[f], 640, 480, COCO, wanted, 0.25)
+        ib, kept = odet.box_filter(list(tlwh), 640, 480)
+        assert list(kp[f, :nk[f]]) == odet.non_max_suppression(ib, 0.6, score[kept])
+
+    def covered(a, b):          # fraction of b's area (+1 convention) covered by a: the reference's overlap measure
+        x1, y1 = np.maximum(a[0], b[:, 0]), np.maximum(a[1], b[:, 1])
+        x2, y2 = np.minimum(a[0] + a[2], b[:, 0] + b[:, 2]), np.minimum(a[1] + a[3], b[:, 1] + b[:, 3])
+        w, h = np.maximum(0, x2 - x1 + 1), np.maximum(0, y2 - y1 + 1)
+        return w * h / ((b[:, 2] + 1) * (b[:, 3] + 1))
+
+    total = 0
+    for f in range(64):
+        n, k = int(cn[f]), int(nk[f])
+        ids = kp[f, :k]
+        assert n > 100 and 0 < k <= n and len(set(ids.tolist())) == k
+        s = sc[f, ids]
+        assert np.all(s[:-1] > s[1:])                                   # descending pick order
+        kb = tl[f, ids]
+        dropped = np.setdiff1d(np.arange(n), ids)
+        for i in range(k):
+            assert not np.any(covered(kb[i], kb[i + 1:]) > 0.6)         # survivors are not suppressed by earlier picks
+        for d in dropped[:: max(1, len(dropped) // 40)]:                # a sample of the dropped candidates
+            higher = ids[sc[f, ids] > sc[f, d]]
+            assert np.any(covered_by(tl[f, higher], tl[f, d]) > 0.6)
+        total += k
+    # idempotence on the device: NMS of the survivors keeps all of them in the same order
+    D2 = int(nk.max())
+    b2 = torch.zeros((64, D2, 4), dtype=torch.float64, device="cuda")
+    s2 = torch.zeros((64, D2), dtype=torch.float32, device="cuda")
+    for f in range(64):
+        b2[f, :nk[f]] = torch.from_numpy(tl[f, kp[f, :nk[f]]]).cuda()
+        s2[f, :nk[f]] = torch.from_numpy(sc[f, kp[f, :nk[f]]]).cuda()
+    k2, n2 = ops.nms(b2, s2, nkeep, 0.6)
+    np.testing.assert_array_equal(n2.cpu().numpy(), nk)
+    k2 = k2.cpu().numpy()
+    for f in range(64):
+        assert list(k2[f, :nk[f]]) == list(range(nk[f]))
+    assert total > 64 * 50
+
+
+def covered_by(boxes, b):
+    """max-over-rows helper: fraction of box b's (+1) area covered by each of `boxes`."""
+    x1, y1 = np.maximum(boxes[:, 0], b[0]), np.maximum(boxes[:, 1], b[1])
+    x2, y2 = np.minimum(boxes[:, 0] + boxes[:, 2], b[0] + b[2]), np.minimum(boxes[:, 1] + boxes[:, 3], b[1] + b[3])
+    w, h = np.maximum(0, x2 - x1 + 1), np.maximum(0, y2 - y1 + 1)
+    return w * h / ((b[2] + 1) * (b[3] + 1))
