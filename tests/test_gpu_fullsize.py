@@ -79,7 +79,8 @@ def test_c4_shard_size_matching_kernels_agree():
     from deepdish_b200 import _lib
     from deepdish_b200.batched import BatchedTracker
     S4, NOBJ4, D4, T4, TICKS4 = 512, 200, 224, 384, 14
-    sc = Scene(S4, NOBJ4, D4, n_labels=3, seed=91, device="cuda")
+    import os
+    sc = Scene(S4, NOBJ4, D4, n_labels=3, seed=int(os.environ.get("DD_C4_SEED", "91")), device="cuda")
     frames = [sc.step() for _ in range(TICKS4)]
     sample = [0, 255, 511]
     orc = OracleStreams(len(sample), LABELS3, budget=BUDGET, max_age=MAX_AGE)
