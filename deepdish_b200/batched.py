@@ -324,32 +324,19 @@ class BatchedTracker:
         Detection objects, deepdish.py:1014): per chunk ONE pinned byte blob
         ``[i32 offsets[n+1] | f64 tlwh[N,4] | f32 conf[N] | i32 label[N] | f32 feat[N,128]]`` holding only the
         detections that exist, so a tick uploads one copy per chunk and no padding."""
-        import numpy as np
-        cnt = batch.count.cpu().numpy().astype(np.int64)
+        from . import ragged
+        cnt = batch.count.cpu().numpy()
         tlwh, conf = batch.tlwh.cpu().numpy(), batch.conf.cpu().numpy()
         label, feat = batch.label.cpu().numpy(), batch.feat.cpu().numpy()
         if int(cnt.max(initial=0)) > self.max_dets:
             raise RuntimeError("detection capacity exceeded (max_dets=%d)" % self.max_dets)
         out = []
         for c in self.chunks:
-            k = cnt[c.lo:c.hi]
-            offs = np.zeros(len(k) + 1, dtype=np.int32)
-            offs[1:] = np.cumsum(k)
-            N = int(offs[-1])
-            sel = np.arange(self.max_dets)[None, :] < k[:, None]
-            o_tlwh = (4 * len(offs) + 15) // 16 * 16
-            o_conf = o_tlwh + 32 * N
-            o_label = o_conf + 4 * N
-            o_feat = (o_label + 4 * N + 15) // 16 * 16
-            total = o_feat + 512 * N
+            _, total = ragged.section_offsets(c.hi - c.lo, int(cnt[c.lo:c.hi].sum()))
             blob = torch.empty(max(total, 16), dtype=torch.uint8).pin_memory()
-            b = blob.numpy()
-            b[:4 * len(offs)].view(np.int32)[:] = offs
-            b[o_tlwh:o_conf].view(np.float64)[:] = tlwh[c.lo:c.hi][sel].reshape(-1)
-            b[o_conf:o_label].view(np.float32)[:] = conf[c.lo:c.hi][sel]
-            b[o_label:o_label + 4 * N].view(np.int32)[:] = label[c.lo:c.hi][sel]
-            b[o_feat:total].view(np.float32)[:] = feat[c.lo:c.hi][sel].reshape(-1)
-            out.append((blob, total, (o_tlwh, o_conf, o_label, o_feat)))
+            _, total, sections = ragged.pack(tlwh[c.lo:c.hi], conf[c.lo:c.hi], label[c.lo:c.hi], feat[c.lo:c.hi],
+                                             cnt[c.lo:c.hi], out=blob.numpy())
+            out.append((blob, total, sections))
         return out
 
     @staticmethod
