@@ -7,7 +7,6 @@ prep / gate / cosine / match / apply in microseconds.
     python benchmarks/timeline.py [--chunks 4] [--ticks 3]
 """
 import argparse
-import ctypes
 import os
 import sys
 

@@ -8,7 +8,7 @@ import torch
 from .. import _lib
 from ..batched import BatchedTracker
 from . import kalman_filter
-from .track import Track, TrackState
+from .track import Track, TrackState  # noqa: F401  (TrackState re-exported like the reference module)
 
 
 class Tracker:

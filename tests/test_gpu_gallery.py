@@ -5,7 +5,6 @@ short galleries (fewer rows than one 16-row step), budgets that are not multiple
 detections per track (several query groups) and more than 32 detections (several gate words)."""
 import numpy as np
 import pytest
-import torch
 
 from deepdish_b200.scene import Scene
 from tests.parity import LABELS3

@@ -1,5 +1,4 @@
 """GPU parity of the stand-alone C-ABI operators against the oracle / scipy / CPython."""
-import ctypes
 import random
 
 import numpy as np
@@ -7,7 +6,7 @@ import pytest
 import torch
 from scipy.optimize import linear_sum_assignment
 
-from oracle import deepsort as od, countline as oc, detect as odet
+from oracle import deepsort as od, countline as oc
 
 pytestmark = pytest.mark.gpu
 
