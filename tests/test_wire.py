@@ -32,7 +32,6 @@ def test_payload_matches_reference_pipeline():
     from oracle import refload
     if not refload.available():
         pytest.skip("reference tree not present")
-    import types
     mod = refload.load_pipeline_module()
     p = object.__new__(mod.Pipeline)
     p.wanted_labels = LABELS
