@@ -35,8 +35,15 @@ def main():
     ap.add_argument("--preroll", type=int, default=40)
     ap.add_argument("--objects", type=int, default=40)
     args = ap.parse_args()
-    dev = torch.device("cuda")
-    gen = torch.Generator(device=dev).manual_seed(0)
+    # under torchrun: one rank per GPU, every rank runs its own share of streams (weak scaling) and the [C,4] counters
+    # are all-reduced over NCCL after every tick -- C5's only collective
+    import torch.distributed as dist
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gen = torch.Generator(device=dev).manual_seed(rank)
     SY, SS, D = args.yolo, args.ssd, 64
     S = SY + SS
     NA, NC = 25200, 80
@@ -69,7 +76,7 @@ def main():
     ident = torch.randn((S, D, 128), device=dev, generator=gen)
     ident = ident / ident.norm(dim=-1, keepdim=True)
 
-    bt = BatchedTracker(S, LABELS, max_tracks=128, max_dets=D, budget=100, max_age=60, n_chunks=4)
+    bt = BatchedTracker(S, LABELS, max_tracks=128, max_dets=D, budget=100, max_age=60, n_chunks=2, device=dev)
     pipe = DetectTrackPipeline(bt, [
         YoloFrontEnd(0, SY, coco, LABELS, LABELS, ncap=1024),
         SsdFrontEnd(SY, S, ssd_names, LABELS, LABELS, anchors)])
@@ -85,30 +92,46 @@ def main():
     bt.join()
     pipe.check()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()
     for t in range(args.steps):
         pipe.detect(heads)
     ev[1].record()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ev[2].record()
     for t in range(args.steps):
         pipe.step(heads, fl[t % 4], join=False)
+        bt.all_reduce_counts(reduced=True, async_op=True)
     bt.join()
-    ev[2].record()
+    bt.wait_counts()
+    ev[3].record()
     torch.cuda.synchronize()
     pipe.check()
+    global_counts = bt.all_reduce_counts(reduced=True).cpu().tolist()
     det_ms = ev[0].elapsed_time(ev[1]) / args.steps
-    all_ms = ev[1].elapsed_time(ev[2]) / args.steps
+    all_ms = ev[2].elapsed_time(ev[3]) / args.steps
+    if world > 1:
+        tm = torch.tensor([all_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        all_ms = float(tm[0])
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     yolo_bytes = SY * NA * (5 + NC) * 4 + SS * 1917 * 95 * 4
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     print(json.dumps({
         "workload": "C5 share of one GPU: %d YOLOv5 (25200x85 f32) + %d SSD-MobileNet (1917x91) streams, decode + box "
                     "filter + NMS + gather + tracker tick + count-line + count reduce" % (SY, SS),
-        "stream_frames_per_s": S / all_ms * 1e3, "ms_per_tick": all_ms, "detect_only_ms": det_ms,
+        "n_gpus": world, "stream_frames_per_s": world * S / all_ms * 1e3, "ms_per_tick": all_ms, "detect_only_ms": det_ms,
         "detect_head_GBps": yolo_bytes / det_ms / 1e6, "detect_frac_of_measured_hbm": yolo_bytes / det_ms / 1e6 / peak,
         "dets_per_stream": float(pipe.det_count.float().mean()), "tracks_per_stream": float(bt.v["n_tracks"].float().mean()),
         "gallery_rows_per_stream": float(bt.gallery_vectors().float().mean()),
-        "counts": bt.total_counts.cpu().tolist()}))
+        "counts_all_ranks": global_counts}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
