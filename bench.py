@@ -200,12 +200,10 @@ def gpu_arm(args):
         cpu = cpu_reference(steps=60, warm=0, preroll=100)
 
     P = args.chunks
-    from deepdish_b200 import _lib
-    for key, val in ((0, args.gate_impl), (1, args.cosine_ctas), (2, args.prio), (3, args.cs), (4, args.pdl), (5, args.match_cta)):
-        if val is not None:
-            _lib.check(_lib.lib().dd_tuning_set(key, val), "dd_tuning_set")
+    knobs = dict(gallery_impl=args.gallery_impl, cosine_ctas_per_sm=args.cosine_ctas, match_warps=args.match_warps,
+                 gallery_stages=args.gallery_stages)
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
-                        n_chunks=P, chain_gallery=bool(args.chain))
+                        n_chunks=P, **knobs)
     scene = Scene(S, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=1234 + rank, device=dev)
     pre = [scene.step() for _ in range(PREROLL)]
     for b in pre:
@@ -250,7 +248,8 @@ def gpu_arm(args):
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms = start.elapsed_time(end)
-    cd = bt.v["cdesc"][..., 1]
+    state_bytes = bt.memory_bytes()
+    cd = bt.v["cdesc"][..., 2]
     cand_per_track = float(cd.sum()) / max(1, int((cd > 0).sum()))      # gate-passing detections per streamed track
     g1 = int(bt.gallery_vectors().sum())
     conf1 = int(((bt.v["state"] == 2).sum()))
@@ -294,7 +293,7 @@ def gpu_arm(args):
     if rank == 0:
         del bt
         torch.cuda.empty_cache()
-        bt1 = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev)
+        bt1 = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev, **knobs)
         for b in pre + frames[:W]:
             bt1.step(b)
         evs = [bt1.new_events(6) for _ in range(K)]
@@ -330,7 +329,7 @@ def gpu_arm(args):
         gc_ms = stage[2]
         achieved = gc_bytes / (gc_ms * 1e-3) / 1e9
         tick_bytes = 512.0 * (G + Dn + Dn) + 1152.0 * (TC * 1.1) + 44.0 * Dn
-        half = args.gate_impl in (None, 3)
+        half = args.gallery_impl != "exact"
         kname = "k_cosine_h" if half else "k_cosine"
         traffic = load_traffic(kname) if WORKLOAD_NAME == "c3" else None
         # bytes the kernel must move with the half-precision pre-pass: 256 B per gallery row + the half queries
@@ -354,6 +353,7 @@ def gpu_arm(args):
             "dtype": "f64 (Kalman/gating/IoU/LSAP/count-line) + f32 (cosine)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": S, "max_tracks": TMAX, "max_dets": DMAX,
                        "preroll_ticks": PREROLL, "stream_chunks": P, "gallery_vectors_per_stream": G / S,
+                       "tracker_state_bytes": state_bytes,
                        "confirmed_tracks_per_stream": TC / S, "dets_per_frame": Dn / S, "gate_passing_dets_per_streamed_track": cand_per_track,
                        "l2": "inputs larger than L2: %.2f GB of galleries streamed per tick" % (512 * G / 1e9)},
             "e2e": {"value": S * world * K / (e2e_all * 1e-3), "unit": "stream-frames/s",
@@ -397,13 +397,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-affinity", action="store_true", help="multi-GPU: do not pin each rank to its GPU's CPUs")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"], help="c3 = the metric's configuration (default)")
-    ap.add_argument("--gate-impl", type=int, default=None, help="A/B knob: gallery kernel 3 half pre-pass + exact re-check (default), 2 exact persistent work list, 0 exact full grid, 1 exact TMA ring")
-    ap.add_argument("--cosine-ctas", type=int, default=None, help="A/B knob: CTAs per SM of the persistent gallery kernel")
-    ap.add_argument("--chain", type=int, default=0, help="A/B knob: chunks take turns on the gallery kernel")
-    ap.add_argument("--cs", type=int, default=None, help="A/B knob: 1 = streaming (evict-first) gallery loads")
-    ap.add_argument("--match-cta", type=int, default=None, help="A/B knob: 1 = four warps per stream in k_match, 0 = one")
-    ap.add_argument("--pdl", type=int, default=None, help="A/B knob: programmatic dependent launch on / off")
-    ap.add_argument("--prio", type=int, default=None, help="A/B knob: 1 = small kernels at high priority, 0 = equal")
+    ap.add_argument("--gallery-impl", default="default", choices=["default", "exact", "half_warp"],
+                    help="A/B knob: gallery kernel (all bit-identical): default, exact f32 pass, half pre-pass with per-warp loads")
+    ap.add_argument("--cosine-ctas", type=int, default=0, help="A/B knob: CTAs per SM of the persistent gallery kernel")
+    ap.add_argument("--gallery-stages", type=int, default=0, help="A/B knob: ring stages per warp pair of the default gallery kernel")
+    ap.add_argument("--match-warps", type=int, default=0, help="A/B knob: warps per stream in the matching kernel (0 = by size)")
     ap.add_argument("--chunks", type=int, default=2, help="stream chunks pipelined on separate CUDA streams")
     args = ap.parse_args()
     set_workload(args.workload)

@@ -11,7 +11,11 @@ LIB_PATH = os.path.join(HERE, "libdeepdish_b200.so")
 
 DD_OK, DD_ERR_INVALID, DD_ERR_CUDA, DD_ERR_CAPACITY = 0, -1, -2, -3
 DD_MAX_LABELS = 128
+DD_MAX_SEGS = 16
+PAGE_ROWS, PAGE_F32_BYTES, PAGE_F16_BYTES = 16, 8192, 4096
 FLAG_TRACK_OVERFLOW, FLAG_DET_OVERFLOW, FLAG_LSAP_INFEASIBLE = 1, 2, 4
+FLAG_POOL_EXHAUSTED, FLAG_GALLERY_OVERFLOW, FLAG_BAD_LABEL = 8, 16, 32
+GALLERY_IMPLS = {"default": 0, "exact": 1, "half_warp": 2}
 
 _i32, _f64, _u64, _vp = ctypes.c_int32, ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p
 
@@ -21,13 +25,17 @@ class TrackerConfig(ctypes.Structure):
                 ("feat_dim", _i32), ("n_labels", _i32), ("max_age", _i32), ("n_init", _i32),
                 ("max_cosine_distance", _f64), ("max_iou_distance", _f64),
                 ("label_motorbike", _i32), ("label_bicycle", _i32),
-                ("label_rank", _i32 * DD_MAX_LABELS)]
+                ("label_rank", _i32 * DD_MAX_LABELS),
+                ("page_cap", _i32), ("seg_pages", _i32), ("n_segs", _i32),
+                ("gallery_impl", _i32), ("cosine_ctas_per_sm", _i32), ("match_warps", _i32),
+                ("gallery_stages", _i32), ("reserved0", _i32),
+                ("pool_f32", _u64 * DD_MAX_SEGS), ("pool_f16", _u64 * DD_MAX_SEGS)]
 
 
 LAYOUT_FIELDS = ["n_tracks", "next_id", "n_deleted", "err", "order", "deleted", "counts", "mean", "cov",
-                 "track_id", "hits", "age", "tsu", "state", "gal_len", "gal_pos", "gal", "lab_cnt",
-                 "lab_sum", "path_n", "path_last", "path_crossed", "gate", "cost", "det_xyah",
-                 "det_featn", "det_slot", "det_kind", "cdesc", "work", "work_ctl", "galh", "det_feath"]
+                 "track_id", "hits", "age", "tsu", "state", "gal_len", "gal_pos", "gal_np", "ptab", "free_stack",
+                 "pool_ctl", "lab_cnt", "lab_sum", "path_n", "path_last", "path_crossed", "gate", "cost", "det_xyah",
+                 "det_featn", "det_slot", "det_kind", "cdesc", "work", "work_ctl", "work_rec", "det_feath"]
 
 
 class TrackerLayout(ctypes.Structure):
@@ -36,34 +44,50 @@ class TrackerLayout(ctypes.Structure):
 
 def field_specs(cfg):
     """name -> (dtype string, shape) of every array in the state blob."""
-    S, T, D, B, C = cfg.n_streams, cfg.max_tracks, cfg.max_dets, cfg.budget, cfg.n_labels
+    S, T, D, C = cfg.n_streams, cfg.max_tracks, cfg.max_dets, cfg.n_labels
     DW = (D + 31) // 32
+    PT = page_cap(cfg)
     i, f, d = "int32", "float32", "float64"
     return {
         "n_tracks": (i, (S,)), "next_id": (i, (S,)), "n_deleted": (i, (S,)), "err": (i, (S,)),
         "order": (i, (S, T)), "deleted": (i, (S, T)), "counts": ("int64", (S, C, 4)),
         "mean": (d, (S, T, 8)), "cov": (d, (S, T, 8, 8)), "track_id": (i, (S, T)),
         "hits": (i, (S, T)), "age": (i, (S, T)), "tsu": (i, (S, T)), "state": (i, (S, T)),
-        "gal_len": (i, (S, T)), "gal_pos": (i, (S, T)), "gal": (f, (S, T, B, 128)),
+        "gal_len": (i, (S, T)), "gal_pos": (i, (S, T)), "gal_np": (i, (S, T)), "ptab": (i, (S, T, PT)),
+        "free_stack": (i, (DD_MAX_SEGS * cfg.seg_pages,)), "pool_ctl": (i, (64,)),
         "lab_cnt": (i, (S, T, C)), "lab_sum": (d, (S, T, C)), "path_n": (i, (S, T)),
         "path_last": (d, (S, T, 2)), "path_crossed": (i, (S, T)), "gate": (i, (S, T, DW)),
         "cost": (f, (S, T, D)), "det_xyah": (d, (S, D, 4)), "det_featn": (f, (S, D, 128)),
-        "det_slot": (i, (S, D)), "det_kind": (i, (S, D)), "cdesc": (i, (S, T, 2)),
-        "work": (i, (S * T,)), "work_ctl": (i, (64,)),
-        "galh": ("float16", (S, T, B, 128)), "det_feath": ("float16", (S, D, 128)),
+        "det_slot": (i, (S, D)), "det_kind": (i, (S, D)), "cdesc": (i, (S, T, 4)),
+        "work": (i, (S * T,)), "work_ctl": (i, (64,)), "work_rec": (i, (S * T, 16)),
+        "det_feath": ("float16", (S, D, 128)),
     }
 
 
+def page_cap(cfg):
+    """Page-table entries per slot (dd_page_cap in csrc/dd_view.h)."""
+    need = (cfg.budget + PAGE_ROWS - 1) // PAGE_ROWS if cfg.budget > 0 else 1
+    return max(cfg.page_cap, need)
+
+
 def make_config(n_streams, max_tracks, max_dets, budget, labels, max_age=30, n_init=3,
-                max_cosine_distance=0.2, max_iou_distance=0.7):
-    """Fill a dd_tracker_config from Python values; ``labels`` is the ordered list of label names."""
+                max_cosine_distance=0.2, max_iou_distance=0.7, page_cap=0, seg_pages=1024,
+                gallery_impl=0, cosine_ctas_per_sm=0, match_warps=0, gallery_stages=0):
+    """Fill a dd_tracker_config from Python values; ``labels`` is the ordered list of label names.
+    ``budget=None`` is the reference's nn_budget=None (deepdish.py:515): unbounded galleries (budget 0 in the C
+    struct).  The pool segment pointers are filled in by the caller that allocates them."""
     labels = list(labels)
     if not 0 < len(labels) <= DD_MAX_LABELS:
         raise ValueError("need 1..%d labels" % DD_MAX_LABELS)
-    if budget is None:
-        raise ValueError("the batched tracker needs a finite nn_budget (gallery ring capacity)")
+    if budget is not None and budget <= 0:
+        raise ValueError("nn_budget must be positive or None")
+    if seg_pages <= 0 or seg_pages & (seg_pages - 1):
+        raise ValueError("seg_pages must be a power of two")
     cfg = TrackerConfig()
-    cfg.n_streams, cfg.max_tracks, cfg.max_dets, cfg.budget = n_streams, max_tracks, max_dets, budget
+    cfg.n_streams, cfg.max_tracks, cfg.max_dets, cfg.budget = n_streams, max_tracks, max_dets, budget or 0
+    cfg.page_cap, cfg.seg_pages, cfg.n_segs = page_cap, seg_pages, 1
+    cfg.gallery_impl = GALLERY_IMPLS[gallery_impl] if isinstance(gallery_impl, str) else int(gallery_impl)
+    cfg.cosine_ctas_per_sm, cfg.match_warps, cfg.gallery_stages = cosine_ctas_per_sm, match_warps, gallery_stages
     cfg.feat_dim, cfg.n_labels, cfg.max_age, cfg.n_init = 128, len(labels), max_age, n_init
     cfg.max_cosine_distance, cfg.max_iou_distance = max_cosine_distance, max_iou_distance
     cfg.label_motorbike = labels.index("motorbike") if "motorbike" in labels else -1
@@ -94,15 +118,19 @@ def lib():
         "dd_tracker_init": [_vp, cfgp, _vp],
         "dd_tracker_predict": [_vp, cfgp, _vp],
         "dd_tracker_update": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-        "dd_tracker_update_profiled": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       ctypes.POINTER(_vp), _vp, _vp],
-        "dd_tuning_set": [_i32, _i32],
+        "dd_tracker_update_profiled": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)],
+        "dd_tracker_pool_attach": [_vp, cfgp, _vp],
+        "dd_tracker_gallery_read": [_vp, cfgp, _i32, _i32, _vp, _i32, _vp],
+        "dd_tracker_gallery_insert": [_vp, cfgp, _i32, _i32, _vp, _i32, _vp],
         "dd_event_create": [ctypes.POINTER(_vp)],
         "dd_event_destroy": [_vp],
         "dd_event_elapsed_ms": [_vp, _vp, ctypes.POINTER(ctypes.c_float)],
+        "dd_event_record": [_vp, _vp],
+        "dd_event_query": [_vp],
+        "dd_event_synchronize": [_vp],
+        "dd_tracker_pool_poll": [_vp, cfgp, _vp, _vp, _vp],
         "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
         "dd_tracker_tick": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
-        "dd_tracker_tick_chained": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
         "dd_tracker_tick_ragged": [_vp, cfgp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
         "dd_unpack_detections": [_vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

@@ -24,20 +24,61 @@ _DT = {"int32": torch.int32, "int64": torch.int64, "float32": torch.float32,
        "float64": torch.float64, "float16": torch.float16}
 
 
+def _pow2_at_least(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
 class _Chunk:
-    """One contiguous block of streams: config, state blob, typed views, CUDA stream."""
+    """One contiguous block of streams: config, state blob, gallery page pool, typed views, CUDA stream.
+
+    Gallery storage is a pool of 16-row pages (f32 page + half page) in up to ``DD_MAX_SEGS`` equal segments
+    allocated with torch; the blob only holds the page tables.  ``grow_pool`` attaches one more segment,
+    ``grow_page_table`` re-lays the blob out with a larger per-slot page table (unbounded galleries)."""
 
     def __init__(self, owner, lo, hi, stream):
         self.lo, self.hi = lo, hi
         self.stream = stream
-        o = owner
-        self.cfg = _lib.make_config(hi - lo, o.max_tracks, o.max_dets, o.budget, o.labels, max_age=o.max_age,
+        self.owner = o = owner
+        n = hi - lo
+        rows = o.budget if o.budget is not None else 64
+        worst = n * o.max_tracks * ((rows + _lib.PAGE_ROWS - 1) // _lib.PAGE_ROWS)
+        seg_pages = o.seg_pages or _pow2_at_least(max(64, -(-worst // (_lib.DD_MAX_SEGS - 4))))
+        want = o.pool_pages if o.pool_pages is not None else max(1, int(worst * o.pool_fraction))
+        n_segs = max(1, min(_lib.DD_MAX_SEGS, -(-want // seg_pages)))
+        self.cfg = _lib.make_config(n, o.max_tracks, o.max_dets, o.budget, o.labels, max_age=o.max_age,
                                     n_init=o.n_init, max_cosine_distance=o.max_cosine_distance,
-                                    max_iou_distance=o.max_iou_distance)
+                                    max_iou_distance=o.max_iou_distance, page_cap=o.page_cap, seg_pages=seg_pages,
+                                    gallery_impl=o.gallery_impl, cosine_ctas_per_sm=o.cosine_ctas_per_sm,
+                                    match_warps=o.match_warps, gallery_stages=o.gallery_stages)
         self.cfgp = ctypes.byref(self.cfg)
+        self.segs = []
+        for _ in range(n_segs):
+            self._alloc_seg()
+        self.cfg.n_segs = n_segs
+        self._bind()
+        self.done = torch.cuda.Event()
+        self.staging = None
+        self.poll = None              # (pinned copy of pool_ctl[:4], event) of the latest tick
+
+    def _alloc_seg(self):
+        k = len(self.segs)
+        if k >= _lib.DD_MAX_SEGS:
+            raise RuntimeError("gallery page pool cannot grow beyond %d segments of %d pages; construct the tracker "
+                               "with a larger seg_pages" % (_lib.DD_MAX_SEGS, self.cfg.seg_pages))
+        dev = self.owner.device
+        f32 = torch.empty(self.cfg.seg_pages * _lib.PAGE_F32_BYTES, dtype=torch.uint8, device=dev)
+        f16 = torch.empty(self.cfg.seg_pages * _lib.PAGE_F16_BYTES, dtype=torch.uint8, device=dev)
+        self.segs.append((f32, f16))
+        self.cfg.pool_f32[k], self.cfg.pool_f16[k] = f32.data_ptr(), f16.data_ptr()
+
+    def _bind(self):
+        """(Re)compute the layout for self.cfg, allocate the blob and make the typed views."""
         self.lay = _lib.TrackerLayout()
-        _lib.check(o.lib.dd_tracker_layout_query(self.cfgp, ctypes.byref(self.lay)), "dd_tracker_layout_query")
-        self.blob = torch.empty(self.lay.total_bytes, dtype=torch.uint8, device=o.device)
+        _lib.check(self.owner.lib.dd_tracker_layout_query(self.cfgp, ctypes.byref(self.lay)), "dd_tracker_layout_query")
+        self.blob = torch.empty(self.lay.total_bytes, dtype=torch.uint8, device=self.owner.device)
         self.state = self.blob.data_ptr()
         self.v = {}
         for name, (dt, shape) in _lib.field_specs(self.cfg).items():
@@ -46,10 +87,29 @@ class _Chunk:
             for d in shape:
                 n *= d
             self.v[name] = self.blob[off:off + n].view(_DT[dt]).view(shape)
-        self.done = torch.cuda.Event()
-        self.staging = None
-        self.turn_done = None     # C-ABI event: this chunk's gallery kernel of the latest tick has finished
-        self.turn_wait = None     # the previous chunk's turn_done
+
+    def pool_bytes(self):
+        return sum(a.numel() + b.numel() for a, b in self.segs)
+
+    def grow_pool(self, sp):
+        """Attach one more pool segment (enqueued on the chunk's stream: ordered after the ticks already there)."""
+        self._alloc_seg()
+        self.cfg.n_segs = len(self.segs)
+        _lib.check(self.owner.lib.dd_tracker_pool_attach(self.state, self.cfgp, sp), "dd_tracker_pool_attach")
+
+    def grow_page_table(self, page_cap):
+        """Re-layout with a larger per-slot page table.  The caller has synchronised the chunk's stream."""
+        old = self.v
+        old_blob = self.blob  # noqa: F841  (keeps the old views alive while copying)
+        self.cfg.page_cap = int(page_cap)
+        self._bind()
+        pt = old["ptab"].shape[2]
+        for name, t in self.v.items():
+            if name == "ptab":
+                t[:, :, :pt].copy_(old[name])
+            else:
+                t.copy_(old[name])
+        self.poll = None
 
 
 class _CatView:
@@ -76,8 +136,19 @@ class _CatView:
 class BatchedTracker:
     def __init__(self, n_streams, labels, max_tracks=128, max_dets=64, budget=100,
                  max_cosine_distance=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
-                 line=None, frame_size=(640, 480), device="cuda", n_chunks=1, chain_gallery=False):
+                 line=None, frame_size=(640, 480), device="cuda", n_chunks=1,
+                 pool_pages=None, pool_fraction=0.5, seg_pages=None, page_cap=0,
+                 gallery_impl="default", cosine_ctas_per_sm=0, match_warps=0, gallery_stages=0):
+        """budget=None is the reference's nn_budget=None (deepdish.py:515-516): galleries grow without bound; the
+        page pool and the per-slot page tables are grown between ticks (``maintain``).
+
+        Gallery memory: ``pool_pages`` 16-row pages per chunk (default: ``pool_fraction`` of the worst case
+        streams x max_tracks x ceil(budget / 16)), in segments of ``seg_pages``; more segments are attached when
+        fewer than 1/8 of the pages are free.  A pool that still runs dry raises in ``check()``."""
         self.lib = _lib.lib()
+        self.pool_pages, self.pool_fraction, self.seg_pages, self.page_cap = pool_pages, pool_fraction, seg_pages, page_cap
+        self.gallery_impl, self.cosine_ctas_per_sm, self.match_warps = gallery_impl, cosine_ctas_per_sm, match_warps
+        self.gallery_stages = gallery_stages
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedTracker runs on a CUDA device only (no CPU fallback)")
@@ -95,9 +166,7 @@ class BatchedTracker:
                 lo, hi = shard_range(n_streams, i, n_chunks)
                 st = None if n_chunks == 1 else torch.cuda.Stream(device=self.device)
                 self.chunks.append(_Chunk(self, lo, hi, st))
-        self.cfg = self.chunks[0].cfg if n_chunks == 1 else _lib.make_config(
-            n_streams, max_tracks, max_dets, budget, self.labels, max_age=max_age, n_init=n_init,
-            max_cosine_distance=max_cosine_distance, max_iou_distance=max_iou_distance)
+        self.cfg = self.chunks[0].cfg          # shape-independent fields (labels, thresholds, capacities per stream)
         self.v = _CatView(self)
         if line is None:                      # deepdish.py:739-744
             w, h = frame_size
@@ -111,20 +180,75 @@ class BatchedTracker:
         self.total_counts = torch.zeros((C, 4), dtype=torch.int64, device=self.device)
         self._tick = 0
         self._sum_done = [None, None]
-        self.chain_gallery = bool(chain_gallery) and n_chunks > 1
-        if n_chunks > 1:          # chunks take turns on the HBM-bound gallery kernel (dd_tracker_tick_chained)
-            for c in self.chunks:
-                h = ctypes.c_void_p()
-                _lib.check(self.lib.dd_event_create(ctypes.byref(h)), "dd_event_create")
-                c.turn_done = h
-            for i, c in enumerate(self.chunks):
-                c.turn_wait = self.chunks[i - 1].turn_done
+        self._poll_pool = any(len(c.segs) * c.cfg.seg_pages < self._worst_pages(c) for c in self.chunks) or budget is None
         torch.cuda.synchronize(self.device)
         for c in self.chunks:
             _lib.check(self.lib.dd_tracker_init(c.state, c.cfgp, self._sp(c)), "dd_tracker_init")
         self.join()
 
     # ------------------------------------------------------------------------------------------
+    def _worst_pages(self, c):
+        if self.budget is None:
+            return float("inf")
+        return (c.hi - c.lo) * self.max_tracks * ((self.budget + _lib.PAGE_ROWS - 1) // _lib.PAGE_ROWS)
+
+    POLL_EVERY = 2        # ticks between polls of the pool counters (the forecast covers 8 appends ahead)
+
+    def _post_tick(self, c, st):
+        """After a chunk's tick was enqueued on stream ``st``: every POLL_EVERY ticks copy its pool counters to
+        pinned memory (dd_tracker_pool_poll; no host synchronisation) so that ``maintain`` can grow the pool ahead
+        of need."""
+        if not self._poll_pool or self._tick % self.POLL_EVERY:
+            return
+        if c.poll is None:
+            ev = ctypes.c_void_p()
+            _lib.check(self.lib.dd_event_create(ctypes.byref(ev)), "dd_event_create")
+            c.poll = [torch.zeros(4, dtype=torch.int32).pin_memory(), ev, -1, True]    # host copy, event, tick, seen
+        host, ev, tick, seen = c.poll
+        if tick >= 0 and not seen and self.lib.dd_event_query(ev) != 1:
+            return                                    # the previous poll is still in flight: keep it
+        _lib.check(self.lib.dd_tracker_pool_poll(c.state, c.cfgp, host.data_ptr(), ev, ctypes.c_void_p(st.cuda_stream)),
+                   "dd_tracker_pool_poll")
+        c.poll[2], c.poll[3] = self._tick, False
+
+    def maintain(self, wait=False):
+        """Grow gallery storage ahead of need, from the latest poll of every chunk's pool counters (``wait=True``:
+        from the state right now, synchronising).  A poll that is 3 ticks old is waited for, so the host never runs
+        further ahead of the device than the 8-append forecast covers.
+        Pool: segments are attached until the free pages cover the forecast (pages the live tracks can take within
+        their next 8 appends) plus one page per detection slot (new tracks).  Unbounded galleries: the page table is doubled when the
+        longest gallery is within 128 rows of its capacity."""
+        for c in self.chunks:
+            st = c.stream if c.stream is not None else self._cur()
+            if wait:
+                st.synchronize()
+                ctl = c.v["pool_ctl"][:4].cpu()
+            elif c.poll is not None and c.poll[2] >= 0 and not c.poll[3]:
+                if self.lib.dd_event_query(c.poll[1]) != 1:
+                    if self._tick - c.poll[2] < 3:
+                        continue
+                    _lib.check(self.lib.dd_event_synchronize(c.poll[1]), "dd_event_synchronize")
+                ctl = c.poll[0]
+                c.poll[3] = True
+            else:
+                continue
+            free, attached, longest, forecast = int(ctl[0]), int(ctl[1]), int(ctl[2]), int(ctl[3])
+            # new tracks take one page each: keep one worst-case tick of them (every detection a new track) in hand
+            want = forecast + forecast // 4 + (c.hi - c.lo) * min(self.max_dets, self.max_tracks)
+            while attached == len(c.segs) * c.cfg.seg_pages and free < want \
+                    and attached < self._worst_pages(c) and len(c.segs) < _lib.DD_MAX_SEGS:
+                c.grow_pool(ctypes.c_void_p(st.cuda_stream))
+                free += c.cfg.seg_pages
+                attached += c.cfg.seg_pages
+            cap_rows = _lib.page_cap(c.cfg) * _lib.PAGE_ROWS
+            if self.budget is None and longest + 128 >= cap_rows:
+                st.synchronize()
+                c.grow_page_table(2 * _lib.page_cap(c.cfg))
+
+    def memory_bytes(self):
+        """Device bytes of the tracker state: blobs + gallery page pool."""
+        return sum(c.blob.numel() + c.pool_bytes() for c in self.chunks)
+
     def _cur(self):
         return torch.cuda.current_stream(self.device)
 
@@ -189,10 +313,13 @@ class BatchedTracker:
         tlwh f64 [S,Dmax,4], conf f32 [S,Dmax], label i32 [S,Dmax], feat f32 [S,Dmax,128], count i32 [S]
         -- device tensors, padded.  Returns det_track_id i32 [S,Dmax] (device; -1 = padding)."""
         self._check_batch(tlwh, conf, label, feat, count)
+        if self._poll_pool:
+            self.maintain()
         self._fork((tlwh, conf, label, feat, count))
         for c in self.chunks:
             p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
             _lib.check(self.lib.dd_tracker_update(c.state, c.cfgp, *p, self._sp(c)), "dd_tracker_update")
+            self._post_tick(c, c.stream if c.stream is not None else self._cur())
         self.join()
         return self.det_track_id
 
@@ -202,7 +329,7 @@ class BatchedTracker:
             raise RuntimeError("update_profiled needs n_chunks=1")
         c = self.chunks[0]
         p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
-        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events6, None, None),
+        _lib.check(self.lib.dd_tracker_update_profiled(c.state, c.cfgp, *p, self._sp(c), events6),
                    "dd_tracker_update_profiled")
         return self.det_track_id
 
@@ -232,6 +359,8 @@ class BatchedTracker:
         object of device tensors: one fused C call per chunk.  join=False only enqueues (call join())."""
         tlwh, conf, label, feat, count = batch.tlwh, batch.conf, batch.label, batch.feat, batch.count
         self._check_batch(tlwh, conf, label, feat, count)
+        if self._poll_pool:
+            self.maintain()
         self._fork((tlwh, conf, label, feat, count))
         par = self._tick & 1
         multi = len(self.chunks) > 1
@@ -242,6 +371,7 @@ class BatchedTracker:
             p = self._ptrs(c, tlwh, conf, label, feat, count, self.det_track_id)
             out = self.partial_counts[par, i].data_ptr() if reduce else None
             self._tick_call(c, p, out, self._sp(c))
+            self._post_tick(c, c.stream if c.stream is not None else self._cur())
         self._mark()
         if reduce:
             self._sum_partials(par)
@@ -251,12 +381,8 @@ class BatchedTracker:
         return self.det_track_id
 
     def _tick_call(self, c, p, out, sp):
-        if self.chain_gallery:
-            _lib.check(self.lib.dd_tracker_tick_chained(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream,
-                                                        out, c.turn_wait, c.turn_done, sp), "dd_tracker_tick_chained")
-        else:
-            _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream, out,
-                                                sp), "dd_tracker_tick")
+        _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream, out, sp),
+                   "dd_tracker_tick")
 
     def _sum_partials(self, par):
         """caller's stream: wait for the chunks' partial counters of this tick, sum them."""
@@ -275,6 +401,8 @@ class BatchedTracker:
         of its det->track ids into the pinned ``out_ids_host``.  Returns total_counts (device, summed on the
         caller's stream)."""
         D = self.max_dets
+        if self._poll_pool:
+            self.maintain()
         par = self._tick & 1
         multi = len(self.chunks) > 1
         if multi and self._sum_done[par] is not None:
@@ -294,6 +422,7 @@ class BatchedTracker:
                                 ctypes.c_void_p(st.cuda_stream))
                 if out_ids_host is not None:
                     out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
+            self._post_tick(c, st)
         self._mark()
         self._sum_partials(par)
         self._tick += 1
@@ -349,6 +478,8 @@ class BatchedTracker:
         tick k --, then on the chunk's compute stream the tick reading the blob directly (dd_tracker_tick_ragged)
         with its partial count reduction and (optionally) the D2H copy of the det->track ids.  The pinned blobs must stay alive until their copy has
         run.  Returns total_counts (device, summed on the caller's stream)."""
+        if self._poll_pool:
+            self.maintain()
         par = self._tick & 1
         multi = len(self.chunks) > 1
         if multi and self._sum_done[par] is not None:
@@ -383,6 +514,7 @@ class BatchedTracker:
                 c.unpacked[par] = st.record_event()
                 if out_ids_host is not None:
                     out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
+            self._post_tick(c, st)
         self._mark()
         self._sum_partials(par)
         self._tick += 1
@@ -455,6 +587,13 @@ class BatchedTracker:
             raise RuntimeError("detection capacity exceeded (max_dets=%d)" % self.max_dets)
         if f & _lib.FLAG_LSAP_INFEASIBLE:
             raise ValueError("cost matrix is infeasible")
+        if f & _lib.FLAG_POOL_EXHAUSTED:
+            raise RuntimeError("gallery page pool exhausted (a feature was not appended); construct the tracker with a "
+                               "larger pool_pages / pool_fraction")
+        if f & _lib.FLAG_GALLERY_OVERFLOW:
+            raise RuntimeError("a gallery outgrew its page table (page_cap); call maintain() more often")
+        if f & _lib.FLAG_BAD_LABEL:
+            raise ValueError("a detection label is outside [0, n_labels)")
 
     # ------------------------------------------------------------------------------------------
     def state_dict(self):
@@ -463,16 +602,32 @@ class BatchedTracker:
         self.join()
         torch.cuda.synchronize(self.device)
         return {"blobs": [c.blob.cpu() for c in self.chunks], "tick": self._tick,
+                "pools": [[(a.cpu(), b.cpu()) for a, b in c.segs] for c in self.chunks],
+                "page_caps": [_lib.page_cap(c.cfg) for c in self.chunks],
                 "shape": (self.n_streams, self.max_tracks, self.max_dets, self.budget, len(self.labels),
-                          len(self.chunks)), "total_counts": self.total_counts.cpu()}
+                          len(self.chunks), self.chunks[0].cfg.seg_pages), "total_counts": self.total_counts.cpu()}
 
     def load_state_dict(self, sd):
-        shape = (self.n_streams, self.max_tracks, self.max_dets, self.budget, len(self.labels), len(self.chunks))
+        shape = (self.n_streams, self.max_tracks, self.max_dets, self.budget, len(self.labels), len(self.chunks),
+                 self.chunks[0].cfg.seg_pages)
         if tuple(sd["shape"]) != shape:
             raise ValueError("checkpoint shape %s does not match tracker %s" % (tuple(sd["shape"]), shape))
         self.join()
-        for c, b in zip(self.chunks, sd["blobs"]):
+        torch.cuda.synchronize(self.device)
+        for c, b, pool, cap in zip(self.chunks, sd["blobs"], sd["pools"], sd["page_caps"]):
+            if len(pool) < len(c.segs):
+                raise ValueError("checkpoint has fewer pool segments (%d) than this tracker (%d)" % (len(pool), len(c.segs)))
+            while len(c.segs) < len(pool):        # page ids in the checkpoint refer to every segment it had
+                c._alloc_seg()
+            c.cfg.n_segs = len(c.segs)
+            if cap != _lib.page_cap(c.cfg):
+                c.cfg.page_cap = cap
+                c._bind()
             c.blob.copy_(b.to(self.device))
+            for (a, h), (pa, ph) in zip(c.segs, pool):
+                a.copy_(pa.to(self.device))
+                h.copy_(ph.to(self.device))
+            c.poll = None
         self.total_counts.copy_(sd["total_counts"].to(self.device))
         self._tick = int(sd["tick"])
         self._sum_done = [None, None]
@@ -480,7 +635,7 @@ class BatchedTracker:
 
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
-        names = names or [n for n in self.v.keys() if n not in ("gal", "galh", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl")]
+        names = names or [n for n in self.v.keys() if n not in ("ptab", "free_stack", "pool_ctl", "work_rec", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl")]
         out = {}
         for n in names:
             t = self.v[n]
@@ -488,6 +643,37 @@ class BatchedTracker:
                 t = t[torch.as_tensor(streams, device=self.device)]
             out[n] = t.cpu().numpy()
         return out
+
+    def _chunk_of(self, stream):
+        for c in self.chunks:
+            if c.lo <= stream < c.hi:
+                return c
+        raise IndexError("stream %d out of range" % stream)
+
+    def gallery(self, stream, slot):
+        """metric.samples of one slot (nn_matching.py:132-154): its unit-normalised gallery rows, oldest first, as a
+        float32 CUDA tensor [len, 128] (dd_tracker_gallery_read)."""
+        c = self._chunk_of(stream)
+        self.join()
+        n = int(c.v["gal_len"][stream - c.lo, slot])
+        out = torch.empty((n, 128), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dd_tracker_gallery_read(c.state, c.cfgp, stream - c.lo, slot, out.data_ptr(), n,
+                                                    ctypes.c_void_p(self._cur().cuda_stream)), "dd_tracker_gallery_read")
+        return out
+
+    def gallery_insert(self, stream, slot, feature, before_newest=False):
+        """Host edit: append one unit-normalised feature to a slot's gallery (before its newest row when
+        ``before_newest``), as metric.partial_fit would (dd_tracker_gallery_insert)."""
+        c = self._chunk_of(stream)
+        self.join()
+        f = torch.as_tensor(feature, dtype=torch.float32).to(self.device).contiguous()
+        if f.numel() != 128:
+            raise ValueError("feature must have 128 components")
+        _lib.check(self.lib.dd_tracker_gallery_insert(c.state, c.cfgp, stream - c.lo, slot, f.data_ptr(),
+                                                      1 if before_newest else 0,
+                                                      ctypes.c_void_p(self._cur().cuda_stream)), "dd_tracker_gallery_insert")
+        if self._poll_pool:
+            self.maintain(wait=True)
 
     def gallery_vectors(self):
         """Total gallery vectors of confirmed live tracks (G in SURVEY.md section 8d), per stream."""

@@ -1,0 +1,521 @@
+// dd_gallery.cuh -- the gallery kernels: min cosine distance between the gate-passing detections of a track and the
+// track's feature gallery (nn_matching.py:31-54,78-96 under tracker.py:97-105), over paged galleries.
+//
+//   k_cosine      exact f32 pass, one warp per track index (gallery_impl = 1; defines the result)
+//   k_cosine_h    half-precision pre-pass on tensor cores + exact re-check, per-warp global loads (gallery_impl = 2)
+//
+// The half pre-pass ("half the bytes, the same bits").  The exact pass is bound by the 512 B per gallery row it must
+// read, so every gallery page has a round-to-nearest HALF shadow (256 B per row) and the kernels stream that:
+//   a(r, n) = tensor-core dot (mma.sync m16n8k16, f16 inputs, f32 accumulate) of half row r and half query n,
+//   e(r, n) = the f32 value the exact pass computes (4 FMAs per lane + the 16-8-4-2-1 butterfly).
+// |a - e| <= E := 1.1e-3 for unit vectors (2^-10 from rounding both operands to half, Cauchy-Schwarz; 1e-4 of
+// slack for the tensor-core accumulation and 1e-5 for the f32 pass itself).  With m = max_r a(r, n) the row
+// r* that maximises e satisfies a(r*, n) >= m - 2E, so the exact maximum is the maximum of e over the rows with
+// a >= m - 2E -- typically one or two rows, read from the f32 page and evaluated with exactly the arithmetic of
+// the exact pass.  The cost matrix is therefore bit-identical, whatever the data; only the number of re-checked
+// rows (speed) depends on it.  Galleries longer than DD_H_BLOCK_ROWS are processed block by block with the running
+// maximum m' <= m of the blocks so far: the window only gets wider, never wrong.
+// Fragment trick: a dot product does not care about the order of its terms, so lane 4 g + t feeds the mma with the
+// eight consecutive halves of one 16-byte chunk (chunk t + 4 j of rows g and g + 8, j = 0..3) and takes the B operand
+// from the same chunk of query g; half pages are stored in that order (dd_half_chunk_off), so every load instruction
+// of a warp covers 512 contiguous bytes.  Up to 8 gate-passing detections share one pass over the gallery.
+#pragma once
+#include "dd_tracker_bodies.cuh"
+
+#define DD_WARPS 4
+#define DD_H_WINDOW 2.2e-3f
+#define DD_H_BLOCK_ROWS 256
+
+__global__ void __launch_bounds__(DD_WARPS * 32, 7)
+k_cosine(const DDView V, const int* __restrict__ det_count) {
+    const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
+    if (w >= V.S * V.T) return;
+    WarpG g;
+    DDDirectPass<WarpG> pass;
+    dd_cosine_track(g, V, w / V.T, w % V.T, det_count, pass);
+}
+
+__device__ __forceinline__ void dd_mma_f16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3,
+                                           unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct DDHalfSmem {          // per warp
+    float* approx;           // [rows_blk][8]  a(r, n); overwritten with e(r, n) for the re-checked entries
+    unsigned short* cand;    // [rows_blk * 8] re-check list, entry = row << 3 | n
+    float* thr;              // [8]            m - 2E per query
+    int* cj;                 // [8]            detection index of each query column
+};
+__host__ __device__ inline int dd_half_rows_blk(int B) {
+    const int pad = (B + 15) & ~15;
+    return (B > 0 && pad < DD_H_BLOCK_ROWS) ? pad : DD_H_BLOCK_ROWS;
+}
+__host__ __device__ inline size_t dd_half_smem_per_warp(int B) {
+    return (size_t)dd_half_rows_blk(B) * 8 * 6 + 64;
+}
+__device__ __forceinline__ void dd_half_carve(char* mine, int rows_blk, DDHalfSmem& sm) {
+    sm.approx = (float*)mine;
+    sm.cand = (unsigned short*)(mine + (size_t)rows_blk * 8 * 4);
+    sm.thr = (float*)(mine + (size_t)rows_blk * 8 * 6);
+    sm.cj = (int*)(mine + (size_t)rows_blk * 8 * 6 + 32);
+}
+
+// Exact values of the listed (row, query) entries of one gallery block, 4 per round: the exact pass's arithmetic, bit
+// for bit.  mypid: lane i holds the page id of the block's i-th page.  The totals replace the approximate values.
+__device__ __forceinline__ void dd_half_recheck(const WarpG& g, const DDView& V, int s, const DDHalfSmem& sm,
+                                                int ncand, int mypid) {
+    for (int c0 = 0; c0 < ncand; c0 += 4) {
+        float v[4];
+        float4 a[4], q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = sm.cand[dd_imin(c0 + k, ncand - 1)];
+            const int d = sm.cj[e & 7];
+            const int row = e >> 3;
+            const int pid = __shfl_sync(0xffffffffu, mypid, row >> 4);
+            a[k] = dd_page_f32(V, pid)[(size_t)(row & 15) * (DD_FEAT_DIM / 4) + g.lane];
+            q[k] = ((const float4*)(V.det_featn + ((size_t)s * V.D + d) * DD_FEAT_DIM))[g.lane];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float p = dd_fmaf(a[k].x, q[k].x, 0.f);
+            p = dd_fmaf(a[k].y, q[k].y, p);
+            p = dd_fmaf(a[k].z, q[k].z, p);
+            p = dd_fmaf(a[k].w, q[k].w, p);
+            v[k] = p;
+        }
+        int n = 4, o = 16;                          // transposing butterfly, as dd_fold_max
+#pragma unroll
+        for (; n > 1; n >>= 1, o >>= 1) {
+            const bool up = (g.lane & o) != 0;
+            const int half = n >> 1;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float send = up ? v[i] : v[i + half];
+                const float keep = up ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+#pragma unroll
+        for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        const int k = g.lane >> 3;                  // lane L owns the total of entry c0 + (L >> 3)
+        if ((g.lane & 7) == 0 && c0 + k < ncand) sm.approx[sm.cand[c0 + k]] = v[0];
+    }
+}
+
+// one track index: all its gate-passing detections, 8 at a time
+__device__ __forceinline__ void dd_cosine_track_half(const WarpG& g, const DDView& V, int s, int t,
+                                                     const int* __restrict__ det_count, const DDHalfSmem& sm,
+                                                     int rows_blk) {
+    const int4 dsc = *(const int4*)(V.cdesc + ((size_t)s * V.T + t) * 4);
+    if (dsc.z <= 0) return;
+    const size_t slot = (size_t)s * V.T + dsc.x;
+    const int glen = dsc.y;
+    int nd = det_count[s];
+    if (nd > V.D) nd = V.D;
+    const int gq = g.lane >> 2, tq = g.lane & 3;
+    const int* pt = V.ptab + slot * V.PT;
+    int base = 0;
+    unsigned word = nd > 0 ? V.gate[slot * V.DW] : 0u;
+    for (;;) {
+        // ---- next group of <= 8 gate-passing detections
+        int nq = 0;
+        while (nq < 8) {
+            if (!word) {
+                base += 32;
+                if (base >= nd) break;
+                word = V.gate[slot * V.DW + (base >> 5)];
+                continue;
+            }
+            if (g.lane == 0) sm.cj[nq] = base + dd_ctz(word);
+            ++nq;
+            word &= word - 1;
+        }
+        if (nq == 0) break;
+        __syncwarp();
+        const int myq = gq < nq ? sm.cj[gq] : 0;       // detection whose half row feeds column gq
+        if (glen <= 0) {
+            if (g.lane < nq) V.cost[slot * V.D + sm.cj[g.lane]] = dd_subf(1.0f, -3.0e38f);
+            __syncwarp();
+            continue;
+        }
+        uint4 qb[4];
+        {
+            const uint4* qh = (const uint4*)(V.det_feath + ((size_t)s * V.D + myq) * DD_FEAT_DIM);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qb[j] = gq < nq ? qh[tq + 4 * j] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float best = -3.0e38f;                          // lane n < nq: exact maximum of query n so far
+        float run0 = -3.0e38f, run1 = -3.0e38f;         // approximate maxima so far of queries 2 tq, 2 tq + 1
+        for (int row0 = 0; row0 < glen; row0 += rows_blk) {
+            const int nrows = dd_imin(rows_blk, glen - row0);
+            const int nsteps = (nrows + 15) >> 4;       // pages of this block
+            const int mypid = pt[(row0 >> 4) + dd_imin(g.lane, nsteps - 1)];
+            // ---- stream the half pages, one page (16 rows) per step, two steps in flight
+            uint4 ga[2][4], gb[2][4];
+            // rows past the end of the gallery are not loaded (sector-granular: 2 lanes share a 32-byte sector of one row)
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+                const uint4* pg = (const uint4*)dd_page_f16(V, __shfl_sync(0xffffffffu, mypid, dd_imin(st, nsteps - 1)));
+                const bool va = st * 16 + gq < nrows, vb = st * 16 + gq + 8 < nrows;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ga[st][j] = va ? pg[j * 64 + g.lane] : zero4;
+                    gb[st][j] = vb ? pg[j * 64 + 32 + g.lane] : zero4;
+                }
+            }
+            float mx0 = -3.0e38f, mx1 = -3.0e38f;
+            for (int step = 0; step < nsteps; step += 2) {
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    const int cur = step + st;
+                    if (cur >= nsteps) break;
+                    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dd_mma_f16(c, ga[st][j].x, gb[st][j].x, ga[st][j].y, gb[st][j].y, qb[j].x, qb[j].y);
+                        dd_mma_f16(c, ga[st][j].z, gb[st][j].z, ga[st][j].w, gb[st][j].w, qb[j].z, qb[j].w);
+                    }
+                    const int nxt = cur + 2;
+                    if (nxt < nsteps) {
+                        const uint4* pg = (const uint4*)dd_page_f16(V, __shfl_sync(0xffffffffu, mypid, nxt));
+                        const bool va = nxt * 16 + gq < nrows, vb = nxt * 16 + gq + 8 < nrows;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ga[st][j] = va ? pg[j * 64 + g.lane] : zero4;
+                            gb[st][j] = vb ? pg[j * 64 + 32 + g.lane] : zero4;
+                        }
+                    }
+                    const int ra = cur * 16 + gq, rb = ra + 8;
+                    if (ra >= nrows) { c[0] = -3.0e38f; c[1] = -3.0e38f; }      // rows past the end never win
+                    if (rb >= nrows) { c[2] = -3.0e38f; c[3] = -3.0e38f; }
+                    *(float2*)(sm.approx + ra * 8 + 2 * tq) = make_float2(c[0], c[1]);
+                    *(float2*)(sm.approx + rb * 8 + 2 * tq) = make_float2(c[2], c[3]);
+                    mx0 = fmaxf(mx0, fmaxf(c[0], c[2]));
+                    mx1 = fmaxf(mx1, fmaxf(c[1], c[3]));
+                }
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+            }
+            run0 = fmaxf(run0, mx0);
+            run1 = fmaxf(run1, mx1);
+            if (gq == 0) { sm.thr[2 * tq] = run0 - DD_H_WINDOW; sm.thr[2 * tq + 1] = run1 - DD_H_WINDOW; }
+            __syncwarp();
+            // ---- re-check list: every (row, query) whose approximate dot is within the window of the maximum
+            int ncand = 0;
+            const int total = nsteps * 16 * 8;
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const int i = i0 + g.lane;
+                const int n = i & 7;
+                const bool p = n < nq && sm.approx[i] >= sm.thr[n];
+                const unsigned m = __ballot_sync(0xffffffffu, p);
+                if (p) sm.cand[ncand + __popc(m & ((1u << g.lane) - 1u))] = (unsigned short)i;
+                ncand += __popc(m);
+            }
+            __syncwarp();
+            dd_half_recheck(g, V, s, sm, ncand, mypid);
+            __syncwarp();
+            if (g.lane < nq) {                              // exact maximum per query over its re-checked rows
+                for (int i = 0; i < ncand; ++i) {
+                    const int e = sm.cand[i];
+                    if ((e & 7) == g.lane) best = fmaxf(best, sm.approx[e]);
+                }
+            }
+            __syncwarp();
+        }
+        if (g.lane < nq) V.cost[slot * V.D + sm.cj[g.lane]] = dd_subf(1.0f, best);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(DD_WARPS * 32, 4)
+k_cosine_h(const DDView V, const int* __restrict__ det_count) {
+    extern __shared__ __align__(16) char smem[];
+    WarpG g;
+    const int rows_blk = dd_half_rows_blk(V.B);
+    DDHalfSmem sm;
+    dd_half_carve(smem + (size_t)(threadIdx.x >> 5) * dd_half_smem_per_warp(V.B), rows_blk, sm);
+    const int n = V.work_ctl[0];
+    for (;;) {
+        int i = 0;
+        if (g.lane == 0) i = atomicAdd(V.work_ctl + 32, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const int w = V.work[i];
+        dd_cosine_track_half(g, V, w / V.T, w % V.T, det_count, sm, rows_blk);
+    }
+}
+
+// ---- k_gallery_stream: the half pre-pass as a producer / consumer stream (gallery_impl = 0, the default) -----------
+// The per-warp kernel above keeps its in-flight gallery bytes in registers and stalls on every per-track bubble
+// (claim -> descriptor -> gate word -> queries -> first rows, then the dependent re-check reads).  Here the bytes in
+// flight live in shared memory and never wait for arithmetic: a CTA is a set of warp PAIRS.
+//   producer warp   walks the work list (self-contained records written by k_gate, claimed two entries ahead) and,
+//                   for every (track, group of <= 8 gate-passing detections, block of <= 128 gallery rows), posts a job
+//                   header + the detections' half rows, then feeds the pair's ring of 4 KB stages with ONE bulk
+//                   asynchronous copy per gallery page (cp.async.bulk, completion on the stage's mbarrier; a ragged
+//                   last page is copied row-block by row-block so that no byte past the gallery's end is read).
+//                   It runs across job and track boundaries, as far ahead as the ring allows.
+//   consumer warp   waits for a stage, takes its mma fragments with conflict-free 16-byte shared loads (pages are
+//                   stored in fragment order), releases the stage at once, does the 8 mma of the page, keeps the
+//                   approximate dots in shared memory; after a block it lists the window candidates and re-checks them
+//                   from the f32 pages (the exact pass's arithmetic) while the producer keeps streaming the next job.
+#include "dd_tma.cuh"
+
+#define DD_GS_BLOCK_ROWS 128                 // gallery rows per job (8 pages): sizes the per-pair approx / cand buffers
+#define DD_GS_HDR_INTS 32                    // job header: 0 slotg 1 stream 2 row0 3 nrows 4 nq 5 flags | 8.. cj[8] | 16.. pid[8]
+#define DD_GS_FIRST 1
+#define DD_GS_LAST 2
+#define DD_GS_STOP 4
+
+__host__ __device__ inline size_t dd_gs_pair_bytes(int stages) {
+    return (size_t)stages * DD_PAGE_F16_BYTES            // ring
+           + 2 * 8 * 256                                 // query half rows, double-buffered
+           + DD_GS_BLOCK_ROWS * 8 * 4                    // approx
+           + DD_GS_BLOCK_ROWS * 8 * 2                    // cand
+           + 2 * DD_GS_HDR_INTS * 4                      // headers, double-buffered
+           + 64                                          // thr[8] + pad
+           + (size_t)(2 * stages + 4) * 8;               // mbarriers: full[stages], empty[stages], hfull[2], hfree[2]
+}
+
+__device__ __forceinline__ void dd_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dd_smem_u32(bar)) : "memory");
+}
+
+struct DDPairSmem {
+    char* ring;
+    char* qbuf;
+    float* approx;
+    unsigned short* cand;
+    int* hdr;
+    float* thr;
+    unsigned long long *full, *empty, *hfull, *hfree;
+};
+__device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDPairSmem& P) {
+    P.ring = base;
+    P.qbuf = P.ring + (size_t)stages * DD_PAGE_F16_BYTES;
+    P.approx = (float*)(P.qbuf + 2 * 8 * 256);
+    P.cand = (unsigned short*)((char*)P.approx + DD_GS_BLOCK_ROWS * 8 * 4);
+    P.hdr = (int*)((char*)P.cand + DD_GS_BLOCK_ROWS * 8 * 2);
+    P.thr = (float*)(P.hdr + 2 * DD_GS_HDR_INTS);
+    P.full = (unsigned long long*)((char*)P.thr + 64);
+    P.empty = P.full + stages;
+    P.hfull = P.empty + stages;
+    P.hfree = P.hfull + 2;
+}
+
+__device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDPairSmem& P, int stages) {
+    const int lane = threadIdx.x & 31;
+    const int n = V.work_ctl[0];
+    int st = 0;                  // next ring stage
+    unsigned ephase = ~0u;       // bit s: parity to wait for on empty[s] (a fresh barrier passes a wait on parity 1)
+    int hb = 0;
+    unsigned hphase = 3u;        // same for hfree[0..1]
+    // claims run two entries ahead of the entry being streamed; a claim is broadcast one entry after it was made
+    int raw = 0;
+    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 1);
+    int i_cur = __shfl_sync(0xffffffffu, raw, 0);
+    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 1);
+    int i_nxt = __shfl_sync(0xffffffffu, raw, 0);
+    int w_cur = i_cur < n ? V.work_rec[(size_t)i_cur * 16 + (lane & 15)] : 0;
+    while (i_cur < n) {
+        const int w_nxt = i_nxt < n ? V.work_rec[(size_t)i_nxt * 16 + (lane & 15)] : 0;     // used one entry later
+        if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 1);                                  // broadcast one entry later
+        const int slotg = __shfl_sync(0xffffffffu, w_cur, 0), s = __shfl_sync(0xffffffffu, w_cur, 1);
+        const int glen = __shfl_sync(0xffffffffu, w_cur, 2), np = __shfl_sync(0xffffffffu, w_cur, 4);
+        const unsigned gw0 = (unsigned)__shfl_sync(0xffffffffu, w_cur, 5), gw1 = (unsigned)__shfl_sync(0xffffffffu, w_cur, 6);
+        const int nd = __shfl_sync(0xffffffffu, w_cur, 7);
+        const int nblocks = glen > 0 ? (glen + DD_GS_BLOCK_ROWS - 1) / DD_GS_BLOCK_ROWS : 1;
+        int base = 0, wi = 0;
+        unsigned word = gw0;
+        for (;;) {
+            // ---- next group of <= 8 gate-passing detections; lane q keeps detection q
+            int nq = 0, cjl = 0;
+            while (nq < 8) {
+                if (!word) {
+                    base += 32;
+                    ++wi;
+                    if (base >= nd) break;
+                    word = wi == 1 ? gw1 : V.gate[(size_t)slotg * V.DW + wi];
+                    continue;
+                }
+                if (lane == nq) cjl = base + dd_ctz(word);
+                ++nq;
+                word &= word - 1;
+            }
+            if (nq == 0) break;
+            for (int b = 0; b < nblocks; ++b) {
+                const int row0 = b * DD_GS_BLOCK_ROWS;
+                const int nrows = glen > 0 ? dd_imin(DD_GS_BLOCK_ROWS, glen - row0) : 0;
+                const int npg = (nrows + 15) >> 4;
+                // page ids of this block: lane k keeps page b * 8 + k (the record carries the first 8)
+                int pidl = 0;
+                {
+                    const int k = b * 8 + (lane & 7);
+                    const int from_rec = __shfl_sync(0xffffffffu, w_cur, 8 + (lane & 7));
+                    pidl = b == 0 ? from_rec : (k < np ? V.ptab[(size_t)slotg * V.PT + k] : 0);
+                }
+                // ---- job header + query rows
+                dd_mbar_wait(P.hfree + hb, (hphase >> hb) & 1u);
+                hphase ^= 1u << hb;
+                int* H = P.hdr + hb * DD_GS_HDR_INTS;
+                if (lane == 0) {
+                    H[0] = slotg; H[1] = s; H[2] = row0; H[3] = nrows; H[4] = nq;
+                    H[5] = (b == 0 ? DD_GS_FIRST : 0) | (b == nblocks - 1 ? DD_GS_LAST : 0);
+                }
+                if (lane < 8) { H[8 + lane] = cjl; H[16 + lane] = pidl; }
+                __syncwarp();
+                if (lane == 0) dd_mbar_expect_tx(P.hfull + hb, (unsigned)nq * 256u);
+                __syncwarp();
+                if (lane < nq)
+                    dd_bulk_g2s(P.qbuf + hb * 2048 + lane * 256, V.det_feath + ((size_t)s * V.D + cjl) * DD_FEAT_DIM, 256u,
+                                P.hfull + hb);
+                hb ^= 1;
+                // ---- the block's pages
+                for (int p = 0; p < npg; ++p) {
+                    dd_mbar_wait(P.empty + st, (ephase >> st) & 1u);
+                    ephase ^= 1u << st;
+                    const int valid = dd_imin(16, nrows - p * 16);
+                    const char* src = dd_page_f16(V, __shfl_sync(0xffffffffu, pidl, p));
+                    char* dst = P.ring + (size_t)st * DD_PAGE_F16_BYTES;
+                    if (valid == 16) {
+                        if (lane == 0) {
+                            dd_mbar_expect_tx(P.full + st, DD_PAGE_F16_BYTES);
+                            dd_bulk_g2s(dst, src, DD_PAGE_F16_BYTES, P.full + st);
+                        }
+                    } else {
+                        // ragged last page: 512-byte block l = (j, h) holds chunk group j of rows 8 h .. 8 h + 7, 64 B per row
+                        if (lane == 0) dd_mbar_expect_tx(P.full + st, (unsigned)valid * 256u);
+                        __syncwarp();
+                        if (lane < 8) {
+                            const int rows = dd_imin(8, dd_imax(0, valid - 8 * (lane & 1)));
+                            if (rows > 0) dd_bulk_g2s(dst + lane * 512, src + lane * 512, (unsigned)rows * 64u, P.full + st);
+                        }
+                    }
+                    st = st + 1 == stages ? 0 : st + 1;
+                }
+            }
+        }
+        i_cur = i_nxt;
+        w_cur = w_nxt;
+        i_nxt = __shfl_sync(0xffffffffu, raw, 0);
+    }
+    // ---- stop job
+    dd_mbar_wait(P.hfree + hb, (hphase >> hb) & 1u);
+    if (lane == 0) {
+        P.hdr[hb * DD_GS_HDR_INTS + 5] = DD_GS_STOP;
+        dd_mbar_arrive(P.hfull + hb);
+    }
+}
+
+__device__ __forceinline__ void dd_gs_consumer(const DDView& V, const DDPairSmem& P, int stages) {
+    WarpG g;
+    const int gq = g.lane >> 2, tq = g.lane & 3;
+    DDHalfSmem sm;
+    sm.approx = P.approx; sm.cand = P.cand; sm.thr = P.thr; sm.cj = nullptr;
+    int st = 0;
+    unsigned fphase = 0u;        // bit s: parity to wait for on full[s]
+    unsigned hphase = 0u;
+    int hb = 0;
+    float best = -3.0e38f, run0 = -3.0e38f, run1 = -3.0e38f;
+    for (;;) {
+        dd_mbar_wait(P.hfull + hb, (hphase >> hb) & 1u);
+        hphase ^= 1u << hb;
+        const int* H = P.hdr + hb * DD_GS_HDR_INTS;
+        const int flags = H[5];
+        if (flags & DD_GS_STOP) break;
+        const int slotg = H[0], s = H[1], nrows = H[3], nq = H[4];
+        sm.cj = const_cast<int*>(H + 8);
+        const int mypid = H[16 + (g.lane & 7)];
+        if (flags & DD_GS_FIRST) { best = -3.0e38f; run0 = -3.0e38f; run1 = -3.0e38f; }
+        uint4 qb[4];
+        {
+            const uint4* qh = (const uint4*)(P.qbuf + hb * 2048 + gq * 256);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qb[j] = gq < nq ? qh[tq + 4 * j] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        const int npg = (nrows + 15) >> 4;
+        float mx0 = -3.0e38f, mx1 = -3.0e38f;
+        for (int p = 0; p < npg; ++p) {
+            dd_mbar_wait(P.full + st, (fphase >> st) & 1u);
+            fphase ^= 1u << st;
+            const uint4* pg = (const uint4*)(P.ring + (size_t)st * DD_PAGE_F16_BYTES);
+            uint4 ga[4], gb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + g.lane]; gb[j] = pg[j * 64 + 32 + g.lane]; }
+            __syncwarp();
+            if (g.lane == 0) dd_mbar_arrive(P.empty + st);         // the stage is free again: its bytes are in registers
+            st = st + 1 == stages ? 0 : st + 1;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dd_mma_f16(c, ga[j].x, gb[j].x, ga[j].y, gb[j].y, qb[j].x, qb[j].y);
+                dd_mma_f16(c, ga[j].z, gb[j].z, ga[j].w, gb[j].w, qb[j].z, qb[j].w);
+            }
+            const int ra = p * 16 + gq, rb = ra + 8;
+            if (ra >= nrows) { c[0] = -3.0e38f; c[1] = -3.0e38f; }      // rows past the end (stale stage bytes) never win
+            if (rb >= nrows) { c[2] = -3.0e38f; c[3] = -3.0e38f; }
+            *(float2*)(sm.approx + ra * 8 + 2 * tq) = make_float2(c[0], c[1]);
+            *(float2*)(sm.approx + rb * 8 + 2 * tq) = make_float2(c[2], c[3]);
+            mx0 = fmaxf(mx0, fmaxf(c[0], c[2]));
+            mx1 = fmaxf(mx1, fmaxf(c[1], c[3]));
+        }
+        if (npg > 0) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+            }
+            run0 = fmaxf(run0, mx0);
+            run1 = fmaxf(run1, mx1);
+            if (gq == 0) { sm.thr[2 * tq] = run0 - DD_H_WINDOW; sm.thr[2 * tq + 1] = run1 - DD_H_WINDOW; }
+            __syncwarp();
+            int ncand = 0;
+            const int total = npg * 16 * 8;
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const int i = i0 + g.lane;
+                const int nn = i & 7;
+                const bool pr = nn < nq && sm.approx[i] >= sm.thr[nn];
+                const unsigned m = __ballot_sync(0xffffffffu, pr);
+                if (pr) sm.cand[ncand + __popc(m & ((1u << g.lane) - 1u))] = (unsigned short)i;
+                ncand += __popc(m);
+            }
+            __syncwarp();
+            dd_half_recheck(g, V, s, sm, ncand, mypid);
+            __syncwarp();
+            if (g.lane < nq) {
+                for (int i = 0; i < ncand; ++i) {
+                    const int e = sm.cand[i];
+                    if ((e & 7) == g.lane) best = fmaxf(best, sm.approx[e]);
+                }
+            }
+        }
+        if ((flags & DD_GS_LAST) && g.lane < nq) V.cost[(size_t)slotg * V.D + sm.cj[g.lane]] = dd_subf(1.0f, best);
+        __syncwarp();
+        if (g.lane == 0) dd_mbar_arrive(P.hfree + hb);              // header + query buffer may be rewritten
+        hb ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(512, 1)
+k_gallery_stream(const DDView V, int stages) {
+    extern __shared__ __align__(128) char smem[];
+    const int warp = threadIdx.x >> 5;
+    const int pair = warp >> 1;
+    DDPairSmem P;
+    dd_gs_carve(smem + (size_t)pair * ((dd_gs_pair_bytes(stages) + 127) & ~(size_t)127), stages, P);
+    if ((warp & 1) == 0 && (threadIdx.x & 31) == 0) {
+        for (int i = 0; i < stages; ++i) { dd_mbar_init(P.full + i, 1); dd_mbar_init(P.empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { dd_mbar_init(P.hfull + i, 1); dd_mbar_init(P.hfree + i, 1); }
+        dd_mbar_fence_init();
+    }
+    __syncthreads();
+    if ((warp & 1) == 0) dd_gs_producer(V, P, stages);
+    else dd_gs_consumer(V, P, stages);
+}

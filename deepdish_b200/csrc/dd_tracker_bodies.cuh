@@ -16,6 +16,7 @@
 #endif
 
 #define DD_INFTY_COST 1e5          // deep_sort/linear_assignment.py:8
+#define DD_POOL_LOOKAHEAD 8        // appends ahead that the page-demand forecast (pool_ctl[3]) covers
 
 #if defined(__CUDA_ARCH__)
 // half copies of unit vectors for the gallery kernel's pre-pass (device only; the host emulation runs the
@@ -29,11 +30,83 @@ DD_D void dd_store_half4(unsigned short* dst, const float4& x) {
 }
 DD_D void dd_atomic_add_ll(long long* p, long long v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 DD_D void dd_atomic_or(int* p, int v) { atomicOr(p, v); }
+DD_D int dd_atomic_add_i(int* p, int v) { return atomicAdd(p, v); }
+DD_D void dd_atomic_max_i(int* p, int v) { atomicMax(p, v); }
 #else
 inline void dd_store_half4(unsigned short*, const float4&) {}
 inline void dd_atomic_add_ll(long long* p, long long v) { *p += v; }
 inline void dd_atomic_or(int* p, int v) { *p |= v; }
+inline int dd_atomic_add_i(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline void dd_atomic_max_i(int* p, int v) { if (v > *p) *p = v; }
 #endif
+
+// ------------------------------------------------------------------------------------------------
+// Gallery page pool: a stack of free page ids.  Pages are popped only while features are appended (k_apply, the
+// host-edit insert) and pushed only while slots are recycled (k_match, pool attach): never both in one kernel, so
+// a counter and plain stores suffice.
+// ------------------------------------------------------------------------------------------------
+DD_HD int dd_page_alloc(const DDView& V) {
+    const int i = dd_atomic_add_i(V.pool_ctl, -1) - 1;
+    if (i < 0) {
+        dd_atomic_add_i(V.pool_ctl, 1);
+        return -1;
+    }
+    return V.free_stack[i];
+}
+DD_HD void dd_page_free(const DDView& V, int pid) { V.free_stack[dd_atomic_add_i(V.pool_ctl, 1)] = pid; }
+
+// one gallery row -> f32 page + half page (chunks x[kk] = float4 number lane + kk * NL of the row)
+template <class G, int KP>
+DD_HD void dd_gallery_store_row(const G& g, const DDView& V, int pid, int r, const float4 (&x)[KP]) {
+    float4* dst = dd_page_f32(V, pid) + (size_t)r * (DD_FEAT_DIM / 4);
+    char* dsth = dd_page_f16(V, pid);
+    int kk = 0;
+    for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
+        dst[k] = x[kk];
+        dd_store_half4((unsigned short*)(dsth + dd_half_chunk_off(r, k >> 1) + (k & 1) * 8), x[kk]);
+    }
+}
+
+// Append one unit-normalised feature (chunks x[kk] = float4 number lane + kk * NL) to the gallery of `slot`:
+// what metric.partial_fit does for one (feature, target) pair (nn_matching.py:148-151).  pos / len / np are the
+// slot's gal_pos / gal_len / gal_np as read by the caller (all lanes hold the same values).
+// pid_hint: the id of page pos / 16 when the caller has already read it (>= 0), else -1.
+template <class G, int KP>
+DD_HD void dd_gallery_append(const G& g, const DDView& V, int s, size_t slot, int pos, int len, int np,
+                             const float4 (&x)[KP], int pid_hint = -1) {
+    const int pg = pos >> 4;
+    int pid = -1;
+    bool ok = true;
+    if (pg < np) {
+        pid = pid_hint >= 0 ? pid_hint : V.ptab[slot * V.PT + pg];
+    } else if (pg >= V.PT) {
+        ok = false;
+        if (g.lane == 0) dd_atomic_or(V.err + s, DD_FLAG_GALLERY_OVERFLOW);
+    } else {
+        if (g.lane == 0) pid = dd_page_alloc(V);
+        pid = g.imax(g.lane == 0 ? pid : (int)0x80000000);
+        if (pid < 0) {
+            ok = false;
+            if (g.lane == 0) dd_atomic_or(V.err + s, DD_FLAG_POOL_EXHAUSTED);
+        } else if (g.lane == 0) {
+            V.ptab[slot * V.PT + pg] = pid;
+            V.gal_np[slot] = np + 1;
+        }
+    }
+    if (!ok) return;
+    dd_gallery_store_row<G, KP>(g, V, pid, pos & 15, x);
+    if (g.lane == 0) {
+        const int nlen = V.B > 0 ? (len < V.B ? len + 1 : V.B) : len + 1;
+        const int npos = V.B > 0 ? ((pos + 1 == V.B) ? 0 : pos + 1) : pos + 1;
+        V.gal_pos[slot] = npos;
+        V.gal_len[slot] = nlen;
+        if (V.B == 0 && nlen > V.pool_ctl[2]) dd_atomic_max_i(V.pool_ctl + 2, nlen);     // longest gallery so far
+        // page-demand forecast (pool_ctl[3]): does this gallery need another page within its next few appends?
+        const int ring_pages = V.B > 0 ? (V.B + DD_PAGE_ROWS - 1) / DD_PAGE_ROWS : 0x7fffffff;
+        const int have = pg < np ? np : np + 1;
+        if (dd_imin((npos + DD_POOL_LOOKAHEAD - 1) >> 4, ring_pages - 1) >= have) dd_atomic_add_i(V.pool_ctl + 3, 1);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Detection.to_xyah (deep_sort/detection.py:43-50) and b / |b| (deep_sort/nn_matching.py:53).
@@ -102,12 +175,7 @@ DD_HD void dd_predict_track(const G& g, const DDView& V, int s, int t) {
 // row, up to DD_CH candidates share one pass over the gallery.
 // ------------------------------------------------------------------------------------------------
 #define DD_CH 4          // candidates sharing one pass over the gallery
-#define DD_ROWS 8        // gallery rows per pipeline step (8 x 512 B = 4 KB); fold size = DD_ROWS x NC
-#ifndef DD_HR1
-#define DD_HR1 8         // pipelined pass: rows per half-buffer for 1 / 2 / 3-4 candidates
-#define DD_HR2 4
-#define DD_HR4 4
-#endif
+#define DD_ROWS 8        // gallery rows per step (8 x 512 B = 4 KB); fold size = DD_ROWS x NC
 
 // Cross-lane sum of N = ROWS * NC per-lane partials v[r * NC + c] by a transposing butterfly
 // (N - 1 + log2(32 / N) shuffles instead of 5 N), folded into a running maximum over rows per candidate.
@@ -153,10 +221,11 @@ inline void dd_fold_finish(const HostG&, float (&acc)[NC], float (&best)[NC]) {
 
 // max over the gallery rows of row . q[c] for NC query vectors; rows are unit vectors, each lane owns
 // float4 chunk(s) of the 128-d row; DD_ROWS rows (4 KB) are loaded back to back before any arithmetic.
-// Rows past glen re-read the last row (duplicates do not change a max).  This is the direct-load
-// variant (host emulation, and the A/B baseline of the TMA-staged pass in dd_tracker.cu).
+// Rows past glen re-read the last row (duplicates do not change a max).  This is the exact f32 pass: the
+// arithmetic that DEFINES the cost entries (the half-precision gallery kernel re-evaluates its candidates with
+// exactly these operations), the host emulation's path and gallery_impl = 1.  pt = the slot's page table.
 template <class G, int NC>
-DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
+DD_HD void dd_cosine_pass(const G& g, const DDView& V, const int* __restrict__ pt, int glen,
                           const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
     constexpr int ROWS = DD_ROWS;
     constexpr int DD_FOLD = DD_ROWS * NC;
@@ -178,7 +247,7 @@ DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 const int row = dd_imin(g0 + r, glen - 1);
-                a[r] = gal4[(size_t)row * (DD_FEAT_DIM / 4) + k];
+                a[r] = dd_gallery_row(V, pt, row)[k];
             }
 #pragma unroll
             for (int r = 0; r < ROWS; ++r)
@@ -199,79 +268,12 @@ DD_HD void dd_cosine_pass(const G& g, const float4* __restrict__ gal4, int glen,
     for (int c = 0; c < NC; ++c) best[c] = b[c];
 }
 
-#if defined(__CUDACC__)
-// The same pass, software-pipelined for a warp.  Two half-buffers of HR rows each: as soon as the FMAs of one
-// half are done its registers are re-loaded with the rows 2*HR further on, before the shuffle butterfly of that
-// half runs, so a warp keeps between HR and 2*HR rows (HR * 512 B each) in flight at all times.
-// Identical arithmetic: per-lane FMA order, the butterfly's pairing by lane offsets 16, 8, 4, 2, 1 (the same
-// summation tree for every fold width) and an order-free max -> identical bits.
-// CS = true: the gallery is read with ld.global.cs (evict-first in L1 and L2): 2.5 GB stream through a 126 MB L2
-// every tick and would otherwise evict the tracker state, gate words and costs the latency-bound kernels re-read.
-template <bool CS>
-__device__ __forceinline__ float4 dd_ld_gallery(const float4* p) { return CS ? __ldcs(p) : *p; }
-
-template <int NC, int HR, bool CS>
-__device__ __forceinline__ void dd_cosine_pass_pipelined(const WarpG& g, const float4* __restrict__ gal4, int glen,
-                                                         const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
-    constexpr int N = HR * NC;
-    float4 q[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) q[c] = qp[c][g.lane];
-    float acc[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = -3.0e38f;
-    const float4* base = gal4 + g.lane;
-    const int last = glen - 1;
-    float4 a[2][HR];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int r = 0; r < HR; ++r) a[h][r] = dd_ld_gallery<CS>(base + (size_t)dd_imin(h * HR + r, last) * (DD_FEAT_DIM / 4));
-    for (int g0 = 0; g0 < glen; g0 += 2 * HR) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 1 && g0 + HR >= glen) break;          // second half entirely past the end
-            float v[N];
-#pragma unroll
-            for (int r = 0; r < HR; ++r)
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    float p = dd_fmaf(a[h][r].x, q[c].x, 0.f);
-                    p = dd_fmaf(a[h][r].y, q[c].y, p);
-                    p = dd_fmaf(a[h][r].z, q[c].z, p);
-                    p = dd_fmaf(a[h][r].w, q[c].w, p);
-                    v[r * NC + c] = p;
-                }
-            const int nxt = g0 + 2 * HR + h * HR;
-            if (nxt < glen) {
-#pragma unroll
-                for (int r = 0; r < HR; ++r) a[h][r] = dd_ld_gallery<CS>(base + (size_t)dd_imin(nxt + r, last) * (DD_FEAT_DIM / 4));
-            }
-            dd_fold_max<NC, N>(g, v, acc);
-        }
-    }
-    float b[NC];
-    dd_fold_finish<NC, N>(g, acc, b);
-#pragma unroll
-    for (int c = 0; c < NC; ++c) best[c] = b[c];
-}
-
-template <bool CS>
-struct DDPipelinedPass {
-    template <int NC>
-    __device__ __forceinline__ void run(const WarpG& g, const float4* gal4, int glen,
-                                        const float4* const (&qp)[DD_CH], float (&best)[DD_CH]) {
-        dd_cosine_pass_pipelined<NC, (NC == 1 ? DD_HR1 : (NC == 2 ? DD_HR2 : DD_HR4)), CS>(g, gal4, glen, qp, best);
-    }
-};
-#endif
-
 template <class G>
 struct DDDirectPass {
     template <int NC>
-    DD_HD void run(const G& g, const float4* gal4, int glen, const float4* const (&qp)[DD_CH],
+    DD_HD void run(const G& g, const DDView& V, const int* pt, int glen, const float4* const (&qp)[DD_CH],
                    float (&best)[DD_CH]) {
-        dd_cosine_pass<G, NC>(g, gal4, glen, qp, best);
+        dd_cosine_pass<G, NC>(g, V, pt, glen, qp, best);
     }
 };
 
@@ -279,7 +281,7 @@ struct DDDirectPass {
 // f64 projection + 4x4 Cholesky per lane (redundant), lanes sweep the detections, ballot -> gate words.
 template <class G>
 DD_HD int dd_gate_track(const G& g, const DDView& V, int s, int t, const int* det_count) {
-    int* desc = V.cdesc + ((size_t)s * V.T + t) * 2;
+    int* desc = V.cdesc + ((size_t)s * V.T + t) * 4;
     bool active = t < V.n_tracks[s];
     size_t slot = 0;
     if (active) {
@@ -287,7 +289,7 @@ DD_HD int dd_gate_track(const G& g, const DDView& V, int s, int t, const int* de
         active = V.state[slot] == DD_STATE_CONFIRMED;
     }
     if (!active) {
-        if (g.lane == 0) { desc[0] = 0; desc[1] = 0; }
+        if (g.lane == 0) { desc[0] = 0; desc[1] = 0; desc[2] = 0; desc[3] = 0; }
         return 0;
     }
     int nd = det_count[s];
@@ -314,8 +316,10 @@ DD_HD int dd_gate_track(const G& g, const DDView& V, int s, int t, const int* de
 #endif
     }
     if (g.lane == 0) {
-        desc[0] = (int)(slot - (size_t)s * V.T) | (V.gal_len[slot] << 16);
-        desc[1] = ncand;
+        desc[0] = (int)(slot - (size_t)s * V.T);
+        desc[1] = V.gal_len[slot];
+        desc[2] = ncand;
+        desc[3] = V.gal_np[slot];
     }
     return ncand;       // > 0: the track index goes on the gallery kernel's work list
 }
@@ -324,14 +328,13 @@ DD_HD int dd_gate_track(const G& g, const DDView& V, int s, int t, const int* de
 // whether anything is streamed; the gallery is then read once per group of <= DD_CH candidates.
 template <class G, class Pass>
 DD_HD void dd_cosine_track(const G& g, const DDView& V, int s, int t, const int* det_count, Pass& pass) {
-    const int* desc = V.cdesc + ((size_t)s * V.T + t) * 2;
-    if (desc[1] <= 0) return;
-    const int d0 = desc[0];
-    const size_t slot = (size_t)s * V.T + (d0 & 0xffff);
-    const int glen = d0 >> 16;
+    const int* desc = V.cdesc + ((size_t)s * V.T + t) * 4;
+    if (desc[2] <= 0) return;
+    const size_t slot = (size_t)s * V.T + desc[0];
+    const int glen = desc[1];
     int nd = det_count[s];
     if (nd > V.D) nd = V.D;
-    const float4* gal4 = (const float4*)(V.gal + slot * (size_t)V.B * DD_FEAT_DIM);
+    const int* pt = V.ptab + slot * V.PT;
     for (int base = 0; base < nd; base += 32) {
         unsigned word = V.gate[slot * V.DW + (base >> 5)];
         while (word) {
@@ -349,11 +352,11 @@ DD_HD void dd_cosine_track(const G& g, const DDView& V, int s, int t, const int*
             if (glen <= 0) {
                 for (int c = 0; c < DD_CH; ++c) best[c] = -3.0e38f;
             } else if (nc == 1) {
-                pass.template run<1>(g, gal4, glen, qp, best);
+                pass.template run<1>(g, V, pt, glen, qp, best);
             } else if (nc == 2) {
-                pass.template run<2>(g, gal4, glen, qp, best);
+                pass.template run<2>(g, V, pt, glen, qp, best);
             } else {
-                pass.template run<4>(g, gal4, glen, qp, best);
+                pass.template run<4>(g, V, pt, glen, qp, best);
             }
             if (g.lane == 0)
                 for (int c = 0; c < nc; ++c) V.cost[slot * V.D + cj[c]] = dd_subf(1.0f, best[c]);
@@ -736,11 +739,22 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
         m.trk_state[t] = (unsigned char)st;
     }
     g.sync();
-    // free slots in ascending slot order -> lista
+    // free slots in ascending slot order -> lista; a free slot that still holds gallery pages (its track was
+    // deleted by the previous update, or dropped by a host edit) returns them to the pool first
     int nfree = 0;
     for (int base = 0; base < V.T; base += G::NL) {
         const int k = base + g.lane;
         const bool p = k < V.T && V.state[sT + k] == DD_STATE_FREE;
+        if (p) {
+            const int np = V.gal_np[sT + k];
+            if (np > 0) {
+                const int* pt = V.ptab + (sT + k) * V.PT;
+                for (int i = 0; i < np; ++i) dd_page_free(V, pt[i]);
+                V.gal_np[sT + k] = 0;
+                V.gal_len[sT + k] = 0;
+                V.gal_pos[sT + k] = 0;
+            }
+        }
         int tot;
         const int pos = g.scan_excl(p, tot);
         if (p) m.lista[nfree + pos] = (short)k;
@@ -813,15 +827,20 @@ DD_HD void dd_apply_det(const G& g, const DDView& V, int s, int d, const float* 
     }
     int pos = V.gal_pos[slot];
     int len = V.gal_len[slot];
-    int lbl = det_label[sd];
+    int np = V.gal_np[slot];
+    // the page the feature will land in, read ahead of the Kalman arithmetic like the other operands of the tail
+    const int pid_hint = (kind == 1 && (pos >> 4) < np) ? V.ptab[slot * V.PT + (pos >> 4)] : -1;
+    const int lbl = det_label[sd];
     const double conf = (double)det_conf[sd];
-    if (lbl < 0) lbl = 0;
-    if (lbl >= V.C) lbl = V.C - 1;
+    const bool lbl_ok = lbl >= 0 && lbl < V.C;
+    if (!lbl_ok && g.lane == 0) dd_atomic_or(V.err + s, DD_FLAG_BAD_LABEL);   // never counted for another class
     int lcnt = 0;
     double lsum = 0.0;
     if (kind == 1) {
-        lcnt = V.lab_cnt[slot * V.C + lbl];
-        lsum = V.lab_sum[slot * V.C + lbl];
+        if (lbl_ok) {
+            lcnt = V.lab_cnt[slot * V.C + lbl];
+            lsum = V.lab_sum[slot * V.C + lbl];
+        }
         dd_kf_update(g, V.mean + slot * 8, V.cov + slot * 64, z, scratch);
     } else {
         dd_kf_initiate(g, z, V.mean + slot * 8, V.cov + slot * 64);
@@ -834,21 +853,11 @@ DD_HD void dd_apply_det(const G& g, const DDView& V, int s, int d, const float* 
             V.path_n[slot] = 0;
             V.path_crossed[slot] = 0;
         }
-        pos = 0;
+        pos = 0;       // a recycled slot gave its pages back in the matching kernel (np == 0 already)
         len = 0;
     }
-    float4* dst = (float4*)(V.gal + (slot * (size_t)V.B + pos) * DD_FEAT_DIM);
-    unsigned short* dsth = V.galh + (slot * (size_t)V.B + pos) * DD_FEAT_DIM;
-    {
-        int kk = 0;
-        for (int k = g.lane; k < DD_FEAT_DIM / 4; k += G::NL, ++kk) {
-            dst[k] = x[kk];
-            dd_store_half4(dsth + 4 * k, x[kk]);
-        }
-    }
-    if (g.lane == 0) {
-        V.gal_pos[slot] = (pos + 1 == V.B) ? 0 : pos + 1;
-        V.gal_len[slot] = len < V.B ? len + 1 : V.B;
+    dd_gallery_append<G, KP>(g, V, s, slot, pos, len, np, x, pid_hint);
+    if (g.lane == 0 && lbl_ok) {
         V.lab_cnt[slot * V.C + lbl] = lcnt + 1;
         V.lab_sum[slot * V.C + lbl] = dd_add(lsum, conf);
     }

@@ -14,7 +14,6 @@ from .track import Track, TrackState  # noqa: F401  (TrackState re-exported like
 class Tracker:
     MAX_TRACKS = 256          # slots (live + deleted-this-tick + new); overflow raises, never truncates
     MAX_DETS = 256
-    UNBOUNDED_GALLERY = 512   # ring capacity used when metric.budget is None; overflow raises
 
     def __init__(self, metric, max_iou_distance=0.7, max_age=30, n_init=3):
         self.metric = metric
@@ -28,7 +27,10 @@ class Tracker:
         self.deleted_tracks = []
         self._labels = []                      # label vocabulary in first-seen order
         self._bt = None
-        self._cap = metric.budget if metric.budget is not None else self.UNBOUNDED_GALLERY
+        if getattr(metric, "_metric_name", "cosine") != "cosine":
+            # the device tick computes the cosine metric only (deepdish.py:516 never builds another one); the
+            # euclidean metric stays available through NearestNeighborDistanceMetric.distance
+            raise NotImplementedError("Tracker runs the 'cosine' metric on the device; got %r" % metric._metric_name)
 
     # -- host edits written back to the device ------------------------------------------------
     @property
@@ -80,31 +82,14 @@ class Tracker:
             t._pending = []
 
     def _apply_late_features(self, matched_ids):
-        """Ring surgery after a matching: a late feature goes in BEFORE the feature the update just appended for the
-        same track (the order partial_fit would produce), or at the end if the track was not matched."""
+        """Gallery surgery after a matching: a late feature goes in BEFORE the feature the update just appended for
+        the same track (the order partial_fit would produce), or at the end if the track was not matched."""
         if not self._late_features:
             return
-        v = self._bt.chunks[0].v
-        B = self._bt.cfg.budget
         slot_of = {t.track_id: t._slot for t in self._tracks}
         for tid, f in self._late_features:
-            if tid not in slot_of:
-                continue
-            s = slot_of[tid]
-            pos, ln = int(v["gal_pos"][0, s]), int(v["gal_len"][0, s])
-            ft = torch.as_tensor(f, device=v["gal"].device)
-            if tid in matched_ids and ln > 0:
-                last = (pos - 1) % B
-                newest = v["gal"][0, s, last].clone()
-                v["gal"][0, s, last] = ft
-                v["galh"][0, s, last] = ft.half()
-                v["gal"][0, s, pos] = newest
-                v["galh"][0, s, pos] = newest.half()
-            else:
-                v["gal"][0, s, pos] = ft
-                v["galh"][0, s, pos] = ft.half()
-            v["gal_pos"][0, s] = (pos + 1) % B
-            v["gal_len"][0, s] = min(ln + 1, B)
+            if tid in slot_of:
+                self._bt.gallery_insert(0, slot_of[tid], f, before_newest=tid in matched_ids)
         self._late_features = []
 
     # -- device state -----------------------------------------------------------------------
@@ -112,9 +97,9 @@ class Tracker:
         if self._bt is None:
             names = ["\x00unused%03d" % i for i in range(_lib.DD_MAX_LABELS)]
             self._bt = BatchedTracker(1, names, max_tracks=self.MAX_TRACKS, max_dets=self.MAX_DETS,
-                                      budget=self._cap, max_cosine_distance=self.metric.matching_threshold,
+                                      budget=self.metric.budget, max_cosine_distance=self.metric.matching_threshold,
                                       max_iou_distance=self.max_iou_distance, max_age=self.max_age,
-                                      n_init=self.n_init)
+                                      n_init=self.n_init, pool_pages=2048, seg_pages=2048, page_cap=64)
         return self._bt
 
     @property
@@ -155,10 +140,6 @@ class Tracker:
         self._tracks = [make(s) for s in v["order"][0, :int(v["n_tracks"][0])]]
         self._device_ids = [t.track_id for t in self._tracks]
         self.deleted_tracks = [make(s) for s in v["deleted"][0, :int(v["n_deleted"][0])]]
-        if self.metric.budget is None and len(self.tracks) and \
-                int(v["gal_len"][0, [t._slot for t in self.tracks]].max()) >= self._cap:
-            raise RuntimeError("gallery capacity %d reached with nn_budget=None; pass a budget" % self._cap)
-        self._gal_meta = (v["gal_len"][0], v["gal_pos"][0])
         self.metric.samples = _LazySamples(self)
 
     # -- reference API ----------------------------------------------------------------------
@@ -186,6 +167,8 @@ class Tracker:
         ids = bt.update(torch.from_numpy(tlwh).cuda(), torch.from_numpy(conf).cuda(), torch.from_numpy(lab).cuda(),
                         torch.from_numpy(feat).cuda(), torch.tensor([n], dtype=torch.int32, device="cuda"))
         self.last_detection_track_ids = ids[0, :n].cpu().numpy()
+        if bt._poll_pool:
+            bt.maintain(wait=True)              # unbounded galleries (nn_budget=None): grow pool / page table
         bt.check()
         self._snapshot()
         self._apply_late_features({int(i) for i in self.last_detection_track_ids})
@@ -212,15 +195,9 @@ class _LazySamples(dict):
             return
         self._loaded = True
         trk = self._trk
-        glen, gpos = trk._gal_meta
-        B = trk._bt.cfg.budget
         for t in trk.tracks:
-            if not t.is_confirmed():
-                continue
-            g = trk._bt.v["gal"][0, t._slot].cpu().numpy()
-            n, p = int(glen[t._slot]), int(gpos[t._slot])
-            idx = [(p - n + k) % B for k in range(n)]
-            dict.__setitem__(self, t.track_id, [g[i] for i in idx])
+            if t.is_confirmed():
+                dict.__setitem__(self, t.track_id, list(trk._bt.gallery(0, t._slot).cpu().numpy()))
 
     def __getitem__(self, k):
         self._load(); return dict.__getitem__(self, k)

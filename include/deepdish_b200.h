@@ -41,6 +41,16 @@ extern "C" {
 #define DD_FLAG_TRACK_OVERFLOW  1   /* needed more than max_tracks slots              */
 #define DD_FLAG_DET_OVERFLOW    2   /* det_count[s] > max_dets                        */
 #define DD_FLAG_LSAP_INFEASIBLE 4   /* scipy would raise ValueError (NaN / inf cost)  */
+#define DD_FLAG_POOL_EXHAUSTED  8   /* the gallery page pool had no free page: a feature was NOT appended */
+#define DD_FLAG_GALLERY_OVERFLOW 16 /* an unbounded gallery outgrew its page table (page_cap): not appended */
+#define DD_FLAG_BAD_LABEL       32  /* det_label outside [0, n_labels): the vote was skipped                */
+
+/* Gallery storage: 16-row pages drawn from a pool (nn_matching.py:137-154 keeps a growing Python list per
+ * track; nn_budget=None -- the only way deepdish.py:515-516 builds its metric -- never trims it). */
+#define DD_PAGE_ROWS        16
+#define DD_PAGE_F32_BYTES   8192    /* 16 rows x 128 f32, row-major                                          */
+#define DD_PAGE_F16_BYTES   4096    /* the same rows rounded to half, stored in mma fragment order (below)   */
+#define DD_MAX_SEGS         16      /* pool segments (equal size, attached one by one as the pool grows)     */
 
 const char* dd_version(void);
 
@@ -53,7 +63,8 @@ typedef struct dd_tracker_config {
     int32_t n_streams;          /* S                                                                */
     int32_t max_tracks;         /* Tmax: slots per stream (live + deleted-this-tick + new)          */
     int32_t max_dets;           /* Dmax: detections per stream per tick                             */
-    int32_t budget;             /* nn_budget: gallery vectors kept per track (nn_matching.py:150)   */
+    int32_t budget;             /* nn_budget: gallery vectors kept per track (nn_matching.py:150);
+                                   0 = None: unbounded, what deepdish.py:515-516 always passes      */
     int32_t feat_dim;           /* must be DD_FEAT_DIM                                              */
     int32_t n_labels;           /* C <= DD_MAX_LABELS                                               */
     int32_t max_age;            /* tracker.py:40 (deepdish.py:1418 default 60)                      */
@@ -64,7 +75,28 @@ typedef struct dd_tracker_config {
     int32_t label_bicycle;
     int32_t label_rank[DD_MAX_LABELS]; /* rank of each label NAME in ascending string order
                                           (tie-break of the reverse sort in track.py:170)           */
+    /* gallery page pool (caller-owned device memory, like the blob) */
+    int32_t page_cap;           /* page-table entries per slot; budget > 0: ceil(budget / 16) (0 = that default);
+                                   budget == 0: rows a gallery can reach before the caller must re-layout with a
+                                   larger page_cap (DD_FLAG_GALLERY_OVERFLOW when it does not)          */
+    int32_t seg_pages;          /* pages per pool segment, a power of two                               */
+    int32_t n_segs;             /* segments attached so far, 1..DD_MAX_SEGS (dd_tracker_pool_attach)    */
+    /* per-tracker tuning (A/B measurements; 0 = default everywhere) */
+    int32_t gallery_impl;       /* 0 = default (the half-precision producer/consumer stream), 1 = exact f32 pass,
+                                   2 = half pre-pass with per-warp global loads (both bit-identical to 0) */
+    int32_t cosine_ctas_per_sm; /* impl 2: persistent grid = SMs x this (default 4); impl 0: warp pairs per CTA,
+                                   one CTA per SM (default 6, at most 8)                                */
+    int32_t match_warps;        /* matching kernel: 0 = by problem size, 1 / 4 / 8 warps per stream     */
+    int32_t gallery_stages;     /* impl 0: 4 KB ring stages per warp pair (default 4)                   */
+    int32_t reserved0;
+    uint64_t pool_f32[DD_MAX_SEGS]; /* device pointers, seg_pages x DD_PAGE_F32_BYTES each, 16-byte aligned */
+    uint64_t pool_f16[DD_MAX_SEGS]; /* device pointers, seg_pages x DD_PAGE_F16_BYTES each, 16-byte aligned */
 } dd_tracker_config;
+
+/* Half page layout ("fragment order"): the 16-byte chunk c (= 8 consecutive halves, c = 0..15) of row r sits at
+ * byte ((c >> 2) * 2 + (r >> 3)) * 512 + ((r & 7) * 4 + (c & 3)) * 16 of the page, so that lane 4 g + t of a warp
+ * reads its mma.m16n8k16 A operands for rows g and g + 8 with fully coalesced (and, from shared memory,
+ * conflict-free) 16-byte loads. */
 
 /* Byte offsets of every array inside the caller-owned state blob (all multiples of 256). */
 typedef struct dd_tracker_layout {
@@ -85,9 +117,16 @@ typedef struct dd_tracker_layout {
     uint64_t age;           /* i32 [S,Tmax]                                                         */
     uint64_t tsu;           /* i32 [S,Tmax]       time_since_update                                 */
     uint64_t state;         /* i32 [S,Tmax]       DD_STATE_*                                        */
-    uint64_t gal_len;       /* i32 [S,Tmax]       valid gallery vectors (<= budget)                 */
-    uint64_t gal_pos;       /* i32 [S,Tmax]       ring write position                               */
-    uint64_t gal;           /* f32 [S,Tmax,budget,128]  unit-normalised features (ring)             */
+    uint64_t gal_len;       /* i32 [S,Tmax]       valid gallery vectors (<= budget when budget > 0)  */
+    uint64_t gal_pos;       /* i32 [S,Tmax]       next write position (ring position when budget > 0) */
+    uint64_t gal_np;        /* i32 [S,Tmax]       pages the slot holds                              */
+    uint64_t ptab;          /* i32 [S,Tmax,page_cap]  page ids: gallery row p lives in page ptab[p / 16], row p % 16;
+                                                  rows are unit-normalised features                 */
+    uint64_t free_stack;    /* i32 [DD_MAX_SEGS * seg_pages]  free page ids                         */
+    uint64_t pool_ctl;      /* i32 [64]           [0] free pages, [1] pages attached, [2] longest gallery so far,
+                                                  [3] forecast: tracks updated this tick that need another page within
+                                                  their next 8 appends (rebuilt every tick; tracks not updated this
+                                                  tick and new tracks come on top) */
     uint64_t lab_cnt;       /* i32 [S,Tmax,C]     votes per label (track.py:75-80,147-151)          */
     uint64_t lab_sum;       /* f64 [S,Tmax,C]     sum of confidences per label                      */
     uint64_t path_n;        /* i32 [S,Tmax]       points in the count-line path db                  */
@@ -100,22 +139,41 @@ typedef struct dd_tracker_layout {
     uint64_t det_featn;     /* f32 [S,Dmax,128]   unit-normalised detection features                */
     uint64_t det_slot;      /* i32 [S,Dmax]       slot the detection was applied to                 */
     uint64_t det_kind;      /* i32 [S,Dmax]       0 none, 1 Kalman update, 2 new track              */
-    uint64_t cdesc;         /* i32 [S,Tmax,2]     per track index: slot | gallery rows << 16, #gate-passing
-                                                  detections (0 = nothing to stream)                        */
+    uint64_t cdesc;         /* i32 [S,Tmax,4]     per track index: slot, gallery rows, #gate-passing detections
+                                                  (0 = nothing to stream), pages                            */
     uint64_t work;          /* i32 [S*Tmax]       work list of the gallery kernel: s * Tmax + track index of
                                                   every track with a gate-passing detection (any order)     */
     uint64_t work_ctl;      /* i32 [64]           [0] = entries in `work`, [32] = claim cursor              */
-    uint64_t galh;          /* f16 [S,Tmax,budget,128]  round-to-nearest half copy of `gal` (same ring positions):
-                                                  what the gallery kernel streams; `gal` rows are re-read only
-                                                  for the few rows that can hold the exact maximum           */
+    uint64_t work_rec;      /* i32 [S*Tmax,16]    one self-contained record per work-list entry (same order): stream * Tmax
+                                                  + slot, stream, gallery rows, #gate-passing detections, pages, gate
+                                                  words 0 and 1, detections this tick, page ids 0..7 -- all the gallery
+                                                  kernel's producer warps need to start the bulk copies of a track   */
     uint64_t det_feath;     /* f16 [S,Dmax,128]   half copy of det_featn                                     */
 } dd_tracker_layout;
 
 /* Host-only arithmetic: fills `host_out`.  No CUDA call. */
 int dd_tracker_layout_query(const dd_tracker_config* host_cfg, dd_tracker_layout* host_out);
 
-/* Zero the blob and set _next_id = 1 (tracker.py:46-49). */
+/* Zero the blob, set _next_id = 1 (tracker.py:46-49) and put the pages of the host_cfg->n_segs attached
+ * segments on the free stack. */
 int dd_tracker_init(void* state, const dd_tracker_config* host_cfg, void* stream);
+
+/* Grow the page pool: the caller has allocated segment number host_cfg->n_segs - 1 (pool_f32 / pool_f16 entries
+ * filled, n_segs already incremented); its seg_pages page ids go on the free stack.  Must not run concurrently
+ * with a tick of the same tracker (same stream, or ordered by events). */
+int dd_tracker_pool_attach(void* state, const dd_tracker_config* host_cfg, void* stream);
+
+/* metric.samples[track] (nn_matching.py:132-154): the gallery of one slot, oldest row first, as unit-normalised
+ * f32 rows.  out f32 [max_rows,128]; rows written = min(gallery length, max_rows) (the length is gal_len). */
+int dd_tracker_gallery_read(void* state, const dd_tracker_config* host_cfg, int32_t stream_index, int32_t slot,
+                            float* out, int32_t max_rows, void* stream);
+
+/* Host edit of one gallery (the FrameRecords hook, deepdish/framerecords.py:157-160, lets a caller run
+ * Track.update outside the tracker; the feature then reaches metric.samples at the next partial_fit,
+ * tracker.py:84-93): append unit-normalised feat f32 [128] to the slot's gallery -- before its newest row when
+ * before_newest != 0 -- with the page allocation, budget trim and half copy an append in the tick performs. */
+int dd_tracker_gallery_insert(void* state, const dd_tracker_config* host_cfg, int32_t stream_index, int32_t slot,
+                              const float* feat, int32_t before_newest, void* stream);
 
 /* Tracker.predict (tracker.py:51-57 -> track.py:113-125 -> kalman_filter.py:88-123). */
 int dd_tracker_predict(void* state, const dd_tracker_config* host_cfg, void* stream);
@@ -136,26 +194,22 @@ int dd_tracker_update(void* state, const dd_tracker_config* host_cfg,
 /* dd_tracker_update that also records six caller-supplied CUDA events on `stream`: before the
  * detection prep kernel and after each of prep / gate / cosine / match / apply (no synchronisation), so a
  * benchmark can time each kernel inside its own timed region.  host_events6: host array of 6 events
- * made by dd_event_create.  gallery_wait / gallery_done (may be NULL): as in dd_tracker_tick_chained. */
+ * made by dd_event_create. */
 int dd_tracker_update_profiled(void* state, const dd_tracker_config* host_cfg,
                                const double* det_tlwh, const float* det_conf, const int32_t* det_label,
                                const float* det_feat, const int32_t* det_count,
-                               int32_t* out_det_track_id, void* stream, void* const* host_events6,
-                               void* gallery_wait, void* gallery_done);
-/* Process-wide tuning knobs for A/B measurements.
- *   key 0: gallery kernel -- 3 = half-precision pre-pass on tensor cores + exact re-check of the rows that can
- *          hold the maximum (default; bit-identical costs), 2 = persistent work-list kernel with a
- *          software-pipelined exact pass, 0 = one warp per track index over the whole grid, 1 = TMA-staged ring;
- *   key 1: CTAs per SM of the persistent gallery kernel (1..16, default 4);
- *   key 2: 1 = launch the latency-bound kernels at the highest priority, 0 = all equal (default);
- *   key 3: 1 = gallery loads use ld.global.cs (evict-first in L2), 0 = default cache policy (default);
- *   key 4: 1 = programmatic dependent launch between the kernels of a tick, 0 = plain stream order (default);
- *   key 5: matching kernel -- -1 = chosen by problem size (default: 4 warps per stream when max_tracks or max_dets > 160),
- *          0 = one warp per stream, 1 = four warps per stream, 2 = eight. */
-int dd_tuning_set(int32_t key, int32_t value);
+                               int32_t* out_det_track_id, void* stream, void* const* host_events6);
 int dd_event_create(void** host_out);
 int dd_event_destroy(void* ev);
 int dd_event_elapsed_ms(void* start, void* end, float* host_ms);   /* both events must have completed */
+int dd_event_record(void* ev, void* stream);
+int dd_event_query(void* ev);          /* 1 = completed, 0 = not yet, negative = error */
+int dd_event_synchronize(void* ev);
+
+/* Copy the pool counters pool_ctl[0..3] (free pages, pages attached, longest gallery, page-demand forecast) to
+ * PINNED host memory on `stream` and record done_event (may be NULL) behind the copy: no host synchronisation. */
+int dd_tracker_pool_poll(void* state, const dd_tracker_config* host_cfg, int32_t* host_pinned4, void* done_event,
+                         void* stream);
 
 /* Count-line step (deepdish.py:1035-1114 counting part, :1303-1312; tools/intersection.py:4-30).
  *   line f64 [S,4] (x1,y1,x2,y2 per stream) or, with line_per_stream = 0, one f64[4] for all streams. */
@@ -168,15 +222,6 @@ int dd_tracker_tick(void* state, const dd_tracker_config* host_cfg, const double
                     const float* det_conf, const int32_t* det_label, const float* det_feat,
                     const int32_t* det_count, int32_t* out_det_track_id, const double* line,
                     int line_per_stream, int64_t* out_counts, void* stream);
-
-/* dd_tracker_tick for one of several stream chunks that share the GPU, each on its own CUDA stream: the chunk
- * waits for `gallery_wait` (a dd_event_create event, may be NULL) before its HBM-bound gallery kernel and records
- * `gallery_done` (may be NULL) after it, so the chunks take turns on that kernel while everything else overlaps. */
-int dd_tracker_tick_chained(void* state, const dd_tracker_config* host_cfg, const double* det_tlwh,
-                            const float* det_conf, const int32_t* det_label, const float* det_feat,
-                            const int32_t* det_count, int32_t* out_det_track_id, const double* line,
-                            int line_per_stream, int64_t* out_counts, void* gallery_wait, void* gallery_done,
-                            void* stream);
 
 /* Ragged detection batch -> the padded arrays dd_tracker_tick consumes.  The reference hands Tracker.update a
  * Python list of Detection objects per stream (deepdish.py:1014); its batched equivalent is one contiguous blob
@@ -202,7 +247,8 @@ int dd_tracker_tick_ragged(void* state, const dd_tracker_config* host_cfg, const
 int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int64_t* out_counts,
                             void* stream);
 
-/* OR of all per-stream DD_FLAG_* bits -> *host_flags.  Synchronises `stream`. */
+/* OR of all per-stream DD_FLAG_* bits -> *host_flags.  Synchronises `stream`.  (The pool counters a caller polls
+ * to grow the pool ahead of need are the blob's pool_ctl words.) */
 int dd_tracker_status(void* state, const dd_tracker_config* host_cfg, int32_t* host_flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -42,6 +42,7 @@ def run_reference_tracker(R, batches, labels, budget, max_age, n_init=3, tcap=64
     deleted = np.full((F, tcap), -1, np.int32)
     counts = np.zeros((F, len(labels), 4), np.int64)
     track_labels = np.full((F, tcap), -1, np.int32)
+    gal_len = np.zeros((F, tcap), np.int32)        # len(metric.samples[track]) after the update (nn_matching.py:137-154)
     for f, b in enumerate(batches):
         tlwh, conf, lab, feat = b.stream(0)
         dets = [R.deep_sort_detection.Detection(tlwh[i], labels[lab[i]], conf[i], feat[i])
@@ -64,11 +65,18 @@ def run_reference_tracker(R, batches, labels, budget, max_age, n_init=3, tcap=64
             ids[f, k], states[f, k], tsu[f, k] = t.track_id, t.state, t.time_since_update
             means[f, k], covs[f, k] = t.mean, t.covariance
             track_labels[f, k] = labels.index(t.get_label())
+            gal_len[f, k] = len(metric.samples.get(t.track_id, []))
         for k, t in enumerate(trk.deleted_tracks):
             deleted[f, k] = t.track_id
         counts[f] = cnt.counts()
-    return dict(det_ids=det_ids, n_tracks=n_tracks, ids=ids, states=states, tsu=tsu, means=means,
-                covs=covs, deleted=deleted, counts=counts, track_labels=track_labels)
+    out = dict(det_ids=det_ids, n_tracks=n_tracks, ids=ids, states=states, tsu=tsu, means=means,
+               covs=covs, deleted=deleted, counts=counts, track_labels=track_labels)
+    if budget is None:         # the unbounded fixture also pins the gallery lengths and the final gallery of track 1
+        out["gal_len"] = gal_len
+        longest = max(metric.samples, key=lambda k: len(metric.samples[k]))
+        out["longest_id"] = longest
+        out["longest_gallery"] = np.asarray(metric.samples[longest], np.float32)
+    return out
 
 
 def golden_tracker(R, name, seed, n_obj, dmax, frames, budget, max_age, store_inputs, **scene_kw):
@@ -76,7 +84,7 @@ def golden_tracker(R, name, seed, n_obj, dmax, frames, budget, max_age, store_in
     sc = Scene(1, n_obj, dmax, n_labels=3, seed=seed, **scene_kw)
     batches = [sc.step() for _ in range(frames)]
     out = run_reference_tracker(R, batches, LABELS3, budget, max_age)
-    out.update(seed=seed, n_obj=n_obj, dmax=dmax, frames=frames, budget=budget, max_age=max_age,
+    out.update(seed=seed, n_obj=n_obj, dmax=dmax, frames=frames, budget=budget or 0, max_age=max_age,
                checksum=scene_checksum(batches),
                scene_kw=np.array(sorted(scene_kw.items()), dtype=object) if scene_kw else np.zeros(0))
     if store_inputs:
@@ -434,6 +442,13 @@ def golden_patches(R):
     print("patches.npz valid", int(valid.sum()), "of", len(valid), "float", int(fvalid.sum()), "dummy", len(dboxes))
 
 
+def golden_unbounded(R):
+    """nn_budget=None -- the only way deepdish.py:515-516 ever builds its metric: galleries are never trimmed
+    (nn_matching.py:137-154).  820 frames, 6 long-lived objects (no re-spawns): every track is matched ~740 times."""
+    golden_tracker(R, "tracker_unbounded.npz", seed=104, n_obj=6, dmax=8, frames=820, budget=None, max_age=60,
+                   store_inputs=False, respawn_prob=0.0, clutter_mean=0.5)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = refload.load()
@@ -445,6 +460,9 @@ def main():
         return
     if os.environ.get("DD_GOLDEN_ONLY") == "tflite":
         golden_tflite_adapter(R)
+        return
+    if os.environ.get("DD_GOLDEN_ONLY") == "unbounded":
+        golden_unbounded(R)
         return
     golden_tflite_adapter(R)
     golden_framerecords(R)
@@ -460,6 +478,7 @@ def main():
                    store_inputs=False)
     golden_tracker(R, "tracker_delcount.npz", seed=103, n_obj=10, dmax=12, frames=240, budget=100, max_age=5,
                    store_inputs=False, clutter_mean=0.0, respawn_prob=0.03)
+    golden_unbounded(R)
 
 
 if __name__ == "__main__":

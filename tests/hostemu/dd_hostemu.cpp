@@ -25,6 +25,9 @@ int ddh_tracker_init(void* state, const dd_tracker_config* cfg) {
     dd_layout_compute(cfg, &L);
     memset(state, 0, L.total_bytes);
     for (int s = 0; s < V.S; ++s) V.next_id[s] = 1;
+    const int n_pages = cfg->n_segs * cfg->seg_pages;
+    for (int i = 0; i < n_pages; ++i) V.free_stack[i] = n_pages - 1 - i;
+    V.pool_ctl[0] = n_pages; V.pool_ctl[1] = n_pages;
     return DD_OK;
 }
 
@@ -58,6 +61,22 @@ int ddh_tracker_update(void* state, const dd_tracker_config* cfg, const double* 
     for (int s = 0; s < V.S; ++s)
         for (int d = 0; d < V.D; ++d) dd_apply_det(g, V, s, d, det_conf, det_label, scratch);
     return DD_OK;
+}
+
+// metric.samples of one slot, oldest row first (what dd_tracker_gallery_read returns on the device).
+int ddh_gallery_read(void* state, const dd_tracker_config* cfg, int s, int slot_in_stream, float* out, int max_rows) {
+    DDView V;
+    int rc = dd_make_view(state, cfg, &V);
+    if (rc != DD_OK) return rc;
+    const size_t slot = (size_t)s * V.T + slot_in_stream;
+    const int len = V.gal_len[slot], pos = V.gal_pos[slot];
+    const int n = len < max_rows ? len : max_rows;
+    for (int i = 0; i < n; ++i) {
+        int row = i;
+        if (V.B > 0) { row = pos - len + i; if (row < 0) row += V.B; }
+        memcpy(out + (size_t)i * DD_FEAT_DIM, dd_gallery_row(V, V.ptab + slot * V.PT, row), DD_FEAT_DIM * 4);
+    }
+    return n;
 }
 
 int ddh_tracker_countline(void* state, const dd_tracker_config* cfg, const double* line,

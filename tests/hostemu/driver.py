@@ -25,6 +25,15 @@ class HostEmuTracker:
 
     def __init__(self, cfg, line=(320.0, 0.0, 320.0, 480.0)):
         self.cfg = cfg
+        # gallery page pool in host memory: one segment that covers the worst case (every slot's table full)
+        need = cfg.n_streams * cfg.max_tracks * L.page_cap(cfg)
+        seg = 1
+        while seg < need:
+            seg <<= 1
+        cfg.seg_pages, cfg.n_segs = seg, 1
+        self.pool_f32 = np.zeros(seg * L.PAGE_F32_BYTES, dtype=np.uint8)
+        self.pool_f16 = np.zeros(seg * L.PAGE_F16_BYTES, dtype=np.uint8)
+        cfg.pool_f32[0], cfg.pool_f16[0] = self.pool_f32.ctypes.data, self.pool_f16.ctypes.data
         self.lay = L.TrackerLayout()
         assert emu().ddh_tracker_layout_query(ctypes.byref(cfg), ctypes.byref(self.lay)) == 0
         self.blob = np.zeros(self.lay.total_bytes, dtype=np.uint8)
@@ -49,6 +58,13 @@ class HostEmuTracker:
                                       _p(a[3]), _p(a[4]), _p(self.det_track_id))
         assert rc == 0
         return self.det_track_id
+
+    def gallery(self, s, slot):
+        n = int(self.v["gal_len"][s, slot])
+        out = np.zeros((max(n, 1), 128), dtype=np.float32)
+        got = emu().ddh_gallery_read(_p(self.blob), ctypes.byref(self.cfg), int(s), int(slot), _p(out), n)
+        assert got == n
+        return out[:n]
 
     def countline(self):
         assert emu().ddh_tracker_countline(_p(self.blob), ctypes.byref(self.cfg), _p(self.line), 0) == 0

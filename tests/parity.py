@@ -43,8 +43,10 @@ class OracleStreams:
         return out
 
 
-def compare_stream(o_trk, o_cnt, view, s, labels, rtol=1e-4, gallery=True):
-    """Compare oracle tracker/counter of one stream with the SoA state `view` (dict of numpy arrays)."""
+def compare_stream(o_trk, o_cnt, view, s, labels, rtol=1e-4, gallery=True, gallery_rows=None):
+    """Compare oracle tracker/counter of one stream with the SoA state `view` (dict of numpy arrays).
+    gallery_rows(s, slot) -> [len,128] float32 (optional): the implementation's gallery of a slot, oldest row first,
+    compared with metric.samples (the implementation stores the rows unit-normalised)."""
     n = int(view["n_tracks"][s])
     slots = view["order"][s, :n]
     assert n == len(o_trk.tracks), (s, n, len(o_trk.tracks))
@@ -68,6 +70,10 @@ def compare_stream(o_trk, o_cnt, view, s, labels, rtol=1e-4, gallery=True):
             if t.is_confirmed():
                 g = np.asarray(o_trk.metric.samples[t.track_id])
                 assert int(view["gal_len"][s, sl]) == len(g)
+                if gallery_rows is not None:
+                    got = np.asarray(gallery_rows(s, int(sl)))
+                    unit = g / np.sqrt(np.sum(g * g, axis=1, dtype=np.float32))[:, None]
+                    np.testing.assert_allclose(got, unit, rtol=2e-6, atol=1e-7)
     if o_cnt is not None:
         np.testing.assert_array_equal(view["counts"][s], o_cnt.counts(labels))
 

@@ -36,11 +36,17 @@ def test_layout_query_and_invalid_config():
         import numpy as np
         dt, shape = specs[n]
         assert o % 256 == 0 and o + int(np.prod(shape)) * np.dtype(dt).itemsize <= o2, n
-    assert lay.gal == getattr(lay, "gal") and lay.total_bytes > 1024 * 128 * 100 * 512
+    # galleries live in the page pool, not in the blob: the blob holds 7-entry page tables for budget 100
+    assert specs["ptab"][1] == (1024, 128, 7) and lay.total_bytes < 1024 * 128 * 100 * 512 // 16
+    unb = _l.make_config(4, 16, 16, None, ["person"], page_cap=40)          # nn_budget=None (deepdish.py:515)
+    assert unb.budget == 0 and _l.field_specs(unb)["ptab"][1] == (4, 16, 40)
+    assert lib.dd_tracker_layout_query(ctypes.byref(unb), ctypes.byref(lay)) == 0
     cfg.feat_dim = 64
     assert lib.dd_tracker_layout_query(ctypes.byref(cfg), ctypes.byref(lay)) == _l.DD_ERR_INVALID
     with pytest.raises(ValueError):
-        _l.make_config(4, 16, 16, None, ["person"])
+        _l.make_config(4, 16, 16, 0, ["person"])
+    bad = _l.make_config(4, 16, 16, 10, ["person"], max_age=40000)           # tsu is kept in 16 bits on the device
+    assert lib.dd_tracker_layout_query(ctypes.byref(bad), ctypes.byref(lay)) == _l.DD_ERR_INVALID
     assert cfg.label_rank[0] == 2 and cfg.label_rank[1] == 0 and cfg.label_rank[2] == 1
 
 

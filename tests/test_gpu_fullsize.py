@@ -49,18 +49,15 @@ def test_c3_full_size_sampled_oracle_and_schedule_invariance():
     del a
     torch.cuda.empty_cache()
     # ---- same frames, different schedule: 3 chunks on 3 CUDA streams, exact f32 gallery pass
-    _lib.check(_lib.lib().dd_tuning_set(0, 0), "dd_tuning_set")
-    try:
-        b3 = BatchedTracker(S, LABELS3, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, n_chunks=3)
-        for f, b in enumerate(frames):
-            b3.step(b, join=False, reduce=True)
-            b3.join()
-            np.testing.assert_array_equal(b3.det_track_id.cpu().numpy(), ids_a[f], err_msg="tick %d" % f)
-        b3.check()
-        vb = b3.host_view()
-        np.testing.assert_array_equal(b3.total_counts.cpu().numpy(), tot_a)
-    finally:
-        _lib.check(_lib.lib().dd_tuning_set(0, 3), "dd_tuning_set")
+    b3 = BatchedTracker(S, LABELS3, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, n_chunks=3,
+                        gallery_impl="exact")
+    for f, b in enumerate(frames):
+        b3.step(b, join=False, reduce=True)
+        b3.join()
+        np.testing.assert_array_equal(b3.det_track_id.cpu().numpy(), ids_a[f], err_msg="tick %d" % f)
+    b3.check()
+    vb = b3.host_view()
+    np.testing.assert_array_equal(b3.total_counts.cpu().numpy(), tot_a)
     for name in ("n_tracks", "next_id", "n_deleted", "counts"):
         np.testing.assert_array_equal(va[name], vb[name], err_msg=name)
     live = np.arange(TMAX)[None, :] < va["n_tracks"][:, None]
@@ -86,25 +83,21 @@ def test_c4_shard_size_matching_kernels_agree():
     orc = OracleStreams(len(sample), LABELS3, budget=BUDGET, max_age=MAX_AGE)
     idx = torch.as_tensor(sample, device="cuda")
     runs = []
-    for impl in (1, 0):
-        _lib.check(_lib.lib().dd_tuning_set(5, impl), "dd_tuning_set")
-        try:
-            bt = BatchedTracker(S4, LABELS3, max_tracks=T4, max_dets=D4, budget=BUDGET, max_age=MAX_AGE)
-            ids = []
-            for f, b in enumerate(frames):
-                got = bt.step(b).cpu().numpy().copy()
-                ids.append(got)
-                if impl == 1:
-                    hb = SceneBatch(*(getattr(b, k)[idx].cpu() for k in SceneBatch.__slots__))
-                    exp = orc.step(hb)
-                    for k, s in enumerate(sample):
-                        assert list(got[s, :int(hb.count[k])]) == exp[k], (f, s)
-            bt.check()
-            runs.append((ids, bt.host_view(["n_tracks", "order", "track_id", "state", "hits", "tsu", "next_id", "mean"])))
-            del bt
-            torch.cuda.empty_cache()
-        finally:
-            _lib.check(_lib.lib().dd_tuning_set(5, -1), "dd_tuning_set")
+    for warps in (4, 1):
+        bt = BatchedTracker(S4, LABELS3, max_tracks=T4, max_dets=D4, budget=BUDGET, max_age=MAX_AGE, match_warps=warps)
+        ids = []
+        for f, b in enumerate(frames):
+            got = bt.step(b).cpu().numpy().copy()
+            ids.append(got)
+            if warps == 4:
+                hb = SceneBatch(*(getattr(b, k)[idx].cpu() for k in SceneBatch.__slots__))
+                exp = orc.step(hb)
+                for k, s in enumerate(sample):
+                    assert list(got[s, :int(hb.count[k])]) == exp[k], (f, s)
+        bt.check()
+        runs.append((ids, bt.host_view(["n_tracks", "order", "track_id", "state", "hits", "tsu", "next_id", "mean"])))
+        del bt
+        torch.cuda.empty_cache()
     (ia, va), (ib, vb) = runs
     for f in range(TICKS4):
         np.testing.assert_array_equal(ia[f], ib[f], err_msg="tick %d" % f)

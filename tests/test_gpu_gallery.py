@@ -13,27 +13,24 @@ pytestmark = pytest.mark.gpu
 
 
 def _history(impl, S, nobj, dmax, tmax, budget, frames, seed, feat_noise, big_boxes=False):
-    from deepdish_b200 import _lib
     from deepdish_b200.batched import BatchedTracker
-    _lib.check(_lib.lib().dd_tuning_set(0, impl), "dd_tuning_set")
-    try:
-        bt = BatchedTracker(S, LABELS3, max_tracks=tmax, max_dets=dmax, budget=budget, max_age=30)
-        sc = Scene(S, nobj, dmax, n_labels=3, seed=seed, feat_noise=feat_noise)
-        if big_boxes:                      # large slow boxes: many detections pass each track's Mahalanobis gate
-            sc.size = sc.size * 4.0
-            sc.vel = sc.vel * 0.2
-        out = []
-        for f in range(frames):
-            b = sc.step().to("cuda")
-            ids = bt.step(b).cpu().numpy().copy()
-            gate = bt.v["gate"].cpu().numpy().astype(np.uint32)
-            cost = bt.v["cost"].cpu().numpy()
-            state = bt.v["state"].cpu().numpy()
-            out.append((ids, gate, cost, state))
-        bt.check()
-        return out
-    finally:
-        _lib.check(_lib.lib().dd_tuning_set(0, 3), "dd_tuning_set")
+    bt = BatchedTracker(S, LABELS3, max_tracks=tmax, max_dets=dmax, budget=budget, max_age=30, gallery_impl=impl,
+                        page_cap=8)
+    sc = Scene(S, nobj, dmax, n_labels=3, seed=seed, feat_noise=feat_noise)
+    if big_boxes:                      # large slow boxes: many detections pass each track's Mahalanobis gate
+        sc.size = sc.size * 4.0
+        sc.vel = sc.vel * 0.2
+    out = []
+    for f in range(frames):
+        b = sc.step().to("cuda")
+        ids = bt.step(b).cpu().numpy().copy()
+        bt.maintain(wait=True)
+        gate = bt.v["gate"].cpu().numpy().astype(np.uint32)
+        cost = bt.v["cost"].cpu().numpy()
+        state = bt.v["state"].cpu().numpy()
+        out.append((ids, gate, cost, state))
+    bt.check()
+    return out
 
 
 @pytest.mark.parametrize("name,kw", [
@@ -43,10 +40,14 @@ def _history(impl, S, nobj, dmax, tmax, budget, frames, seed, feat_noise, big_bo
     ("short_gallery_budget_5", dict(S=4, nobj=12, dmax=16, tmax=48, budget=5, frames=40, seed=44, feat_noise=0.02)),
     ("many_candidates_two_gate_words", dict(S=3, nobj=40, dmax=48, tmax=128, budget=33, frames=40, seed=45,
                                             feat_noise=0.05, big_boxes=True)),
+    # nn_budget=None: galleries of ~300 rows span several 256-row blocks of the half pre-pass (running maximum)
+    ("unbounded_multi_block", dict(S=2, nobj=8, dmax=12, tmax=32, budget=None, frames=340, seed=46, feat_noise=0.01)),
+    ("unbounded_identical_rows", dict(S=2, nobj=6, dmax=8, tmax=32, budget=None, frames=300, seed=47, feat_noise=0.0)),
 ])
-def test_half_prepass_costs_are_bit_identical_to_the_exact_pass(name, kw):
-    half = _history(3, **kw)
-    exact = _history(0, **kw)
+@pytest.mark.parametrize("impl", ["default", "half_warp"])
+def test_half_prepass_costs_are_bit_identical_to_the_exact_pass(name, kw, impl):
+    half = _history(impl, **kw)
+    exact = _history("exact", **kw)
     checked = many = 0
     for f, ((ih, gh, ch, sh), (ie, ge, ce, se)) in enumerate(zip(half, exact)):
         np.testing.assert_array_equal(ih, ie, err_msg="%s ids frame %d" % (name, f))

@@ -10,7 +10,7 @@ from tests.goldens import LABELS3
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["tracker_small.npz", "tracker_c1.npz", "tracker_delcount.npz"])
+@pytest.mark.parametrize("name", ["tracker_small.npz", "tracker_c1.npz", "tracker_delcount.npz", "tracker_unbounded.npz"])
 def test_tracker_vs_reference_fixture(name):
     from deepdish_b200.batched import BatchedTracker
     g = goldens.load(name)
@@ -18,13 +18,19 @@ def test_tracker_vs_reference_fixture(name):
     if batches is None:
         pytest.skip("regenerated inputs do not match the fixture checksum")
     D = int(g["dmax"])
-    bt = BatchedTracker(1, LABELS3, max_tracks=96, max_dets=D, budget=int(g["budget"]), max_age=int(g["max_age"]))
+    # budget 0 in a fixture = nn_budget None, the reference's own configuration (deepdish.py:515-516); the small pool
+    # and page table make the run grow both several times (pool segments attached, page table re-laid out)
+    unb = int(g["budget"]) == 0
+    kw = dict(pool_pages=64, seg_pages=64, page_cap=4) if unb else {}
+    bt = BatchedTracker(1, LABELS3, max_tracks=96, max_dets=D, budget=int(g["budget"]) or None, max_age=int(g["max_age"]), **kw)
     stored = "in_feat" in g.files
     for f, b in enumerate(batches):
         got = bt.step(b.to("cuda")).cpu().numpy()[0]
         n = int(b.count[0])
         assert list(got[:n]) == list(g["det_ids"][f, :n]), f
-        v = bt.host_view(["n_tracks", "order", "track_id", "state", "tsu", "n_deleted", "deleted", "mean", "cov", "counts"])
+        if unb:
+            bt.maintain(wait=True)
+        v = bt.host_view(["n_tracks", "order", "track_id", "state", "tsu", "n_deleted", "deleted", "mean", "cov", "counts", "gal_len"])
         nt = int(v["n_tracks"][0]); sl = v["order"][0, :nt]
         assert nt == int(g["n_tracks"][f])
         assert list(v["track_id"][0, sl]) == list(g["ids"][f, :nt])
@@ -33,6 +39,9 @@ def test_tracker_vs_reference_fixture(name):
         dl = v["deleted"][0, :int(v["n_deleted"][0])]
         assert list(v["track_id"][0, dl]) == [x for x in g["deleted"][f] if x >= 0]
         np.testing.assert_array_equal(v["counts"][0], g["counts"][f])
+        if unb:
+            conf = v["state"][0, sl] == 2          # metric.samples holds confirmed tracks only
+            assert list(v["gal_len"][0, sl][conf]) == list(g["gal_len"][f, :nt][conf]), f
         if stored:
             np.testing.assert_allclose(v["mean"][0, sl], g["means"][f, :nt], rtol=1e-4, atol=1e-9)
             np.testing.assert_allclose(v["cov"][0, sl], g["covs"][f, :nt], rtol=1e-4, atol=1e-12)
@@ -41,6 +50,45 @@ def test_tracker_vs_reference_fixture(name):
     bt.check()
     if name == "tracker_delcount.npz":
         assert int(v["counts"][0, :, 3].sum()) > 0       # the del counter was exercised
+    if unb:
+        slot = int(sl[list(v["track_id"][0, sl]).index(int(g["longest_id"]))])
+        ref = g["longest_gallery"]
+        assert len(ref) >= 700 and len(bt.chunks[0].segs) > 1 and bt.chunks[0].v["ptab"].shape[2] > 4
+        unit = ref / np.sqrt(np.sum(ref * ref, axis=1, dtype=np.float32))[:, None]
+        np.testing.assert_allclose(bt.gallery(0, slot).cpu().numpy(), unit, rtol=2e-6, atol=1e-7)
+
+
+def test_drop_in_tracker_with_nn_budget_none_vs_reference_fixture():
+    """The reference's own configuration -- NearestNeighborDistanceMetric("cosine", thr, None), deepdish.py:515-517 --
+    through the deep_sort API mirror: 820 frames, four tracks matched > 700 times, ids / states / gallery lengths
+    against the unmodified reference's run."""
+    from deepdish_b200.deep_sort import nn_matching
+    from deepdish_b200.deep_sort.detection import Detection
+    from deepdish_b200.deep_sort.tracker import Tracker
+    g = goldens.load("tracker_unbounded.npz")
+    batches = goldens.tracker_batches(g)
+    if batches is None:
+        pytest.skip("regenerated inputs do not match the fixture checksum")
+    metric = nn_matching.NearestNeighborDistanceMetric("cosine", 0.2, None)
+    trk = Tracker(metric, max_iou_distance=0.7, max_age=int(g["max_age"]), n_init=3)
+    for f, b in enumerate(batches):
+        tlwh, conf, lab, feat = b.stream(0)
+        dets = [Detection(tlwh[i], LABELS3[lab[i]], conf[i], feat[i]) for i in range(len(conf))]
+        trk.predict()
+        trk.update(dets)
+        n = int(g["n_tracks"][f])
+        assert [t.track_id for t in trk.tracks] == list(g["ids"][f, :n]), f
+        assert [t.state for t in trk.tracks] == list(g["states"][f, :n]), f
+        assert [t.track_id for t in trk.deleted_tracks] == [x for x in g["deleted"][f] if x >= 0]
+        if f % 10 == 0:
+            np.testing.assert_allclose(np.stack([t.mean for t in trk.tracks]), g["means"][f // 10, :n], rtol=1e-4, atol=1e-9)
+            assert [LABELS3.index(t.get_label()) for t in trk.tracks] == list(g["track_labels"][f, :n])
+    ref = g["longest_gallery"]
+    got = np.asarray(metric.samples[int(g["longest_id"])])
+    assert got.shape == ref.shape and len(ref) >= 700
+    np.testing.assert_allclose(got, ref / np.sqrt(np.sum(ref * ref, axis=1, dtype=np.float32))[:, None], rtol=2e-6, atol=1e-7)
+    assert {k: len(v) for k, v in metric.samples.items()} == {
+        int(i): int(l) for i, l, s in zip(g["ids"][-1], g["gal_len"][-1], g["states"][-1]) if s == 2}
 
 
 def test_nms_vs_reference_fixture():

@@ -12,9 +12,9 @@ from tests.parity import OracleStreams, compare_stream, compare_costs, LABELS3
 pytestmark = pytest.mark.gpu
 
 
-def _run(S, nobj, dmax, tmax, frames, max_age, seed, budget=100, check_every=1):
+def _run(S, nobj, dmax, tmax, frames, max_age, seed, budget=100, check_every=1, **kw):
     from deepdish_b200.batched import BatchedTracker
-    bt = BatchedTracker(S, LABELS3, max_tracks=tmax, max_dets=dmax, budget=budget, max_age=max_age)
+    bt = BatchedTracker(S, LABELS3, max_tracks=tmax, max_dets=dmax, budget=budget, max_age=max_age, **kw)
     orc = OracleStreams(S, LABELS3, budget=budget, max_age=max_age)
     sc = Scene(S, nobj, dmax, n_labels=3, seed=seed)
     for f in range(frames):
@@ -25,10 +25,14 @@ def _run(S, nobj, dmax, tmax, frames, max_age, seed, budget=100, check_every=1):
             n = int(b.count[s])
             assert list(got[s, :n]) == ids[s], (f, s)
         if f % check_every == 0 or f == frames - 1:
+            bt.check()
             v = bt.host_view()
+            rows = (lambda s, slot: bt.gallery(s, slot).cpu().numpy()) if (f % 25 == 24 or f == frames - 1) else None
             for s in range(S):
-                compare_stream(orc.trk[s], orc.cnt[s], v, s, LABELS3)
+                compare_stream(orc.trk[s], orc.cnt[s], v, s, LABELS3, gallery_rows=rows)
     bt.check()
+    ctl = [c.v["pool_ctl"].cpu().numpy() for c in bt.chunks]       # every page is free or in exactly one slot's table
+    assert sum(int(c[0]) for c in ctl) + int(bt.v["gal_np"].sum()) == sum(int(c[1]) for c in ctl)
     return bt, orc
 
 
@@ -54,6 +58,37 @@ def test_c3_like_50_objects():
 def test_small_budget_and_short_age():
     """Ring wrap-around (budget 5) and early deletion (max_age 3)."""
     _run(4, 12, 16, 48, 120, 3, seed=9, budget=5, check_every=4)
+
+
+def test_unbounded_galleries_and_pool_growth_multi_stream():
+    """nn_budget=None on several streams and two chunks, starting from a pool and page tables that are far too small:
+    pool segments are attached and the page tables re-laid out while the run goes on; parity with the oracle throughout."""
+    bt, orc = _run(6, 10, 14, 40, 260, 20, seed=21, budget=None, check_every=13, n_chunks=2,
+                   pool_pages=64, seg_pages=64, page_cap=2)
+    assert all(len(c.segs) > 1 for c in bt.chunks) and all(c.v["ptab"].shape[2] >= 16 for c in bt.chunks)
+    assert max(len(g) for t in orc.trk for g in t.metric.samples.values()) > 200
+
+
+def test_pool_exhaustion_is_reported_not_silent():
+    from deepdish_b200.batched import BatchedTracker
+    bt = BatchedTracker(2, LABELS3, max_tracks=32, max_dets=12, budget=40, max_age=30, pool_pages=8, seg_pages=8)
+    bt._poll_pool = False                          # no growth: the 8-page pool must run dry
+    sc = Scene(2, 10, 12, n_labels=3, seed=5)
+    for _ in range(30):
+        bt.step(sc.step().to("cuda"))
+    with pytest.raises(RuntimeError, match="pool exhausted"):
+        bt.check()
+
+
+def test_bad_label_is_flagged_and_not_counted():
+    from deepdish_b200.batched import BatchedTracker
+    bt = BatchedTracker(1, LABELS3, max_tracks=16, max_dets=4, budget=10)
+    b = Scene(1, 3, 4, n_labels=3, seed=2).step().to("cuda")
+    b.label[0, 0] = 7
+    bt.step(b)
+    assert int(bt.v["lab_cnt"].sum()) == int(b.count[0]) - 1
+    with pytest.raises(ValueError, match="label"):
+        bt.check()
 
 
 def test_empty_frames_and_capacity_flags():
@@ -229,18 +264,13 @@ def test_checkpoint_resume_is_bit_identical():
 def test_four_warp_matching_kernel(shape):
     """k_match_cta (4 warps per stream, picked automatically for crowded scenes) forced on for several shapes: the
     same oracle parity as the one-warp kernel."""
-    from deepdish_b200 import _lib
-    _lib.check(_lib.lib().dd_tuning_set(5, 1), "dd_tuning_set")
-    try:
-        if shape == "crowd":
-            bt, orc = _run(3, 190, 224, 384, 40, 60, seed=18, check_every=5)
-            assert max(len(t.tracks) for t in orc.trk) > 200
-        elif shape == "c3":
-            _run(12, 50, 64, 128, 70, 60, seed=6, check_every=10)
-        else:
-            _run(4, 12, 16, 48, 100, 3, seed=10, budget=5, check_every=4)
-    finally:
-        _lib.check(_lib.lib().dd_tuning_set(5, -1), "dd_tuning_set")
+    if shape == "crowd":
+        bt, orc = _run(3, 190, 224, 384, 40, 60, seed=18, check_every=5, match_warps=4)
+        assert max(len(t.tracks) for t in orc.trk) > 200
+    elif shape == "c3":
+        _run(12, 50, 64, 128, 70, 60, seed=6, check_every=10, match_warps=4)
+    else:
+        _run(4, 12, 16, 48, 100, 3, seed=10, budget=5, check_every=4, match_warps=4)
 
 
 def test_unpack_detections_entry():

@@ -3,6 +3,7 @@ source files the CUDA kernels are built from, compiled with a one-lane group.  N
 import random
 
 import numpy as np
+import pytest
 from scipy.optimize import linear_sum_assignment
 
 from deepdish_b200 import _lib as L
@@ -70,10 +71,42 @@ def test_trajectory_parity_host_emulation():
         for s in range(S):
             n = int(b.count[s])
             assert list(got[s, :n]) == ids[s], (f, s)
-            compare_stream(orc.trk[s], orc.cnt[s], emu.v, s, LABELS3)
+            compare_stream(orc.trk[s], orc.cnt[s], emu.v, s, LABELS3, gallery_rows=emu.gallery if f % 10 == 9 else None)
             if f > 5:
                 checked += compare_costs(orc.trk[s], pre, emu.v, s)
     assert checked > 500 and int(emu.v["err"].sum()) == 0
+    # every page is either on the free stack or in exactly one live slot's table
+    ctl, np_ = emu.v["pool_ctl"], emu.v["gal_np"]
+    assert int(ctl[0]) + int(np_.sum()) == int(ctl[1])
+
+
+@pytest.mark.parametrize("budget", [None, 5, 16, 37])
+def test_paged_galleries_host_emulation(budget):
+    """nn_budget=None (deepdish.py:515-516: galleries never trimmed, nn_matching.py:137-154) and ring budgets that
+    are smaller than / equal to / not a multiple of the 16-row page: ids, states, gallery contents and the page
+    accounting against the oracle."""
+    S = 2
+    cfg = L.make_config(S, 48, 16, budget, LABELS3, max_age=8, page_cap=8)
+    emu = hd.HostEmuTracker(cfg)
+    orc = OracleStreams(S, LABELS3, budget=budget, max_age=8)
+    sc = Scene(S, 10, 16, n_labels=3, seed=11)
+    for f in range(100):
+        b = sc.step()
+        ids = orc.step(b)
+        emu.predict()
+        got = emu.update(b.tlwh.numpy(), b.conf.numpy(), b.label.numpy(), b.feat.numpy(), b.count.numpy())
+        emu.countline()
+        for s in range(S):
+            n = int(b.count[s])
+            assert list(got[s, :n]) == ids[s], (f, s)
+            compare_stream(orc.trk[s], orc.cnt[s], emu.v, s, LABELS3, gallery_rows=emu.gallery if f % 7 == 6 else None)
+    assert int(emu.v["err"].sum()) == 0
+    ctl = emu.v["pool_ctl"]
+    assert int(ctl[0]) + int(emu.v["gal_np"].sum()) == int(ctl[1])
+    if budget is None:
+        assert int(ctl[2]) > 64          # longest gallery so far (tracked for unbounded galleries only)
+    else:
+        assert int(emu.v["gal_len"].max()) == budget
 
 
 def test_detection_bodies_vs_reference_fixtures():
