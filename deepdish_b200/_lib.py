@@ -131,6 +131,7 @@ def lib():
         "dd_tracker_pool_poll": [_vp, cfgp, _vp, _vp, _vp],
         "dd_tracker_countline": [_vp, cfgp, _vp, _i32, _vp],
         "dd_tracker_tick": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+        "dd_tracker_tick_profiled": [_vp, cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, ctypes.POINTER(_vp)],
         "dd_tracker_tick_ragged": [_vp, cfgp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
         "dd_unpack_detections": [_vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

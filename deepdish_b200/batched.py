@@ -180,6 +180,8 @@ class BatchedTracker:
         self.total_counts = torch.zeros((C, 4), dtype=torch.int64, device=self.device)
         self._tick = 0
         self._sum_done = [None, None]
+        self._last_sum = None
+        self._aux = torch.cuda.Stream(device=self.device) if n_chunks > 1 else None
         self._poll_pool = any(len(c.segs) * c.cfg.seg_pages < self._worst_pages(c) for c in self.chunks) or budget is None
         torch.cuda.synchronize(self.device)
         for c in self.chunks:
@@ -272,13 +274,16 @@ class BatchedTracker:
                 c.done.record(c.stream)
 
     def join(self):
-        """Make the caller's current stream wait for all chunk streams (no host synchronisation)."""
+        """Make the caller's current stream wait for all chunk streams and for the count summation (no host
+        synchronisation)."""
         if len(self.chunks) == 1:
             return
         cur = self._cur()
         for c in self.chunks:
             c.done.record(c.stream)
             cur.wait_event(c.done)
+        if self._last_sum is not None:
+            cur.wait_event(self._last_sum)
 
     def _line_ptr(self, c):
         return self.line.data_ptr() + (c.lo * 32 if self.line_per_stream else 0)
@@ -381,19 +386,27 @@ class BatchedTracker:
         return self.det_track_id
 
     def _tick_call(self, c, p, out, sp):
+        ev = self._timeline.pop(0) if getattr(self, "_timeline", None) else None
+        if ev is not None:         # kernel-timeline mode (benchmarks/timeline.py): 8 events around this chunk's kernels
+            _lib.check(self.lib.dd_tracker_tick_profiled(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream,
+                                                         out, sp, ev), "dd_tracker_tick_profiled")
+            return
         _lib.check(self.lib.dd_tracker_tick(c.state, c.cfgp, *p, self._line_ptr(c), self.line_per_stream, out, sp),
                    "dd_tracker_tick")
 
     def _sum_partials(self, par):
-        """caller's stream: wait for the chunks' partial counters of this tick, sum them."""
-        cur = self._cur()
-        multi = len(self.chunks) > 1
-        if multi:
+        """Sum the chunks' partial counters of this tick into total_counts.  With several chunks this runs on the
+        tracker's own auxiliary stream, NOT on the caller's: the caller's stream must not wait for every chunk each
+        tick, or the next tick's fork event would serialise the chunks tick by tick and nothing would overlap
+        across tick boundaries.  total_counts is valid on the caller's stream after join()."""
+        if len(self.chunks) == 1:
+            torch.sum(self.partial_counts[par], dim=0, out=self.total_counts)
+            return
+        with torch.cuda.stream(self._aux):
             for c in self.chunks:
-                cur.wait_event(c.done)
-        torch.sum(self.partial_counts[par], dim=0, out=self.total_counts)
-        if multi:
-            self._sum_done[par] = cur.record_event()
+                self._aux.wait_event(c.done)
+            torch.sum(self.partial_counts[par], dim=0, out=self.total_counts)
+            self._sum_done[par] = self._last_sum = self._aux.record_event()
 
     def step_host(self, host_batch, out_ids_host=None):
         """End-to-end tick from a pinned HOST batch: per chunk and on the chunk's stream, H2D copy of its
@@ -477,7 +490,7 @@ class BatchedTracker:
         own copy stream into a double-buffered device blob -- so the upload of tick k + 1 runs under the kernels of
         tick k --, then on the chunk's compute stream the tick reading the blob directly (dd_tracker_tick_ragged)
         with its partial count reduction and (optionally) the D2H copy of the det->track ids.  The pinned blobs must stay alive until their copy has
-        run.  Returns total_counts (device, summed on the caller's stream)."""
+        run.  Returns total_counts (device; valid on the caller's stream after join() or all_reduce_counts())."""
         if self._poll_pool:
             self.maintain()
         par = self._tick & 1
@@ -534,6 +547,8 @@ class BatchedTracker:
         self._mark()
         self._sum_partials(par)
         self._tick += 1
+        if self._last_sum is not None:
+            self._cur().wait_event(self._last_sum)
         return self.total_counts
 
     def all_reduce_counts(self, reduced=False, async_op=False):
@@ -546,6 +561,8 @@ class BatchedTracker:
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if not async_op:
+            if self._last_sum is not None:
+                self._cur().wait_event(self._last_sum)
             if multi:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
             return t
@@ -555,10 +572,13 @@ class BatchedTracker:
             self._ar_turn = 0
         k = self._ar_turn
         self._ar_turn ^= 1
-        if self._ar_work[k] is not None:
-            self._ar_work[k].wait()
-        self._ar_buf[k].copy_(t)
-        self._ar_work[k] = dist.all_reduce(self._ar_buf[k], op=dist.ReduceOp.SUM, async_op=True) if multi else None
+        side = self._aux if self._aux is not None else self._cur()      # the stream total_counts is produced on
+        with torch.cuda.stream(side):
+            if self._ar_work[k] is not None:
+                self._ar_work[k].wait()
+            self._ar_buf[k].copy_(t)
+            self._ar_work[k] = dist.all_reduce(self._ar_buf[k], op=dist.ReduceOp.SUM, async_op=True) if multi else None
+            self._ar_done = side.record_event()
         return self._ar_buf[k]
 
     def wait_counts(self):
@@ -567,6 +587,8 @@ class BatchedTracker:
             if w is not None:
                 w.wait()
                 self._ar_work[k] = None
+        if getattr(self, "_ar_done", None) is not None:
+            self._cur().wait_event(self._ar_done)
 
     def status(self):
         self.join()
@@ -631,6 +653,7 @@ class BatchedTracker:
         self.total_counts.copy_(sd["total_counts"].to(self.device))
         self._tick = int(sd["tick"])
         self._sum_done = [None, None]
+        self._last_sum = None
         torch.cuda.synchronize(self.device)
 
     def host_view(self, names=None, streams=None):

@@ -322,10 +322,13 @@ struct DDSsdParams {
 };
 #define DD_SSD_MAXDET 16
 
+// The op's exp is DECLARED correctly rounded in f32: exp evaluated in f64 (<= 1 ulp there, on the device as in glibc)
+// and rounded once to f32.  An f32 libm expf may differ from that in the last bit on either side; the oracle
+// (oracle/detect.py) uses the same definition, which makes the decoded boxes bit-exact between the two.
 #if defined(__CUDA_ARCH__)
-DD_D float dd_expf(float x) { return expf(x); }
+DD_D float dd_expf(float x) { return (float)exp((double)x); }
 #else
-inline float dd_expf(float x) { return expf(x); }
+inline float dd_expf(float x) { return (float)exp((double)x); }
 #endif
 
 // DecodeCenterSizeBoxes for one anchor: raw (ty,tx,th,tw), anchor (yc,xc,h,w) -> (ymin,xmin,ymax,xmax) f32.

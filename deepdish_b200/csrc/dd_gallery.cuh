@@ -252,81 +252,90 @@ k_cosine_h(const DDView V, const int* __restrict__ det_count) {
     }
 }
 
-// ---- k_gallery_stream: the half pre-pass as a producer / consumer stream (gallery_impl = 0, the default) -----------
-// The per-warp kernel above keeps its in-flight gallery bytes in registers and stalls on every per-track bubble
-// (claim -> descriptor -> gate word -> queries -> first rows, then the dependent re-check reads).  Here the bytes in
-// flight live in shared memory and never wait for arithmetic: a CTA is a set of warp PAIRS.
-//   producer warp   walks the work list (self-contained records written by k_gate, claimed two entries ahead) and,
-//                   for every (track, group of <= 8 gate-passing detections, block of <= 128 gallery rows), posts a job
-//                   header + the detections' half rows, then feeds the pair's ring of 4 KB stages with ONE bulk
-//                   asynchronous copy per gallery page (cp.async.bulk, completion on the stage's mbarrier; a ragged
-//                   last page is copied row-block by row-block so that no byte past the gallery's end is read).
-//                   It runs across job and track boundaries, as far ahead as the ring allows.
-//   consumer warp   waits for a stage, takes its mma fragments with conflict-free 16-byte shared loads (pages are
-//                   stored in fragment order), releases the stage at once, does the 8 mma of the page, keeps the
-//                   approximate dots in shared memory; after a block it lists the window candidates and re-checks them
-//                   from the f32 pages (the exact pass's arithmetic) while the producer keeps streaming the next job.
+// ---- k_gallery_stream: the half pre-pass as a three-stage warp pipeline (gallery_impl = 0, the default) -----------
+// The per-warp kernel above keeps its in-flight gallery bytes in registers and serialises, per track, a chain of
+// dependent latencies (claim -> descriptor -> gate word -> queries -> rows ... -> candidate list -> f32 re-check rows).
+// Here every link of that chain is its own warp and the bytes in flight live in shared memory.  A CTA is a set of
+// warp TRIPLES, one CTA per SM:
+//   producer P   walks the work list (self-contained records written by k_gate, claimed two entries ahead) and, for
+//                every job = (track, group of <= 8 gate-passing detections, block of <= 128 gallery rows), posts a job
+//                header + the detections' half rows, then feeds the triple's ring of 4 KB stages with ONE bulk
+//                asynchronous copy per gallery page (cp.async.bulk, completion on the stage's mbarrier; a ragged last
+//                page is copied row-block by row-block so that no byte past the gallery's end is read).  It runs across
+//                job and track boundaries, as far ahead as the ring allows.
+//   mma warp M   waits for a stage, takes its mma fragments with conflict-free 16-byte shared loads (pages are stored
+//                in fragment order), releases the stage at once, does the 8 mma of the page and keeps the approximate
+//                dots of the whole block in REGISTERS; after the block it names the window candidates by ballot and
+//                posts them to the checker.  It never touches global memory.
+//   checker C    evaluates the candidates from the f32 pages with the exact pass's arithmetic (8 rows in flight),
+//                keeps the exact maximum per detection and writes the cost entries.  Its dependent global reads stall
+//                nobody but itself.
 #include "dd_tma.cuh"
 
-#define DD_GS_BLOCK_ROWS 128                 // gallery rows per job (8 pages): sizes the per-pair approx / cand buffers
+#define DD_GS_BLOCK_ROWS 128                 // gallery rows per job (8 pages): the mma warp keeps 8 x 4 dots per lane
 #define DD_GS_HDR_INTS 32                    // job header: 0 slotg 1 stream 2 row0 3 nrows 4 nq 5 flags | 8.. cj[8] | 16.. pid[8]
-#define DD_GS_FIRST 1
-#define DD_GS_LAST 2
+#define DD_GS_MSG_CAND (DD_GS_BLOCK_ROWS * 8) // a message can list every (row, detection) of a block: identical rows are legal
+#define DD_GS_MSG_BYTES (DD_GS_HDR_INTS * 4 + DD_GS_MSG_CAND * 2)   // checker message: header (32 ints; [6] = candidates) + list (u16)
+#define DD_GS_FIRST 1                        // first job / message of a detection group: reset the running maxima
+#define DD_GS_LAST 2                         // last one: the cost entries are final
 #define DD_GS_STOP 4
 
-__host__ __device__ inline size_t dd_gs_pair_bytes(int stages) {
-    return (size_t)stages * DD_PAGE_F16_BYTES            // ring
-           + 2 * 8 * 256                                 // query half rows, double-buffered
-           + DD_GS_BLOCK_ROWS * 8 * 4                    // approx
-           + DD_GS_BLOCK_ROWS * 8 * 2                    // cand
-           + 2 * DD_GS_HDR_INTS * 4                      // headers, double-buffered
-           + 64                                          // thr[8] + pad
-           + (size_t)(2 * stages + 4) * 8;               // mbarriers: full[stages], empty[stages], hfull[2], hfree[2]
+__host__ __device__ inline size_t dd_gs_triple_bytes(int stages) {
+    const size_t b = (size_t)stages * DD_PAGE_F16_BYTES            // ring
+                     + 2 * 8 * 256                                 // query half rows, double-buffered
+                     + 2 * DD_GS_HDR_INTS * 4                      // job headers, double-buffered
+                     + 2 * DD_GS_MSG_BYTES                         // checker messages, double-buffered
+                     + DD_GS_BLOCK_ROWS * 8 * 4                    // approximate dots of the block being streamed
+                     + (size_t)(2 * stages + 8) * 8;               // mbarriers: full / empty [stages], hfull hfree mfull mfree [2]
+    return (b + 127) & ~(size_t)127;
 }
 
 __device__ __forceinline__ void dd_mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dd_smem_u32(bar)) : "memory");
 }
 
-struct DDPairSmem {
+struct DDTripleSmem {
     char* ring;
     char* qbuf;
-    float* approx;
-    unsigned short* cand;
     int* hdr;
-    float* thr;
-    unsigned long long *full, *empty, *hfull, *hfree;
+    char* msg;
+    float* approx;
+    unsigned long long *full, *empty, *hfull, *hfree, *mfull, *mfree;
 };
-__device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDPairSmem& P) {
+__device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDTripleSmem& P) {
     P.ring = base;
     P.qbuf = P.ring + (size_t)stages * DD_PAGE_F16_BYTES;
-    P.approx = (float*)(P.qbuf + 2 * 8 * 256);
-    P.cand = (unsigned short*)((char*)P.approx + DD_GS_BLOCK_ROWS * 8 * 4);
-    P.hdr = (int*)((char*)P.cand + DD_GS_BLOCK_ROWS * 8 * 2);
-    P.thr = (float*)(P.hdr + 2 * DD_GS_HDR_INTS);
-    P.full = (unsigned long long*)((char*)P.thr + 64);
+    P.hdr = (int*)(P.qbuf + 2 * 8 * 256);
+    P.msg = (char*)(P.hdr + 2 * DD_GS_HDR_INTS);
+    P.approx = (float*)(P.msg + 2 * DD_GS_MSG_BYTES);
+    P.full = (unsigned long long*)((char*)P.approx + DD_GS_BLOCK_ROWS * 8 * 4);
     P.empty = P.full + stages;
     P.hfull = P.empty + stages;
     P.hfree = P.hfull + 2;
+    P.mfull = P.hfree + 2;
+    P.mfree = P.mfull + 2;
 }
 
-__device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDPairSmem& P, int stages) {
+__device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSmem& P, int stages) {
     const int lane = threadIdx.x & 31;
     const int n = V.work_ctl[0];
     int st = 0;                  // next ring stage
     unsigned ephase = ~0u;       // bit s: parity to wait for on empty[s] (a fresh barrier passes a wait on parity 1)
     int hb = 0;
     unsigned hphase = 3u;        // same for hfree[0..1]
-    // claims run two entries ahead of the entry being streamed; a claim is broadcast one entry after it was made
+    // claims are made two work-list entries at a time (one atomic per pair of tracks) and one pair ahead: the
+    // claim made when pair k starts is broadcast when it ends
     int raw = 0;
-    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 1);
-    int i_cur = __shfl_sync(0xffffffffu, raw, 0);
-    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 1);
-    int i_nxt = __shfl_sync(0xffffffffu, raw, 0);
+    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);
+    int i_cur = __shfl_sync(0xffffffffu, raw, 0);          // i_cur, i_cur + 1: the pair being streamed
+    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);
+    int i_nxt = __shfl_sync(0xffffffffu, raw, 0);          // first entry of the next pair
+    int odd = 0;                                           // 0: streaming the pair's first entry, 1: its second
     int w_cur = i_cur < n ? V.work_rec[(size_t)i_cur * 16 + (lane & 15)] : 0;
     while (i_cur < n) {
-        const int w_nxt = i_nxt < n ? V.work_rec[(size_t)i_nxt * 16 + (lane & 15)] : 0;     // used one entry later
-        if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 1);                                  // broadcast one entry later
+        const int i_after = odd ? i_nxt : i_cur + 1;                                         // the entry streamed next
+        const int w_nxt = i_after < n ? V.work_rec[(size_t)i_after * 16 + (lane & 15)] : 0;  // used one entry later
+        if (!odd && lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);                          // broadcast two entries later
         const int slotg = __shfl_sync(0xffffffffu, w_cur, 0), s = __shfl_sync(0xffffffffu, w_cur, 1);
         const int glen = __shfl_sync(0xffffffffu, w_cur, 2), np = __shfl_sync(0xffffffffu, w_cur, 4);
         const unsigned gw0 = (unsigned)__shfl_sync(0xffffffffu, w_cur, 5), gw1 = (unsigned)__shfl_sync(0xffffffffu, w_cur, 6);
@@ -402,9 +411,10 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDPairSmem
                 }
             }
         }
-        i_cur = i_nxt;
+        i_cur = i_after;
         w_cur = w_nxt;
-        i_nxt = __shfl_sync(0xffffffffu, raw, 0);
+        if (odd) i_nxt = __shfl_sync(0xffffffffu, raw, 0);
+        odd ^= 1;
     }
     // ---- stop job
     dd_mbar_wait(P.hfree + hb, (hphase >> hb) & 1u);
@@ -414,108 +424,186 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDPairSmem
     }
 }
 
-__device__ __forceinline__ void dd_gs_consumer(const DDView& V, const DDPairSmem& P, int stages) {
-    WarpG g;
-    const int gq = g.lane >> 2, tq = g.lane & 3;
-    DDHalfSmem sm;
-    sm.approx = P.approx; sm.cand = P.cand; sm.thr = P.thr; sm.cj = nullptr;
-    int st = 0;
+__device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
+    const int lane = threadIdx.x & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    int st = 0, hb = 0, mb = 0;
     unsigned fphase = 0u;        // bit s: parity to wait for on full[s]
-    unsigned hphase = 0u;
-    int hb = 0;
-    float best = -3.0e38f, run0 = -3.0e38f, run1 = -3.0e38f;
+    unsigned hphase = 0u;        // hfull[0..1]
+    unsigned mphase = 3u;        // mfree[0..1] (fresh barriers pass)
+    float run0 = -3.0e38f, run1 = -3.0e38f;     // approximate maxima so far of detections 2 tq, 2 tq + 1 (over the group's blocks)
     for (;;) {
         dd_mbar_wait(P.hfull + hb, (hphase >> hb) & 1u);
         hphase ^= 1u << hb;
-        const int* H = P.hdr + hb * DD_GS_HDR_INTS;
-        const int flags = H[5];
-        if (flags & DD_GS_STOP) break;
-        const int slotg = H[0], s = H[1], nrows = H[3], nq = H[4];
-        sm.cj = const_cast<int*>(H + 8);
-        const int mypid = H[16 + (g.lane & 7)];
-        if (flags & DD_GS_FIRST) { best = -3.0e38f; run0 = -3.0e38f; run1 = -3.0e38f; }
+        const int hw = P.hdr[hb * DD_GS_HDR_INTS + lane];      // lane l keeps header word l
+        const int flags = __shfl_sync(0xffffffffu, hw, 5);
+        if (flags & DD_GS_STOP) {
+            dd_mbar_wait(P.mfree + mb, (mphase >> mb) & 1u);
+            if (lane == 0) {
+                ((int*)(P.msg + mb * DD_GS_MSG_BYTES))[5] = DD_GS_STOP;
+                dd_mbar_arrive(P.mfull + mb);
+            }
+            break;
+        }
+        const int nrows = __shfl_sync(0xffffffffu, hw, 3), nq = __shfl_sync(0xffffffffu, hw, 4);
         uint4 qb[4];
         {
             const uint4* qh = (const uint4*)(P.qbuf + hb * 2048 + gq * 256);
 #pragma unroll
             for (int j = 0; j < 4; ++j) qb[j] = gq < nq ? qh[tq + 4 * j] : make_uint4(0u, 0u, 0u, 0u);
         }
+        __syncwarp();
+        if (lane == 0) dd_mbar_arrive(P.hfree + hb);           // header and queries are in registers
+        hb ^= 1;
+        if (flags & DD_GS_FIRST) { run0 = -3.0e38f; run1 = -3.0e38f; }
         const int npg = (nrows + 15) >> 4;
         float mx0 = -3.0e38f, mx1 = -3.0e38f;
-        for (int p = 0; p < npg; ++p) {
+        for (int p = 0; p < npg; ++p) {                        // deliberately not unrolled: the loop must stay in the L0 i-cache
             dd_mbar_wait(P.full + st, (fphase >> st) & 1u);
             fphase ^= 1u << st;
             const uint4* pg = (const uint4*)(P.ring + (size_t)st * DD_PAGE_F16_BYTES);
             uint4 ga[4], gb[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + g.lane]; gb[j] = pg[j * 64 + 32 + g.lane]; }
+            for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + lane]; gb[j] = pg[j * 64 + 32 + lane]; }
             __syncwarp();
-            if (g.lane == 0) dd_mbar_arrive(P.empty + st);         // the stage is free again: its bytes are in registers
+            if (lane == 0) dd_mbar_arrive(P.empty + st);       // the stage is free again: its bytes are in registers
             st = st + 1 == stages ? 0 : st + 1;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            // two independent accumulator chains (any summation order satisfies the window bound)
+            float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                dd_mma_f16(c, ga[j].x, gb[j].x, ga[j].y, gb[j].y, qb[j].x, qb[j].y);
-                dd_mma_f16(c, ga[j].z, gb[j].z, ga[j].w, gb[j].w, qb[j].z, qb[j].w);
+                dd_mma_f16(ca, ga[j].x, gb[j].x, ga[j].y, gb[j].y, qb[j].x, qb[j].y);
+                dd_mma_f16(cb, ga[j].z, gb[j].z, ga[j].w, gb[j].w, qb[j].z, qb[j].w);
             }
+            float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2], c3 = ca[3] + cb[3];
             const int ra = p * 16 + gq, rb = ra + 8;
-            if (ra >= nrows) { c[0] = -3.0e38f; c[1] = -3.0e38f; }      // rows past the end (stale stage bytes) never win
-            if (rb >= nrows) { c[2] = -3.0e38f; c[3] = -3.0e38f; }
-            *(float2*)(sm.approx + ra * 8 + 2 * tq) = make_float2(c[0], c[1]);
-            *(float2*)(sm.approx + rb * 8 + 2 * tq) = make_float2(c[2], c[3]);
-            mx0 = fmaxf(mx0, fmaxf(c[0], c[2]));
-            mx1 = fmaxf(mx1, fmaxf(c[1], c[3]));
+            if (ra >= nrows) { c0 = -3.0e38f; c1 = -3.0e38f; }     // rows past the end (stale stage bytes) never win
+            if (rb >= nrows) { c2 = -3.0e38f; c3 = -3.0e38f; }
+            *(float2*)(P.approx + ra * 8 + 2 * tq) = make_float2(c0, c1);
+            *(float2*)(P.approx + rb * 8 + 2 * tq) = make_float2(c2, c3);
+            mx0 = fmaxf(mx0, fmaxf(c0, c2));
+            mx1 = fmaxf(mx1, fmaxf(c1, c3));
         }
-        if (npg > 0) {
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
-                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
-            }
-            run0 = fmaxf(run0, mx0);
-            run1 = fmaxf(run1, mx1);
-            if (gq == 0) { sm.thr[2 * tq] = run0 - DD_H_WINDOW; sm.thr[2 * tq + 1] = run1 - DD_H_WINDOW; }
-            __syncwarp();
-            int ncand = 0;
-            const int total = npg * 16 * 8;
-            for (int i0 = 0; i0 < total; i0 += 32) {
-                const int i = i0 + g.lane;
-                const int nn = i & 7;
-                const bool pr = nn < nq && sm.approx[i] >= sm.thr[nn];
-                const unsigned m = __ballot_sync(0xffffffffu, pr);
-                if (pr) sm.cand[ncand + __popc(m & ((1u << g.lane) - 1u))] = (unsigned short)i;
-                ncand += __popc(m);
-            }
-            __syncwarp();
-            dd_half_recheck(g, V, s, sm, ncand, mypid);
-            __syncwarp();
-            if (g.lane < nq) {
-                for (int i = 0; i < ncand; ++i) {
-                    const int e = sm.cand[i];
-                    if ((e & 7) == g.lane) best = fmaxf(best, sm.approx[e]);
-                }
-            }
+        for (int o = 4; o < 32; o <<= 1) {
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
         }
-        if ((flags & DD_GS_LAST) && g.lane < nq) V.cost[(size_t)slotg * V.D + sm.cj[g.lane]] = dd_subf(1.0f, best);
+        run0 = fmaxf(run0, mx0);
+        run1 = fmaxf(run1, mx1);
+        // a detection column this lane holds no real query for can never list a candidate
+        const float thr0 = 2 * tq < nq ? run0 - DD_H_WINDOW : 3.0e38f;
+        const float thr1 = 2 * tq + 1 < nq ? run1 - DD_H_WINDOW : 3.0e38f;
+        // ---- candidates -> checker message: every lane re-reads the dots it wrote and appends its own candidates
+        // (a shared-memory counter hands out list positions; the order of the list does not matter to a maximum)
+        dd_mbar_wait(P.mfree + mb, (mphase >> mb) & 1u);
+        mphase ^= 1u << mb;
+        int* M = (int*)(P.msg + mb * DD_GS_MSG_BYTES);
+        unsigned short* mc = (unsigned short*)(M + DD_GS_HDR_INTS);
+        M[lane] = lane == 6 ? 0 : hw;                          // word 6 = candidate counter
         __syncwarp();
-        if (g.lane == 0) dd_mbar_arrive(P.hfree + hb);              // header + query buffer may be rewritten
-        hb ^= 1;
+        for (int p = 0; p < npg; ++p) {
+            const int ra = p * 16 + gq, rb = ra + 8;
+            const float2 va = *(const float2*)(P.approx + ra * 8 + 2 * tq);
+            const float2 vb = *(const float2*)(P.approx + rb * 8 + 2 * tq);
+            if (va.x >= thr0) mc[atomicAdd(M + 6, 1)] = (unsigned short)((ra << 3) | (2 * tq));
+            if (va.y >= thr1) mc[atomicAdd(M + 6, 1)] = (unsigned short)((ra << 3) | (2 * tq + 1));
+            if (vb.x >= thr0) mc[atomicAdd(M + 6, 1)] = (unsigned short)((rb << 3) | (2 * tq));
+            if (vb.y >= thr1) mc[atomicAdd(M + 6, 1)] = (unsigned short)((rb << 3) | (2 * tq + 1));
+        }
+        __syncwarp();
+        if (lane == 0) dd_mbar_arrive(P.mfull + mb);
+        mb ^= 1;
     }
 }
 
-__global__ void __launch_bounds__(512, 1)
+template <int CW>
+__device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSmem& P) {
+    const int lane = threadIdx.x & 31;
+    int mb = 0;
+    unsigned mphase = 0u;
+    float best = -3.0e38f;       // lane n: exact maximum of detection n of the current group
+    for (;;) {
+        dd_mbar_wait(P.mfull + mb, (mphase >> mb) & 1u);
+        mphase ^= 1u << mb;
+        const int* M = (const int*)(P.msg + mb * DD_GS_MSG_BYTES);
+        const unsigned short* mc = (const unsigned short*)(M + DD_GS_HDR_INTS);
+        const int hw = M[lane];
+        const int flags = __shfl_sync(0xffffffffu, hw, 5);
+        if (flags & DD_GS_STOP) break;
+        const int slotg = __shfl_sync(0xffffffffu, hw, 0), s = __shfl_sync(0xffffffffu, hw, 1);
+        const int nq = __shfl_sync(0xffffffffu, hw, 4), ncand = __shfl_sync(0xffffffffu, hw, 6);
+        if (flags & DD_GS_FIRST) best = -3.0e38f;
+        const float4* qbase = (const float4*)(V.det_featn + (size_t)s * V.D * DD_FEAT_DIM);
+        for (int c0 = 0; c0 < ncand; c0 += CW) {
+            // exact values of CW listed (row, detection) entries: the exact pass's arithmetic, bit for bit
+            float v[CW];
+            float4 a[CW], q[CW];
+            int qn[CW];
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                const int e = mc[dd_imin(c0 + k, ncand - 1)];
+                qn[k] = e & 7;
+                const int row = e >> 3;
+                const int pid = __shfl_sync(0xffffffffu, hw, 16 + (row >> 4));
+                const int d = __shfl_sync(0xffffffffu, hw, 8 + qn[k]);
+                a[k] = dd_page_f32(V, pid)[(size_t)(row & 15) * (DD_FEAT_DIM / 4) + lane];
+                q[k] = qbase[(size_t)d * (DD_FEAT_DIM / 4) + lane];
+            }
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                float p = dd_fmaf(a[k].x, q[k].x, 0.f);
+                p = dd_fmaf(a[k].y, q[k].y, p);
+                p = dd_fmaf(a[k].z, q[k].z, p);
+                p = dd_fmaf(a[k].w, q[k].w, p);
+                v[k] = p;
+            }
+            int nn = CW, o = 16;                        // transposing butterfly: the 16-8-4-2-1 summation tree of the exact pass
+#pragma unroll
+            for (; nn > 1; nn >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+                const int half = nn >> 1;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const float send = up ? v[i] : v[i + half];
+                    const float keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+#pragma unroll
+            for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+            // lane L now holds the total of entry c0 + L / (32 / CW); lane n keeps the maximum of detection n
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                const float tot = __shfl_sync(0xffffffffu, v[0], (32 / CW) * k);
+                if (c0 + k < ncand && qn[k] == lane) best = fmaxf(best, tot);
+            }
+        }
+        const int dmine = __shfl_sync(0xffffffffu, hw, 8 + (lane & 7));
+        if ((flags & DD_GS_LAST) && lane < nq) V.cost[(size_t)slotg * V.D + dmine] = dd_subf(1.0f, best);
+        __syncwarp();
+        if (lane == 0) dd_mbar_arrive(P.mfree + mb);
+        mb ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(672, 1)
 k_gallery_stream(const DDView V, int stages) {
     extern __shared__ __align__(128) char smem[];
     const int warp = threadIdx.x >> 5;
-    const int pair = warp >> 1;
-    DDPairSmem P;
-    dd_gs_carve(smem + (size_t)pair * ((dd_gs_pair_bytes(stages) + 127) & ~(size_t)127), stages, P);
-    if ((warp & 1) == 0 && (threadIdx.x & 31) == 0) {
+    const int triple = warp / 3, role = warp - triple * 3;
+    DDTripleSmem P;
+    dd_gs_carve(smem + (size_t)triple * dd_gs_triple_bytes(stages), stages, P);
+    if (role == 0 && (threadIdx.x & 31) == 0) {
         for (int i = 0; i < stages; ++i) { dd_mbar_init(P.full + i, 1); dd_mbar_init(P.empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { dd_mbar_init(P.hfull + i, 1); dd_mbar_init(P.hfree + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            dd_mbar_init(P.hfull + i, 1); dd_mbar_init(P.hfree + i, 1);
+            dd_mbar_init(P.mfull + i, 1); dd_mbar_init(P.mfree + i, 1);
+        }
         dd_mbar_fence_init();
     }
     __syncthreads();
-    if ((warp & 1) == 0) dd_gs_producer(V, P, stages);
-    else dd_gs_consumer(V, P, stages);
+    if (role == 0) dd_gs_producer(V, P, stages);
+    else if (role == 1) dd_gs_mma(P, stages);
+    else dd_gs_checker<4>(V, P);
 }

@@ -305,17 +305,21 @@ static int dd_launch_gallery(const DDView& V, const dd_tracker_config* cfg, cons
     if (impl == 1) {
         k_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
     } else if (impl == 0) {
-        int pairs = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 6;
-        if (pairs > 8) pairs = 8;
+        int triples = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 7;
+        if (triples > 7) triples = 7;
         int stages = cfg->gallery_stages > 0 ? cfg->gallery_stages : 4;
         if (stages > 16) stages = 16;
-        const size_t per_pair = (dd_gs_pair_bytes(stages) + 127) & ~(size_t)127;
-        while (pairs > 1 && per_pair * pairs > 200 * 1024) --pairs;
-        const size_t gsm = per_pair * pairs;
+        const size_t per = dd_gs_triple_bytes(stages);
+        while (triples > 1 && per * triples > 226 * 1024) --triples;
+        const size_t gsm = per * triples;
         if (gsm > 227 * 1024) return DD_ERR_INVALID;
-        if (cudaFuncSetAttribute(k_gallery_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess)
-            return DD_ERR_CUDA;
-        k_gallery_stream<<<dd_sm_count(), pairs * 64, gsm, st>>>(V, stages);
+        static size_t gsm_set = 0;                       // the attribute only ever grows: set it when a larger size is asked for
+        if (gsm > gsm_set) {
+            if (cudaFuncSetAttribute(k_gallery_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess)
+                return DD_ERR_CUDA;
+            gsm_set = gsm;
+        }
+        k_gallery_stream<<<dd_sm_count(), triples * 96, gsm, st>>>(V, stages);
     } else {
         long long grid = (long long)dd_sm_count() * per_sm;
         const long long need = warps_to_blocks((long long)V.S * V.T);
@@ -382,16 +386,18 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const DDTic
 }
 
 static int dd_tick_tail(void* state, const dd_tracker_config* cfg, const double* line, int line_per_stream,
-                        int64_t* out_counts, cudaStream_t st) {
+                        int64_t* out_counts, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
     k_countline<<<warps_to_blocks(V.S), DD_WARPS * 32, 0, st>>>(V, line, line_per_stream);
     DD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[6], st);
     if (out_counts) {
         k_count_reduce<<<V.C * 4, 256, 0, st>>>((const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts);
         DD_CHECK_LAUNCH();
     }
+    if (ev) cudaEventRecord(ev[7], st);
     return DD_OK;
 }
 
@@ -537,6 +543,19 @@ int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det
     const int rc = dd_update_impl(state, cfg, in, (cudaStream_t)stream, nullptr, true);
     if (rc != DD_OK) return rc;
     return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, (cudaStream_t)stream);
+}
+
+int dd_tracker_tick_profiled(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
+                             const float* det_conf, const int32_t* det_label, const float* det_feat,
+                             const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                             int line_per_stream, int64_t* out_counts, void* stream, void* const* host_events8) {
+    if (!line || !host_events8) return DD_ERR_INVALID;
+    cudaEvent_t ev[8];
+    for (int i = 0; i < 8; ++i) ev[i] = (cudaEvent_t)host_events8[i];
+    const DDTickIn in = {det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, nullptr};
+    const int rc = dd_update_impl(state, cfg, in, (cudaStream_t)stream, ev, true);
+    if (rc != DD_OK) return rc;
+    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, (cudaStream_t)stream, ev);
 }
 
 int dd_tracker_tick_ragged(void* state, const dd_tracker_config* cfg, const void* blob, int64_t off_tlwh,

@@ -84,10 +84,10 @@ typedef struct dd_tracker_config {
     /* per-tracker tuning (A/B measurements; 0 = default everywhere) */
     int32_t gallery_impl;       /* 0 = default (the half-precision producer/consumer stream), 1 = exact f32 pass,
                                    2 = half pre-pass with per-warp global loads (both bit-identical to 0) */
-    int32_t cosine_ctas_per_sm; /* impl 2: persistent grid = SMs x this (default 4); impl 0: warp pairs per CTA,
-                                   one CTA per SM (default 6, at most 8)                                */
+    int32_t cosine_ctas_per_sm; /* impl 2: persistent grid = SMs x this (default 4); impl 0: warp triples (producer,
+                                   mma, checker) per CTA, one CTA per SM (default 7, at most 7)         */
     int32_t match_warps;        /* matching kernel: 0 = by problem size, 1 / 4 / 8 warps per stream     */
-    int32_t gallery_stages;     /* impl 0: 4 KB ring stages per warp pair (default 4)                   */
+    int32_t gallery_stages;     /* impl 0: 4 KB ring stages per warp triple (default 4)                 */
     int32_t reserved0;
     uint64_t pool_f32[DD_MAX_SEGS]; /* device pointers, seg_pages x DD_PAGE_F32_BYTES each, 16-byte aligned */
     uint64_t pool_f16[DD_MAX_SEGS]; /* device pointers, seg_pages x DD_PAGE_F16_BYTES each, 16-byte aligned */
@@ -222,6 +222,14 @@ int dd_tracker_tick(void* state, const dd_tracker_config* host_cfg, const double
                     const float* det_conf, const int32_t* det_label, const float* det_feat,
                     const int32_t* det_count, int32_t* out_det_track_id, const double* line,
                     int line_per_stream, int64_t* out_counts, void* stream);
+
+/* dd_tracker_tick that also records eight caller-supplied CUDA events on `stream` (before the first kernel and after
+ * each of prep / gate / gallery / match / apply / count-line / count-reduce), so that a benchmark can draw the kernel
+ * timeline of several stream chunks running concurrently.  host_events8: host array of dd_event_create events. */
+int dd_tracker_tick_profiled(void* state, const dd_tracker_config* host_cfg, const double* det_tlwh,
+                             const float* det_conf, const int32_t* det_label, const float* det_feat,
+                             const int32_t* det_count, int32_t* out_det_track_id, const double* line,
+                             int line_per_stream, int64_t* out_counts, void* stream, void* const* host_events8);
 
 /* Ragged detection batch -> the padded arrays dd_tracker_tick consumes.  The reference hands Tracker.update a
  * Python list of Detection objects per stream (deepdish.py:1014); its batched equivalent is one contiguous blob

@@ -128,8 +128,9 @@ def tflite_detection_postprocess(raw_boxes, raw_scores, anchors, max_det=10, sco
     rb, an = np.asarray(raw_boxes, f), np.asarray(anchors, f)
     yc = rb[:, 0] / f(scales[0]) * an[:, 2] + an[:, 0]
     xc = rb[:, 1] / f(scales[1]) * an[:, 3] + an[:, 1]
-    hh = f(0.5) * np.exp(rb[:, 2] / f(scales[2])).astype(f) * an[:, 2]
-    hw = f(0.5) * np.exp(rb[:, 3] / f(scales[3])).astype(f) * an[:, 3]
+    # exp: correctly rounded f32 by declaration (f64 exp, one rounding) -- the CUDA kernel's dd_expf does the same
+    hh = f(0.5) * np.exp((rb[:, 2] / f(scales[2])).astype(np.float64)).astype(f) * an[:, 2]
+    hw = f(0.5) * np.exp((rb[:, 3] / f(scales[3])).astype(np.float64)).astype(f) * an[:, 3]
     dec = np.stack([yc - hh, xc - hw, yc + hh, xc + hw], axis=1).astype(f)
     cls_scores = np.asarray(raw_scores, f)[:, 1:]
     best = np.argmax(cls_scores, axis=1)

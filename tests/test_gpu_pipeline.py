@@ -75,12 +75,8 @@ def test_mixed_yolo_ssd_pipeline_matches_oracle_chain():
             labels = [labels[i] for i in kept]
             keep = odet.non_max_suppression(ib, 0.6, score) if len(ib) else []
             assert got_count[s] == len(keep), (f, s)
-            if s >= SY and len(keep):              # SSD anchor decode: expf vs np.exp may move a box by a pixel
-                assert np.abs(got_tlwh[s, :len(keep)] - ib[keep]).max() <= 1
-                use = got_tlwh[s, :len(keep)]
-            else:
-                np.testing.assert_array_equal(got_tlwh[s, :len(keep)], ib[keep].astype(float).reshape(-1, 4))
-                use = ib[keep].astype(float).reshape(-1, 4)
+            np.testing.assert_array_equal(got_tlwh[s, :len(keep)], ib[keep].astype(float).reshape(-1, 4))
+            use = ib[keep].astype(float).reshape(-1, 4)
             dets = [od.Det(use[k], labels[i], score[i], feats[s, k]) for k, i in enumerate(keep)]
             trk[s].trace = {}
             trk[s].predict(); trk[s].update(dets); cnt[s].step(trk[s])
