@@ -85,6 +85,22 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def c1_cpu_port(batches, labels, budget, max_age):
+    """cpu_baseline leg of configs.c1: the oracle port of the reference on the same 300 frames, one host core."""
+    import torch
+    from oracle import deepsort as od
+    torch.set_num_threads(1)
+    trk = od.Trkr(od.Metric("cosine", 0.2, budget), 0.7, max_age, 3)
+    t0 = time.perf_counter()
+    n_conf = 0
+    for tlwh, conf, lab, feat in batches:
+        dets = [od.Det(tlwh[i], labels[lab[i]], conf[i], feat[i]) for i in range(len(conf))]
+        trk.predict()
+        trk.update(dets)
+        n_conf += sum(1 for t in trk.tracks if t.is_confirmed() and t.time_since_update <= 1)
+    return time.perf_counter() - t0, [t.track_id for t in trk.tracks], n_conf
+
+
 def cpu_reference(steps, warm, preroll=100, workers=None):
     import multiprocessing as mp
     cores = workers or os.cpu_count() or 1
@@ -249,8 +265,14 @@ def gpu_arm(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms = start.elapsed_time(end)
     state_bytes = bt.memory_bytes()
-    cd = bt.v["cdesc"][..., 2]
+    cdv = bt.v["cdesc"]
+    cd = cdv[..., 2]
     cand_per_track = float(cd.sum()) / max(1, int((cd > 0).sum()))      # gate-passing detections per streamed track
+    # what the default gallery kernel must move from HBM for the last tick: every streamed track's half pages ONCE (a
+    # track with more than 8 gate-passing detections is streamed again per group of 8, but those passes hit L2), the
+    # detections' half rows, one 64-byte work record per track
+    g_streamed = float((cdv[..., 1] * (cd > 0)).sum())
+    q_rows, w_items = float(cd.sum()), float((cd > 0).sum())
     g1 = int(bt.gallery_vectors().sum())
     conf1 = int(((bt.v["state"] == 2).sum()))
     bt.check()
@@ -316,7 +338,8 @@ def gpu_arm(args):
     del pre
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(g0 + g1) / 2, float(conf0 + conf1) / 2, float(dets)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(g0 + g1) / 2, float(conf0 + conf1) / 2, float(dets), g_streamed, q_rows, w_items],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -325,27 +348,36 @@ def gpu_arm(args):
         peak, peak_src = load_peaks()
         G, TC = float(tot[0]) / world, float(tot[1]) / world            # per GPU, per tick
         Dn = float(tot[2]) / world / K
-        gc_bytes = 512.0 * G + 512.0 * Dn + 16.0 * TC
         gc_ms = stage[2]
-        achieved = gc_bytes / (gc_ms * 1e-3) / 1e9
-        tick_bytes = 512.0 * (G + Dn + Dn) + 1152.0 * (TC * 1.1) + 44.0 * Dn
+        tick_bytes = 512.0 * (G + Dn + Dn) + 1152.0 * (TC * 1.1) + 44.0 * Dn      # SURVEY 8d B_trk summed over streams
+        f32_bytes = 512.0 * G + 512.0 * Dn + 16.0 * TC                            # SURVEY 8d figure for this kernel (f32 rows)
         half = args.gallery_impl != "exact"
-        kname = "k_cosine_h" if half else "k_cosine"
+        kname = {"default": "k_gallery_stream", "half_warp": "k_cosine_h", "exact": "k_cosine"}[args.gallery_impl]
         traffic = load_traffic(kname) if WORKLOAD_NAME == "c3" else None
-        # bytes the kernel must move with the half-precision pre-pass: 256 B per gallery row + the half queries
-        # (the exact re-check adds ~2 f32 rows per confirmed track; counted in `traffic`, not here)
-        moved = (256.0 * G + 256.0 * Dn + 16.0 * TC) if half else gc_bytes
+        # bytes the kernel MUST move from HBM: the half page rows of every streamed track (once), the detections' half
+        # rows and the work records; the exact re-check (a few f32 rows per track) comes on top and is in `traffic`
+        Gs, Qr, Wi = (float(tot[k]) / world for k in (3, 4, 5))
+        must = (256.0 * Gs + 256.0 * Qr + 64.0 * Wi + 4.0 * Qr) if half else f32_bytes
+        achieved = must / (gc_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": gc_bytes, "ms_per_launch": gc_ms,
-                "dram_achieved": (traffic if traffic else moved) / (gc_ms * 1e-3) / 1e9,
-                "dram_frac": (traffic if traffic else moved) / (gc_ms * 1e-3) / 1e9 / peak,
-                "note": ("achieved = SURVEY 8d algorithmic bytes (512 B per f32 gallery row) / kernel time; the kernel "
-                         "streams a half-precision copy (256 B per row) and re-reads only the rows that can hold the "
-                         "exact maximum, so it moves about half the algorithmic bytes and `frac` can exceed 1; "
-                         "dram_achieved / dram_frac use the bytes actually moved (ncu `traffic` when profiled)"
-                         if half else "exact f32 gallery pass"),
+                "bytes_per_launch": must, "ms_per_launch": gc_ms,
+                "dram_achieved": (traffic / (gc_ms * 1e-3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (gc_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "f32_equivalent": {"bytes_per_launch": f32_bytes, "achieved": f32_bytes / (gc_ms * 1e-3) / 1e9,
+                                   "frac": f32_bytes / (gc_ms * 1e-3) / 1e9 / peak,
+                                   "note": "SURVEY 8d counts 512 B per f32 gallery row; the kernel streams the half shadow, "
+                                           "so this figure can exceed 1 and is not a physical fraction"},
+                "note": ("achieved = bytes the kernel must move (256 B per streamed half gallery row + half query rows + work "
+                         "records) / its CUDA-event time in this run; traffic = dram__bytes_read+write of one launch from the "
+                         "committed ncu capture (profiles/ncu_traffic.json), dram_frac = traffic / time / peak"
+                         if half else "exact f32 gallery pass: 512 B per gallery row"),
                 "tick_bytes": tick_bytes, "tick_frac": tick_bytes / (ms_all / K * 1e-3) / 1e9 / peak}
+        extras = None
+        if world == 1 and not args.no_configs:
+            sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+            import configs as extra_configs
+            extras = extra_configs.run_all(knobs=knobs, cpu_port=None if args.no_cpu_baseline else c1_cpu_port)
         out = {
             "metric": "tracked stream-frames/s", "value": S * world * K / (ms_all * 1e-3),
             "unit": "stream-frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -367,6 +399,7 @@ def gpu_arm(args):
                          "gate": stage[1], "cosine": stage[2], "match": stage[3], "apply": stage[4],
                          "tick_total_single_stream": single_ms / K, "tick_total_pipelined": ms_all / K},
             "cpu_baseline": cpu,
+            "configs": extras,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -395,6 +428,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C2 / C4 / C5 measurements folded into `configs` (N = 1 only)")
     ap.add_argument("--no-affinity", action="store_true", help="multi-GPU: do not pin each rank to its GPU's CPUs")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"], help="c3 = the metric's configuration (default)")
     ap.add_argument("--gallery-impl", default="default", choices=["default", "exact", "half_warp"],

@@ -151,6 +151,7 @@ def lib():
         "dd_nms": [_vp, _vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp],
         "dd_ssd_decode": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, ctypes.c_float, _f64, _i32, _i32, _i32, _i32, _i32,
                           _vp, _vp, _vp, _vp, _vp, _vp],
+        "dd_box_filter": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
         "dd_gather_detections": [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
         "dd_tflite_postprocess": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, ctypes.c_float, _vp, _vp, _i32, _i32, _i32,
                                   _vp, _vp, _vp, _vp, _vp, _vp],

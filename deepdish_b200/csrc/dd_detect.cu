@@ -507,6 +507,49 @@ int dd_ssd_decode(const float* raw_boxes, const float* raw_scores, const float* 
     return DD_OK;
 }
 
+// The pre-NMS box filter as its own step (deepdish.py:941-960): one warp per frame; a NaN anywhere in the frame's
+// boxes drops the whole frame, survivors keep their order.
+__global__ void __launch_bounds__(128)
+k_box_filter(const double* __restrict__ boxes, const int* __restrict__ counts, int b, int nmax, int frame_w, int frame_h,
+             double max_area, double* __restrict__ out_tlwh, int* __restrict__ out_index, int* __restrict__ out_count) {
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= b) return;
+    int n = counts ? counts[f] : nmax;
+    if (n > nmax) n = nmax;
+    const double* bx = boxes + (size_t)f * nmax * 4;
+    bool nan = false;
+    for (int e = lane; e < n * 4; e += 32) nan = nan || (bx[e] != bx[e]);
+    int nk = 0;
+    if (!__any_sync(0xffffffffu, nan)) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            int ib[4];
+            const bool ok = i < n && dd_box_clip(bx[i * 4], bx[i * 4 + 1], bx[i * 4 + 2], bx[i * 4 + 3], frame_w, frame_h,
+                                                 max_area, ib);
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const size_t o = (size_t)f * nmax + nk + __popc(m & ((1u << lane) - 1u));
+                out_tlwh[o * 4] = ib[0]; out_tlwh[o * 4 + 1] = ib[1]; out_tlwh[o * 4 + 2] = ib[2]; out_tlwh[o * 4 + 3] = ib[3];
+                out_index[o] = i;
+            }
+            nk += __popc(m);
+        }
+    }
+    if (lane == 0) out_count[f] = nk;
+}
+
+int dd_box_filter(const double* boxes, const int32_t* counts, int32_t b, int32_t nmax, int32_t frame_w, int32_t frame_h,
+                  double* out_tlwh, int32_t* out_index, int32_t* out_count, void* stream) {
+    if (!boxes || !out_tlwh || !out_index || !out_count || b < 0 || nmax <= 0 || frame_w <= 0 || frame_h <= 0)
+        return DD_ERR_INVALID;
+    if (b == 0) return DD_OK;
+    k_box_filter<<<(b + 3) / 4, 128, 0, (cudaStream_t)stream>>>(boxes, counts, b, nmax, frame_w, frame_h,
+                                                               0.9 * frame_w * frame_h, out_tlwh, out_index, out_count);
+    DD_CHECK_LAUNCH();
+    return DD_OK;
+}
+
 int dd_gather_detections(const double* cand_tlwh, const float* cand_score, const int32_t* cand_label,
                          const int32_t* label_map, int32_t n_map, int32_t ncap, const int32_t* keep,
                          const int32_t* nkeep, int32_t nmax, int32_t b, int32_t dmax, double* det_tlwh,

@@ -93,8 +93,11 @@ DD_HD bool dd_nms_suppresses(double ax1, double ay1, double ax2, double ay2, dou
 
 // deep_sort/preprocessing.py:6-73.  boxes f64 [n,4] tlwh, scores f32 [n].  keep[] receives the
 // original indices in pick order (descending score); returns their number through *nkeep.
-//   rank     : descending score (ties: lower index first -- the reference's np.argsort is unstable, so
-//              callers keep scores unique) by counting smaller keys (n^2 / 32 warp ops);
+//   rank     : descending score; among equal scores the HIGHER original index is picked first.  That is what the
+//              reference does for the frame sizes deepdish sees: np.argsort(scores) (preprocessing.py:50) is a
+//              stable insertion sort for n <= 16 and the loop pops from the end of the ascending order.  For
+//              n > 16 numpy switches to an unstable (SIMD) sort and the order of tied scores is numpy's
+//              implementation detail; this rule is kept there too.  Ranks by counting smaller keys (n^2 / 32 warp ops);
 //   greedy   : the reference keeps a candidate unless an earlier survivor suppresses it
 //              (inter(i,j) / area(j) > max_overlap, +1 pixel convention, f64 like boxes.astype(float)).  Only
 //              survivors' suppression rows are ever needed, so they are built lazily: take the next <= 32
@@ -114,7 +117,7 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
     dd_nms_carve(smem, nmax, m);
     const int nh = (n + 31) / 32;
     for (int i = g.lane; i < n; i += g.nl)
-        m.ukeys[i] = ((unsigned long long)(~dd_f32_key(scores[i])) << 32) | (unsigned)i;
+        m.ukeys[i] = ((unsigned long long)(~dd_f32_key(scores[i])) << 32) | (0xffffffffu - (unsigned)i);
     for (int w = g.lane; w < nh; w += g.nl) m.remv[w] = 0u;
     if (g.lane == 0) { *m.allint = 1; m.batch[DD_NMS_BATCH + 1] = 0; }
     g.sync();
@@ -123,7 +126,7 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
         int r = 0;
         for (int j = 0; j < n; ++j) r += m.ukeys[j] < k;
         m.keys[r] = k;
-        const int o = (int)(k & 0xffffffffu);
+        const int o = (int)(0xffffffffu - (unsigned)(k & 0xffffffffu));
         const double x = boxes[o * 4 + 0], y = boxes[o * 4 + 1], w = boxes[o * 4 + 2], h = boxes[o * 4 + 3];
         const double xx2 = dd_add(w, x), yy2 = dd_add(h, y);
         m.x1[r] = x; m.y1[r] = y; m.x2[r] = xx2; m.y2[r] = yy2;
@@ -229,7 +232,7 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
                     const int i = __shfl_sync(0xffffffffu, mine, b);
                     const unsigned word = __shfl_sync(0xffffffffu, remv_reg, i >> 5);
                     if ((word >> (i & 31)) & 1u) continue;                 // suppressed inside the batch
-                    if (g.lane == 0) keep[nk] = (int)(m.keys[i] & 0xffffffffu);
+                    if (g.lane == 0) keep[nk] = (int)(0xffffffffu - (unsigned)(m.keys[i] & 0xffffffffu));
                     ++nk;
                     if (g.lane >= (i >> 5) && g.lane < nh) remv_reg |= m.rows[b * nh + g.lane];
                 }
@@ -240,7 +243,7 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
                 for (int b = 0; b < nb; ++b) {
                     const int i = m.batch[b];
                     if ((m.remv[i >> 5] >> (i & 31)) & 1u) continue;       // suppressed inside the batch
-                    if (g.lane == 0) keep[nk] = (int)(m.keys[i] & 0xffffffffu);
+                    if (g.lane == 0) keep[nk] = (int)(0xffffffffu - (unsigned)(m.keys[i] & 0xffffffffu));
                     ++nk;
                     for (int w = (i >> 5) + g.lane; w < nh; w += nscan) m.remv[w] |= m.rows[b * nh + w];
                     dd_first_warp_sync();
@@ -250,6 +253,25 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
         g.sync();
     }
     if (g.lane == 0) *nkeep = nk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The pre-NMS box filter of Pipeline.detect_objects for ONE box (deepdish.py:950-955):
+//   x, y = int(np.clip(x, 0, W)), int(np.clip(y, 0, H));  w, h = int(np.clip(w, 0, W - x)), int(np.clip(h, 0, H - y))
+//   reject w * h > 0.9 * W * H.   int() truncates toward zero; f32 inputs are widened exactly.
+// The frame-level NaN rule (:947-949: one NaN anywhere drops every box of the frame) is the caller's.
+// ------------------------------------------------------------------------------------------------
+DD_HD bool dd_box_clip(double x, double y, double w, double h, int frame_w, int frame_h, double max_area, int* o) {
+    const double fx = x < 0.0 ? 0.0 : (x > (double)frame_w ? (double)frame_w : x);
+    const double fy = y < 0.0 ? 0.0 : (y > (double)frame_h ? (double)frame_h : y);
+    const int ix = (int)fx, iy = (int)fy;
+    const double mw = (double)(frame_w - ix), mh = (double)(frame_h - iy);
+    const double fw = w < 0.0 ? 0.0 : (w > mw ? mw : w);
+    const double fh = h < 0.0 ? 0.0 : (h > mh ? mh : h);
+    const int iw = (int)fw, ih = (int)fh;
+    if ((double)((long long)iw * ih) > max_area) return false;
+    o[0] = ix; o[1] = iy; o[2] = iw; o[3] = ih;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,16 +311,9 @@ DD_HD bool dd_yolo_row(const Row& row, const DDYoloParams& p, const unsigned cha
         return true;
     }
     *out_nan = (x1 != x1) || (y1 != y1) || (bw != bw) || (bh != bh);
-    // deepdish.py:950-951: int(np.clip(...)) truncates toward zero
-    const float fx = x1 < 0.f ? 0.f : (x1 > (float)p.frame_w ? (float)p.frame_w : x1);
-    const float fy = y1 < 0.f ? 0.f : (y1 > (float)p.frame_h ? (float)p.frame_h : y1);
-    const int ix = (int)fx, iy = (int)fy;
-    const float mw = (float)(p.frame_w - ix), mh = (float)(p.frame_h - iy);
-    const float fw = bw < 0.f ? 0.f : (bw > mw ? mw : bw);
-    const float fh = bh < 0.f ? 0.f : (bh > mh ? mh : bh);
-    const int iw = (int)fw, ih = (int)fh;
-    if ((double)((long long)iw * ih) > p.max_area) return false;  // deepdish.py:953
-    out_tlwh[0] = ix; out_tlwh[1] = iy; out_tlwh[2] = iw; out_tlwh[3] = ih;
+    int ib[4];
+    if (!dd_box_clip(x1, y1, bw, bh, p.frame_w, p.frame_h, p.max_area, ib)) return false;      // deepdish.py:950-953
+    out_tlwh[0] = ib[0]; out_tlwh[1] = ib[1]; out_tlwh[2] = ib[2]; out_tlwh[3] = ib[3];
     *out_score = best;
     *out_class = bi;
     return true;
@@ -445,16 +460,10 @@ DD_HD int dd_ssd_post(const float* sel_box, const int* sel_cls, const float* sel
     }
     if (any_nan) return 0;                               // deepdish.py:947-949
     for (int i = 0; i < nc; ++i) {                       // box filter (deepdish.py:950-955)
-        const double fx = cand[i][0] < 0.0 ? 0.0 : (cand[i][0] > p.frame_w ? (double)p.frame_w : cand[i][0]);
-        const double fy = cand[i][1] < 0.0 ? 0.0 : (cand[i][1] > p.frame_h ? (double)p.frame_h : cand[i][1]);
-        const int ix = (int)fx, iy = (int)fy;
-        const double mw = (double)(p.frame_w - ix), mh = (double)(p.frame_h - iy);
-        const double fw = cand[i][2] < 0.0 ? 0.0 : (cand[i][2] > mw ? mw : cand[i][2]);
-        const double fh = cand[i][3] < 0.0 ? 0.0 : (cand[i][3] > mh ? mh : cand[i][3]);
-        const int iw = (int)fw, ih = (int)fh;
-        if ((double)((long long)iw * ih) > p.max_area) continue;
-        out_tlwh[n_out * 4 + 0] = ix; out_tlwh[n_out * 4 + 1] = iy;
-        out_tlwh[n_out * 4 + 2] = iw; out_tlwh[n_out * 4 + 3] = ih;
+        int ib[4];
+        if (!dd_box_clip(cand[i][0], cand[i][1], cand[i][2], cand[i][3], p.frame_w, p.frame_h, p.max_area, ib)) continue;
+        out_tlwh[n_out * 4 + 0] = ib[0]; out_tlwh[n_out * 4 + 1] = ib[1];
+        out_tlwh[n_out * 4 + 2] = ib[2]; out_tlwh[n_out * 4 + 3] = ib[3];
         out_score[n_out] = cand_s[i];
         out_label[n_out] = cand_l[i];
         ++n_out;

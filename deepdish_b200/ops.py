@@ -173,6 +173,20 @@ def nms(boxes, scores, counts, max_overlap, out=None):
     return keep, nkeep
 
 
+def box_filter(boxes, counts=None, frame_size=(640, 480)):
+    """The pre-NMS box filter of Pipeline.detect_objects (deepdish.py:941-960) for b frames of float tlwh boxes.
+    boxes f64 [b,nmax,4], counts i32 [b] or None -> (tlwh f64 [b,nmax,4] integer-valued, index i32 [b,nmax], count i32 [b])."""
+    _need_cuda(boxes)
+    b, nmax = boxes.shape[:2]
+    out = torch.zeros((b, nmax, 4), dtype=torch.float64, device=boxes.device)
+    idx = torch.full((b, nmax), -1, dtype=torch.int32, device=boxes.device)
+    cnt = torch.zeros((b,), dtype=torch.int32, device=boxes.device)
+    _lib.check(_lib.lib().dd_box_filter(boxes.data_ptr(), counts.data_ptr() if counts is not None else None, b, nmax,
+                                        int(frame_size[0]), int(frame_size[1]), out.data_ptr(), idx.data_ptr(),
+                                        cnt.data_ptr(), _stream(boxes.device)), "dd_box_filter")
+    return out, idx, cnt
+
+
 def yolo_decode(head, wanted_mask, score_thr=0.25, img_size=(640, 480), frame_size=(640, 480), ncap=1024,
                 quant=None, out=None):
     """YOLOv5 head decode + box filter for b frames (tools/yolov5.py:115-146, deepdish.py:946-955).

@@ -359,6 +359,15 @@ int dd_tflite_postprocess(const float* op_boxes, const float* op_classes, const 
                           int32_t max_results, int32_t ncap, double* out_tlwh, float* out_score, int32_t* out_label,
                           int32_t* out_count, int32_t* out_flags, void* stream);
 
+/* The pre-NMS box filter of Pipeline.detect_objects (deepdish.py:941-960, motion test excluded) on the float boxes a
+ * detector adapter returns, for b frames: a NaN anywhere in a frame's boxes drops the whole frame; x, y, w, h are
+ * clipped to the camera viewport and truncated toward zero; boxes larger than 0.9 W H are rejected.
+ *   boxes f64 [b,nmax,4] tlwh, counts i32 [b] (NULL = nmax); out_tlwh f64 [b,nmax,4] (integers), out_index i32 [b,nmax]
+ *   (input index of each survivor, input order kept), out_count i32 [b].  (dd_yolo_decode / dd_ssd_decode fuse the
+ *   same filter when given frame_w > 0.) */
+int dd_box_filter(const double* boxes, const int32_t* counts, int32_t b, int32_t nmax, int32_t frame_w, int32_t frame_h,
+                  double* out_tlwh, int32_t* out_index, int32_t* out_count, void* stream);
+
 /* The step between NMS and the tracker (deepdish.py:996-998,1014): gather the kept candidates, in NMS pick
  * order, into the tracker's padded detection batch for b streams.
  *   cand_* [b,ncap] candidate arrays (dd_yolo_decode / dd_ssd_decode outputs), keep i32 [b,nmax] + nkeep i32 [b]

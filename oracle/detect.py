@@ -4,7 +4,8 @@ the pre-NMS box filter and NMS.  TEST INFRASTRUCTURE.
 Follows tools/yolov5.py:115-146, tools/ssd_mobilenet.py:59-150,198-213, deepdish.py:941-960 and
 deep_sort/preprocessing.py:6-73 (paths relative to /root/reference).
 
-Pinned: YOLO decode, box filter + NMS and the SSD *post*-processing against the unmodified reference
+Pinned: YOLO decode, the box filter (the reference's own loop, driven through Pipeline.detect_objects by
+oracle/refload.RefBoxFilter), NMS and the SSD *post*-processing against the unmodified reference
 (fixtures in tests/golden/).  PARITY UNPINNED: ``tflite_detection_postprocess`` (the 1917-anchor decode
 and first NMS) is the third-party TFLite custom op ``TFLite_Detection_PostProcess``
 (tensorflow/lite/kernels/detection_postprocess.cc; pinned runtime tflite_runtime 2.5.0.post1 in the
@@ -66,14 +67,18 @@ def box_filter(boxes, frame_w, frame_h):
 # ----------------------------------------------------------------------------- NMS
 def non_max_suppression(boxes, max_overlap, scores=None):
     """deep_sort/preprocessing.py:6-73 -- greedy, overlap = inter / area(other), +1 px convention.
-    Returns indices in pick order (descending score).  Scores must be unique (np.argsort is unstable)."""
+    Returns indices in pick order (descending score).  Equal scores: the reference's np.argsort (preprocessing.py:50)
+    is unstable and build-dependent -- numpy's scalar introsort (the reference's ARM targets) is an insertion sort,
+    i.e. stable, for n <= 16, numpy's x86 SIMD argsort is not.  The oracle pins the scalar-path behaviour with an
+    explicitly stable sort (identical to the reference whenever scores are unique, and for ties at n <= 16 on the
+    scalar path: fixture nms_ties.npz); ties at n > 16 are implementation-defined in the reference."""
     if len(boxes) == 0:
         return []
     b = np.asarray(boxes).astype(float)
     x1, y1 = b[:, 0], b[:, 1]
     x2, y2 = b[:, 2] + b[:, 0], b[:, 3] + b[:, 1]
     area = (x2 - x1 + 1) * (y2 - y1 + 1)
-    order = np.argsort(scores) if scores is not None else np.argsort(y2)
+    order = np.argsort(scores, kind="stable") if scores is not None else np.argsort(y2, kind="stable")
     pick = []
     while len(order) > 0:
         i = order[-1]

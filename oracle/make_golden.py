@@ -180,6 +180,99 @@ def golden_nms(R):
     print("nms.npz", nkeep.tolist())
 
 
+NPY_SCALAR_SORT = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2 FMA3"
+
+
+def golden_nms_ties(R):
+    """Tied scores at the frame sizes deepdish sees (n <= 16).  np.argsort (preprocessing.py:50) is not a stable sort
+    and the order it gives equal scores depends on the numpy build and the CPU: numpy's scalar introsort -- the path
+    taken on the reference's own targets (Raspberry Pi / Jetson, README.md:7-10) -- finishes every n <= 16 with an
+    insertion sort, i.e. stable, so the reference picks the HIGHER index first among equal scores; numpy's AVX-512 /
+    AVX2 argsort on an x86 build host orders them differently.  The fixture is therefore generated with numpy's SIMD
+    dispatch switched off (NPY_DISABLE_CPU_FEATURES, re-executing this module), which pins the scalar path.
+    Quantised detector heads (the default int8 YOLOv5 model multiplies two 256-level values) produce such ties.
+    Also covers scores=None (rank by y2)."""
+    if os.environ.get("NPY_DISABLE_CPU_FEATURES") != NPY_SCALAR_SORT:
+        import subprocess
+        import sys
+        env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=NPY_SCALAR_SORT, DD_GOLDEN_ONLY="nms_ties")
+        subprocess.check_call([sys.executable, "-m", "oracle.make_golden"], env=env, cwd=ROOT)
+        return
+    probe = (np.arange(16) % 3).astype(np.float32)
+    assert np.array_equal(np.argsort(probe), np.argsort(probe, kind="stable")), "numpy's scalar argsort is expected here"
+    rng = np.random.default_rng(12)
+    cases = []
+    for case in range(60):
+        n = int(rng.integers(2, 17))
+        k = max(1, n // 3)
+        cx, cy = rng.uniform(40, 600, k), rng.uniform(40, 440, k)
+        pick = rng.integers(0, k, n)
+        x = np.clip(cx[pick] + rng.normal(0, 5, n), 0, 630).astype(np.int64)
+        y = np.clip(cy[pick] + rng.normal(0, 5, n), 0, 470).astype(np.int64)
+        w = rng.integers(10, 60, n); h = rng.integers(20, 120, n)
+        boxes = np.stack([x, y, w, h], axis=1).astype(np.int64).reshape(n, 4)
+        levels = rng.integers(2, 6)
+        scores = (rng.integers(0, levels, n) / np.float32(levels) * 0.5 + 0.25).astype(np.float32)   # few distinct values
+        use_scores = case % 4 != 3
+        thr = [0.6, 0.3, 0.9][case % 3]
+        keep = R.deep_sort_preprocessing.non_max_suppression(boxes, thr, scores if use_scores else None)
+        cases.append((boxes, scores, thr, np.array(keep, dtype=np.int32), use_scores))
+    nmax, B = 16, len(cases)
+    boxes = np.zeros((B, nmax, 4)); scores = np.zeros((B, nmax), np.float32)
+    counts = np.zeros(B, np.int32); thr = np.zeros(B); keep = np.full((B, nmax), -1, np.int32)
+    nkeep = np.zeros(B, np.int32); use = np.zeros(B, np.int32)
+    for i, (b, s_, t, k_, u) in enumerate(cases):
+        n = len(b)
+        boxes[i, :n], scores[i, :n], counts[i], thr[i], use[i] = b, s_, n, t, int(u)
+        keep[i, :len(k_)], nkeep[i] = k_, len(k_)
+    np.savez_compressed(os.path.join(OUT, "nms_ties.npz"), boxes=boxes, scores=scores, counts=counts, thr=thr,
+                        keep=keep, nkeep=nkeep, use_scores=use)
+    print("nms_ties.npz", nkeep.tolist())
+
+
+_BOXF = None
+
+
+def ref_box_filter(boxes, labels, scores, w=640, h=480):
+    """Reference box filter (deepdish.py:941-960 inside detect_objects) -> (int boxes [K,4] int64, kept input indices).
+    Labels are replaced by the input index so that the survivors can be identified."""
+    global _BOXF
+    if _BOXF is None or _BOXF.p.input_size != (w, h):
+        _BOXF = refload.RefBoxFilter(w, h)
+    ob, ol, _ = _BOXF(list(boxes), list(range(len(boxes))), list(scores))
+    return np.array(ob, dtype=np.int64).reshape(-1, 4), np.array(ol, dtype=np.int64)
+
+
+def golden_box_filter(R):
+    """The pre-NMS box filter as the reference runs it (deepdish.py:941-960), on adversarial float boxes: negative and
+    out-of-frame corners, boxes wider than the frame, boxes above the 0.9 W H area limit, zero-size results, a NaN
+    anywhere in the frame (drops every box of the frame), f32 and f64 inputs."""
+    rng = np.random.default_rng(31)
+    cases, res = [], {}
+    for c in range(48):
+        n = int(rng.integers(0, 14))
+        b = np.stack([rng.uniform(-60, 700, n), rng.uniform(-60, 540, n), rng.uniform(0, 400, n), rng.uniform(0, 300, n)], 1)
+        if n and c % 5 == 1:
+            b[rng.integers(0, n)] = [1.5, 2.5, 637.9, 478.2]           # almost the whole viewport: rejected
+        if n and c % 5 == 2:
+            b[rng.integers(0, n), 2:] = [700.0, 500.0]                 # clipped to the frame, then rejected
+        if n and c % 7 == 3:
+            b[rng.integers(0, n), rng.integers(0, 4)] = np.nan         # one NaN drops the whole frame
+        if c % 2:
+            b = b.astype(np.float32)
+        ib, kept = ref_box_filter([list(r) for r in b], None, [0.5] * n)
+        cases.append(b.astype(np.float64))
+        res["dtype%d" % c] = np.array(str(b.dtype))
+        res["out%d" % c] = ib
+        res["kept%d" % c] = kept
+    nmax = max(len(b) for b in cases)
+    boxes = np.zeros((len(cases), nmax, 4)); counts = np.zeros(len(cases), np.int32)
+    for i, b in enumerate(cases):
+        boxes[i, :len(b)], counts[i] = b, len(b)
+    np.savez_compressed(os.path.join(OUT, "box_filter.npz"), boxes=boxes, counts=counts, **res)
+    print("box_filter.npz kept", [len(res["kept%d" % c]) for c in range(len(cases))])
+
+
 def synth_yolo_head(rng, frames, na, nc=80, hot=0.02):
     """[frames, na, 5+nc] f32 head in the TFLite export's format (normalised xywh, obj, cls)."""
     h = np.empty((frames, na, 5 + nc), np.float32)
@@ -215,8 +308,9 @@ def golden_yolo(R):
         out["tlwh%d" % f] = np.array(boxes, np.float32).reshape(-1, 4)
         out["cls%d" % f] = np.array([names.index(l) for l in labels], np.int32)
         out["score%d" % f] = np.array(scores, np.float32)
-        # downstream: box filter (restated from deepdish.py:946-955) + the reference's own NMS
-        ib, kept = odet.box_filter(boxes, 640, 480)
+        # downstream: the reference's own box filter (the loop inside Pipeline.detect_objects, deepdish.py:941-960,
+        # driven by refload.RefBoxFilter) + the reference's own NMS
+        ib, kept = ref_box_filter(boxes, labels, scores)
         sc = np.array(scores, np.float32)[kept]
         keep = R.deep_sort_preprocessing.non_max_suppression(np.array(ib), 0.6, sc) if len(ib) else []
         out["fbox%d" % f] = ib
@@ -257,6 +351,8 @@ def golden_ssd_post(R):
         res["tlwh%d" % c] = np.array(boxes, float).reshape(-1, 4)
         res["lab%d" % c] = np.array([names.index(l) for l in labels], np.int32)
         res["score%d" % c] = np.array(scores, np.float32)
+        fb, fk = ref_box_filter(boxes, labels, scores)          # the reference's own box filter on its own float boxes
+        res["fbox%d" % c], res["fidx%d" % c] = fb, fk
     refload.FakeInterpreter.input_shape = (1, 640, 640, 3)
     np.savez_compressed(os.path.join(OUT, "ssd_post.npz"), op_boxes=ob, op_classes=ocl, op_scores=osc,
                         names=np.array(names), wanted=np.array(wanted), **res)
@@ -464,12 +560,24 @@ def main():
     if os.environ.get("DD_GOLDEN_ONLY") == "unbounded":
         golden_unbounded(R)
         return
+    if os.environ.get("DD_GOLDEN_ONLY") == "box_filter":
+        golden_box_filter(R)
+        return
+    if os.environ.get("DD_GOLDEN_ONLY") == "detect":
+        golden_yolo(R)
+        golden_ssd_post(R)
+        return
+    if os.environ.get("DD_GOLDEN_ONLY") == "nms_ties":
+        golden_nms_ties(R)
+        return
     golden_tflite_adapter(R)
     golden_framerecords(R)
     golden_patches(R)
     golden_kalman(R)
     golden_metric_iou(R)
     golden_nms(R)
+    golden_box_filter(R)
+    golden_nms_ties(R)
     golden_yolo(R)
     golden_ssd_post(R)
     golden_tracker(R, "tracker_small.npz", seed=101, n_obj=12, dmax=16, frames=100, budget=20, max_age=30,

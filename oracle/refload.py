@@ -209,3 +209,62 @@ class RefCounter:
         p = self.p
         return np.array([[p.poscount[l], p.negcount[l], p.intcount[l], p.delcount[l]] for l in self.labels],
                         dtype=np.int64)
+
+
+class RefBoxFilter:
+    """Runs the reference's own pre-NMS box filter -- the loop inside the coroutine Pipeline.detect_objects
+    (deepdish.py:887-982, filter at :941-960) -- on a detector result, without camera, CNN or encoder: the queues,
+    the executor and the detector are stubs, background subtraction is off (--disable-background-subtraction)."""
+
+    def __init__(self, frame_w=640, frame_h=480):
+        mod = load_pipeline_module()
+        p = object.__new__(mod.Pipeline)
+        p.running = True
+        p.input_size = (frame_w, frame_h)
+        p.frame_count = 0
+        p.everyframe = None
+        p.background_subtraction = False
+        p.args = types.SimpleNamespace(enable_background_masking=False, object_detector_skip_frames=0,
+                                       disable_powersaving=True, background_subtraction_ratio=0.0)
+        p.powersave_delay = 0
+        p.cameracountline = np.array([[frame_w / 2, 0], [frame_w / 2, frame_h]], dtype=float)
+        p.pipeline_sem = types.SimpleNamespace(release=lambda: None)
+        p.kickstart = types.SimpleNamespace(set=lambda: None)
+        enc = lambda frame, boxes: None               # noqa: E731  (the encoder is only warmed up here)
+        enc.width, enc.height = 64, 128
+        p.encoder = enc
+        self.p, self.mod = p, mod
+        self.frame = 0
+
+    def __call__(self, boxes0, labels0, scores0):
+        """-> (boxes [(x, y, w, h) ints], labels, scores) exactly as detect_objects puts them on its output queue."""
+        import asyncio
+        p = self.p
+        result = {}
+        outer = self
+
+        async def run_in_executor(_ex, fn, *a):
+            if getattr(fn, "__name__", "") == "run_object_detector":
+                return (boxes0, labels0, scores0, 0.0)
+            return None                                   # the encoder warm-up call
+
+        class Loop:
+            pass
+
+        loop = Loop()
+        loop.run_in_executor = run_in_executor
+        p.loop = loop
+
+        class QIn:
+            async def get(self_inner):
+                outer.frame += 1
+                return (outer.frame, np.zeros((4, 4, 4), np.uint8), 0.0, 0.0, 0.0)
+
+        class QOut:
+            async def put(self_inner, item):
+                result["boxes"], result["labels"], result["scores"] = item[2], item[3], item[4]
+                p.running = False
+
+        p.running = True
+        asyncio.run(p.detect_objects(QIn(), QOut()))
+        return result["boxes"], result["labels"], result["scores"]

@@ -158,6 +158,20 @@ int ddh_ssd_post(const float* sel_box, const int32_t* sel_cls, const float* sel_
     return dd_ssd_post(sel_box, sel_cls, sel_score, n, P, class_to_label, out_tlwh, out_score, out_label);
 }
 
+// The box filter device function (dd_box_clip + the frame-level NaN rule) on one frame of host boxes.
+int ddh_box_filter(const double* boxes, int n, int frame_w, int frame_h, double* out_tlwh, int32_t* out_index) {
+    for (int e = 0; e < n * 4; ++e) if (boxes[e] != boxes[e]) return 0;
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+        int ib[4];
+        if (!dd_box_clip(boxes[i * 4], boxes[i * 4 + 1], boxes[i * 4 + 2], boxes[i * 4 + 3], frame_w, frame_h,
+                         0.9 * frame_w * frame_h, ib)) continue;
+        for (int q = 0; q < 4; ++q) out_tlwh[nk * 4 + q] = ib[q];
+        out_index[nk++] = i;
+    }
+    return nk;
+}
+
 // NMS device body on host arrays (one frame).
 int ddh_nms(const double* boxes, const float* scores, int n, double max_overlap, int32_t* keep) {
     HostG g;

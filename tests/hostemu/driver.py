@@ -106,6 +106,14 @@ def ssd_post(sel_box, sel_cls, sel_score, class_to_label, conf_thr=0.5, nms_iou=
     return tl[:k], sc[:k], lb[:k]
 
 
+def box_filter(boxes, frame=(640, 480)):
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+    n = len(boxes)
+    out = np.zeros((max(n, 1), 4)); idx = np.zeros(max(n, 1), np.int32)
+    k = emu().ddh_box_filter(_p(boxes), n, frame[0], frame[1], _p(out), _p(idx))
+    return out[:k], idx[:k]
+
+
 def nms(boxes, scores, max_overlap):
     boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
     scores = np.ascontiguousarray(scores, np.float32)

@@ -105,6 +105,34 @@ def test_nms_vs_reference_fixture():
             assert list(keep[k, :nkeep[k]]) == list(g["keep"][i, :g["nkeep"][i]]), i
 
 
+def test_box_filter_vs_reference_fixture():
+    """dd_box_filter against the reference's own loop (deepdish.py:941-960 inside Pipeline.detect_objects)."""
+    from deepdish_b200 import ops
+    g = goldens.load("box_filter.npz")
+    out, idx, cnt = ops.box_filter(ops._dev(g["boxes"], torch.float64), ops._dev(g["counts"], torch.int32))
+    out, idx, cnt = out.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy()
+    for c in range(len(g["counts"])):
+        k = len(g["kept%d" % c])
+        assert cnt[c] == k, c
+        np.testing.assert_array_equal(out[c, :k], g["out%d" % c].astype(float).reshape(-1, 4))
+        np.testing.assert_array_equal(idx[c, :k], g["kept%d" % c])
+
+
+def test_nms_tied_scores_vs_reference_fixture():
+    """Tied scores (quantised heads produce them) at n <= 16, and scores=None (rank by y2): the reference's pick order
+    -- higher index first among equals -- through the deep_sort.preprocessing mirror."""
+    from deepdish_b200.deep_sort import preprocessing
+    g = goldens.load("nms_ties.npz")
+    ties = 0
+    for i in range(len(g["counts"])):
+        n = int(g["counts"][i])
+        sc = g["scores"][i, :n] if g["use_scores"][i] else None
+        keep = preprocessing.non_max_suppression(g["boxes"][i, :n].astype(np.int64), float(g["thr"][i]), sc)
+        assert keep == list(g["keep"][i, :g["nkeep"][i]]), i
+        ties += int(len(np.unique(g["scores"][i, :n])) < n)
+    assert ties > 40
+
+
 def test_yolo_decode_vs_reference_fixture():
     from deepdish_b200 import ops
     g = goldens.load("yolo.npz")

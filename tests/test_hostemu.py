@@ -117,6 +117,17 @@ def test_detection_bodies_vs_reference_fixtures():
     for i in range(len(g["counts"])):
         n = int(g["counts"][i])
         assert hd.nms(g["boxes"][i, :n], g["scores"][i, :n], float(g["thr"][i])) == list(g["keep"][i, :g["nkeep"][i]])
+    g = goldens.load("box_filter.npz")         # the reference's own filter loop (deepdish.py:941-960) on adversarial boxes
+    for c in range(len(g["counts"])):
+        out, idx = hd.box_filter(g["boxes"][c, :int(g["counts"][c])])
+        np.testing.assert_array_equal(out, g["out%d" % c].astype(float).reshape(-1, 4), err_msg=str(c))
+        np.testing.assert_array_equal(idx, g["kept%d" % c])
+    g = goldens.load("nms_ties.npz")           # tied scores: the reference picks the higher index first (n <= 16)
+    for i in range(len(g["counts"])):
+        n = int(g["counts"][i])
+        b = g["boxes"][i, :n]
+        sc = g["scores"][i, :n] if g["use_scores"][i] else (b[:, 1] + b[:, 3]).astype(np.float32)
+        assert hd.nms(b, sc, float(g["thr"][i])) == list(g["keep"][i, :g["nkeep"][i]]), i
     g = goldens.load("yolo.npz")
     names, wanted = list(g["names"]), list(g["wanted"])
     mask = np.array([1 if n in wanted else 0 for n in names], np.uint8)
@@ -133,10 +144,9 @@ def test_detection_bodies_vs_reference_fixtures():
     total = 0
     for c in range(len(g["op_boxes"])):
         tl, sc, lb = hd.ssd_post(g["op_boxes"][c], g["op_classes"][c].astype(np.int32), g["op_scores"][c], c2l)
-        exp = g["tlwh%d" % c]
-        # the fixture holds detect_image's float boxes; the device function also applies the box filter
-        from oracle import detect as odet
-        ib, kept = odet.box_filter([tuple(r) for r in exp], 640, 480)
+        # the fixture holds detect_image's float boxes and what the reference's own box filter makes of them; the
+        # device function applies that filter too
+        ib, kept = g["fbox%d" % c], g["fidx%d" % c]
         np.testing.assert_array_equal(tl, ib.astype(float).reshape(-1, 4))
         np.testing.assert_array_equal(sc, g["score%d" % c][kept])
         np.testing.assert_array_equal(lb, g["lab%d" % c][kept])
