@@ -79,12 +79,44 @@ def c2(frames=64, iters=20, dev="cuda"):
     nbytes = frames * NA * (5 + NC) * 4
     pk = hbm_peak()
     assert int(y["flags"].max()) == 0
-    return {"workload": "C2: YOLOv5s raw head [%d,25200,85] f32 -> decode + conf filter + box filter + NMS" % frames,
-            "metric": "frames/s", "value": frames / ms * 1e3, "ms_per_batch": ms, "ms_decode": ms_dec, "ms_nms": ms_nms,
+    # steady-state stream of batches: the NMS of batch k (latency-bound, one CTA per frame) runs on a second CUDA
+    # stream under the HBM-bound decode of batch k + 1; outputs are double-buffered
+    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+    outs, dec_done, nms_done = [{}, {}], [None, None], [None, None]
+
+    def piped(i):
+        k = i & 1
+        with torch.cuda.stream(sA):
+            if nms_done[k] is not None:
+                sA.wait_event(nms_done[k])
+            outs[k]["y"] = ops.yolo_decode(heads[i % 3], mask, 0.25, (640, 480), (640, 480), ncap=1024, out=outs[k].get("y"))
+            dec_done[k] = sA.record_event()
+        with torch.cuda.stream(sB):
+            sB.wait_event(dec_done[k])
+            outs[k]["k"] = ops.nms(outs[k]["y"]["tlwh"], outs[k]["y"]["score"], outs[k]["y"]["count"], 0.6, out=outs[k].get("k"))
+            nms_done[k] = sB.record_event()
+
+    for i in range(4):
+        piped(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    sA.wait_event(s); sB.wait_event(s)
+    for i in range(iters):
+        piped(i)
+    cur = torch.cuda.current_stream()
+    cur.wait_event(dec_done[0]); cur.wait_event(dec_done[1]); cur.wait_event(nms_done[0]); cur.wait_event(nms_done[1])
+    e.record()
+    torch.cuda.synchronize()
+    ms_serial, ms = ms, s.elapsed_time(e) / iters
+    return {"workload": "C2: YOLOv5s raw head [%d,25200,85] f32 -> decode + conf filter + box filter + NMS, batches streamed "
+                        "(NMS of batch k under the decode of batch k+1)" % frames,
+            "metric": "frames/s", "value": frames / ms * 1e3, "ms_per_batch": ms, "ms_per_batch_serial": ms_serial,
+            "ms_decode": ms_dec, "ms_nms": ms_nms,
             "candidates_per_frame": float(y["count"].float().mean()), "kept_per_frame": float(out["k"][1].float().mean()),
             "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": pk, "unit": "GB/s",
                          "frac": nbytes / ms / 1e6 / pk, "bytes_per_batch": nbytes,
-                         "decode_only_frac": nbytes / ms_dec / 1e6 / pk}}
+                         "serial_frac": nbytes / ms_serial / 1e6 / pk, "decode_only_frac": nbytes / ms_dec / 1e6 / pk}}
 
 
 # ---------------------------------------------------------------------------------------------------- C4

@@ -423,7 +423,112 @@ k_tflite_post(const float* __restrict__ boxes, const float* __restrict__ classes
     }
 }
 
+// ---- Keras YOLOv3 adapter: one CTA per frame ------------------------------------------------------
+//   phase A  all threads sweep the frame's boxes reading only the objectness logit: a class score is obj * cls <= obj,
+//            so a box whose objectness sigmoid is not above the threshold has no non-zero class score -- it can neither
+//            suppress nor be returned -- and its other 84 logits are never read;
+//   phase B  the surviving ("active") boxes, in box order: one thread per (box, class) evaluates the thresholded class
+//            scores, one thread per box decodes the integer box;
+//   phase C  do_nms: one thread per class (the classes are independent);  phase D  thread 0 emits.
+struct DDYolo3Maps { const float* map[3]; };
+
+__global__ void __launch_bounds__(256)
+k_yolo3_post(const DDYolo3Maps M, const DDYolo3Params P, const unsigned char* __restrict__ wanted, int ncap,
+             double* __restrict__ out_box, float* __restrict__ out_score, int* __restrict__ out_label,
+             int* __restrict__ out_count, int* __restrict__ out_flags) {
+    extern __shared__ __align__(16) char smem[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int rw = 5 + P.nc;
+    int* act = (int*)smem;                                   // [MAX_ACTIVE] global box index (map << 24 | cell * 3 + b)
+    int* box = act + DD_Y3_MAX_ACTIVE;                       // [MAX_ACTIVE][4]
+    int* order = box + DD_Y3_MAX_ACTIVE * 4;                 // [nc][MAX_ACTIVE] per-class sort scratch
+    float* cls = (float*)(order + P.nc * DD_Y3_MAX_ACTIVE);  // [MAX_ACTIVE][nc]
+    __shared__ int s_n, s_bad, s_over;
+    if (tid == 0) { s_n = 0; s_bad = 0; s_over = 0; }
+    __syncthreads();
+    for (int k = 0; k < 3; ++k) {
+        const int cells = P.g[k] * P.g[k];
+        const float* base = M.map[k] + (size_t)f * cells * 3 * rw;
+        for (int e = tid; e < cells * 3; e += blockDim.x) {
+            const float obj = dd_sigmoid_f32(base[(size_t)e * rw + 4]);
+            if (obj > P.thr) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < DD_Y3_MAX_ACTIVE) act[pos] = (k << 24) | e;
+            }
+        }
+    }
+    __syncthreads();
+    int n = s_n;
+    if (n > DD_Y3_MAX_ACTIVE) { n = DD_Y3_MAX_ACTIVE; if (tid == 0) s_over = 1; }
+    if (tid == 0) {                                          // box order = the reference's append order (map, cell, anchor)
+        for (int i = 1; i < n; ++i) {
+            const int v = act[i];
+            int j = i;
+            while (j > 0 && act[j - 1] > v) { act[j] = act[j - 1]; --j; }
+            act[j] = v;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < n * P.nc; e += blockDim.x) {
+        const int i = e / P.nc, c = e - i * P.nc;
+        const int k = act[i] >> 24, cell = act[i] & 0xffffff;
+        const float* raw = M.map[k] + ((size_t)f * P.g[k] * P.g[k] * 3 + cell) * rw;
+        const float v = dd_mulf(dd_sigmoid_f32(raw[4]), dd_sigmoid_f32(raw[5 + c]));      // yolo.py:54-55
+        cls[e] = v > P.thr ? v : 0.f;                                                     // :56
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int k = act[i] >> 24, cell = act[i] & 0xffffff;
+        const float* raw = M.map[k] + ((size_t)f * P.g[k] * P.g[k] * 3 + cell) * rw;
+        dd_yolo3_box(raw, k, cell / 3, cell % 3, P, box + i * 4);
+    }
+    __syncthreads();
+    for (int c = tid; c < P.nc; c += blockDim.x) {
+        int bad = 0;
+        dd_y3_nms_class(c, n, P.nc, cls, box, P.nms_thresh, order + c * DD_Y3_MAX_ACTIVE, &bad);
+        if (bad) s_bad = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int over = s_over;
+        const int k = dd_y3_emit(n, P.nc, cls, box, P.thr, wanted, ncap, out_box + (size_t)f * ncap * 4,
+                                 out_score + (size_t)f * ncap, out_label + (size_t)f * ncap, &over);
+        out_count[f] = k;
+        out_flags[f] = (over ? DD_FLAG_DET_OVERFLOW : 0) | (s_bad ? DD_Y3_BAD_BOX : 0);
+    }
+}
+
 extern "C" {
+
+int dd_yolo3_decode(const float* map0, const float* map1, const float* map2, const int32_t* host_grids3,
+                    const int32_t* host_anchors18, int32_t b, int32_t nc, const uint8_t* wanted, float score_thr,
+                    double nms_thresh, int32_t image_w, int32_t image_h, int32_t net_w, int32_t net_h, int32_t ncap,
+                    double* out_box, float* out_score, int32_t* out_label, int32_t* out_count, int32_t* out_flags,
+                    void* stream) {
+    if (!map0 || !map1 || !map2 || !host_grids3 || !host_anchors18 || !wanted || !out_box || !out_score || !out_label ||
+        !out_count || !out_flags)
+        return DD_ERR_INVALID;
+    if (b < 0 || nc <= 0 || nc > 256 || ncap <= 0 || net_w <= 0 || net_h <= 0) return DD_ERR_INVALID;
+    if (b == 0) return DD_OK;
+    DDYolo3Maps M;
+    M.map[0] = map0; M.map[1] = map1; M.map[2] = map2;
+    DDYolo3Params P;
+    P.nc = nc; P.thr = score_thr; P.nms_thresh = nms_thresh;
+    P.image_w = image_w; P.image_h = image_h; P.net_w = net_w; P.net_h = net_h;
+    for (int k = 0; k < 3; ++k) {
+        P.g[k] = host_grids3[k];
+        if (P.g[k] <= 0 || (long long)P.g[k] * P.g[k] * 3 >= (1 << 24)) return DD_ERR_INVALID;
+        for (int a = 0; a < 6; ++a) P.anchors[k][a] = host_anchors18[k * 6 + a];
+    }
+    const size_t smem = (size_t)DD_Y3_MAX_ACTIVE * 4 * (1 + 4 + nc) + (size_t)DD_Y3_MAX_ACTIVE * nc * 4;
+    if (smem > 200 * 1024) return DD_ERR_INVALID;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_yolo3_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DD_ERR_CUDA;
+    k_yolo3_post<<<b, 256, smem, (cudaStream_t)stream>>>(M, P, wanted, ncap, out_box, out_score, out_label, out_count,
+                                                         out_flags);
+    DD_CHECK_LAUNCH();
+    return DD_OK;
+}
 
 int dd_nms(const double* boxes, const float* scores, const int32_t* counts, int32_t b, int32_t nmax,
            double max_overlap, int32_t* out_keep, int32_t* out_nkeep, void* stream) {

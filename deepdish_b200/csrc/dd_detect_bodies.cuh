@@ -105,6 +105,10 @@ DD_HD bool dd_nms_suppresses(double ax1, double ay1, double ax2, double ay2, dou
 //              (one warp per 32 candidates, ballots give the bits; integer-valued boxes -- the pipeline's
 //              case -- are tested for disjointness in int32 first), then scan the batch serially with the
 //              removed bits held in the scanning warp's registers.
+// (Measured and dropped, round 2: building the WHOLE upper-triangular suppression matrix in one parallel sweep followed by
+// a single serial scan -- no barrier per 32 survivors -- takes 0.135 ms for C2's 64 frames x 540 candidates against
+// 0.125 ms for the lazy batches below: the frame's CTA is bound by its instruction count, and the full matrix tests 3x
+// the pairs.)
 template <class G>
 DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, int n, int nmax,
                         double max_overlap, int* keep, int* nkeep, char* smem) {
@@ -469,4 +473,107 @@ DD_HD int dd_ssd_post(const float* sel_box, const int* sel_cls, const float* sel
         ++n_out;
     }
     return n_out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Keras YOLOv3 adapter (tools/yolo.py): decode_netout (:48-81), correct_yolo_boxes (:83-91), do_nms (:122-137),
+// get_boxes (:140-153) and the tail of YOLO.detect_image (:207-237).  Quirks kept on purpose: every cell emits a box
+// (the `objectness.all() <= obj_thresh` test only skips an objectness of exactly 0), y uses the FRACTIONAL row
+// i / grid_w, a box with two labels above the threshold is returned twice (both times with its arg-max label), the
+// returned boxes are transposed (x = box[1], y = box[0]) and come out in reversed get_boxes order.  Scalar arithmetic
+// follows numpy 2 (Python ints / floats do not widen float32); exp is dd_expf (correctly rounded f32 by declaration).
+// ------------------------------------------------------------------------------------------------
+#define DD_Y3_MAX_ACTIVE 128      // boxes of one frame with a class score above the threshold (more -> DD_FLAG_DET_OVERFLOW)
+#define DD_Y3_BAD_BOX 64          // flag: two zero-area boxes met in do_nms (ZeroDivisionError in the reference)
+
+struct DDYolo3Params {
+    int nc;                       // classes
+    int g[3];                     // grid size of each output map (g x g cells, 3 boxes per cell)
+    int anchors[3][6];            // tools/yolo.py:166
+    float thr;                    // score_threshold (obj_thresh of decode_netout and get_boxes' thresh)
+    double nms_thresh;            // 0.5 (:205)
+    int image_w, image_h, net_w, net_h;
+};
+
+DD_HD float dd_sigmoid_f32(float x) { return dd_divf(1.0f, dd_addf(1.0f, dd_expf(-x))); }      // yolo.py:45-46
+
+// box (map k, cell i, anchor b) of a frame: raw = its 5 + nc logits.  Integer box (xmin, ymin, xmax, ymax) after
+// correct_yolo_boxes; returns the objectness sigmoid.
+DD_HD float dd_yolo3_box(const float* raw, int k, int i, int b, const DDYolo3Params& p, int* box) {
+    const int gw = p.g[k], gh = p.g[k];
+    const int col = i % gw;
+    const float rowf = (float)((double)i / (double)gw);                    // python float row (:59), narrowed at :67
+    const float sx = dd_sigmoid_f32(raw[0]), sy = dd_sigmoid_f32(raw[1]);
+    const float x = dd_divf(dd_addf((float)col, sx), (float)gw);
+    const float y = dd_divf(dd_addf(rowf, sy), (float)gh);
+    const float w = dd_divf(dd_mulf((float)p.anchors[k][2 * b], dd_expf(raw[2])), (float)p.net_w);
+    const float h = dd_divf(dd_mulf((float)p.anchors[k][2 * b + 1], dd_expf(raw[3])), (float)p.net_h);
+    const float hw = dd_divf(w, 2.0f), hh = dd_divf(h, 2.0f);
+    box[0] = (int)dd_mulf(dd_subf(x, hw), (float)p.image_w);               // int() truncates toward zero (:88-91)
+    box[1] = (int)dd_mulf(dd_subf(y, hh), (float)p.image_h);
+    box[2] = (int)dd_mulf(dd_addf(x, hw), (float)p.image_w);
+    box[3] = (int)dd_mulf(dd_addf(y, hh), (float)p.image_h);
+    return dd_sigmoid_f32(raw[4]);
+}
+
+DD_HD int dd_y3_overlap(int a1, int a2, int b1, int b2) {                  // _interval_overlap (:93-107)
+    if (b1 < a1) return b2 < a1 ? 0 : dd_imin(a2, b2) - a1;
+    return a2 < b1 ? 0 : dd_imin(a2, b2) - b1;
+}
+
+// bbox_iou (:109-116) >= nms_thresh; *bad is set when the reference would divide by zero
+DD_HD bool dd_y3_suppresses(const int* p, const int* q, double nms_thresh, int* bad) {
+    const long long iw = dd_y3_overlap(p[0], p[2], q[0], q[2]), ih = dd_y3_overlap(p[1], p[3], q[1], q[3]);
+    const long long inter = iw * ih;
+    const long long uni = (long long)(p[2] - p[0]) * (p[3] - p[1]) + (long long)(q[2] - q[0]) * (q[3] - q[1]) - inter;
+    if (uni == 0) { *bad = 1; return false; }
+    return dd_div((double)inter, (double)uni) >= nms_thresh;
+}
+
+// do_nms for one class c over the n active boxes (in box order): cls [n][nc] thresholded scores, box [n][4].
+// scratch: n ints.  Sort by descending score, stable (equal scores: lower box index first).
+DD_HD void dd_y3_nms_class(int c, int n, int nc, float* cls, const int* box, double nms_thresh, int* order, int* bad) {
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (cls[i * nc + c] != 0.f) {                                      // zero scores sort last and never suppress
+            int j = m++;
+            while (j > 0 && cls[order[j - 1] * nc + c] < cls[i * nc + c]) { order[j] = order[j - 1]; --j; }
+            order[j] = i;
+        }
+    for (int a = 0; a < m; ++a) {
+        const int p = order[a];
+        if (cls[p * nc + c] == 0.f) continue;
+        for (int e = a + 1; e < m; ++e) {
+            const int q = order[e];
+            if (dd_y3_suppresses(box + p * 4, box + q * 4, nms_thresh, bad)) cls[q * nc + c] = 0.f;
+        }
+        // boxes whose score for c is already zero stay zero whatever their IoU: nothing to do for them
+    }
+}
+
+// get_boxes + the detect_image tail over the n active boxes (box order); returns the number of detections written
+// (at most ncap; *overflow set beyond).  out_box [ncap][4] = x, y, w, h (ints, transposed like the reference).
+DD_HD int dd_y3_emit(int n, int nc, const float* cls, const int* box, float thr, const unsigned char* wanted, int ncap,
+                     double* out_box, float* out_score, int* out_label, int* overflow) {
+    int k = 0;
+    for (int p = n - 1; p >= 0; --p) {
+        int lab = 0, above = 0;
+        for (int c = 0; c < nc; ++c) {
+            if (cls[p * nc + c] > cls[p * nc + lab]) lab = c;              // np.argmax: first maximum
+            above += cls[p * nc + c] > thr ? 1 : 0;
+        }
+        const float score = cls[p * nc + lab];
+        if (!wanted[lab] || score < thr) continue;
+        int x = box[p * 4 + 1], y = box[p * 4 + 0];
+        int w = box[p * 4 + 3] - box[p * 4 + 1], h = box[p * 4 + 2] - box[p * 4 + 0];
+        if (x < 0) { w += x; x = 0; }
+        if (y < 0) { h += y; y = 0; }
+        for (int rep = 0; rep < above; ++rep) {                            // once per label above the threshold (:145-152)
+            if (k >= ncap) { *overflow = 1; return k; }
+            out_box[k * 4 + 0] = x; out_box[k * 4 + 1] = y; out_box[k * 4 + 2] = w; out_box[k * 4 + 3] = h;
+            out_score[k] = score; out_label[k] = lab;
+            ++k;
+        }
+    }
+    return k;
 }

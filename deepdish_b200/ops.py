@@ -218,6 +218,29 @@ def yolo_decode(head, wanted_mask, score_thr=0.25, img_size=(640, 480), frame_si
     return out
 
 
+def yolo3_decode(maps, anchors, wanted_mask, score_thr=0.5, nms_thresh=0.5, image_size=(640, 480), net_size=(416, 416),
+                 ncap=256):
+    """Keras YOLOv3 adapter post-processing for b frames (tools/yolo.py:48-153,207-237).  maps: three f32 CUDA tensors
+    [b,g,g,3*(5+nc)]; anchors: 3 x 6 ints.  Returns dict(box f64 [b,ncap,4] (x, y, w, h), score f32, label i32,
+    count i32 [b], flags i32 [b])."""
+    import ctypes
+    m = [_need_cuda(t) or t.contiguous() for t in maps]
+    b, nc = m[0].shape[0], m[0].shape[-1] // 3 - 5
+    dev = m[0].device
+    out = dict(box=torch.zeros((b, ncap, 4), dtype=torch.float64, device=dev),
+               score=torch.zeros((b, ncap), dtype=torch.float32, device=dev),
+               label=torch.zeros((b, ncap), dtype=torch.int32, device=dev),
+               count=torch.zeros((b,), dtype=torch.int32, device=dev), flags=torch.zeros((b,), dtype=torch.int32, device=dev))
+    grids = (ctypes.c_int32 * 3)(*[int(t.shape[1]) for t in m])
+    anch = (ctypes.c_int32 * 18)(*[int(a) for row in anchors for a in row])
+    _lib.check(_lib.lib().dd_yolo3_decode(m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), grids, anch, b, nc,
+                                          wanted_mask.data_ptr(), float(score_thr), float(nms_thresh), int(image_size[0]),
+                                          int(image_size[1]), int(net_size[0]), int(net_size[1]), ncap, out["box"].data_ptr(),
+                                          out["score"].data_ptr(), out["label"].data_ptr(), out["count"].data_ptr(),
+                                          out["flags"].data_ptr(), _stream(dev)), "dd_yolo3_decode")
+    return out
+
+
 def ssd_decode(raw_boxes, raw_scores, anchors, class_to_label, conf_thr=0.5, nms_iou=0.5, img_size=(640, 480),
                frame_size=(640, 480), ncap=16, out=None):
     """SSD-MobileNet post-processing for b frames (TFLite_Detection_PostProcess restated +

@@ -327,6 +327,20 @@ int dd_yolo_decode(const void* head, int32_t head_is_u8, float scale, int32_t ze
                    float* out_score, int32_t* out_class, int32_t* out_anchor, int32_t* out_count,
                    int32_t* out_flags, void* stream);
 
+/* Keras YOLOv3 adapter post-processing for b frames (tools/yolo.py: decode_netout :48-81, correct_yolo_boxes :83-91,
+ * do_nms :122-137, get_boxes :140-153 and the tail of YOLO.detect_image :207-237, including its quirks: transposed
+ * boxes x = box[1], y = box[0]; a box with two labels above the threshold is returned twice; reversed order).
+ *   map0..2 f32 [b,g,g,3*(5+nc)] raw output maps (g = host_grids3[k]), host_anchors18 = the model's 3 x 6 anchor sizes
+ *   (host arrays); wanted u8 [nc].  out_box f64 [b,ncap,4] (x, y, w, h integers), out_score f32, out_label i32 (class
+ *   index), out_count i32 [b]; out_flags i32 [b]: DD_FLAG_DET_OVERFLOW (more than ncap results or more than 128 boxes
+ *   above the threshold), 64 = two zero-area boxes met in do_nms (the reference raises ZeroDivisionError).
+ *   float32 exp is correctly rounded by declaration (see dd_ssd_decode). */
+int dd_yolo3_decode(const float* map0, const float* map1, const float* map2, const int32_t* host_grids3,
+                    const int32_t* host_anchors18, int32_t b, int32_t nc, const uint8_t* wanted, float score_thr,
+                    double nms_thresh, int32_t image_w, int32_t image_h, int32_t net_w, int32_t net_h, int32_t ncap,
+                    double* out_box, float* out_score, int32_t* out_label, int32_t* out_count, int32_t* out_flags,
+                    void* stream);
+
 /* SSD-MobileNet post-processing for b frames: the TFLite custom op TFLite_Detection_PostProcess
  * (1917-anchor centre-size decode, best non-background class per anchor, greedy IoU NMS at 0.6, <= 10
  * boxes; third-party, restated -- see DESIGN.md "parity unpinned") followed by SSDMobileNet.predict /

@@ -272,3 +272,97 @@ def tflite_adapter_postprocess(op_boxes, op_classes, op_scores, count, img_w, im
             labels.append(lab)
             scores.append(sc)
     return boxes, labels, scores
+
+
+# ----------------------------------------------------------------------------- Keras YOLOv3 adapter
+def _exp_f32(x):
+    """float32 exp, correctly rounded by declaration (f64 exp, one rounding): numpy's own float32 exp differs between
+    builds (x86 SIMD vs libm) in the last bit; the CUDA kernel uses the same definition (dd_expf)."""
+    return np.exp(np.asarray(x, np.float32).astype(np.float64)).astype(np.float32)
+
+
+def _sigmoid_f32(x):
+    f = np.float32
+    return (f(1.0) / (f(1.0) + _exp_f32(-np.asarray(x, f)))).astype(f)
+
+
+def yolo3_detect(netouts, anchors, class_names, wanted, thr, image_w, image_h, net_w, net_h, nms_thresh=0.5):
+    """tools/yolo.py: decode_netout (:48-81) for each output map, correct_yolo_boxes (:83-91), do_nms (:122-137),
+    get_boxes (:140-153) and the tail of YOLO.detect_image (:207-237).  netouts: list of [g, g, 3*(5+C)] f32 raw maps.
+    Quirks kept: every cell emits a box (the `objectness.all() <= obj_thresh` test, :63, only skips an objectness of
+    exactly 0); the row used for y is the FRACTIONAL i / grid_w (:59,67); a box with two labels above the threshold is
+    returned twice, both times with its arg-max label (:145-152, :210-214); the returned boxes are transposed
+    (x = box[1], y = box[0], :222-225); order = reversed get_boxes order.  Scalar arithmetic follows numpy 2 (NEP 50:
+    Python ints / floats do not widen float32).  Returns (boxes int64 [K,4], class indices, scores f32)."""
+    f = np.float32
+    xmin, ymin, xmax, ymax, classes = [], [], [], [], []
+    for k, raw in enumerate(netouts):
+        gh, gw = raw.shape[:2]
+        o = np.array(raw, dtype=f).reshape(gh, gw, 3, -1)
+        o[..., :2] = _sigmoid_f32(o[..., :2])
+        o[..., 4:] = _sigmoid_f32(o[..., 4:])
+        o[..., 5:] = o[..., 4][..., None] * o[..., 5:]
+        o[..., 5:] *= o[..., 5:] > f(thr)
+        i = np.arange(gh * gw)
+        rowf = (i / gw).astype(f)                          # python float row, narrowed to float32 when it meets y (:67)
+        ri, ci = (i / gw).astype(np.int64), i % gw
+        cell = o[ri, ci]                                   # [gh*gw, 3, 5+C], i-major then b: the reference's append order
+        for b in range(3):
+            c = cell[:, b]
+            keep = c[:, 4] != 0                            # :63
+            x = ((ci.astype(f) + c[:, 0]) / f(gw)).astype(f)
+            y = ((rowf + c[:, 1]) / f(gh)).astype(f)
+            w = (f(anchors[k][2 * b]) * _exp_f32(c[:, 2]) / f(net_w)).astype(f)
+            h = (f(anchors[k][2 * b + 1]) * _exp_f32(c[:, 3]) / f(net_h)).astype(f)
+            cell_boxes = np.stack([x - w / f(2), y - h / f(2), x + w / f(2), y + h / f(2)], 1).astype(f)
+            cell[:, b, :4] = cell_boxes
+            cell[:, b, 4] = np.where(keep, f(1), f(0))
+        flat = cell.reshape(-1, cell.shape[-1])            # box order: i, then b
+        flat = flat[flat[:, 4] != 0]
+        xmin.append(flat[:, 0]); ymin.append(flat[:, 1]); xmax.append(flat[:, 2]); ymax.append(flat[:, 3])
+        classes.append(flat[:, 5:])
+    xmin, ymin, xmax, ymax = (np.concatenate(a) for a in (xmin, ymin, xmax, ymax))
+    cls = np.concatenate(classes).copy()
+    # correct_yolo_boxes with new_w, new_h = net_w, net_h: offsets 0, scales 1 -> int(v * image size), truncation
+    bx = np.stack([(xmin * f(image_w)).astype(f), (ymin * f(image_h)).astype(f), (xmax * f(image_w)).astype(f),
+                   (ymax * f(image_h)).astype(f)], 1).astype(np.int64)        # astype(int64) truncates toward zero
+
+    def overlap(a1, a2, b1, b2):
+        if b1 < a1:
+            return 0 if b2 < a1 else min(a2, b2) - a1
+        return 0 if a2 < b1 else min(a2, b2) - b1
+
+    def iou(p, q):
+        iw = overlap(bx[p, 0], bx[p, 2], bx[q, 0], bx[q, 2])
+        ih = overlap(bx[p, 1], bx[p, 3], bx[q, 1], bx[q, 3])
+        inter = iw * ih
+        union = (bx[p, 2] - bx[p, 0]) * (bx[p, 3] - bx[p, 1]) + (bx[q, 2] - bx[q, 0]) * (bx[q, 3] - bx[q, 1]) - inter
+        return float(inter) / union
+
+    n = len(bx)
+    for c in range(cls.shape[1]):                          # do_nms: only boxes with a non-zero score can suppress
+        if not np.any(cls[:, c]):
+            continue
+        order = np.argsort(-cls[:, c], kind="stable")
+        for a in range(n):
+            p = order[a]
+            if cls[p, c] == 0:
+                continue
+            for q in order[a + 1:]:
+                if iou(p, q) >= nms_thresh:
+                    cls[q, c] = 0
+    v = [(p, c) for p in range(n) for c in np.nonzero(cls[p] > f(thr))[0]]          # get_boxes order
+    out_b, out_l, out_s = [], [], []
+    for p, _ in reversed(v):
+        lab = int(np.argmax(cls[p]))
+        score = cls[p, lab]
+        if class_names[lab] not in wanted or score < thr:
+            continue
+        x, y = int(bx[p, 1]), int(bx[p, 0])                # transposed, like the reference (:222-225)
+        w, h = int(bx[p, 3] - bx[p, 1]), int(bx[p, 2] - bx[p, 0])
+        if x < 0:
+            w, x = w + x, 0
+        if y < 0:
+            h, y = h + y, 0
+        out_b.append([x, y, w, h]); out_l.append(lab); out_s.append(score)
+    return np.array(out_b, np.int64).reshape(-1, 4), np.array(out_l, np.int32), np.array(out_s, f)

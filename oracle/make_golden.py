@@ -538,6 +538,89 @@ def golden_patches(R):
     print("patches.npz valid", int(valid.sum()), "of", len(valid), "float", int(fvalid.sum()), "dummy", len(dboxes))
 
 
+def synth_yolo3_heads(rng, net=128, n_hot=14, nc=80):
+    """Three Keras-YOLOv3 output maps [g, g, 3*(5+nc)] f32 (raw logits) for a net x net input: background cells with
+    very negative objectness / class logits and a few confident cells (clusters, so that do_nms has work to do)."""
+    outs = []
+    for g in (net // 32, net // 16, net // 8):
+        o = np.empty((g, g, 3, 5 + nc), np.float32)
+        o[..., 0:2] = rng.normal(0, 1.0, (g, g, 3, 2))
+        o[..., 2:4] = rng.uniform(-0.6, 0.8, (g, g, 3, 2))
+        o[..., 4] = rng.normal(-7.0, 1.0, (g, g, 3))
+        o[..., 5:] = rng.normal(-6.0, 1.0, (g, g, 3, nc))
+        for _ in range(max(2, n_hot * g * g // 336)):
+            y, x, b = rng.integers(0, g), rng.integers(0, g), rng.integers(0, 3)
+            for dy, dx in ((0, 0), (0, 1), (1, 0)) if rng.random() < 0.6 else ((0, 0),):      # neighbouring cells: overlaps
+                yy, xx = min(g - 1, y + dy), min(g - 1, x + dx)
+                o[yy, xx, b, 4] = rng.uniform(1.0, 5.0)
+                cls = rng.choice([0, 1, 2, 3, 5, 7], 2, replace=False)
+                o[yy, xx, b, 5 + cls[0]] = rng.uniform(1.0, 5.0)
+                if rng.random() < 0.3:
+                    o[yy, xx, b, 5 + cls[1]] = rng.uniform(0.5, 3.0)                          # a second label above threshold
+        outs.append(o.reshape(g, g, 3 * (5 + nc)))
+    return outs
+
+
+def golden_yolo3(R):
+    """tools/yolo.py (the Keras YOLOv3 adapter, UNMODIFIED): decode_netout + correct_yolo_boxes + do_nms + get_boxes and the
+    tail of YOLO.detect_image (reversed order, label = argmax after NMS, transposed boxes x = box[1], y = box[0],
+    :222-225) on synthetic output maps.  Stand-ins: tensorflow.keras (import only), the model (serves the maps) and
+    the camera image.  float32 exp / sigmoid are numpy's: generated with numpy's SIMD dispatch switched off (the
+    scalar libm path of the reference's ARM targets, see golden_nms_ties) -- stored as the fixture -- and once more
+    with numpy's x86 SIMD exp, stored beside it so that the tests can COUNT the differences the exp makes."""
+    import contextlib
+    import importlib
+    import io
+    import sys
+    import types
+    from PIL import Image
+    scalar = os.environ.get("NPY_DISABLE_CPU_FEATURES") == NPY_SCALAR_SORT
+    if not scalar and os.environ.get("DD_YOLO3_PASS") != "simd":
+        import subprocess
+        env = dict(os.environ, DD_GOLDEN_ONLY="yolo3")
+        subprocess.check_call([sys.executable, "-m", "oracle.make_golden"], env=dict(env, DD_YOLO3_PASS="simd"), cwd=ROOT)
+        subprocess.check_call([sys.executable, "-m", "oracle.make_golden"],
+                              env=dict(env, NPY_DISABLE_CPU_FEATURES=NPY_SCALAR_SORT), cwd=ROOT)
+        return
+    for name in ("tensorflow", "tensorflow.keras", "tensorflow.keras.models", "tensorflow.keras.preprocessing",
+                 "tensorflow.keras.preprocessing.image"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["tensorflow.keras.models"].load_model = lambda *a, **k: None
+    sys.modules["tensorflow.keras.preprocessing.image"].load_img = None
+    sys.modules["tensorflow.keras.preprocessing.image"].img_to_array = None
+    yolo = importlib.import_module("tools.yolo")
+    rng = np.random.default_rng(41)
+    frames, net = 12, 128
+    det = object.__new__(yolo.YOLO)
+    yolo.YOLO.__init__.__globals__["load_model"] = lambda *a, **k: None
+    det.__init__(wanted_labels=["person", "bicycle", "car", "motorbike", "bus"], score_threshold=0.5)
+    det.model_image_size = (net, net)
+    det.height, det.width = det.model_image_size
+    img = Image.new("RGB", (640, 480))
+    maps = [synth_yolo3_heads(rng, net) for _ in range(frames)]
+    res = {}
+    for f in range(frames):
+        det.model = types.SimpleNamespace(predict=lambda x, m=maps[f]: [o[None].copy() for o in m])
+        with contextlib.redirect_stdout(io.StringIO()):
+            boxes, labels, scores = det.detect_image(img)
+        res["box%d" % f] = np.array(boxes, np.int64).reshape(-1, 4)
+        res["lab%d" % f] = np.array([det.class_names.index(l) for l in labels], np.int32)
+        res["score%d" % f] = np.array(scores, np.float32)
+    path = os.path.join(OUT, "yolo3.npz")
+    if scalar:
+        prev = dict(np.load(path, allow_pickle=True)) if os.path.exists(path) else {}
+        simd = {k: v for k, v in prev.items() if k.startswith("simd_")}
+        np.savez_compressed(path, net=net, anchors=np.array(det.anchors, np.int32), names=np.array(det.class_names),
+                            wanted=np.array(det.wanted_labels), thr=0.5,
+                            **{"map%d_%d" % (f, k): maps[f][k] for f in range(frames) for k in range(3)}, **res, **simd)
+        print("yolo3.npz (scalar exp)", [len(res["lab%d" % f]) for f in range(frames)])
+    else:
+        prev = dict(np.load(path, allow_pickle=True)) if os.path.exists(path) else {}
+        prev.update({"simd_" + k: v for k, v in res.items()})
+        np.savez_compressed(path, **prev)
+        print("yolo3.npz (x86 SIMD exp pass)", [len(res["lab%d" % f]) for f in range(frames)])
+
+
 def golden_unbounded(R):
     """nn_budget=None -- the only way deepdish.py:515-516 ever builds its metric: galleries are never trimmed
     (nn_matching.py:137-154).  820 frames, 6 long-lived objects (no re-spawns): every track is matched ~740 times."""
@@ -560,6 +643,9 @@ def main():
     if os.environ.get("DD_GOLDEN_ONLY") == "unbounded":
         golden_unbounded(R)
         return
+    if os.environ.get("DD_GOLDEN_ONLY") == "yolo3":
+        golden_yolo3(R)
+        return
     if os.environ.get("DD_GOLDEN_ONLY") == "box_filter":
         golden_box_filter(R)
         return
@@ -579,6 +665,7 @@ def main():
     golden_box_filter(R)
     golden_nms_ties(R)
     golden_yolo(R)
+    golden_yolo3(R)
     golden_ssd_post(R)
     golden_tracker(R, "tracker_small.npz", seed=101, n_obj=12, dmax=16, frames=100, budget=20, max_age=30,
                    store_inputs=True)

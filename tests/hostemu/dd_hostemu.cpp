@@ -172,6 +172,39 @@ int ddh_box_filter(const double* boxes, int n, int frame_w, int frame_h, double*
     return nk;
 }
 
+// Keras YOLOv3 post-processing device functions on one frame of host maps (same helpers as k_yolo3_post, serial).
+int ddh_yolo3(const float* m0, const float* m1, const float* m2, const int32_t* grids, const int32_t* anchors18, int nc,
+              const uint8_t* wanted, float thr, double nms_thresh, int image_w, int image_h, int net_w, int net_h, int ncap,
+              double* out_box, float* out_score, int32_t* out_label, int32_t* out_flags) {
+    DDYolo3Params P;
+    P.nc = nc; P.thr = thr; P.nms_thresh = nms_thresh;
+    P.image_w = image_w; P.image_h = image_h; P.net_w = net_w; P.net_h = net_h;
+    for (int k = 0; k < 3; ++k) { P.g[k] = grids[k]; for (int a = 0; a < 6; ++a) P.anchors[k][a] = anchors18[k * 6 + a]; }
+    const float* maps[3] = {m0, m1, m2};
+    const int rw = 5 + nc;
+    std::vector<int> box;
+    std::vector<float> cls;
+    for (int k = 0; k < 3; ++k)
+        for (int e = 0; e < P.g[k] * P.g[k] * 3; ++e) {
+            const float* raw = maps[k] + (size_t)e * rw;
+            if (!(dd_sigmoid_f32(raw[4]) > thr)) continue;
+            int b4[4];
+            dd_yolo3_box(raw, k, e / 3, e % 3, P, b4);
+            box.insert(box.end(), b4, b4 + 4);
+            for (int c = 0; c < nc; ++c) {
+                const float v = dd_mulf(dd_sigmoid_f32(raw[4]), dd_sigmoid_f32(raw[5 + c]));
+                cls.push_back(v > thr ? v : 0.f);
+            }
+        }
+    const int n = (int)box.size() / 4;
+    std::vector<int> order(n + 1);
+    int bad = 0, over = 0;
+    for (int c = 0; c < nc; ++c) dd_y3_nms_class(c, n, nc, cls.data(), box.data(), nms_thresh, order.data(), &bad);
+    const int k = dd_y3_emit(n, nc, cls.data(), box.data(), thr, wanted, ncap, out_box, out_score, out_label, &over);
+    *out_flags = (over ? DD_FLAG_DET_OVERFLOW : 0) | (bad ? DD_Y3_BAD_BOX : 0);
+    return k;
+}
+
 // NMS device body on host arrays (one frame).
 int ddh_nms(const double* boxes, const float* scores, int n, double max_overlap, int32_t* keep) {
     HostG g;

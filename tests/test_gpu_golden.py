@@ -105,6 +105,35 @@ def test_nms_vs_reference_fixture():
             assert list(keep[k, :nkeep[k]]) == list(g["keep"][i, :g["nkeep"][i]]), i
 
 
+def test_keras_yolo3_adapter_vs_reference_fixture():
+    """tools.yolo.YOLO mirror (k_yolo3_post) against the unmodified tools/yolo.py: boxes (transposed like the reference's),
+    labels and scores bit for bit, batched and through detect_image with a stand-in model."""
+    from PIL import Image
+    from deepdish_b200.tools.yolo import YOLO
+    g = goldens.load("yolo3.npz")
+    net = int(g["net"])
+    det = YOLO(wanted_labels=list(g["wanted"]), score_threshold=float(g["thr"]), model_image_size=(net, net),
+               class_names=list(g["names"]))
+    maps = [np.stack([g["map%d_%d" % (f, k)] for f in range(12)]) for k in range(3)]
+    res = det.detect_maps(maps, (640, 480))
+    total = 0
+    for f, (boxes, labels, scores) in enumerate(res):
+        np.testing.assert_array_equal(np.array(boxes, np.int64).reshape(-1, 4), g["box%d" % f])
+        assert [list(g["names"]).index(l) for l in labels] == list(g["lab%d" % f])
+        np.testing.assert_array_equal(np.array(scores, np.float32).view(np.uint32), g["score%d" % f].view(np.uint32))
+        total += len(labels)
+    assert total > 300
+
+    class Model:
+        def predict(self, data):
+            assert data.shape == (1, net, net, 3) and data.dtype == np.float32
+            return [g["map3_%d" % k][None] for k in range(3)]
+
+    det.model = Model()
+    boxes, labels, scores = det.detect_image(Image.new("RGB", (640, 480)))
+    np.testing.assert_array_equal(np.array(boxes, np.int64).reshape(-1, 4), g["box3"])
+
+
 def test_box_filter_vs_reference_fixture():
     """dd_box_filter against the reference's own loop (deepdish.py:941-960 inside Pipeline.detect_objects)."""
     from deepdish_b200 import ops

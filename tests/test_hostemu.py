@@ -122,6 +122,16 @@ def test_detection_bodies_vs_reference_fixtures():
         out, idx = hd.box_filter(g["boxes"][c, :int(g["counts"][c])])
         np.testing.assert_array_equal(out, g["out%d" % c].astype(float).reshape(-1, 4), err_msg=str(c))
         np.testing.assert_array_equal(idx, g["kept%d" % c])
+    g = goldens.load("yolo3.npz")              # Keras YOLOv3 adapter: unmodified tools/yolo.py (scalar-exp run), bit for bit
+    names, wanted = list(g["names"]), list(g["wanted"])
+    wm = np.array([1 if n in wanted else 0 for n in names], np.uint8)
+    for f in range(12):
+        b, s_, l, fl = hd.yolo3([g["map%d_%d" % (f, k)] for k in range(3)], g["anchors"], len(names), wm, float(g["thr"]),
+                                (640, 480), (int(g["net"]), int(g["net"])))
+        assert fl == 0
+        np.testing.assert_array_equal(b, g["box%d" % f].astype(float))
+        np.testing.assert_array_equal(l, g["lab%d" % f])
+        np.testing.assert_array_equal(s_.view(np.uint32), g["score%d" % f].view(np.uint32))
     g = goldens.load("nms_ties.npz")           # tied scores: the reference picks the higher index first (n <= 16)
     for i in range(len(g["counts"])):
         n = int(g["counts"][i])
