@@ -35,7 +35,7 @@ class TrackerConfig(ctypes.Structure):
 LAYOUT_FIELDS = ["n_tracks", "next_id", "n_deleted", "err", "order", "deleted", "counts", "mean", "cov",
                  "track_id", "hits", "age", "tsu", "state", "gal_len", "gal_pos", "gal_np", "ptab", "free_stack",
                  "pool_ctl", "lab_cnt", "lab_sum", "path_n", "path_last", "path_crossed", "gate", "cost", "det_xyah",
-                 "det_featn", "det_slot", "det_kind", "cdesc", "work", "work_ctl", "work_rec", "det_feath"]
+                 "det_featn", "det_slot", "det_kind", "cdesc", "work", "work_ctl", "work_rec", "det_feath", "tick_args"]
 
 
 class TrackerLayout(ctypes.Structure):
@@ -60,7 +60,7 @@ def field_specs(cfg):
         "cost": (f, (S, T, D)), "det_xyah": (d, (S, D, 4)), "det_featn": (f, (S, D, 128)),
         "det_slot": (i, (S, D)), "det_kind": (i, (S, D)), "cdesc": (i, (S, T, 4)),
         "work": (i, (S * T,)), "work_ctl": (i, (64,)), "work_rec": (i, (S * T, 16)),
-        "det_feath": ("float16", (S, D, 128)),
+        "det_feath": ("float16", (S, D, 128)), "tick_args": (i, (64,)),
     }
 
 
@@ -138,6 +138,18 @@ def lib():
                                  _vp, _vp, _vp, _vp, _vp, _vp],
         "dd_tracker_count_reduce": [_vp, cfgp, _vp, _vp],
         "dd_tracker_status": [_vp, cfgp, ctypes.POINTER(_i32), _vp],
+        "dd_engine_create": [_i32, ctypes.POINTER(_vp), ctypes.POINTER(cfgp), ctypes.POINTER(_i32), ctypes.POINTER(_vp), _vp,
+                             _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(_vp)],
+        "dd_engine_destroy": [_vp],
+        "dd_engine_rebind": [_vp, _i32, _vp, cfgp],
+        "dd_engine_bind_host": [_vp, _i32, _vp, _vp, _u64, _vp, _vp, _vp, _vp],
+        "dd_engine_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+        "dd_engine_step_host": [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_int64), _vp, _vp],
+        "dd_engine_join": [_vp, _vp],
+        "dd_engine_wait_counts": [_vp, _vp],
+        "dd_engine_pool_latest": [_vp, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_int64)],
+        "dd_engine_stats": [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                            ctypes.POINTER(ctypes.c_double)],
         "dd_kalman_initiate": [_vp, _vp, _vp, _i32, _vp],
         "dd_kalman_predict": [_vp, _vp, _i32, _vp],
         "dd_kalman_project": [_vp, _vp, _vp, _vp, _i32, _vp],

@@ -183,12 +183,67 @@ class BatchedTracker:
         self._last_sum = None
         self._aux = torch.cuda.Stream(device=self.device) if n_chunks > 1 else None
         self._poll_pool = any(len(c.segs) * c.cfg.seg_pages < self._worst_pages(c) for c in self.chunks) or budget is None
+        self._engine = None           # native tick engine (csrc/dd_engine.cu), created at the first step()
+        self._mode = None             # "eng": the last tick ran through the engine, "py": through the per-call path
         torch.cuda.synchronize(self.device)
         for c in self.chunks:
             _lib.check(self.lib.dd_tracker_init(c.state, c.cfgp, self._sp(c)), "dd_tracker_init")
         self.join()
 
     # ------------------------------------------------------------------------------------------
+    def _eng(self):
+        """The native tick engine of this tracker (dd_engine_create): one captured CUDA graph per chunk and tick, the
+        event plumbing between chunk streams, the count summation and the pool polls behind ONE C call per tick."""
+        if self._engine is None:
+            P = len(self.chunks)
+            states = (ctypes.c_void_p * P)(*[c.state for c in self.chunks])
+            cfgs = (ctypes.POINTER(_lib.TrackerConfig) * P)(*[ctypes.pointer(c.cfg) for c in self.chunks])
+            los = (ctypes.c_int32 * P)(*[c.lo for c in self.chunks])
+            sts = (ctypes.c_void_p * P)(*[c.stream.cuda_stream if c.stream is not None else 0 for c in self.chunks])
+            h = ctypes.c_void_p()
+            _lib.check(self.lib.dd_engine_create(P, states, cfgs, los, sts,
+                                                 ctypes.c_void_p(self._aux.cuda_stream if self._aux is not None else 0),
+                                                 self.line.data_ptr(), self.line_per_stream, self.partial_counts.data_ptr(),
+                                                 self.total_counts.data_ptr(), self.det_track_id.data_ptr(),
+                                                 self.POLL_EVERY if self._poll_pool else 0, ctypes.byref(h)),
+                       "dd_engine_create")
+            self._engine = h
+        return self._engine
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None) is not None:
+                torch.cuda.synchronize(self.device)
+                self.lib.dd_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+    def _enter(self, mode):
+        """Ticks can be issued through the engine ("eng") or call by call from Python ("py": update(), step_host(), the
+        kernel-timeline mode).  Each side tracks its own cross-tick events, so a switch re-orders every stream first."""
+        if mode == self._mode:
+            return
+        if self._mode is not None and len(self.chunks) > 1:
+            self.join()
+            ev = self._cur().record_event()
+            for c in self.chunks:
+                c.stream.wait_event(ev)
+            self._aux.wait_event(ev)
+        self._mode = mode
+
+    def _rebind(self, c):
+        if self._engine is not None:
+            _lib.check(self.lib.dd_engine_rebind(self._engine, self.chunks.index(c), c.state, c.cfgp), "dd_engine_rebind")
+
+    def engine_stats(self):
+        """(ticks stepped, kernels launched, host ms blocked in the run-ahead throttle) of the native engine."""
+        if self._engine is None:
+            return 0, 0, 0.0
+        t, n, b = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0)
+        _lib.check(self.lib.dd_engine_stats(self._engine, ctypes.byref(t), ctypes.byref(n), ctypes.byref(b)), "dd_engine_stats")
+        return t.value, n.value, b.value
+
     def _worst_pages(self, c):
         if self.budget is None:
             return float("inf")
@@ -220,11 +275,20 @@ class BatchedTracker:
         Pool: segments are attached until the free pages cover the forecast (pages the live tracks can take within
         their next 8 appends) plus one page per detection slot (new tracks).  Unbounded galleries: the page table is doubled when the
         longest gallery is within 128 rows of its capacity."""
-        for c in self.chunks:
+        for i, c in enumerate(self.chunks):
             st = c.stream if c.stream is not None else self._cur()
             if wait:
                 st.synchronize()
                 ctl = c.v["pool_ctl"][:4].cpu()
+            elif self._mode == "eng":
+                if self._engine is None:
+                    continue
+                out, tick = (ctypes.c_int32 * 4)(), ctypes.c_int64(-1)
+                _lib.check(self.lib.dd_engine_pool_latest(self._engine, i, 3, out, ctypes.byref(tick)), "dd_engine_pool_latest")
+                if tick.value < 0 or tick.value == getattr(c, "eng_poll_seen", -1):
+                    continue
+                c.eng_poll_seen = tick.value
+                ctl = out
             elif c.poll is not None and c.poll[2] >= 0 and not c.poll[3]:
                 if self.lib.dd_event_query(c.poll[1]) != 1:
                     if self._tick - c.poll[2] < 3:
@@ -237,15 +301,21 @@ class BatchedTracker:
             free, attached, longest, forecast = int(ctl[0]), int(ctl[1]), int(ctl[2]), int(ctl[3])
             # new tracks take one page each: keep one worst-case tick of them (every detection a new track) in hand
             want = forecast + forecast // 4 + (c.hi - c.lo) * min(self.max_dets, self.max_tracks)
+            grown = False
             while attached == len(c.segs) * c.cfg.seg_pages and free < want \
                     and attached < self._worst_pages(c) and len(c.segs) < _lib.DD_MAX_SEGS:
                 c.grow_pool(ctypes.c_void_p(st.cuda_stream))
                 free += c.cfg.seg_pages
                 attached += c.cfg.seg_pages
+                grown = True
             cap_rows = _lib.page_cap(c.cfg) * _lib.PAGE_ROWS
             if self.budget is None and longest + 128 >= cap_rows:
                 st.synchronize()
                 c.grow_page_table(2 * _lib.page_cap(c.cfg))
+                grown = True
+            if grown:
+                self._rebind(c)
+                c.eng_poll_seen = -1
 
     def memory_bytes(self):
         """Device bytes of the tracker state: blobs + gallery page pool."""
@@ -284,6 +354,8 @@ class BatchedTracker:
             cur.wait_event(c.done)
         if self._last_sum is not None:
             cur.wait_event(self._last_sum)
+        if self._engine is not None:
+            _lib.check(self.lib.dd_engine_join(self._engine, ctypes.c_void_p(cur.cuda_stream)), "dd_engine_join")
 
     def _line_ptr(self, c):
         return self.line.data_ptr() + (c.lo * 32 if self.line_per_stream else 0)
@@ -307,6 +379,7 @@ class BatchedTracker:
     # ------------------------------------------------------------------------------------------
     def predict(self):
         """Tracker.predict for every stream (tracker.py:51-57)."""
+        self._enter("py")
         self._fork()
         for c in self.chunks:
             _lib.check(self.lib.dd_tracker_predict(c.state, c.cfgp, self._sp(c)), "dd_tracker_predict")
@@ -318,6 +391,7 @@ class BatchedTracker:
         tlwh f64 [S,Dmax,4], conf f32 [S,Dmax], label i32 [S,Dmax], feat f32 [S,Dmax,128], count i32 [S]
         -- device tensors, padded.  Returns det_track_id i32 [S,Dmax] (device; -1 = padding)."""
         self._check_batch(tlwh, conf, label, feat, count)
+        self._enter("py")
         if self._poll_pool:
             self.maintain()
         self._fork((tlwh, conf, label, feat, count))
@@ -353,6 +427,7 @@ class BatchedTracker:
 
     def countline(self):
         """Count-line step (deepdish.py:1041-1112) on the state left by update()."""
+        self._enter("py")
         self._fork()
         for c in self.chunks:
             _lib.check(self.lib.dd_tracker_countline(c.state, c.cfgp, self._line_ptr(c), self.line_per_stream,
@@ -360,10 +435,33 @@ class BatchedTracker:
         self.join()
 
     def step(self, batch, join=True, reduce=False):
-        """One tick (predict + update + count-line [+ per-chunk count reduction]) for a SceneBatch-like
-        object of device tensors: one fused C call per chunk.  join=False only enqueues (call join())."""
+        """One tick (predict + update + count-line [+ count reduction into total_counts]) for a SceneBatch-like object
+        of device tensors: ONE call into the native engine, which launches one captured graph per chunk.  join=False
+        only enqueues (call join())."""
         tlwh, conf, label, feat, count = batch.tlwh, batch.conf, batch.label, batch.feat, batch.count
         self._check_batch(tlwh, conf, label, feat, count)
+        if getattr(self, "_timeline", None):
+            return self._step_py(batch, join, reduce)
+        self._enter("eng")
+        if self._poll_pool:
+            self.maintain()
+        if len(self.chunks) > 1:
+            for t in (tlwh, conf, label, feat, count):
+                for c in self.chunks:
+                    t.record_stream(c.stream)
+        _lib.check(self.lib.dd_engine_step(self._eng(), tlwh.data_ptr(), conf.data_ptr(), label.data_ptr(), feat.data_ptr(),
+                                           count.data_ptr(), 1 if reduce else 0, ctypes.c_void_p(self._cur().cuda_stream)),
+                   "dd_engine_step")
+        self._tick += 1
+        if join:
+            self.join()
+        return self.det_track_id
+
+    def _step_py(self, batch, join=True, reduce=False):
+        """step() issued call by call from Python (one dd_tracker_tick per chunk): the kernel-timeline mode of
+        benchmarks/timeline.py, which needs events between the kernels."""
+        tlwh, conf, label, feat, count = batch.tlwh, batch.conf, batch.label, batch.feat, batch.count
+        self._enter("py")
         if self._poll_pool:
             self.maintain()
         self._fork((tlwh, conf, label, feat, count))
@@ -414,6 +512,7 @@ class BatchedTracker:
         of its det->track ids into the pinned ``out_ids_host``.  Returns total_counts (device, summed on the
         caller's stream)."""
         D = self.max_dets
+        self._enter("py")
         if self._poll_pool:
             self.maintain()
         par = self._tick & 1
@@ -486,55 +585,40 @@ class BatchedTracker:
         return sum(p[1] for p in packed)
 
     def step_host_packed(self, packed, out_ids_host=None):
-        """End-to-end tick from a ragged pinned host batch (``pack_host``).  Per chunk: ONE H2D copy on the chunk's
-        own copy stream into a double-buffered device blob -- so the upload of tick k + 1 runs under the kernels of
-        tick k --, then on the chunk's compute stream the tick reading the blob directly (dd_tracker_tick_ragged)
-        with its partial count reduction and (optionally) the D2H copy of the det->track ids.  The pinned blobs must stay alive until their copy has
-        run.  Returns total_counts (device; valid on the caller's stream after join() or all_reduce_counts())."""
+        """End-to-end tick from a ragged pinned host batch (``pack_host``): one call into the native engine
+        (dd_engine_step_host).  Per chunk: ONE H2D copy on the chunk's own copy stream into a double-buffered device
+        blob -- so the upload of tick k + 1 runs under the kernels of tick k --, then on the chunk's compute stream the
+        captured tick reading the blob in place, its partial count reduction and (optionally) the D2H copy of the
+        det->track ids.  The pinned blobs must stay alive until their copy has run.  Returns total_counts (device;
+        valid on the caller's stream after join() or all_reduce_counts())."""
+        self._enter("eng")
         if self._poll_pool:
             self.maintain()
-        par = self._tick & 1
-        multi = len(self.chunks) > 1
-        if multi and self._sum_done[par] is not None:
-            for c in self.chunks:
-                c.stream.wait_event(self._sum_done[par])
-        for i, (c, (blob, total, offs)) in enumerate(zip(self.chunks, packed)):
-            n = c.hi - c.lo
-            st = c.stream if multi else self._cur()
-            if getattr(c, "copy_stream", None) is None:
-                c.copy_stream = torch.cuda.Stream(device=self.device)
+        eng = self._eng()
+        P = len(self.chunks)
+        if getattr(self, "_host_bound", None) is None:
+            for i, c in enumerate(self.chunks):
+                n = c.hi - c.lo
                 cap = 4 * (n + 1) + 64 + n * self.max_dets * (32 + 4 + 4 + 512)
                 c.blob_dev = [torch.empty(cap, dtype=torch.uint8, device=self.device) for _ in range(2)]
-                c.unpacked = [None, None]
-            dev_blob = c.blob_dev[par]
-            if c.unpacked[par] is not None:               # the unpack kernel of tick k - 2 has read this buffer
-                c.copy_stream.wait_event(c.unpacked[par])
-            with torch.cuda.stream(c.copy_stream):
-                dev_blob[:total].copy_(blob[:total], non_blocking=True)
-                copied = c.copy_stream.record_event()
-            with torch.cuda.stream(st):
-                st.wait_event(copied)
                 t, cf, lb, ct = self._staging_small(c)
-                sp = ctypes.c_void_p(st.cuda_stream)
-                ids = self.det_track_id[c.lo:c.hi]
-                # the tick's first kernel reads the blob (features normalised straight from it); later kernels read
-                # box / confidence / label from the small padded arrays it fills, so the blob is free after the tick
-                _lib.check(self.lib.dd_tracker_tick_ragged(c.state, c.cfgp, dev_blob.data_ptr(), *offs, t.data_ptr(),
-                                                           cf.data_ptr(), lb.data_ptr(), ct.data_ptr(), ids.data_ptr(),
-                                                           self._line_ptr(c), self.line_per_stream,
-                                                           self.partial_counts[par, i].data_ptr(), sp),
-                           "dd_tracker_tick_ragged")
-                c.unpacked[par] = st.record_event()
-                if out_ids_host is not None:
-                    out_ids_host[c.lo:c.hi].copy_(ids, non_blocking=True)
-            self._post_tick(c, st)
-        self._mark()
-        self._sum_partials(par)
+                _lib.check(self.lib.dd_engine_bind_host(eng, i, c.blob_dev[0].data_ptr(), c.blob_dev[1].data_ptr(), cap,
+                                                        t.data_ptr(), cf.data_ptr(), lb.data_ptr(), ct.data_ptr()),
+                           "dd_engine_bind_host")
+            self._host_bound = ((ctypes.c_void_p * P)(), (ctypes.c_uint64 * P)(), (ctypes.c_int64 * (4 * P))())
+        blobs, sizes, offs = self._host_bound
+        for i, (blob, total, sec) in enumerate(packed):
+            blobs[i], sizes[i] = blob.data_ptr(), total
+            offs[4 * i], offs[4 * i + 1], offs[4 * i + 2], offs[4 * i + 3] = sec
+        _lib.check(self.lib.dd_engine_step_host(eng, blobs, sizes, offs,
+                                                out_ids_host.data_ptr() if out_ids_host is not None else None,
+                                                ctypes.c_void_p(self._cur().cuda_stream)), "dd_engine_step_host")
         self._tick += 1
         return self.total_counts
 
     def reduce_counts(self):
         """Sum the per-stream counters -> i64 [C,4] (pos, neg, int, del per label), this GPU only."""
+        self._enter("py")
         self._fork()
         par = self._tick & 1
         multi = len(self.chunks) > 1
@@ -560,9 +644,10 @@ class BatchedTracker:
         t = self.total_counts if reduced else self.reduce_counts()
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if async_op and not multi:
+            return t                    # one rank: nothing to exchange, total_counts is the result (valid after join())
         if not async_op:
-            if self._last_sum is not None:
-                self._cur().wait_event(self._last_sum)
+            self._wait_sum()
             if multi:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
             return t
@@ -580,6 +665,14 @@ class BatchedTracker:
             self._ar_work[k] = dist.all_reduce(self._ar_buf[k], op=dist.ReduceOp.SUM, async_op=True) if multi else None
             self._ar_done = side.record_event()
         return self._ar_buf[k]
+
+    def _wait_sum(self):
+        """The caller's stream waits for the latest count summation (Python-issued or the engine's)."""
+        if self._last_sum is not None:
+            self._cur().wait_event(self._last_sum)
+        if self._engine is not None:
+            _lib.check(self.lib.dd_engine_wait_counts(self._engine, ctypes.c_void_p(self._cur().cuda_stream)),
+                       "dd_engine_wait_counts")
 
     def wait_counts(self):
         """Make the caller's stream wait for every outstanding asynchronous count all-reduce."""
@@ -650,6 +743,8 @@ class BatchedTracker:
                 a.copy_(pa.to(self.device))
                 h.copy_(ph.to(self.device))
             c.poll = None
+            c.eng_poll_seen = -1
+            self._rebind(c)
         self.total_counts.copy_(sd["total_counts"].to(self.device))
         self._tick = int(sd["tick"])
         self._sum_done = [None, None]
@@ -658,7 +753,7 @@ class BatchedTracker:
 
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
-        names = names or [n for n in self.v.keys() if n not in ("ptab", "free_stack", "pool_ctl", "work_rec", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl")]
+        names = names or [n for n in self.v.keys() if n not in ("ptab", "free_stack", "pool_ctl", "work_rec", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl", "tick_args")]
         out = {}
         for n in names:
             t = self.v[n]

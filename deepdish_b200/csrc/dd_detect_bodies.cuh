@@ -39,6 +39,8 @@ DD_HD int dd_next_pow2(int n) {
     return p;
 }
 
+struct alignas(16) DDIBox { int x1, y1, x2, y2; };
+
 // Shared-memory plan of dd_nms_frame for up to nmax candidates.
 #define DD_NMS_BATCH 32          // survivors-so-far whose suppression rows are evaluated together
 struct DDNmsSmem {
@@ -48,13 +50,13 @@ struct DDNmsSmem {
     unsigned* rows;             // [DD_NMS_BATCH][nh] suppression rows of the current batch
     int* batch;                 // [DD_NMS_BATCH + 2] ranks of the batch, then {count, next cursor}
     double *x1, *y1, *x2, *y2, *area;   // [nmax] in rank order
-    int *ix1, *iy1, *ix2, *iy2;         // [nmax] integer copies (valid when every box is integer-valued)
+    DDIBox* ibox;                       // [nmax] integer copies (valid when every box is integer-valued)
     int* allint;                        // [1]
 };
 DD_HD size_t dd_nms_smem_bytes(int nmax) {
     const int nh = (nmax + 31) / 32;
     return (size_t)nmax * 16 + (size_t)nh * 4 * (1 + DD_NMS_BATCH) + (DD_NMS_BATCH + 2) * 4 + 16 +
-           (size_t)nmax * 5 * 8 + (size_t)nmax * 16 + 16;
+           (size_t)nmax * 5 * 8 + (size_t)nmax * 16 + 32;
 }
 DD_HD void dd_nms_carve(char* mem, int nmax, DDNmsSmem& m) {
     const int nh = (nmax + 31) / 32;
@@ -62,9 +64,8 @@ DD_HD void dd_nms_carve(char* mem, int nmax, DDNmsSmem& m) {
     m.keys = m.ukeys + nmax;
     m.x1 = (double*)(m.keys + nmax);
     m.y1 = m.x1 + nmax; m.x2 = m.y1 + nmax; m.y2 = m.x2 + nmax; m.area = m.y2 + nmax;
-    m.ix1 = (int*)(m.area + nmax);
-    m.iy1 = m.ix1 + nmax; m.ix2 = m.iy1 + nmax; m.iy2 = m.ix2 + nmax;
-    m.remv = (unsigned*)(m.iy2 + nmax);
+    m.ibox = (DDIBox*)(((uintptr_t)(m.area + nmax) + 15) & ~(uintptr_t)15);
+    m.remv = (unsigned*)(m.ibox + nmax);
     m.rows = m.remv + nh;
     m.batch = (int*)(m.rows + (size_t)DD_NMS_BATCH * nh);
     m.allint = m.batch + DD_NMS_BATCH + 2;
@@ -138,7 +139,7 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
         // |coords| < 2^20 keeps every int32 intermediate of the disjointness test exact
         const bool isint = x == (double)(int)x && y == (double)(int)y && xx2 == (double)(int)xx2 && yy2 == (double)(int)yy2 &&
                            fabs(x) < 1048576.0 && fabs(y) < 1048576.0 && fabs(xx2) < 1048576.0 && fabs(yy2) < 1048576.0;
-        if (isint) { m.ix1[r] = (int)x; m.iy1[r] = (int)y; m.ix2[r] = (int)xx2; m.iy2[r] = (int)yy2; }
+        if (isint) { DDIBox q; q.x1 = (int)x; q.y1 = (int)y; q.x2 = (int)xx2; q.y2 = (int)yy2; m.ibox[r] = q; }
         else *m.allint = 0;
     }
     g.sync();
@@ -192,26 +193,32 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
         // ---- suppression rows of the batch over the later candidates
 #if defined(__CUDA_ARCH__)
         {
+            // one warp per batch member: its box stays in registers while the warp sweeps the later candidates, 32 per
+            // step; candidates already removed need no bit (OR-ing them into the removed set again changes nothing)
             const int wid = g.lane >> 5, ln = g.lane & 31, nwarp = g.nl >> 5;
-            for (int e = wid; e < nb * nh; e += nwarp) {
-                const int b = e / nh, hw = e - b * nh;
+            for (int b = wid; b < nb; b += nwarp) {
                 const int i = m.batch[b];
-                unsigned bits = 0;
-                if (hw >= (i >> 5)) {                        // warp-uniform
+                DDIBox bi;
+                bi.x1 = bi.y1 = bi.x2 = bi.y2 = 0;
+                if (ints) bi = m.ibox[i];
+                for (int hw = i >> 5; hw < nh; ++hw) {
                     const int j = hw * 32 + ln;
+                    const unsigned gone = m.remv[hw];
                     bool sup = false;
-                    if (j > i && j < n) {
+                    if (j > i && j < n && !((gone >> ln) & 1u)) {
                         bool test = true;
-                        if (ints)
-                            test = (min(m.ix2[i], m.ix2[j]) - max(m.ix1[i], m.ix1[j]) + 1 > 0) &&
-                                   (min(m.iy2[i], m.iy2[j]) - max(m.iy1[i], m.iy1[j]) + 1 > 0);
+                        if (ints) {
+                            const DDIBox bj = m.ibox[j];
+                            test = (min(bi.x2, bj.x2) - max(bi.x1, bj.x1) + 1 > 0) &&
+                                   (min(bi.y2, bj.y2) - max(bi.y1, bj.y1) + 1 > 0);
+                        }
                         if (test)
                             sup = dd_nms_suppresses(m.x1[i], m.y1[i], m.x2[i], m.y2[i], m.x1[j], m.y1[j], m.x2[j],
                                                     m.y2[j], m.area[j], max_overlap, fast);
                     }
-                    bits = __ballot_sync(0xffffffffu, sup);
+                    const unsigned bits = __ballot_sync(0xffffffffu, sup);
+                    if (ln == 0) m.rows[b * nh + hw] = bits;
                 }
-                if (ln == 0) m.rows[b * nh + hw] = bits;
             }
         }
 #else
@@ -240,6 +247,7 @@ DD_HD void dd_nms_frame(const G& g, const double* boxes, const float* scores, in
                     ++nk;
                     if (g.lane >= (i >> 5) && g.lane < nh) remv_reg |= m.rows[b * nh + g.lane];
                 }
+                if (g.lane < nh) m.remv[g.lane] = remv_reg;                // the next batch's row builders skip removed candidates
             } else
 #endif
             {

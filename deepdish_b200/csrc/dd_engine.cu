@@ -1,0 +1,394 @@
+// dd_engine.cu -- native host-side executor of the batched tick: per stream chunk ONE captured CUDA graph per tick
+// (prep -> gate -> gallery -> match -> apply -> count-line -> count reduce), launched on the chunk's own stream, plus
+// the event plumbing between chunks, the count summation on an auxiliary stream, the double-buffered upload of ragged
+// host batches on per-chunk copy streams and the asynchronous polling of the page-pool counters.
+//
+// Why native: the reference's per-frame driver loop is Python (deepdish.py:1245-1262); batched over 1024 streams the
+// tick is 0.5 ms of device time, and 14 launches + a dozen event / stream calls per tick through ctypes cost as much on
+// the host.  Here a tick costs the host one C call: per chunk a 1-CTA argument kernel + one cudaGraphLaunch.
+// A graph's kernel parameters are frozen at capture, so the per-tick inputs (detection arrays, the ragged blob and
+// its section offsets, the output slots) travel through the blob's tick_args words (DDTickArgs, dd_view.h).
+#include <cuda_runtime.h>
+#include <new>
+#include <vector>
+#include "dd_view.h"
+
+// dd_tracker.cu
+int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, const double* line,
+                    int line_per_stream, cudaStream_t st);
+int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg);
+size_t dd_tick_args_offset(const dd_tracker_config* cfg);
+
+#define DD_CU(x) do { if ((x) != cudaSuccess) return DD_ERR_CUDA; } while (0)
+
+#include <chrono>
+extern "C" int dd_engine_destroy(void* engine);
+
+__global__ void k_set_args(DDTickArgs* dst, const DDTickArgs a) {
+    if (threadIdx.x == 0) *dst = a;
+}
+
+// total[e] = sum over chunks of partial[c][e]
+__global__ void k_sum_partials(const long long* __restrict__ partial, int n_chunks, int n, long long* __restrict__ total) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    long long acc = 0;
+    for (int c = 0; c < n_chunks; ++c) acc += partial[(size_t)c * n + e];
+    total[e] = acc;
+}
+
+namespace {
+
+struct Chunk {
+    void* state = nullptr;
+    dd_tracker_config cfg;
+    int lo = 0, n = 0;
+    cudaStream_t st = nullptr, copy_st = nullptr;
+    cudaEvent_t done = nullptr, copied = nullptr, unpacked[2] = {nullptr, nullptr};
+    bool unpacked_valid[2] = {false, false};
+    cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [ragged][reduce]
+    // host path (dd_engine_bind_host): double-buffered device blob + the small padded arrays the tick fills
+    unsigned char* dev_blob[2] = {nullptr, nullptr};
+    size_t blob_cap = 0;
+    double* s_tlwh = nullptr;
+    float* s_conf = nullptr;
+    int *s_label = nullptr, *s_count = nullptr;
+    // pool polling: two pinned copies of pool_ctl[0..3], alternating
+    int* poll_host = nullptr;
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    long long poll_tick[2] = {-1, -1};
+    int poll_turn = 0;
+};
+
+struct Engine {
+    int P = 0, D = 0, C4 = 0, line_per_stream = 0, poll_every = 0;
+    std::vector<Chunk> ch;
+    cudaStream_t aux = nullptr, cap = nullptr;
+    cudaEvent_t fork_ev = nullptr, sum_done[2] = {nullptr, nullptr};
+    bool sum_valid[2] = {false, false};
+    int last_sum = -1;
+    const double* line = nullptr;
+    long long *partial = nullptr, *total = nullptr;
+    int* ids = nullptr;
+    long long tick = 0;
+    long long launches = 0;          // kernels launched through graphs + argument kernels (bench.py's gpu_launches)
+    double blocked_ms = 0.0;         // host time spent waiting on the run-ahead throttle (pool polls)
+};
+
+// cudaEventSynchronize that accounts the time the host was blocked
+cudaError_t blocked_sync(Engine& E, cudaEvent_t ev) {
+    if (cudaEventQuery(ev) == cudaSuccess) return cudaSuccess;
+    cudaGetLastError();
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaEventSynchronize(ev);
+    E.blocked_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return e;
+}
+
+void drop_graphs(Chunk& c) {
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+            if (c.graph[a][b]) { cudaGraphExecDestroy(c.graph[a][b]); c.graph[a][b] = nullptr; }
+}
+
+int ensure_graph(Engine& E, Chunk& c, int ragged, int reduce) {
+    if (c.graph[ragged][reduce]) return DD_OK;
+    int rc = dd_tick_prepare_host(c.state, &c.cfg);        // function attributes: outside the capture
+    if (rc != DD_OK) return rc;
+    const double* line = E.line + (E.line_per_stream ? (size_t)c.lo * 4 : 0);
+    DD_CU(cudaStreamBeginCapture(E.cap, cudaStreamCaptureModeRelaxed));
+    rc = dd_capture_tick(c.state, &c.cfg, ragged, reduce, line, E.line_per_stream, E.cap);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(E.cap, &g);
+    if (rc != DD_OK || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc != DD_OK ? rc : DD_ERR_CUDA;
+    }
+    cudaGraphExec_t x = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&x, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) return DD_ERR_CUDA;
+    c.graph[ragged][reduce] = x;
+    return DD_OK;
+}
+
+int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce, cudaStream_t st) {
+    const int rc = ensure_graph(E, c, ragged, reduce);
+    if (rc != DD_OK) return rc;
+    DDTickArgs* dst = (DDTickArgs*)((char*)c.state + dd_tick_args_offset(&c.cfg));
+    k_set_args<<<1, 32, 0, st>>>(dst, A);
+    DD_CU(cudaGetLastError());
+    DD_CU(cudaGraphLaunch(c.graph[ragged][reduce], st));
+    E.launches += 8 + (reduce ? 1 : 0);      // argument kernel + the graph's 7 (8) kernel nodes
+    if (E.poll_every > 0 && E.tick % E.poll_every == 0) {
+        // the slot written two polls ago is reused: its copy has long completed unless the host runs far ahead
+        const int k = c.poll_turn;
+        if (c.poll_tick[k] >= 0) DD_CU(blocked_sync(E, c.poll_ev[k]));
+        dd_tracker_layout L;
+        dd_layout_compute(&c.cfg, &L);
+        DD_CU(cudaMemcpyAsync(c.poll_host + 4 * k, (char*)c.state + L.pool_ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        DD_CU(cudaEventRecord(c.poll_ev[k], st));
+        c.poll_tick[k] = E.tick;
+        c.poll_turn ^= 1;
+    }
+    return DD_OK;
+}
+
+int sum_partials(Engine& E, int par, cudaStream_t cur) {
+    const long long* src = E.partial + (size_t)par * E.P * E.C4;
+    if (E.P == 1) {
+        k_sum_partials<<<(E.C4 + 127) / 128, 128, 0, cur>>>(src, 1, E.C4, E.total);
+        DD_CU(cudaGetLastError());
+        ++E.launches;
+        return DD_OK;
+    }
+    // on the auxiliary stream, NOT the caller's: the caller's stream must not wait for every chunk each tick, or the
+    // next tick's fork event would serialise the chunks tick by tick
+    for (auto& c : E.ch) DD_CU(cudaStreamWaitEvent(E.aux, c.done, 0));
+    k_sum_partials<<<(E.C4 + 127) / 128, 128, 0, E.aux>>>(src, E.P, E.C4, E.total);
+    DD_CU(cudaGetLastError());
+    DD_CU(cudaEventRecord(E.sum_done[par], E.aux));
+    ++E.launches;
+    E.sum_valid[par] = true;
+    E.last_sum = par;
+    return DD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracker_config* const* host_cfgs,
+                     const int32_t* host_first_stream, void* const* host_streams, void* aux_stream, const double* line,
+                     int32_t line_per_stream, int64_t* partial_counts, int64_t* total_counts, int32_t* det_track_id,
+                     int32_t poll_every, void** host_out_engine) {
+    if (n_chunks <= 0 || !host_states || !host_cfgs || !host_first_stream || !line || !partial_counts || !total_counts ||
+        !det_track_id || !host_out_engine)
+        return DD_ERR_INVALID;
+    if (n_chunks > 1 && (!host_streams || !aux_stream)) return DD_ERR_INVALID;
+    Engine* E = new (std::nothrow) Engine();
+    if (!E) return DD_ERR_INVALID;
+    E->P = n_chunks;
+    E->line = line;
+    E->line_per_stream = line_per_stream;
+    E->partial = (long long*)partial_counts;
+    E->total = (long long*)total_counts;
+    E->ids = det_track_id;
+    E->aux = (cudaStream_t)aux_stream;
+    E->poll_every = poll_every;
+    E->ch.resize(n_chunks);
+    bool ok = cudaStreamCreateWithFlags(&E->cap, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&E->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&E->sum_done[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&E->sum_done[1], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < n_chunks; ++i) {
+        Chunk& c = E->ch[i];
+        dd_tracker_layout L;
+        if (!host_states[i] || !host_cfgs[i] || dd_layout_compute(host_cfgs[i], &L) != DD_OK) { ok = false; break; }
+        c.state = host_states[i];
+        c.cfg = *host_cfgs[i];
+        c.lo = host_first_stream[i];
+        c.n = c.cfg.n_streams;
+        c.st = n_chunks > 1 ? (cudaStream_t)host_streams[i] : nullptr;
+        if (i == 0) { E->D = c.cfg.max_dets; E->C4 = c.cfg.n_labels * 4; }
+        ok = c.cfg.max_dets == E->D && c.cfg.n_labels * 4 == E->C4 &&
+             cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.copied, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.unpacked[0], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.unpacked[1], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.poll_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.poll_ev[1], cudaEventDisableTiming) == cudaSuccess &&
+             cudaHostAlloc((void**)&c.poll_host, 8 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        dd_engine_destroy(E);
+        *host_out_engine = nullptr;
+        return DD_ERR_CUDA;
+    }
+    *host_out_engine = E;
+    return DD_OK;
+}
+
+int dd_engine_destroy(void* engine) {
+    Engine* E = (Engine*)engine;
+    if (!E) return DD_ERR_INVALID;
+    for (auto& c : E->ch) {
+        drop_graphs(c);
+        if (c.copy_st) cudaStreamDestroy(c.copy_st);
+        for (cudaEvent_t e : {c.done, c.copied, c.unpacked[0], c.unpacked[1], c.poll_ev[0], c.poll_ev[1]})
+            if (e) cudaEventDestroy(e);
+        if (c.poll_host) cudaFreeHost(c.poll_host);
+    }
+    for (cudaEvent_t e : {E->fork_ev, E->sum_done[0], E->sum_done[1]})
+        if (e) cudaEventDestroy(e);
+    if (E->cap) cudaStreamDestroy(E->cap);
+    delete E;
+    return DD_OK;
+}
+
+int dd_engine_rebind(void* engine, int32_t chunk, void* state, const dd_tracker_config* host_cfg) {
+    Engine* E = (Engine*)engine;
+    if (!E || chunk < 0 || chunk >= E->P || !state || !host_cfg) return DD_ERR_INVALID;
+    Chunk& c = E->ch[chunk];
+    drop_graphs(c);                  // the DDView frozen in the captured kernels is stale
+    c.state = state;
+    c.cfg = *host_cfg;
+    c.poll_tick[0] = c.poll_tick[1] = -1;
+    return DD_OK;
+}
+
+int dd_engine_bind_host(void* engine, int32_t chunk, void* dev_blob0, void* dev_blob1, uint64_t blob_capacity,
+                        double* det_tlwh, float* det_conf, int32_t* det_label, int32_t* det_count) {
+    Engine* E = (Engine*)engine;
+    if (!E || chunk < 0 || chunk >= E->P || !dev_blob0 || !dev_blob1 || !det_tlwh || !det_conf || !det_label || !det_count)
+        return DD_ERR_INVALID;
+    if (((uintptr_t)dev_blob0 & 15) || ((uintptr_t)dev_blob1 & 15)) return DD_ERR_INVALID;
+    Chunk& c = E->ch[chunk];
+    c.dev_blob[0] = (unsigned char*)dev_blob0;
+    c.dev_blob[1] = (unsigned char*)dev_blob1;
+    c.blob_cap = blob_capacity;
+    c.s_tlwh = det_tlwh; c.s_conf = det_conf; c.s_label = det_label; c.s_count = det_count;
+    if (!c.copy_st) DD_CU(cudaStreamCreateWithFlags(&c.copy_st, cudaStreamNonBlocking));
+    return DD_OK;
+}
+
+int dd_engine_step(void* engine, const double* det_tlwh, const float* det_conf, const int32_t* det_label,
+                   const float* det_feat, const int32_t* det_count, int32_t reduce, void* caller_stream) {
+    Engine* E = (Engine*)engine;
+    if (!E || !det_tlwh || !det_conf || !det_label || !det_feat || !det_count) return DD_ERR_INVALID;
+    cudaStream_t cur = (cudaStream_t)caller_stream;
+    const int par = (int)(E->tick & 1);
+    const bool multi = E->P > 1;
+    reduce = reduce ? 1 : 0;
+    if (multi) {
+        DD_CU(cudaEventRecord(E->fork_ev, cur));
+        for (auto& c : E->ch) DD_CU(cudaStreamWaitEvent(c.st, E->fork_ev, 0));
+        if (reduce && E->sum_valid[par])            // partial_counts[par] of tick - 2 must have been summed
+            for (auto& c : E->ch) DD_CU(cudaStreamWaitEvent(c.st, E->sum_done[par], 0));
+    }
+    for (int i = 0; i < E->P; ++i) {
+        Chunk& c = E->ch[i];
+        const size_t o = (size_t)c.lo * E->D;
+        DDTickArgs A;
+        A.det_tlwh = det_tlwh + o * 4; A.det_conf = det_conf + o; A.det_label = det_label + o;
+        A.det_feat = det_feat + o * DD_FEAT_DIM; A.det_count = det_count + c.lo;
+        A.out_ids = E->ids + o;
+        A.out_counts = reduce ? E->partial + ((size_t)par * E->P + i) * E->C4 : nullptr;
+        A.blob = nullptr;
+        A.off_tlwh = A.off_conf = A.off_label = A.off_feat = 0;
+        A.indirect = 0;
+        cudaStream_t st = multi ? c.st : cur;
+        const int rc = launch_tick(*E, c, A, 0, reduce, st);
+        if (rc != DD_OK) return rc;
+        if (multi) DD_CU(cudaEventRecord(c.done, st));
+    }
+    if (reduce) {
+        const int rc = sum_partials(*E, par, cur);
+        if (rc != DD_OK) return rc;
+    }
+    ++E->tick;
+    return DD_OK;
+}
+
+int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint64_t* host_blob_bytes,
+                        const int64_t* host_offsets4, int32_t* host_out_ids, void* caller_stream) {
+    Engine* E = (Engine*)engine;
+    if (!E || !host_blobs || !host_blob_bytes || !host_offsets4) return DD_ERR_INVALID;
+    cudaStream_t cur = (cudaStream_t)caller_stream;
+    const int par = (int)(E->tick & 1);
+    const bool multi = E->P > 1;
+    for (int i = 0; i < E->P; ++i) {
+        const int64_t* of = host_offsets4 + 4 * i;
+        if (!host_blobs[i] || !E->ch[i].dev_blob[0] || host_blob_bytes[i] > E->ch[i].blob_cap) return DD_ERR_INVALID;
+        if ((of[0] & 7) || (of[1] & 3) || (of[2] & 3) || (of[3] & 15)) return DD_ERR_INVALID;
+    }
+    if (multi && E->sum_valid[par])
+        for (auto& c : E->ch) DD_CU(cudaStreamWaitEvent(c.st, E->sum_done[par], 0));
+    for (int i = 0; i < E->P; ++i) {
+        Chunk& c = E->ch[i];
+        cudaStream_t st = multi ? c.st : cur;
+        // upload on the chunk's copy stream into the buffer the tick before last has finished reading
+        if (c.unpacked_valid[par]) DD_CU(cudaStreamWaitEvent(c.copy_st, c.unpacked[par], 0));
+        DD_CU(cudaMemcpyAsync(c.dev_blob[par], host_blobs[i], host_blob_bytes[i], cudaMemcpyHostToDevice, c.copy_st));
+        DD_CU(cudaEventRecord(c.copied, c.copy_st));
+        DD_CU(cudaStreamWaitEvent(st, c.copied, 0));
+        const size_t o = (size_t)c.lo * E->D;
+        const int64_t* of = host_offsets4 + 4 * i;
+        DDTickArgs A;
+        A.det_tlwh = c.s_tlwh; A.det_conf = c.s_conf; A.det_label = c.s_label; A.det_feat = nullptr; A.det_count = c.s_count;
+        A.out_ids = E->ids + o;
+        A.out_counts = E->partial + ((size_t)par * E->P + i) * E->C4;
+        A.blob = c.dev_blob[par];
+        A.off_tlwh = of[0]; A.off_conf = of[1]; A.off_label = of[2]; A.off_feat = of[3];
+        A.indirect = 0;
+        const int rc = launch_tick(*E, c, A, 1, 1, st);
+        if (rc != DD_OK) return rc;
+        // the tick's first kernel has read the blob once the whole graph is done; later kernels read the small arrays
+        DD_CU(cudaEventRecord(c.unpacked[par], st));
+        c.unpacked_valid[par] = true;
+        if (host_out_ids)
+            DD_CU(cudaMemcpyAsync(host_out_ids + o, E->ids + o, (size_t)c.n * E->D * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (multi) DD_CU(cudaEventRecord(c.done, st));
+    }
+    const int rc = sum_partials(*E, par, cur);
+    if (rc != DD_OK) return rc;
+    ++E->tick;
+    return DD_OK;
+}
+
+int dd_engine_join(void* engine, void* caller_stream) {
+    Engine* E = (Engine*)engine;
+    if (!E) return DD_ERR_INVALID;
+    if (E->P == 1) return DD_OK;
+    cudaStream_t cur = (cudaStream_t)caller_stream;
+    for (auto& c : E->ch) {
+        DD_CU(cudaEventRecord(c.done, c.st));
+        DD_CU(cudaStreamWaitEvent(cur, c.done, 0));
+    }
+    if (E->last_sum >= 0) DD_CU(cudaStreamWaitEvent(cur, E->sum_done[E->last_sum], 0));
+    return DD_OK;
+}
+
+int dd_engine_wait_counts(void* engine, void* caller_stream) {
+    Engine* E = (Engine*)engine;
+    if (!E) return DD_ERR_INVALID;
+    if (E->P > 1 && E->last_sum >= 0) DD_CU(cudaStreamWaitEvent((cudaStream_t)caller_stream, E->sum_done[E->last_sum], 0));
+    return DD_OK;
+}
+
+int dd_engine_pool_latest(void* engine, int32_t chunk, int32_t max_age_ticks, int32_t* host_out4, int64_t* host_out_tick) {
+    Engine* E = (Engine*)engine;
+    if (!E || chunk < 0 || chunk >= E->P || !host_out4 || !host_out_tick) return DD_ERR_INVALID;
+    Chunk& c = E->ch[chunk];
+    *host_out_tick = -1;
+    const int newest = c.poll_turn ^ 1, older = c.poll_turn;          // poll_turn = the slot the NEXT poll writes
+    int use = -1;
+    if (c.poll_tick[newest] >= 0) {
+        const cudaError_t q = cudaEventQuery(c.poll_ev[newest]);
+        if (q == cudaSuccess) use = newest;
+        else if (q != cudaErrorNotReady) return DD_ERR_CUDA;
+        else if (E->tick - c.poll_tick[newest] >= max_age_ticks) {   // the host is too far ahead: wait for it
+            DD_CU(blocked_sync(*E, c.poll_ev[newest]));
+            use = newest;
+        }
+    }
+    if (use < 0 && c.poll_tick[older] >= 0 && cudaEventQuery(c.poll_ev[older]) == cudaSuccess) use = older;
+    cudaGetLastError();
+    if (use < 0) return DD_OK;
+    for (int k = 0; k < 4; ++k) host_out4[k] = c.poll_host[4 * use + k];
+    *host_out_tick = c.poll_tick[use];
+    return DD_OK;
+}
+
+int dd_engine_stats(void* engine, int64_t* host_out_ticks, int64_t* host_out_launches, double* host_out_blocked_ms) {
+    Engine* E = (Engine*)engine;
+    if (!E) return DD_ERR_INVALID;
+    if (host_out_ticks) *host_out_ticks = E->tick;
+    if (host_out_launches) *host_out_launches = E->launches;
+    if (host_out_blocked_ms) *host_out_blocked_ms = E->blocked_ms;
+    return DD_OK;
+}
+
+}  // extern "C"

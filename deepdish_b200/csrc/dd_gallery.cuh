@@ -27,7 +27,8 @@
 #define DD_H_BLOCK_ROWS 256
 
 __global__ void __launch_bounds__(DD_WARPS * 32, 7)
-k_cosine(const DDView V, const int* __restrict__ det_count) {
+k_cosine(const DDView V, const DDTickArgs A) {
+    const int* __restrict__ det_count = DD_ARG(det_count);
     const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
     if (w >= V.S * V.T) return;
     WarpG g;
@@ -235,7 +236,8 @@ __device__ __forceinline__ void dd_cosine_track_half(const WarpG& g, const DDVie
 }
 
 __global__ void __launch_bounds__(DD_WARPS * 32, 4)
-k_cosine_h(const DDView V, const int* __restrict__ det_count) {
+k_cosine_h(const DDView V, const DDTickArgs A) {
+    const int* __restrict__ det_count = DD_ARG(det_count);
     extern __shared__ __align__(16) char smem[];
     WarpG g;
     const int rows_blk = dd_half_rows_blk(V.B);

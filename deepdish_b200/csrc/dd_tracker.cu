@@ -18,12 +18,17 @@
     } while (0)
 
 // Small per-item kernels: DD_SUB lanes per item, 32 / DD_SUB items per warp (SubG).
+#ifndef DD_APPLY_MIN_CTAS
+#define DD_APPLY_MIN_CTAS 1
+#endif
 #define DD_SUB 8
 #define DD_ITEMS_PER_CTA (DD_WARPS * 32 / DD_SUB)
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
-k_prep(const DDView V, const double* __restrict__ det_tlwh, const float* __restrict__ det_feat,
-       const int* __restrict__ det_count) {
+k_prep(const DDView V, const DDTickArgs A) {
+    const double* __restrict__ det_tlwh = DD_ARG(det_tlwh);
+    const float* __restrict__ det_feat = DD_ARG(det_feat);
+    const int* __restrict__ det_count = DD_ARG(det_count);
     const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (blockIdx.x == 0 && threadIdx.x == 0) {      // new tick: empty work list, claim cursor at 0
         V.work_ctl[0] = 0;
@@ -57,7 +62,12 @@ struct DDRagged {
 };
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
-k_prep_ragged(const DDView V, const DDRagged R) {
+k_prep_ragged(const DDView V, const DDTickArgs A) {
+    DDRagged R;
+    R.blob = DD_ARG(blob);
+    R.off_tlwh = DD_ARG(off_tlwh); R.off_conf = DD_ARG(off_conf); R.off_label = DD_ARG(off_label); R.off_feat = DD_ARG(off_feat);
+    R.det_tlwh = (double*)DD_ARG(det_tlwh); R.det_conf = (float*)DD_ARG(det_conf);
+    R.det_label = (int*)DD_ARG(det_label); R.det_count = (int*)DD_ARG(det_count);
     const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (blockIdx.x == 0 && threadIdx.x == 0) {      // new tick: empty work list, claim cursor at 0
         V.work_ctl[0] = 0;
@@ -82,7 +92,8 @@ k_prep_ragged(const DDView V, const DDRagged R) {
 
 template <bool PREDICT>
 __global__ void __launch_bounds__(DD_WARPS * 32)
-k_gate(const DDView V, const int* __restrict__ det_count) {
+k_gate(const DDView V, const DDTickArgs A) {
+    const int* __restrict__ det_count = DD_ARG(det_count);
     // gate, then append the track indices that have something to stream to the work list of the gallery
     // kernel: one atomicAdd per CTA (16 track indices), entries of a CTA stay in ascending order.
     __shared__ int s_has[DD_ITEMS_PER_CTA];
@@ -144,26 +155,26 @@ static int dd_sm_count() {
 }
 
 __global__ void __launch_bounds__(32)
-k_match(const DDView V, const double* __restrict__ det_tlwh, const int* __restrict__ det_count,
-        int* out_det_track_id) {
+k_match(const DDView V, const DDTickArgs A) {
     extern __shared__ __align__(128) char smem[];
     WarpG g;
-    dd_match_stream(g, V, blockIdx.x, det_tlwh, det_count, out_det_track_id, smem);
+    dd_match_stream(g, V, blockIdx.x, DD_ARG(det_tlwh), DD_ARG(det_count), DD_ARG(out_ids), smem);
 }
 
 // Crowded scenes (C4: ~260 tracks x ~180 detections per stream): the same matching body run by 4 (or 8) warps of
 // one CTA per stream, so every column scan, list compaction and staging loop is 4x (8x) wider.
 template <int NW>
 __global__ void __launch_bounds__(NW * 32)
-k_match_cta(const DDView V, const double* __restrict__ det_tlwh, const int* __restrict__ det_count,
-            int* out_det_track_id) {
+k_match_cta(const DDView V, const DDTickArgs A) {
     extern __shared__ __align__(128) char smem[];
     CtaG<NW> g(smem);
-    dd_match_stream(g, V, blockIdx.x, det_tlwh, det_count, out_det_track_id, smem + 256);
+    dd_match_stream(g, V, blockIdx.x, DD_ARG(det_tlwh), DD_ARG(det_count), DD_ARG(out_ids), smem + 256);
 }
 
-__global__ void __launch_bounds__(DD_WARPS * 32)
-k_apply(const DDView V, const float* __restrict__ det_conf, const int* __restrict__ det_label) {
+__global__ void __launch_bounds__(DD_WARPS * 32, DD_APPLY_MIN_CTAS)
+k_apply(const DDView V, const DDTickArgs A) {
+    const float* __restrict__ det_conf = DD_ARG(det_conf);
+    const int* __restrict__ det_label = DD_ARG(det_label);
     __shared__ double scratch[DD_ITEMS_PER_CTA][64];
     const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
     if (w >= V.S * V.D) return;
@@ -181,7 +192,9 @@ k_countline(const DDView V, const double* __restrict__ line, int line_per_stream
 
 // counts [S, C*4] -> out [C*4]; one CTA per output element, tree reduction over streams.
 __global__ void __launch_bounds__(256)
-k_count_reduce(const long long* __restrict__ counts, int S, int n, long long* __restrict__ out) {
+k_count_reduce(const long long* __restrict__ counts, int S, int n, long long* __restrict__ out,
+               const DDTickArgs* __restrict__ ind) {
+    if (ind) out = ind->out_counts;                  // captured tick: the output alternates between ticks
     __shared__ long long sh[256];
     const int e = blockIdx.x;
     long long acc = 0;
@@ -289,116 +302,160 @@ static inline int warps_to_blocks(long long n_warps) { return (int)((n_warps + D
 static inline int items_to_blocks(long long n) { return (int)((n + DD_ITEMS_PER_CTA - 1) / DD_ITEMS_PER_CTA); }
 
 // ---- the launches of one update (shared by every entry point) --------------------------------------------
-struct DDTickIn {
-    const double* det_tlwh;
-    const float* det_conf;
-    const int* det_label;
-    const float* det_feat;       // NULL when ragged != NULL
-    const int* det_count;
-    int* out_det_track_id;
-    const DDRagged* ragged;
-};
-
-static int dd_launch_gallery(const DDView& V, const dd_tracker_config* cfg, const int* det_count, cudaStream_t st) {
-    const int impl = cfg->gallery_impl;
-    const int per_sm = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 4;
-    if (impl == 1) {
-        k_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, det_count);
-    } else if (impl == 0) {
-        int triples = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 7;
+// Function attributes (opt-in shared memory) are set here, outside any stream capture.
+static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* triples_out, int* stages_out, int* mw_out) {
+    const size_t smem = dd_match_smem_bytes(V.T, V.D, V.tab_cap);
+    if (smem > 227 * 1024) return DD_ERR_INVALID;
+    int mw = cfg->match_warps;
+    if (mw != 1 && mw != 4 && mw != 8) mw = (V.T > 160 || V.D > 160) ? 4 : 1;
+    if (mw > 1 && smem + 256 > 227 * 1024) mw = 1;
+    static size_t match_set = 0, cta_set = 0, gsm_set = 0, hsm_set = 0;     // the attributes only ever grow
+    if (mw == 1 && smem > 48 * 1024 && smem > match_set) {
+        if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DD_ERR_CUDA;
+        match_set = smem;
+    }
+    if (mw > 1 && smem + 256 > 48 * 1024 && smem + 256 > cta_set) {
+        if (cudaFuncSetAttribute(k_match_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 256)) != cudaSuccess ||
+            cudaFuncSetAttribute(k_match_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 256)) != cudaSuccess)
+            return DD_ERR_CUDA;
+        cta_set = smem + 256;
+    }
+    int triples = 0, stages = 0;
+    if (cfg->gallery_impl == 0) {
+        triples = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 7;
         if (triples > 7) triples = 7;
-        int stages = cfg->gallery_stages > 0 ? cfg->gallery_stages : 4;
+        stages = cfg->gallery_stages > 0 ? cfg->gallery_stages : 4;
         if (stages > 16) stages = 16;
         const size_t per = dd_gs_triple_bytes(stages);
         while (triples > 1 && per * triples > 226 * 1024) --triples;
         const size_t gsm = per * triples;
         if (gsm > 227 * 1024) return DD_ERR_INVALID;
-        static size_t gsm_set = 0;                       // the attribute only ever grows: set it when a larger size is asked for
         if (gsm > gsm_set) {
             if (cudaFuncSetAttribute(k_gallery_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess)
                 return DD_ERR_CUDA;
             gsm_set = gsm;
         }
-        k_gallery_stream<<<dd_sm_count(), triples * 96, gsm, st>>>(V, stages);
+    } else if (cfg->gallery_impl == 2) {
+        const size_t hsm = dd_half_smem_per_warp(V.B) * DD_WARPS;
+        if (hsm > 48 * 1024 && hsm > hsm_set) {
+            if (cudaFuncSetAttribute(k_cosine_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm) != cudaSuccess)
+                return DD_ERR_CUDA;
+            hsm_set = hsm;
+        }
+    }
+    *triples_out = triples; *stages_out = stages; *mw_out = mw;
+    return DD_OK;
+}
+
+static int dd_launch_gallery(const DDView& V, const dd_tracker_config* cfg, const DDTickArgs& A, int triples, int stages,
+                             cudaStream_t st) {
+    const int impl = cfg->gallery_impl;
+    if (impl == 1) {
+        k_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, A);
+    } else if (impl == 0) {
+        k_gallery_stream<<<dd_sm_count(), triples * 96, dd_gs_triple_bytes(stages) * triples, st>>>(V, stages);
     } else {
+        const int per_sm = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 4;
         long long grid = (long long)dd_sm_count() * per_sm;
         const long long need = warps_to_blocks((long long)V.S * V.T);
         if (grid > need) grid = need;
-        const size_t hsm = dd_half_smem_per_warp(V.B) * DD_WARPS;
-        if (hsm > 48 * 1024 &&
-            cudaFuncSetAttribute(k_cosine_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm) != cudaSuccess)
-            return DD_ERR_CUDA;
-        k_cosine_h<<<(unsigned)grid, DD_WARPS * 32, hsm, st>>>(V, det_count);
+        k_cosine_h<<<(unsigned)grid, DD_WARPS * 32, dd_half_smem_per_warp(V.B) * DD_WARPS, st>>>(V, A);
     }
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
 
-static int dd_update_impl(void* state, const dd_tracker_config* cfg, const DDTickIn& in, cudaStream_t st,
+// `prepared`: dd_tick_prepare already ran for this (V, cfg) -- the captured path calls it before the capture begins.
+static int dd_update_impl(void* state, const dd_tracker_config* cfg, const DDTickArgs& A, cudaStream_t st,
                           cudaEvent_t* ev, bool with_predict) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
-    if (!in.det_tlwh || !in.det_conf || !in.det_label || (!in.det_feat && !in.ragged) || !in.det_count) return DD_ERR_INVALID;
+    if (!A.indirect && (!A.det_tlwh || !A.det_conf || !A.det_label || (!A.det_feat && !A.blob) || !A.det_count))
+        return DD_ERR_INVALID;
+    int triples = 0, stages = 0, mw = 1;
+    rc = dd_tick_prepare(V, cfg, &triples, &stages, &mw);
+    if (rc != DD_OK) return rc;
     const size_t smem = dd_match_smem_bytes(V.T, V.D, V.tab_cap);
-    if (smem > 227 * 1024) return DD_ERR_INVALID;
+    const bool ragged = A.blob != nullptr;       // (captured tick: a non-NULL marker, the kernels read V.targs->blob)
     if (ev) cudaEventRecord(ev[0], st);
-    if (in.ragged)
-        k_prep_ragged<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, *in.ragged);
+    if (ragged)
+        k_prep_ragged<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, A);
     else
-        k_prep<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, in.det_tlwh, in.det_feat, in.det_count);
+        k_prep<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, A);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
     if (with_predict)
-        k_gate<true><<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, in.det_count);
+        k_gate<true><<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, A);
     else
-        k_gate<false><<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, in.det_count);
+        k_gate<false><<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, A);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[2], st);
-    rc = dd_launch_gallery(V, cfg, in.det_count, st);
+    rc = dd_launch_gallery(V, cfg, A, triples, stages, st);
     if (rc != DD_OK) return rc;
     if (ev) cudaEventRecord(ev[3], st);
-    int mw = cfg->match_warps;
-    if (mw != 1 && mw != 4 && mw != 8) mw = (V.T > 160 || V.D > 160) ? 4 : 1;
-    if (mw > 1 && smem + 256 > 227 * 1024) mw = 1;
-    if (mw == 1) {
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return DD_ERR_CUDA;
-        k_match<<<V.S, 32, smem, st>>>(V, in.det_tlwh, in.det_count, in.out_det_track_id);
-    } else {
-        const size_t wsm = smem + 256;
-        if (wsm > 48 * 1024 &&
-            (cudaFuncSetAttribute(k_match_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm) != cudaSuccess ||
-             cudaFuncSetAttribute(k_match_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm) != cudaSuccess))
-            return DD_ERR_CUDA;
-        if (mw == 8)
-            k_match_cta<8><<<V.S, 8 * 32, wsm, st>>>(V, in.det_tlwh, in.det_count, in.out_det_track_id);
-        else
-            k_match_cta<4><<<V.S, 4 * 32, wsm, st>>>(V, in.det_tlwh, in.det_count, in.out_det_track_id);
-    }
+    if (mw == 1)
+        k_match<<<V.S, 32, smem, st>>>(V, A);
+    else if (mw == 8)
+        k_match_cta<8><<<V.S, 8 * 32, smem + 256, st>>>(V, A);
+    else
+        k_match_cta<4><<<V.S, 4 * 32, smem + 256, st>>>(V, A);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[4], st);
-    k_apply<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, in.det_conf, in.det_label);
+    k_apply<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, A);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[5], st);
     return DD_OK;
 }
 
+// out_counts: by value, or (captured tick) `indirect` = read args->out_counts from the blob
 static int dd_tick_tail(void* state, const dd_tracker_config* cfg, const double* line, int line_per_stream,
-                        int64_t* out_counts, cudaStream_t st, cudaEvent_t* ev = nullptr) {
+                        int64_t* out_counts, bool indirect, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
     k_countline<<<warps_to_blocks(V.S), DD_WARPS * 32, 0, st>>>(V, line, line_per_stream);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[6], st);
-    if (out_counts) {
-        k_count_reduce<<<V.C * 4, 256, 0, st>>>((const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts);
+    if (out_counts || indirect) {
+        k_count_reduce<<<V.C * 4, 256, 0, st>>>((const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts,
+                                                indirect ? V.targs : nullptr);
         DD_CHECK_LAUNCH();
     }
     if (ev) cudaEventRecord(ev[7], st);
     return DD_OK;
+}
+
+static DDTickArgs dd_args_padded(const double* det_tlwh, const float* det_conf, const int* det_label, const float* det_feat,
+                                 const int* det_count, int* out_ids) {
+    DDTickArgs A;
+    A.det_tlwh = det_tlwh; A.det_conf = det_conf; A.det_label = det_label; A.det_feat = det_feat; A.det_count = det_count;
+    A.out_ids = out_ids; A.out_counts = nullptr; A.blob = nullptr;
+    A.off_tlwh = A.off_conf = A.off_label = A.off_feat = 0;
+    A.indirect = 0;
+    return A;
+}
+
+// One captured tick (dd_engine.cu): every per-tick input comes from the blob's tick_args words.
+int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, const double* line,
+                    int line_per_stream, cudaStream_t st) {
+    DDTickArgs A = dd_args_padded(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    A.indirect = 1;
+    A.blob = ragged ? (const unsigned char*)(uintptr_t)16 : nullptr;      // marker only: the kernels read V.targs->blob
+    const int rc = dd_update_impl(state, cfg, A, st, nullptr, true);
+    if (rc != DD_OK) return rc;
+    return dd_tick_tail(state, cfg, line, line_per_stream, nullptr, reduce != 0, st);
+}
+int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg) {
+    DDView V;
+    int rc = dd_make_view(state, cfg, &V);
+    if (rc != DD_OK) return rc;
+    int a, b, c;
+    return dd_tick_prepare(V, cfg, &a, &b, &c);
+}
+size_t dd_tick_args_offset(const dd_tracker_config* cfg) {
+    dd_tracker_layout L;
+    return dd_layout_compute(cfg, &L) == DD_OK ? (size_t)L.tick_args : 0;
 }
 
 extern "C" {
@@ -473,7 +530,7 @@ int dd_tracker_predict(void* state, const dd_tracker_config* cfg, void* stream) 
 int dd_tracker_update(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
                       const float* det_conf, const int32_t* det_label, const float* det_feat,
                       const int32_t* det_count, int32_t* out_det_track_id, void* stream) {
-    const DDTickIn in = {det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, nullptr};
+    const DDTickArgs in = dd_args_padded(det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id);
     return dd_update_impl(state, cfg, in, (cudaStream_t)stream, nullptr, false);
 }
 
@@ -484,7 +541,7 @@ int dd_tracker_update_profiled(void* state, const dd_tracker_config* cfg, const 
     if (!host_events6) return DD_ERR_INVALID;
     cudaEvent_t ev[6];
     for (int i = 0; i < 6; ++i) ev[i] = (cudaEvent_t)host_events6[i];
-    const DDTickIn in = {det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, nullptr};
+    const DDTickArgs in = dd_args_padded(det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id);
     return dd_update_impl(state, cfg, in, (cudaStream_t)stream, ev, false);
 }
 
@@ -531,7 +588,7 @@ int dd_tracker_pool_poll(void* state, const dd_tracker_config* cfg, int32_t* hos
 int dd_tracker_countline(void* state, const dd_tracker_config* cfg, const double* line,
                          int line_per_stream, void* stream) {
     if (!line) return DD_ERR_INVALID;
-    return dd_tick_tail(state, cfg, line, line_per_stream, nullptr, (cudaStream_t)stream);
+    return dd_tick_tail(state, cfg, line, line_per_stream, nullptr, false, (cudaStream_t)stream);
 }
 
 int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
@@ -539,10 +596,10 @@ int dd_tracker_tick(void* state, const dd_tracker_config* cfg, const double* det
                     const int32_t* det_count, int32_t* out_det_track_id, const double* line,
                     int line_per_stream, int64_t* out_counts, void* stream) {
     if (!line) return DD_ERR_INVALID;
-    const DDTickIn in = {det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, nullptr};
+    const DDTickArgs in = dd_args_padded(det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id);
     const int rc = dd_update_impl(state, cfg, in, (cudaStream_t)stream, nullptr, true);
     if (rc != DD_OK) return rc;
-    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, (cudaStream_t)stream);
+    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, false, (cudaStream_t)stream);
 }
 
 int dd_tracker_tick_profiled(void* state, const dd_tracker_config* cfg, const double* det_tlwh,
@@ -552,10 +609,10 @@ int dd_tracker_tick_profiled(void* state, const dd_tracker_config* cfg, const do
     if (!line || !host_events8) return DD_ERR_INVALID;
     cudaEvent_t ev[8];
     for (int i = 0; i < 8; ++i) ev[i] = (cudaEvent_t)host_events8[i];
-    const DDTickIn in = {det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id, nullptr};
+    const DDTickArgs in = dd_args_padded(det_tlwh, det_conf, det_label, det_feat, det_count, out_det_track_id);
     const int rc = dd_update_impl(state, cfg, in, (cudaStream_t)stream, ev, true);
     if (rc != DD_OK) return rc;
-    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, (cudaStream_t)stream, ev);
+    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, false, (cudaStream_t)stream, ev);
 }
 
 int dd_tracker_tick_ragged(void* state, const dd_tracker_config* cfg, const void* blob, int64_t off_tlwh,
@@ -564,14 +621,12 @@ int dd_tracker_tick_ragged(void* state, const dd_tracker_config* cfg, const void
                            int line_per_stream, int64_t* out_counts, void* stream) {
     if (!line || !blob) return DD_ERR_INVALID;
     if ((off_tlwh & 7) || (off_conf & 3) || (off_label & 3) || (off_feat & 15) || ((uintptr_t)blob & 15)) return DD_ERR_INVALID;
-    DDRagged R;
-    R.blob = (const unsigned char*)blob;
-    R.off_tlwh = off_tlwh; R.off_conf = off_conf; R.off_label = off_label; R.off_feat = off_feat;
-    R.det_tlwh = det_tlwh; R.det_conf = det_conf; R.det_label = det_label; R.det_count = det_count;
-    const DDTickIn in = {det_tlwh, det_conf, det_label, nullptr, det_count, out_det_track_id, &R};
+    DDTickArgs in = dd_args_padded(det_tlwh, det_conf, det_label, nullptr, det_count, out_det_track_id);
+    in.blob = (const unsigned char*)blob;
+    in.off_tlwh = off_tlwh; in.off_conf = off_conf; in.off_label = off_label; in.off_feat = off_feat;
     const int rc = dd_update_impl(state, cfg, in, (cudaStream_t)stream, nullptr, true);
     if (rc != DD_OK) return rc;
-    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, (cudaStream_t)stream);
+    return dd_tick_tail(state, cfg, line, line_per_stream, out_counts, false, (cudaStream_t)stream);
 }
 
 int dd_unpack_detections(const void* blob, int32_t n_streams, int32_t max_dets, int64_t off_tlwh, int64_t off_conf,
@@ -592,7 +647,7 @@ int dd_tracker_count_reduce(void* state, const dd_tracker_config* cfg, int64_t* 
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
     if (!out_counts) return DD_ERR_INVALID;
-    k_count_reduce<<<V.C * 4, 256, 0, (cudaStream_t)stream>>>(V.counts, V.S, V.C * 4, (long long*)out_counts);
+    k_count_reduce<<<V.C * 4, 256, 0, (cudaStream_t)stream>>>(V.counts, V.S, V.C * 4, (long long*)out_counts, nullptr);
     DD_CHECK_LAUNCH();
     return DD_OK;
 }

@@ -5,6 +5,22 @@
 #include "dd_common.cuh"
 #include "dd_lsap.cuh"
 
+// Per-tick inputs of the tick kernels: by value in the kernel parameters or, for a captured tick (dd_engine.cu),
+// read from the blob's tick_args words (indirect != 0), so that one CUDA graph serves every tick.
+struct DDTickArgs {
+    const double* det_tlwh;      // f64 [S,D,4]   (ragged: written by the first kernel, read by the later ones)
+    const float* det_conf;       // f32 [S,D]
+    const int* det_label;        // i32 [S,D]
+    const float* det_feat;       // f32 [S,D,128] (NULL when blob != NULL)
+    const int* det_count;        // i32 [S]
+    int* out_ids;                // i32 [S,D] or NULL
+    long long* out_counts;       // i64 [C,4] or NULL
+    const unsigned char* blob;   // ragged batch (dd_unpack_detections' format) or NULL
+    long long off_tlwh, off_conf, off_label, off_feat;
+    int indirect;
+};
+#define DD_ARG(f) (A.indirect ? V.targs->f : A.f)
+
 struct DDView {
     int S, T, D, B, C, DW;           // streams, slots, det capacity, budget (0 = unbounded), labels, gate words / row
     int PT;                          // page-table entries per slot
@@ -30,6 +46,7 @@ struct DDView {
     int* cdesc;
     int *work, *work_ctl, *work_rec;
     unsigned short* det_feath;
+    const DDTickArgs* targs;         // the blob's tick_args words
     char* segf[DD_MAX_SEGS];         // f32 pages of each pool segment
     char* segh[DD_MAX_SEGS];         // half pages
     int label_rank[DD_MAX_LABELS];
@@ -108,6 +125,7 @@ static inline int dd_layout_compute(const dd_tracker_config* c, dd_tracker_layou
     DD_PUT(work_ctl, 4 * 64);
     DD_PUT(work_rec, 4 * S * T * 16);
     DD_PUT(det_feath, 2 * S * D * F);
+    DD_PUT(tick_args, 256);
 #undef DD_PUT
     L->total_bytes = off;
     return DD_OK;
@@ -148,6 +166,7 @@ static inline int dd_make_view(void* blob, const dd_tracker_config* c, DDView* v
     v->det_slot = (int*)(b + L.det_slot); v->det_kind = (int*)(b + L.det_kind);
     v->cdesc = (int*)(b + L.cdesc);
     v->det_feath = (unsigned short*)(b + L.det_feath);
+    v->targs = (const DDTickArgs*)(b + L.tick_args);
     v->work = (int*)(b + L.work); v->work_ctl = (int*)(b + L.work_ctl); v->work_rec = (int*)(b + L.work_rec);
     for (int i = 0; i < DD_MAX_SEGS; ++i) {
         const bool on = i < c->n_segs;

@@ -149,6 +149,7 @@ typedef struct dd_tracker_layout {
                                                   words 0 and 1, detections this tick, page ids 0..7 -- all the gallery
                                                   kernel's producer warps need to start the bulk copies of a track   */
     uint64_t det_feath;     /* f16 [S,Dmax,128]   half copy of det_featn                                     */
+    uint64_t tick_args;     /* 256 bytes          per-tick input pointers of a captured tick (written by dd_engine_step) */
 } dd_tracker_layout;
 
 /* Host-only arithmetic: fills `host_out`.  No CUDA call. */
@@ -258,6 +259,59 @@ int dd_tracker_count_reduce(void* state, const dd_tracker_config* host_cfg, int6
 /* OR of all per-stream DD_FLAG_* bits -> *host_flags.  Synchronises `stream`.  (The pool counters a caller polls
  * to grow the pool ahead of need are the blob's pool_ctl words.) */
 int dd_tracker_status(void* state, const dd_tracker_config* host_cfg, int32_t* host_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tick engine: the native executor of the batched per-frame loop (the batched form of the reference's driver loop,
+ * deepdish.py:1245-1262 -> Pipeline.process_results :1035-1114 around Tracker.predict / update).  One engine drives
+ * the n_chunks trackers ("stream chunks": contiguous blocks of streams with their own state blob and CUDA stream) of
+ * one GPU: per chunk and tick ONE captured CUDA graph (the 7-8 kernels of dd_tracker_tick) preceded by a 1-CTA kernel
+ * that writes the tick's input pointers into the blob's tick_args words; chunks overlap freely across tick
+ * boundaries; the chunks' partial counters are summed into total_counts on the auxiliary stream.
+ * The engine is a HOST object owning only CUDA events / graphs / one capture stream / per-chunk copy streams and 32
+ * bytes of pinned memory per chunk; all device buffers stay caller-owned.  Not thread-safe.
+ * ---------------------------------------------------------------------------------------------- */
+/*   host_states[i], host_cfgs[i]  blob and config of chunk i (configs are copied), host_first_stream[i] its first stream;
+ *   host_streams[i]               the chunk's CUDA stream, aux_stream the summation stream (both ignored -- everything runs
+ *                                 on the caller's stream -- when n_chunks == 1);
+ *   line f64 [4] or [S,4]; partial_counts i64 [2,n_chunks,C,4]; total_counts i64 [C,4]; det_track_id i32 [S,Dmax];
+ *   poll_every > 0: every that many ticks the chunk's pool counters are copied to pinned memory behind its tick
+ *   (dd_engine_pool_latest reads them without synchronising). */
+int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracker_config* const* host_cfgs,
+                     const int32_t* host_first_stream, void* const* host_streams, void* aux_stream, const double* line,
+                     int32_t line_per_stream, int64_t* partial_counts, int64_t* total_counts, int32_t* det_track_id,
+                     int32_t poll_every, void** host_out_engine);
+int dd_engine_destroy(void* engine);
+/* A chunk's blob was re-laid out or its pool grew (cfg->n_segs / page_cap / segment pointers changed): its captured
+ * graphs are dropped and re-captured at the next tick. */
+int dd_engine_rebind(void* engine, int32_t chunk, void* state, const dd_tracker_config* host_cfg);
+/* Buffers of the end-to-end path of one chunk: two device blobs of blob_capacity bytes (16-byte aligned) the ragged
+ * host batches are uploaded into alternately, and the small padded arrays (f64 [n,Dmax,4], f32 [n,Dmax], i32 [n,Dmax],
+ * i32 [n]) the tick's first kernel expands box / confidence / label / count into. */
+int dd_engine_bind_host(void* engine, int32_t chunk, void* dev_blob0, void* dev_blob1, uint64_t blob_capacity,
+                        double* det_tlwh, float* det_conf, int32_t* det_label, int32_t* det_count);
+/* One tick of every chunk from a padded, HBM-resident batch of all S streams (arrays as dd_tracker_update);
+ * det_track_id is written; reduce != 0: counters reduced into total_counts (valid after dd_engine_join).  Only
+ * enqueues: chunk streams wait for what is already on caller_stream, nothing waits for the chunks. */
+int dd_engine_step(void* engine, const double* det_tlwh, const float* det_conf, const int32_t* det_label,
+                   const float* det_feat, const int32_t* det_count, int32_t reduce, void* caller_stream);
+/* One end-to-end tick from ragged PINNED host blobs (one per chunk, dd_unpack_detections' format; host_offsets4[4 i ..]
+ * = byte offsets of chunk i's tlwh / conf / label / feat sections): upload on the chunk's copy stream (the upload of
+ * tick k + 1 runs under the kernels of tick k), the tick reading the blob in place, the count reduction, and -- when
+ * host_out_ids (pinned, i32 [S,Dmax]) is given -- the device-to-host copy of the det -> track ids.  The host blobs
+ * must stay untouched until their copy has run. */
+int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint64_t* host_blob_bytes,
+                        const int64_t* host_offsets4, int32_t* host_out_ids, void* caller_stream);
+/* caller_stream waits for every chunk and for the latest count summation (no host synchronisation). */
+int dd_engine_join(void* engine, void* caller_stream);
+/* caller_stream waits for the latest count summation only (total_counts of the last reduced tick). */
+int dd_engine_wait_counts(void* engine, void* caller_stream);
+/* Latest completed poll of chunk's pool counters -> host_out4 (free pages, pages attached, longest gallery, forecast)
+ * and the tick it was taken behind (-1: none yet).  If the newest poll is still in flight and the engine is already
+ * max_age_ticks ticks past it, waits for it: the host never runs further ahead than the forecast covers. */
+int dd_engine_pool_latest(void* engine, int32_t chunk, int32_t max_age_ticks, int32_t* host_out4, int64_t* host_out_tick);
+/* Ticks stepped, kernels launched (graph nodes + argument kernels), host milliseconds spent blocked in the run-ahead
+ * throttle.  Any output may be NULL. */
+int dd_engine_stats(void* engine, int64_t* host_out_ticks, int64_t* host_out_launches, double* host_out_blocked_ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone batched operators behind the per-function deep_sort API.
