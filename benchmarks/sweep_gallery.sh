@@ -1,5 +1,11 @@
-# A/B sweep of the gallery kernel shape: warp triples per CTA, ring stages per triple, stream chunks (run on the GPU box)
-for cfg in "5 4 2" "5 4 4" "4 7 2" "4 7 4" "3 9 2" "3 9 4" "6 3 4" "5 5 3" "6 4 3"; do
+# A/B sweep of the gallery kernel shape (run on the GPU box): warp triples per SM, ring stages per triple, stream
+# chunks, waves (0 = one persistent CTA per SM, W = one triple per CTA in W waves), extra bench.py flags.
+# usage: bash benchmarks/sweep_gallery.sh TAG "T S P W [flags]" ...
+tag=$1; shift
+for cfg in "$@"; do
   set -- $cfg
-  python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-configs --cosine-ctas $1 --gallery-stages $2 --chunks $3 > gpurun_out/r2o_$1_$2_$3.json 2> gpurun_out/r2o.err
+  t=$1; s=$2; p=$3; w=$4; shift 4
+  name=$(echo "${t}_${s}_${p}_${w}$*" | tr -d ' -')
+  python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-configs --cosine-ctas $t --gallery-stages $s --chunks $p \
+      --gallery-waves $w $* > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}.err
 done

@@ -52,7 +52,9 @@ class _Chunk:
                                     n_init=o.n_init, max_cosine_distance=o.max_cosine_distance,
                                     max_iou_distance=o.max_iou_distance, page_cap=o.page_cap, seg_pages=seg_pages,
                                     gallery_impl=o.gallery_impl, cosine_ctas_per_sm=o.cosine_ctas_per_sm,
-                                    match_warps=o.match_warps, gallery_stages=o.gallery_stages)
+                                    match_warps=o.match_warps, gallery_stages=o.gallery_stages,
+                                    gallery_waves=o.gallery_waves,
+                                    timeline=o.timeline)
         self.cfgp = ctypes.byref(self.cfg)
         self.segs = []
         for _ in range(n_segs):
@@ -138,7 +140,8 @@ class BatchedTracker:
                  max_cosine_distance=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
                  line=None, frame_size=(640, 480), device="cuda", n_chunks=1,
                  pool_pages=None, pool_fraction=0.5, seg_pages=None, page_cap=0,
-                 gallery_impl="default", cosine_ctas_per_sm=0, match_warps=0, gallery_stages=0):
+                 gallery_impl="default", cosine_ctas_per_sm=0, match_warps=0, gallery_stages=0, gallery_waves=0,
+                 timeline=0, gallery_turns=True):
         """budget=None is the reference's nn_budget=None (deepdish.py:515-516): galleries grow without bound; the
         page pool and the per-slot page tables are grown between ticks (``maintain``).
 
@@ -148,7 +151,8 @@ class BatchedTracker:
         self.lib = _lib.lib()
         self.pool_pages, self.pool_fraction, self.seg_pages, self.page_cap = pool_pages, pool_fraction, seg_pages, page_cap
         self.gallery_impl, self.cosine_ctas_per_sm, self.match_warps = gallery_impl, cosine_ctas_per_sm, match_warps
-        self.gallery_stages = gallery_stages
+        self.gallery_stages, self.gallery_waves = gallery_stages, gallery_waves
+        self.timeline, self.gallery_turns = timeline, gallery_turns
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedTracker runs on a CUDA device only (no CPU fallback)")
@@ -205,7 +209,8 @@ class BatchedTracker:
                                                  ctypes.c_void_p(self._aux.cuda_stream if self._aux is not None else 0),
                                                  self.line.data_ptr(), self.line_per_stream, self.partial_counts.data_ptr(),
                                                  self.total_counts.data_ptr(), self.det_track_id.data_ptr(),
-                                                 self.POLL_EVERY if self._poll_pool else 0, ctypes.byref(h)),
+                                                 self.POLL_EVERY if self._poll_pool else 0, 1 if self.gallery_turns else 0,
+                                                 ctypes.byref(h)),
                        "dd_engine_create")
             self._engine = h
         return self._engine
@@ -753,7 +758,7 @@ class BatchedTracker:
 
     def host_view(self, names=None, streams=None):
         """numpy copies of state arrays (optionally a subset of streams) for inspection / tests."""
-        names = names or [n for n in self.v.keys() if n not in ("ptab", "free_stack", "pool_ctl", "work_rec", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl", "tick_args")]
+        names = names or [n for n in self.v.keys() if n not in ("ptab", "free_stack", "pool_ctl", "work_rec", "cost", "gate", "det_featn", "det_feath", "work", "work_ctl", "tick_args", "timeline")]
         out = {}
         for n in names:
             t = self.v[n]

@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
             os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
+    extra = os.environ.get("DD_NVCC_EXTRA", "").split()       # A/B builds: e.g. DD_NVCC_EXTRA="-DDD_GS_CW=8"
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
     subprocess.check_call(cmd)
     return OUT
 

@@ -14,9 +14,10 @@
 #include "dd_view.h"
 
 // dd_tracker.cu
-int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, const double* line,
+int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, int parts, const double* line,
                     int line_per_stream, cudaStream_t st);
 int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg);
+enum { PART_PREP = 1, PART_GATE = 2, PART_GALLERY = 4, PART_POST = 8, PART_TAIL = 16 };      // DD_PART_* of dd_tracker.cu
 size_t dd_tick_args_offset(const dd_tracker_config* cfg);
 
 #define DD_CU(x) do { if ((x) != cudaSuccess) return DD_ERR_CUDA; } while (0)
@@ -44,9 +45,11 @@ struct Chunk {
     dd_tracker_config cfg;
     int lo = 0, n = 0;
     cudaStream_t st = nullptr, copy_st = nullptr;
-    cudaEvent_t done = nullptr, copied = nullptr, unpacked[2] = {nullptr, nullptr};
+    cudaEvent_t done = nullptr, copied = nullptr, unpacked[2] = {nullptr, nullptr}, gal_done = nullptr;
     bool unpacked_valid[2] = {false, false};
-    cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [ragged][reduce]
+    // captured pieces of a tick, [ragged][reduce][piece]: 0 = everything (or, with gallery turns, the kernels before the
+    // gallery stream), 1 = the gallery stream, 2 = the kernels behind it
+    cudaGraphExec_t graph[2][2][3] = {};
     // host path (dd_engine_bind_host): double-buffered device blob + the small padded arrays the tick fills
     unsigned char* dev_blob[2] = {nullptr, nullptr};
     size_t blob_cap = 0;
@@ -62,6 +65,8 @@ struct Chunk {
 
 struct Engine {
     int P = 0, D = 0, C4 = 0, line_per_stream = 0, poll_every = 0;
+    bool turns = false;              // chunks take turns on the gallery stream (see dd_engine_create)
+    cudaEvent_t last_gal = nullptr;  // end of the most recently enqueued gallery stream
     std::vector<Chunk> ch;
     cudaStream_t aux = nullptr, cap = nullptr;
     cudaEvent_t fork_ev = nullptr, sum_done[2] = {nullptr, nullptr};
@@ -88,16 +93,14 @@ cudaError_t blocked_sync(Engine& E, cudaEvent_t ev) {
 void drop_graphs(Chunk& c) {
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b)
-            if (c.graph[a][b]) { cudaGraphExecDestroy(c.graph[a][b]); c.graph[a][b] = nullptr; }
+            for (int k = 0; k < 3; ++k)
+                if (c.graph[a][b][k]) { cudaGraphExecDestroy(c.graph[a][b][k]); c.graph[a][b][k] = nullptr; }
 }
 
-int ensure_graph(Engine& E, Chunk& c, int ragged, int reduce) {
-    if (c.graph[ragged][reduce]) return DD_OK;
-    int rc = dd_tick_prepare_host(c.state, &c.cfg);        // function attributes: outside the capture
-    if (rc != DD_OK) return rc;
+int capture_piece(Engine& E, Chunk& c, int ragged, int reduce, int parts, cudaGraphExec_t* out) {
     const double* line = E.line + (E.line_per_stream ? (size_t)c.lo * 4 : 0);
     DD_CU(cudaStreamBeginCapture(E.cap, cudaStreamCaptureModeRelaxed));
-    rc = dd_capture_tick(c.state, &c.cfg, ragged, reduce, line, E.line_per_stream, E.cap);
+    const int rc = dd_capture_tick(c.state, &c.cfg, ragged, reduce, parts, line, E.line_per_stream, E.cap);
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(E.cap, &g);
     if (rc != DD_OK || e != cudaSuccess || !g) {
@@ -109,18 +112,57 @@ int ensure_graph(Engine& E, Chunk& c, int ragged, int reduce) {
     const cudaError_t e2 = cudaGraphInstantiate(&x, g, 0);
     cudaGraphDestroy(g);
     if (e2 != cudaSuccess) return DD_ERR_CUDA;
-    c.graph[ragged][reduce] = x;
+    *out = x;
     return DD_OK;
 }
 
-int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce, cudaStream_t st) {
-    const int rc = ensure_graph(E, c, ragged, reduce);
+int ensure_graphs(Engine& E, Chunk& c, int ragged, int reduce) {
+    cudaGraphExec_t* g = c.graph[ragged][reduce];
+    if (g[0]) return DD_OK;
+    static bool carve_set = false;       // see dd_tick_prepare: every kernel of the tick asks for the maximum carve-out
+    if (!carve_set) {
+        cudaFuncSetAttribute(k_set_args, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_sum_partials, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
+    int rc = dd_tick_prepare_host(c.state, &c.cfg);        // function attributes: outside the capture
     if (rc != DD_OK) return rc;
+    const int prep = ragged ? 0 : PART_PREP;               // a ragged tick's prep kernel runs in front of the graphs
+    if (!E.turns) return capture_piece(E, c, ragged, reduce, prep | PART_GATE | PART_GALLERY | PART_POST | PART_TAIL, &g[0]);
+    rc = capture_piece(E, c, ragged, reduce, PART_GALLERY, &g[1]);
+    if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, PART_POST | PART_TAIL, &g[2]);
+    if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, prep | PART_GATE, &g[0]);
+    return rc;
+}
+
+// consumed: (ragged ticks) recorded right behind the detection-prep kernel, the only reader of the uploaded blob
+int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce, cudaStream_t st,
+                cudaEvent_t consumed = nullptr) {
+    int rc = ensure_graphs(E, c, ragged, reduce);
+    if (rc != DD_OK) return rc;
+    cudaGraphExec_t* g = c.graph[ragged][reduce];
     DDTickArgs* dst = (DDTickArgs*)((char*)c.state + dd_tick_args_offset(&c.cfg));
     k_set_args<<<1, 32, 0, st>>>(dst, A);
     DD_CU(cudaGetLastError());
-    DD_CU(cudaGraphLaunch(c.graph[ragged][reduce], st));
-    E.launches += 8 + (reduce ? 1 : 0);      // argument kernel + the graph's 7 (8) kernel nodes
+    if (ragged) {
+        const double* line = E.line + (E.line_per_stream ? (size_t)c.lo * 4 : 0);
+        rc = dd_capture_tick(c.state, &c.cfg, 1, reduce, PART_PREP, line, E.line_per_stream, st);      // plain launch
+        if (rc != DD_OK) return rc;
+        if (consumed) DD_CU(cudaEventRecord(consumed, st));
+    }
+    DD_CU(cudaGraphLaunch(g[0], st));
+    if (E.turns) {
+        // the gallery stream is the HBM-bound kernel: two of them side by side gain nothing, and chunks that drift into
+        // phase run their gallery streams AND their latency-bound kernels at the same time.  So every gallery stream
+        // waits for the previously enqueued one (of another chunk): chunks stay in anti-phase, the matching of one runs
+        // under the gallery stream of the other.
+        if (E.last_gal && E.last_gal != c.gal_done) DD_CU(cudaStreamWaitEvent(st, E.last_gal, 0));
+        DD_CU(cudaGraphLaunch(g[1], st));
+        DD_CU(cudaEventRecord(c.gal_done, st));
+        E.last_gal = c.gal_done;
+        DD_CU(cudaGraphLaunch(g[2], st));
+    }
+    E.launches += 8 + (reduce ? 1 : 0);      // argument kernel + the tick's 7 (8) kernels
     if (E.poll_every > 0 && E.tick % E.poll_every == 0) {
         // the slot written two polls ago is reused: its copy has long completed unless the host runs far ahead
         const int k = c.poll_turn;
@@ -162,7 +204,7 @@ extern "C" {
 int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracker_config* const* host_cfgs,
                      const int32_t* host_first_stream, void* const* host_streams, void* aux_stream, const double* line,
                      int32_t line_per_stream, int64_t* partial_counts, int64_t* total_counts, int32_t* det_track_id,
-                     int32_t poll_every, void** host_out_engine) {
+                     int32_t poll_every, int32_t gallery_turns, void** host_out_engine) {
     if (n_chunks <= 0 || !host_states || !host_cfgs || !host_first_stream || !line || !partial_counts || !total_counts ||
         !det_track_id || !host_out_engine)
         return DD_ERR_INVALID;
@@ -177,6 +219,7 @@ int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracke
     E->ids = det_track_id;
     E->aux = (cudaStream_t)aux_stream;
     E->poll_every = poll_every;
+    E->turns = gallery_turns != 0 && n_chunks > 1;
     E->ch.resize(n_chunks);
     bool ok = cudaStreamCreateWithFlags(&E->cap, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&E->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
@@ -195,6 +238,7 @@ int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracke
         ok = c.cfg.max_dets == E->D && c.cfg.n_labels * 4 == E->C4 &&
              cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.copied, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.gal_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.unpacked[0], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.unpacked[1], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.poll_ev[0], cudaEventDisableTiming) == cudaSuccess &&
@@ -217,7 +261,7 @@ int dd_engine_destroy(void* engine) {
     for (auto& c : E->ch) {
         drop_graphs(c);
         if (c.copy_st) cudaStreamDestroy(c.copy_st);
-        for (cudaEvent_t e : {c.done, c.copied, c.unpacked[0], c.unpacked[1], c.poll_ev[0], c.poll_ev[1]})
+        for (cudaEvent_t e : {c.done, c.copied, c.gal_done, c.unpacked[0], c.unpacked[1], c.poll_ev[0], c.poll_ev[1]})
             if (e) cudaEventDestroy(e);
         if (c.poll_host) cudaFreeHost(c.poll_host);
     }
@@ -279,6 +323,7 @@ int dd_engine_step(void* engine, const double* det_tlwh, const float* det_conf, 
         A.blob = nullptr;
         A.off_tlwh = A.off_conf = A.off_label = A.off_feat = 0;
         A.indirect = 0;
+        A.tick = (int)E->tick;
         cudaStream_t st = multi ? c.st : cur;
         const int rc = launch_tick(*E, c, A, 0, reduce, st);
         if (rc != DD_OK) return rc;
@@ -323,10 +368,10 @@ int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint6
         A.blob = c.dev_blob[par];
         A.off_tlwh = of[0]; A.off_conf = of[1]; A.off_label = of[2]; A.off_feat = of[3];
         A.indirect = 0;
-        const int rc = launch_tick(*E, c, A, 1, 1, st);
+        A.tick = (int)E->tick;
+        // only the tick's first kernel reads the blob (later kernels read the small padded arrays it fills)
+        const int rc = launch_tick(*E, c, A, 1, 1, st, c.unpacked[par]);
         if (rc != DD_OK) return rc;
-        // the tick's first kernel has read the blob once the whole graph is done; later kernels read the small arrays
-        DD_CU(cudaEventRecord(c.unpacked[par], st));
         c.unpacked_valid[par] = true;
         if (host_out_ids)
             DD_CU(cudaMemcpyAsync(host_out_ids + o, E->ids + o, (size_t)c.n * E->D * sizeof(int), cudaMemcpyDeviceToHost, st));

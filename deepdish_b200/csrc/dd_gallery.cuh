@@ -276,8 +276,9 @@ k_cosine_h(const DDView V, const DDTickArgs A) {
 
 #define DD_GS_BLOCK_ROWS 128                 // gallery rows per job (8 pages): the mma warp keeps 8 x 4 dots per lane
 #define DD_GS_HDR_INTS 32                    // job header: 0 slotg 1 stream 2 row0 3 nrows 4 nq 5 flags | 8.. cj[8] | 16.. pid[8]
-#define DD_GS_MSG_CAND (DD_GS_BLOCK_ROWS * 8) // a message can list every (row, detection) of a block: identical rows are legal
-#define DD_GS_MSG_BYTES (DD_GS_HDR_INTS * 4 + DD_GS_MSG_CAND * 2)   // checker message: header (32 ints; [6] = candidates) + list (u16)
+#define DD_GS_MSG_CAP 240                    // candidates a message can list; a block with more (near-identical rows: legal,
+                                             // never seen outside the adversarial tests) is re-evaluated in full by the checker
+#define DD_GS_MSG_BYTES (DD_GS_HDR_INTS * 4 + DD_GS_MSG_CAP * 2)    // checker message: header (32 ints; [6] = candidates) + list (u16)
 #define DD_GS_FIRST 1                        // first job / message of a detection group: reset the running maxima
 #define DD_GS_LAST 2                         // last one: the cost entries are final
 #define DD_GS_STOP 4
@@ -287,7 +288,7 @@ __host__ __device__ inline size_t dd_gs_triple_bytes(int stages) {
                      + 2 * 8 * 256                                 // query half rows, double-buffered
                      + 2 * DD_GS_HDR_INTS * 4                      // job headers, double-buffered
                      + 2 * DD_GS_MSG_BYTES                         // checker messages, double-buffered
-                     + DD_GS_BLOCK_ROWS * 8 * 4                    // approximate dots of the block being streamed
+                     + DD_GS_BLOCK_ROWS * 8 * 2                    // approximate dots of the block being streamed (half)
                      + (size_t)(2 * stages + 8) * 8;               // mbarriers: full / empty [stages], hfull hfree mfull mfree [2]
     return (b + 127) & ~(size_t)127;
 }
@@ -301,7 +302,7 @@ struct DDTripleSmem {
     char* qbuf;
     int* hdr;
     char* msg;
-    float* approx;
+    unsigned* approx;            // [DD_GS_BLOCK_ROWS][4] half2: dots of row r with detections 2 t, 2 t + 1
     unsigned long long *full, *empty, *hfull, *hfree, *mfull, *mfree;
 };
 __device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDTripleSmem& P) {
@@ -309,8 +310,8 @@ __device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDTripleSmem
     P.qbuf = P.ring + (size_t)stages * DD_PAGE_F16_BYTES;
     P.hdr = (int*)(P.qbuf + 2 * 8 * 256);
     P.msg = (char*)(P.hdr + 2 * DD_GS_HDR_INTS);
-    P.approx = (float*)(P.msg + 2 * DD_GS_MSG_BYTES);
-    P.full = (unsigned long long*)((char*)P.approx + DD_GS_BLOCK_ROWS * 8 * 4);
+    P.approx = (unsigned*)(P.msg + 2 * DD_GS_MSG_BYTES);
+    P.full = (unsigned long long*)((char*)P.approx + DD_GS_BLOCK_ROWS * 8 * 2);
     P.empty = P.full + stages;
     P.hfull = P.empty + stages;
     P.hfree = P.hfull + 2;
@@ -318,26 +319,41 @@ __device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDTripleSmem
     P.mfree = P.mfull + 2;
 }
 
-__device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSmem& P, int stages) {
+// quota: work-list entries this producer may claim (even; INT_MAX = until the list is empty).  With the one-triple-
+// per-CTA launch every CTA streams a bounded share and exits, so that its shared memory becomes available to
+// whatever kernel is waiting (the quotas of all CTAs together cover the list).
+__device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSmem& P, int stages, int quota) {
     const int lane = threadIdx.x & 31;
     const int n = V.work_ctl[0];
+    int claimed = 0;
     int st = 0;                  // next ring stage
     unsigned ephase = ~0u;       // bit s: parity to wait for on empty[s] (a fresh barrier passes a wait on parity 1)
     int hb = 0;
     unsigned hphase = 3u;        // same for hfree[0..1]
     // claims are made two work-list entries at a time (one atomic per pair of tracks) and one pair ahead: the
     // claim made when pair k starts is broadcast when it ends
-    int raw = 0;
+    int raw = n;
     if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);
+    claimed += 2;
     int i_cur = __shfl_sync(0xffffffffu, raw, 0);          // i_cur, i_cur + 1: the pair being streamed
-    if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);
+    raw = n;
+    if (claimed < quota) {
+        if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);
+        claimed += 2;
+    }
     int i_nxt = __shfl_sync(0xffffffffu, raw, 0);          // first entry of the next pair
     int odd = 0;                                           // 0: streaming the pair's first entry, 1: its second
     int w_cur = i_cur < n ? V.work_rec[(size_t)i_cur * 16 + (lane & 15)] : 0;
     while (i_cur < n) {
         const int i_after = odd ? i_nxt : i_cur + 1;                                         // the entry streamed next
         const int w_nxt = i_after < n ? V.work_rec[(size_t)i_after * 16 + (lane & 15)] : 0;  // used one entry later
-        if (!odd && lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);                          // broadcast two entries later
+        if (!odd) {                                                                          // broadcast two entries later
+            raw = n;
+            if (claimed < quota) {
+                if (lane == 0) raw = atomicAdd(V.work_ctl + 32, 2);
+                claimed += 2;
+            }
+        }
         const int slotg = __shfl_sync(0xffffffffu, w_cur, 0), s = __shfl_sync(0xffffffffu, w_cur, 1);
         const int glen = __shfl_sync(0xffffffffu, w_cur, 2), np = __shfl_sync(0xffffffffu, w_cur, 4);
         const unsigned gw0 = (unsigned)__shfl_sync(0xffffffffu, w_cur, 5), gw1 = (unsigned)__shfl_sync(0xffffffffu, w_cur, 6);
@@ -481,8 +497,13 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
             const int ra = p * 16 + gq, rb = ra + 8;
             if (ra >= nrows) { c0 = -3.0e38f; c1 = -3.0e38f; }     // rows past the end (stale stage bytes) never win
             if (rb >= nrows) { c2 = -3.0e38f; c3 = -3.0e38f; }
-            *(float2*)(P.approx + ra * 8 + 2 * tq) = make_float2(c0, c1);
-            *(float2*)(P.approx + rb * 8 + 2 * tq) = make_float2(c2, c3);
+            // parked as half2 (every kilobyte of shared memory here is a matching warp of another chunk that fits on the
+            // SM): the candidate test below widens the window by the rounding error, so the list stays a superset
+            {
+                const __half2 ha = __floats2half2_rn(c0, c1), hb = __floats2half2_rn(c2, c3);
+                P.approx[ra * 4 + tq] = *(const unsigned*)&ha;
+                P.approx[rb * 4 + tq] = *(const unsigned*)&hb;
+            }
             mx0 = fmaxf(mx0, fmaxf(c0, c2));
             mx1 = fmaxf(mx1, fmaxf(c1, c3));
         }
@@ -494,8 +515,9 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         run0 = fmaxf(run0, mx0);
         run1 = fmaxf(run1, mx1);
         // a detection column this lane holds no real query for can never list a candidate
-        const float thr0 = 2 * tq < nq ? run0 - DD_H_WINDOW : 3.0e38f;
-        const float thr1 = 2 * tq + 1 < nq ? run1 - DD_H_WINDOW : 3.0e38f;
+        // the parked dots are rounded to half: |half(a) - a| <= 2^-11 |a| < 5e-4 for |a| <= 1.001
+        const float thr0 = 2 * tq < nq ? run0 - DD_H_WINDOW - 5.0e-4f : 3.0e38f;
+        const float thr1 = 2 * tq + 1 < nq ? run1 - DD_H_WINDOW - 5.0e-4f : 3.0e38f;
         // ---- candidates -> checker message: every lane re-reads the dots it wrote and appends its own candidates
         // (a shared-memory counter hands out list positions; the order of the list does not matter to a maximum)
         dd_mbar_wait(P.mfree + mb, (mphase >> mb) & 1u);
@@ -506,12 +528,15 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         __syncwarp();
         for (int p = 0; p < npg; ++p) {
             const int ra = p * 16 + gq, rb = ra + 8;
-            const float2 va = *(const float2*)(P.approx + ra * 8 + 2 * tq);
-            const float2 vb = *(const float2*)(P.approx + rb * 8 + 2 * tq);
-            if (va.x >= thr0) mc[atomicAdd(M + 6, 1)] = (unsigned short)((ra << 3) | (2 * tq));
-            if (va.y >= thr1) mc[atomicAdd(M + 6, 1)] = (unsigned short)((ra << 3) | (2 * tq + 1));
-            if (vb.x >= thr0) mc[atomicAdd(M + 6, 1)] = (unsigned short)((rb << 3) | (2 * tq));
-            if (vb.y >= thr1) mc[atomicAdd(M + 6, 1)] = (unsigned short)((rb << 3) | (2 * tq + 1));
+            const unsigned ua = P.approx[ra * 4 + tq], ub = P.approx[rb * 4 + tq];
+            const float2 va = __half22float2(*(const __half2*)&ua);
+            const float2 vb = __half22float2(*(const __half2*)&ub);
+            // the counter keeps counting past the capacity: that is how the checker learns the list is incomplete
+            const bool a0 = va.x >= thr0, a1 = va.y >= thr1, b0 = vb.x >= thr0, b1 = vb.y >= thr1;
+            if (a0) { const int k = atomicAdd(M + 6, 1); if (k < DD_GS_MSG_CAP) mc[k] = (unsigned short)((ra << 3) | (2 * tq)); }
+            if (a1) { const int k = atomicAdd(M + 6, 1); if (k < DD_GS_MSG_CAP) mc[k] = (unsigned short)((ra << 3) | (2 * tq + 1)); }
+            if (b0) { const int k = atomicAdd(M + 6, 1); if (k < DD_GS_MSG_CAP) mc[k] = (unsigned short)((rb << 3) | (2 * tq)); }
+            if (b1) { const int k = atomicAdd(M + 6, 1); if (k < DD_GS_MSG_CAP) mc[k] = (unsigned short)((rb << 3) | (2 * tq + 1)); }
         }
         __syncwarp();
         if (lane == 0) dd_mbar_arrive(P.mfull + mb);
@@ -534,7 +559,10 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
         const int flags = __shfl_sync(0xffffffffu, hw, 5);
         if (flags & DD_GS_STOP) break;
         const int slotg = __shfl_sync(0xffffffffu, hw, 0), s = __shfl_sync(0xffffffffu, hw, 1);
-        const int nq = __shfl_sync(0xffffffffu, hw, 4), ncand = __shfl_sync(0xffffffffu, hw, 6);
+        const int nq = __shfl_sync(0xffffffffu, hw, 4), listed = __shfl_sync(0xffffffffu, hw, 6);
+        // more candidates than a message holds: every (row, detection) of the block is evaluated exactly instead
+        const bool all = listed > DD_GS_MSG_CAP;
+        const int ncand = all ? __shfl_sync(0xffffffffu, hw, 3) * nq : listed;
         if (flags & DD_GS_FIRST) best = -3.0e38f;
         const float4* qbase = (const float4*)(V.det_featn + (size_t)s * V.D * DD_FEAT_DIM);
         for (int c0 = 0; c0 < ncand; c0 += CW) {
@@ -544,7 +572,10 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
             int qn[CW];
 #pragma unroll
             for (int k = 0; k < CW; ++k) {
-                const int e = mc[dd_imin(c0 + k, ncand - 1)];
+                const int idx = dd_imin(c0 + k, ncand - 1);
+                int e;
+                if (all) e = ((idx / nq) << 3) | (idx % nq);
+                else e = mc[idx];
                 qn[k] = e & 7;
                 const int row = e >> 3;
                 const int pid = __shfl_sync(0xffffffffu, hw, 16 + (row >> 4));
@@ -589,12 +620,16 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
     }
 }
 
-__global__ void __launch_bounds__(672, 1)
-k_gallery_stream(const DDView V, int stages) {
+// 72 registers (8 bytes of spills): the register file is four 16 K partitions, the CTA's 21 warps land 6 + 5 + 5 + 5,
+// and at 72 every partition still has room for one 80-register matching warp of another chunk (at 80 the six-warp
+// partition has not).
+__global__ void __maxnreg__(72)
+k_gallery_stream(const DDView V, int stages, int bounded) {
     extern __shared__ __align__(128) char smem[];
     const int warp = threadIdx.x >> 5;
     const int triple = warp / 3, role = warp - triple * 3;
     DDTripleSmem P;
+    DD_TL_BEGIN(2);
     dd_gs_carve(smem + (size_t)triple * dd_gs_triple_bytes(stages), stages, P);
     if (role == 0 && (threadIdx.x & 31) == 0) {
         for (int i = 0; i < stages; ++i) { dd_mbar_init(P.full + i, 1); dd_mbar_init(P.empty + i, 1); }
@@ -605,7 +640,16 @@ k_gallery_stream(const DDView V, int stages) {
         dd_mbar_fence_init();
     }
     __syncthreads();
-    if (role == 0) dd_gs_producer(V, P, stages);
+    int quota = 0x7ffffffe;
+    if (bounded) {                       // even share of the list, rounded up: gridDim.x * quota >= entries
+        const int n = V.work_ctl[0];
+        quota = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 1) & ~1;
+        if (quota < 2) quota = 2;
+    }
+    if (role == 0) dd_gs_producer(V, P, stages, quota);
     else if (role == 1) dd_gs_mma(P, stages);
-    else dd_gs_checker<4>(V, P);
+    else {
+        dd_gs_checker<4>(V, P);
+        if (V.tl && (threadIdx.x & 31) == 0) atomicMax(DD_TL_SLOT(2) + 1, dd_globaltimer());   // the checker drains last
+    }
 }

@@ -18,14 +18,18 @@
     } while (0)
 
 // Small per-item kernels: DD_SUB lanes per item, 32 / DD_SUB items per warp (SubG).
-#ifndef DD_APPLY_MIN_CTAS
-#define DD_APPLY_MIN_CTAS 1
+#ifndef DD_MATCH_MIN_CTAS
+#define DD_MATCH_MIN_CTAS 24     // <= 80 registers: a matching warp must fit beside the gallery stream of another chunk
 #endif
+#ifndef DD_APPLY_MIN_CTAS
+#define DD_APPLY_MIN_CTAS 10     // <= 96 registers (88 bytes of spills): an apply warp must fit into what a register-file
+#endif                           // partition has left beside five gallery warps of another chunk
 #define DD_SUB 8
 #define DD_ITEMS_PER_CTA (DD_WARPS * 32 / DD_SUB)
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_prep(const DDView V, const DDTickArgs A) {
+    DDTlScope tl_(V, 0);
     const double* __restrict__ det_tlwh = DD_ARG(det_tlwh);
     const float* __restrict__ det_feat = DD_ARG(det_feat);
     const int* __restrict__ det_count = DD_ARG(det_count);
@@ -63,6 +67,7 @@ struct DDRagged {
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_prep_ragged(const DDView V, const DDTickArgs A) {
+    DDTlScope tl_(V, 0);
     DDRagged R;
     R.blob = DD_ARG(blob);
     R.off_tlwh = DD_ARG(off_tlwh); R.off_conf = DD_ARG(off_conf); R.off_label = DD_ARG(off_label); R.off_feat = DD_ARG(off_feat);
@@ -93,6 +98,7 @@ k_prep_ragged(const DDView V, const DDTickArgs A) {
 template <bool PREDICT>
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_gate(const DDView V, const DDTickArgs A) {
+    DDTlScope tl_(V, 1);
     const int* __restrict__ det_count = DD_ARG(det_count);
     // gate, then append the track indices that have something to stream to the work list of the gallery
     // kernel: one atomicAdd per CTA (16 track indices), entries of a CTA stay in ascending order.
@@ -154,8 +160,9 @@ static int dd_sm_count() {
     return n;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, DD_MATCH_MIN_CTAS)
 k_match(const DDView V, const DDTickArgs A) {
+    DDTlScope tl_(V, 3);
     extern __shared__ __align__(128) char smem[];
     WarpG g;
     dd_match_stream(g, V, blockIdx.x, DD_ARG(det_tlwh), DD_ARG(det_count), DD_ARG(out_ids), smem);
@@ -166,17 +173,23 @@ k_match(const DDView V, const DDTickArgs A) {
 template <int NW>
 __global__ void __launch_bounds__(NW * 32)
 k_match_cta(const DDView V, const DDTickArgs A) {
+    DDTlScope tl_(V, 3);
     extern __shared__ __align__(128) char smem[];
     CtaG<NW> g(smem);
     dd_match_stream(g, V, blockIdx.x, DD_ARG(det_tlwh), DD_ARG(det_count), DD_ARG(out_ids), smem + 256);
 }
 
-__global__ void __launch_bounds__(DD_WARPS * 32, DD_APPLY_MIN_CTAS)
+// 64-thread CTAs: at ~150 registers per thread a 128-thread CTA would not fit beside the persistent gallery CTA of
+// another chunk (672 threads x 80 registers leave 11.7 K of the SM's 64 K) and the whole kernel would wait for it.
+#define DD_APPLY_WARPS 2
+#define DD_APPLY_ITEMS (DD_APPLY_WARPS * 32 / DD_SUB)
+__global__ void __launch_bounds__(DD_APPLY_WARPS * 32, DD_APPLY_MIN_CTAS)
 k_apply(const DDView V, const DDTickArgs A) {
+    DDTlScope tl_(V, 4);
     const float* __restrict__ det_conf = DD_ARG(det_conf);
     const int* __restrict__ det_label = DD_ARG(det_label);
-    __shared__ double scratch[DD_ITEMS_PER_CTA][64];
-    const int w = blockIdx.x * DD_ITEMS_PER_CTA + threadIdx.x / DD_SUB;
+    __shared__ double scratch[DD_APPLY_ITEMS][64];
+    const int w = blockIdx.x * DD_APPLY_ITEMS + threadIdx.x / DD_SUB;
     if (w >= V.S * V.D) return;
     SubG<DD_SUB> g;
     dd_apply_det(g, V, w / V.D, w % V.D, det_conf, det_label, scratch[threadIdx.x / DD_SUB]);
@@ -184,6 +197,7 @@ k_apply(const DDView V, const DDTickArgs A) {
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_countline(const DDView V, const double* __restrict__ line, int line_per_stream) {
+    DDTlScope tl_(V, 5);
     const int w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5);
     if (w >= V.S) return;
     WarpG g;
@@ -302,6 +316,10 @@ static inline int warps_to_blocks(long long n_warps) { return (int)((n_warps + D
 static inline int items_to_blocks(long long n) { return (int)((n + DD_ITEMS_PER_CTA - 1) / DD_ITEMS_PER_CTA); }
 
 // ---- the launches of one update (shared by every entry point) --------------------------------------------
+template <class... KArgs, class... Args>
+static void dd_launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    kernel<<<grid, block, smem, st>>>(KArgs(args)...);
+}
 // Function attributes (opt-in shared memory) are set here, outside any stream capture.
 static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* triples_out, int* stages_out, int* mw_out) {
     const size_t smem = dd_match_smem_bytes(V.T, V.D, V.tab_cap);
@@ -310,6 +328,21 @@ static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* t
     if (mw != 1 && mw != 4 && mw != 8) mw = (V.T > 160 || V.D > 160) ? 4 : 1;
     if (mw > 1 && smem + 256 > 227 * 1024) mw = 1;
     static size_t match_set = 0, cta_set = 0, gsm_set = 0, hsm_set = 0;     // the attributes only ever grow
+    // Shared-memory carve-out: an SM's L1 / shared split is fixed by the first CTA that lands on it and cannot change
+    // while CTAs are resident.  The driver would give the gallery stream the smallest configuration that holds ONE of
+    // its CTAs (196 KB for 170 KB), leaving 25 KB -- one matching warp -- for everything else of the other stream
+    // chunks.  Every tick kernel therefore asks for the maximum carve-out (228 KB), whichever reaches an idle SM first.
+    static bool carve_set = false;
+    if (!carve_set) {
+        const int mx = cudaSharedmemCarveoutMaxShared;
+        const void* ks[] = {(const void*)k_prep, (const void*)k_prep_ragged, (const void*)k_gate<true>, (const void*)k_gate<false>,
+                            (const void*)k_gallery_stream, (const void*)k_cosine_h, (const void*)k_cosine, (const void*)k_match,
+                            (const void*)k_match_cta<4>, (const void*)k_match_cta<8>, (const void*)k_apply,
+                            (const void*)k_countline, (const void*)k_count_reduce, (const void*)k_predict};
+        for (const void* k : ks)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, mx) != cudaSuccess) return DD_ERR_CUDA;
+        carve_set = true;
+    }
     if (mw == 1 && smem > 48 * 1024 && smem > match_set) {
         if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DD_ERR_CUDA;
         match_set = smem;
@@ -322,13 +355,14 @@ static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* t
     }
     int triples = 0, stages = 0;
     if (cfg->gallery_impl == 0) {
+        const bool split = cfg->gallery_waves > 0;             // one triple per CTA
         triples = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 7;
-        if (triples > 7) triples = 7;
+        if (triples > (split ? 8 : 7)) triples = split ? 8 : 7;
         stages = cfg->gallery_stages > 0 ? cfg->gallery_stages : 4;
         if (stages > 16) stages = 16;
         const size_t per = dd_gs_triple_bytes(stages);
-        while (triples > 1 && per * triples > 226 * 1024) --triples;
-        const size_t gsm = per * triples;
+        while (triples > 1 && (split ? (per + 1024) * triples > 228 * 1024 : per * triples > 226 * 1024)) --triples;
+        const size_t gsm = split ? per : per * triples;
         if (gsm > 227 * 1024) return DD_ERR_INVALID;
         if (gsm > gsm_set) {
             if (cudaFuncSetAttribute(k_gallery_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess)
@@ -353,7 +387,10 @@ static int dd_launch_gallery(const DDView& V, const dd_tracker_config* cfg, cons
     if (impl == 1) {
         k_cosine<<<warps_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, A);
     } else if (impl == 0) {
-        k_gallery_stream<<<dd_sm_count(), triples * 96, dd_gs_triple_bytes(stages) * triples, st>>>(V, stages);
+        if (cfg->gallery_waves > 0)
+            k_gallery_stream<<<dd_sm_count() * triples * cfg->gallery_waves, 96, dd_gs_triple_bytes(stages), st>>>(V, stages, 1);
+        else
+            k_gallery_stream<<<dd_sm_count(), triples * 96, dd_gs_triple_bytes(stages) * triples, st>>>(V, stages, 0);
     } else {
         const int per_sm = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 4;
         long long grid = (long long)dd_sm_count() * per_sm;
@@ -366,8 +403,15 @@ static int dd_launch_gallery(const DDView& V, const dd_tracker_config* cfg, cons
 }
 
 // `prepared`: dd_tick_prepare already ran for this (V, cfg) -- the captured path calls it before the capture begins.
+// parts: which kernels of the update to launch (the engine captures a tick in pieces so that it can put events between them)
+#define DD_PART_PREP 1      // detection prep (the only reader of a ragged blob)
+#define DD_PART_GATE 2      // Track.predict + gating + work list
+#define DD_PART_GALLERY 4   // the gallery stream
+#define DD_PART_POST 8      // matching + apply
+#define DD_PART_TAIL 16     // count-line (+ count reduce): dd_tick_tail
+#define DD_PART_ALL 31
 static int dd_update_impl(void* state, const dd_tracker_config* cfg, const DDTickArgs& A, cudaStream_t st,
-                          cudaEvent_t* ev, bool with_predict) {
+                          cudaEvent_t* ev, bool with_predict, int parts = DD_PART_ALL) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
@@ -379,31 +423,41 @@ static int dd_update_impl(void* state, const dd_tracker_config* cfg, const DDTic
     const size_t smem = dd_match_smem_bytes(V.T, V.D, V.tab_cap);
     const bool ragged = A.blob != nullptr;       // (captured tick: a non-NULL marker, the kernels read V.targs->blob)
     if (ev) cudaEventRecord(ev[0], st);
-    if (ragged)
-        k_prep_ragged<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, A);
-    else
-        k_prep<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, A);
-    DD_CHECK_LAUNCH();
+    if (parts & DD_PART_PREP) {
+        if (ragged)
+            dd_launch(k_prep_ragged, items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st, V, A);
+        else
+            dd_launch(k_prep, items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st, V, A);
+        DD_CHECK_LAUNCH();
+    }
     if (ev) cudaEventRecord(ev[1], st);
-    if (with_predict)
-        k_gate<true><<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, A);
-    else
-        k_gate<false><<<items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st>>>(V, A);
-    DD_CHECK_LAUNCH();
+    if (parts & DD_PART_GATE) {
+        if (with_predict)
+            dd_launch(k_gate<true>, items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st, V, A);
+        else
+            dd_launch(k_gate<false>, items_to_blocks((long long)V.S * V.T), DD_WARPS * 32, 0, st, V, A);
+        DD_CHECK_LAUNCH();
+    }
     if (ev) cudaEventRecord(ev[2], st);
-    rc = dd_launch_gallery(V, cfg, A, triples, stages, st);
-    if (rc != DD_OK) return rc;
+    if (parts & DD_PART_GALLERY) {
+        rc = dd_launch_gallery(V, cfg, A, triples, stages, st);
+        if (rc != DD_OK) return rc;
+    }
     if (ev) cudaEventRecord(ev[3], st);
-    if (mw == 1)
-        k_match<<<V.S, 32, smem, st>>>(V, A);
-    else if (mw == 8)
-        k_match_cta<8><<<V.S, 8 * 32, smem + 256, st>>>(V, A);
-    else
-        k_match_cta<4><<<V.S, 4 * 32, smem + 256, st>>>(V, A);
-    DD_CHECK_LAUNCH();
+    if (parts & DD_PART_POST) {
+        if (mw == 1)
+            dd_launch(k_match, V.S, 32, smem, st, V, A);
+        else if (mw == 8)
+            dd_launch(k_match_cta<8>, V.S, 8 * 32, smem + 256, st, V, A);
+        else
+            dd_launch(k_match_cta<4>, V.S, 4 * 32, smem + 256, st, V, A);
+        DD_CHECK_LAUNCH();
+    }
     if (ev) cudaEventRecord(ev[4], st);
-    k_apply<<<items_to_blocks((long long)V.S * V.D), DD_WARPS * 32, 0, st>>>(V, A);
-    DD_CHECK_LAUNCH();
+    if (parts & DD_PART_POST) {
+        dd_launch(k_apply, (unsigned)(((long long)V.S * V.D + DD_APPLY_ITEMS - 1) / DD_APPLY_ITEMS), DD_APPLY_WARPS * 32, 0, st, V, A);
+        DD_CHECK_LAUNCH();
+    }
     if (ev) cudaEventRecord(ev[5], st);
     return DD_OK;
 }
@@ -414,12 +468,12 @@ static int dd_tick_tail(void* state, const dd_tracker_config* cfg, const double*
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
     if (rc != DD_OK) return rc;
-    k_countline<<<warps_to_blocks(V.S), DD_WARPS * 32, 0, st>>>(V, line, line_per_stream);
+    dd_launch(k_countline, warps_to_blocks(V.S), DD_WARPS * 32, 0, st, V, line, line_per_stream);
     DD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[6], st);
     if (out_counts || indirect) {
-        k_count_reduce<<<V.C * 4, 256, 0, st>>>((const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts,
-                                                indirect ? V.targs : nullptr);
+        dd_launch(k_count_reduce, V.C * 4, 256, 0, st, (const long long*)V.counts, V.S, V.C * 4, (long long*)out_counts,
+                  indirect ? V.targs : (const DDTickArgs*)nullptr);
         DD_CHECK_LAUNCH();
     }
     if (ev) cudaEventRecord(ev[7], st);
@@ -433,18 +487,24 @@ static DDTickArgs dd_args_padded(const double* det_tlwh, const float* det_conf, 
     A.out_ids = out_ids; A.out_counts = nullptr; A.blob = nullptr;
     A.off_tlwh = A.off_conf = A.off_label = A.off_feat = 0;
     A.indirect = 0;
+    A.tick = 0;
     return A;
 }
 
 // One captured tick (dd_engine.cu): every per-tick input comes from the blob's tick_args words.
-int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, const double* line,
+// The kernels `parts` (DD_PART_*) of one tick, every per-tick input read from the blob's tick_args words: what the engine
+// captures (a ragged tick's prep kernel runs in front of the graphs so that "blob consumed" can be recorded behind it).
+int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, int parts, const double* line,
                     int line_per_stream, cudaStream_t st) {
     DDTickArgs A = dd_args_padded(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     A.indirect = 1;
     A.blob = ragged ? (const unsigned char*)(uintptr_t)16 : nullptr;      // marker only: the kernels read V.targs->blob
-    const int rc = dd_update_impl(state, cfg, A, st, nullptr, true);
-    if (rc != DD_OK) return rc;
-    return dd_tick_tail(state, cfg, line, line_per_stream, nullptr, reduce != 0, st);
+    if (parts & (DD_PART_ALL & ~DD_PART_TAIL)) {
+        const int rc = dd_update_impl(state, cfg, A, st, nullptr, true, parts);
+        if (rc != DD_OK) return rc;
+    }
+    if (parts & DD_PART_TAIL) return dd_tick_tail(state, cfg, line, line_per_stream, nullptr, reduce != 0, st);
+    return DD_OK;
 }
 int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg) {
     DDView V;

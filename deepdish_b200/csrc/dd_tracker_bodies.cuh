@@ -381,21 +381,28 @@ struct DDMatchSmem {
     double* dbox;      // [D][4]  this stream's detection boxes (the IoU-stage scan reads them per column)
 };
 
+// Three regions are never live at the same time and share one union: the gate words + staged costs (matching cascade
+// only), the three CPython-set tables (set-order step between the cascade and the IoU stage) and tbox (IoU stage
+// only).  The matching warp's shared memory decides how many streams fit on an SM beside another chunk's gallery
+// stream, so every kilobyte here is occupancy.
+#define DD_CVAL 4       // gate-passing costs per track kept in shared memory (the rest is read from global)
+DD_HD size_t dd_match_union_bytes(int T, int D, int tab_cap) {
+    const size_t a = (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4;
+    const size_t b = (size_t)tab_cap * 2 * 3;
+    const size_t c = (size_t)T * 5 * 8;
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    return (m + 15) & ~(size_t)15;
+}
 DD_HD size_t dd_match_smem_base_bytes(int T, int D, int tab_cap) {
     const int n = T > D ? T : D;
     size_t b = dd_lsap_scratch_bytes(n);
     b += (size_t)T * 2 * 6 + (size_t)D * 2 * 2 + (size_t)n * 2 * 2;
     b += (size_t)T * 2;
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)tab_cap * 2 * 3;
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)T * 5 * 8;
     return (b + 15) & ~(size_t)15;
 }
-#define DD_CVAL 4       // gate-passing costs per track kept in shared memory (the rest is read from global)
 DD_HD size_t dd_match_smem_bytes(int T, int D, int tab_cap) {
-    return dd_match_smem_base_bytes(T, D, tab_cap) + (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4 +
-           (size_t)D * 32 + 16;
+    return dd_match_smem_base_bytes(T, D, tab_cap) + (size_t)D * 32 + dd_match_union_bytes(T, D, tab_cap) + 16;
 }
 
 DD_HD void dd_match_carve(char* mem, int T, int D, int tab_cap, DDMatchSmem& m) {
@@ -414,16 +421,16 @@ DD_HD void dd_match_carve(char* mem, int T, int D, int tab_cap, DDMatchSmem& m) 
     m.c2r = (short*)p; p += n * 2;
     m.trk_state = (unsigned char*)p; p += T;
     m.flag = (unsigned char*)p; p += T;
-    p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    p = mem + dd_match_smem_base_bytes(T, D, tab_cap);
+    m.dbox = (double*)p; p += (size_t)D * 32;
+    // the union
     m.tab_cap = tab_cap;
-    m.tabA = (short*)p; p += m.tab_cap * 2;
-    m.tabB = (short*)p; p += m.tab_cap * 2;
-    m.tabC = (short*)p; p += m.tab_cap * 2;
-    p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    m.tbox = (double*)p;
-    m.gate_sm = (unsigned*)(mem + dd_match_smem_base_bytes(T, D, tab_cap));
+    m.gate_sm = (unsigned*)p;
     m.cval = (float*)(m.gate_sm + (size_t)T * ((D + 31) / 32));
-    m.dbox = (double*)(((uintptr_t)(m.cval + (size_t)T * DD_CVAL) + 15) & ~(uintptr_t)15);
+    m.tabA = (short*)p;
+    m.tabB = m.tabA + tab_cap;
+    m.tabC = m.tabB + tab_cap;
+    m.tbox = (double*)p;
 }
 
 // cost functors: (r, c) are positions in the rows[] / cols[] lists of the current sub-problem.

@@ -18,8 +18,22 @@ struct DDTickArgs {
     const unsigned char* blob;   // ragged batch (dd_unpack_detections' format) or NULL
     long long off_tlwh, off_conf, off_label, off_feat;
     int indirect;
+    int tick;                    // engine tick number (timeline slot)
 };
 #define DD_ARG(f) (A.indirect ? V.targs->f : A.f)
+// timeline stamps (config.timeline, captured ticks only): kernel k's earliest CTA start / latest CTA end of this tick
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long dd_globaltimer() {
+    unsigned long long t = 0;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#endif
+    return t;
+}
+#define DD_TL_SLOT(k) (V.tl + (size_t)(((V.targs->tick & 63) * 8 + (k)) * 2))
+#define DD_TL_BEGIN(k) do { if (V.tl && threadIdx.x == 0) atomicMin(DD_TL_SLOT(k), dd_globaltimer()); } while (0)
+#define DD_TL_END(k) do { if (V.tl && threadIdx.x == 0) atomicMax(DD_TL_SLOT(k) + 1, dd_globaltimer()); } while (0)
+#endif
 
 struct DDView {
     int S, T, D, B, C, DW;           // streams, slots, det capacity, budget (0 = unbounded), labels, gate words / row
@@ -47,6 +61,7 @@ struct DDView {
     int *work, *work_ctl, *work_rec;
     unsigned short* det_feath;
     const DDTickArgs* targs;         // the blob's tick_args words
+    unsigned long long* tl;          // timeline words, NULL unless config.timeline
     char* segf[DD_MAX_SEGS];         // f32 pages of each pool segment
     char* segh[DD_MAX_SEGS];         // half pages
     int label_rank[DD_MAX_LABELS];
@@ -67,6 +82,16 @@ DD_HD const float4* dd_gallery_row(const DDView& V, const int* pt, int row) {
 DD_HD int dd_half_chunk_off(int r, int c) {
     return (((c >> 2) * 2 + (r >> 3)) * 32 + (r & 7) * 4 + (c & 3)) * 16;
 }
+
+#if defined(__CUDACC__)
+// stamps kernel k's timeline slot at construction and at scope exit (early returns included); thread 0 of each CTA
+struct DDTlScope {
+    const DDView& V;
+    const int k;
+    __device__ __forceinline__ DDTlScope(const DDView& v, int k_) : V(v), k(k_) { DD_TL_BEGIN(k); }
+    __device__ __forceinline__ ~DDTlScope() { DD_TL_END(k); }
+};
+#endif
 
 static inline uint64_t dd_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
 
@@ -126,6 +151,7 @@ static inline int dd_layout_compute(const dd_tracker_config* c, dd_tracker_layou
     DD_PUT(work_rec, 4 * S * T * 16);
     DD_PUT(det_feath, 2 * S * D * F);
     DD_PUT(tick_args, 256);
+    DD_PUT(timeline, 8 * 64 * 8 * 2);
 #undef DD_PUT
     L->total_bytes = off;
     return DD_OK;
@@ -167,6 +193,7 @@ static inline int dd_make_view(void* blob, const dd_tracker_config* c, DDView* v
     v->cdesc = (int*)(b + L.cdesc);
     v->det_feath = (unsigned short*)(b + L.det_feath);
     v->targs = (const DDTickArgs*)(b + L.tick_args);
+    v->tl = c->timeline ? (unsigned long long*)(b + L.timeline) : nullptr;
     v->work = (int*)(b + L.work); v->work_ctl = (int*)(b + L.work_ctl); v->work_rec = (int*)(b + L.work_rec);
     for (int i = 0; i < DD_MAX_SEGS; ++i) {
         const bool on = i < c->n_segs;

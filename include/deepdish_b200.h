@@ -85,10 +85,15 @@ typedef struct dd_tracker_config {
     int32_t gallery_impl;       /* 0 = default (the half-precision producer/consumer stream), 1 = exact f32 pass,
                                    2 = half pre-pass with per-warp global loads (both bit-identical to 0) */
     int32_t cosine_ctas_per_sm; /* impl 2: persistent grid = SMs x this (default 4); impl 0: warp triples (producer,
-                                   mma, checker) per CTA, one CTA per SM (default 7, at most 7)         */
+                                   mma, checker) per SM (default 7; at most 7, 8 with gallery_waves)   */
     int32_t match_warps;        /* matching kernel: 0 = by problem size, 1 / 4 / 8 warps per stream     */
     int32_t gallery_stages;     /* impl 0: 4 KB ring stages per warp triple (default 4)                 */
+    int32_t gallery_waves;      /* impl 0: 0 = one persistent CTA per SM holding all the triples (default); W > 0 = one
+                                   triple per CTA, SMs x triples x W CTAs that each stream a bounded share of the work
+                                   list and exit (measured equal on C3, kept as an A/B knob)                         */
     int32_t reserved0;
+    int32_t timeline;           /* != 0: every tick kernel stamps its first CTA's start and its last CTA's end
+                                   (%globaltimer, ns) into the blob's `timeline` words (benchmarks/timeline.py)    */
     uint64_t pool_f32[DD_MAX_SEGS]; /* device pointers, seg_pages x DD_PAGE_F32_BYTES each, 16-byte aligned */
     uint64_t pool_f16[DD_MAX_SEGS]; /* device pointers, seg_pages x DD_PAGE_F16_BYTES each, 16-byte aligned */
 } dd_tracker_config;
@@ -150,6 +155,9 @@ typedef struct dd_tracker_layout {
                                                   kernel's producer warps need to start the bulk copies of a track   */
     uint64_t det_feath;     /* f16 [S,Dmax,128]   half copy of det_featn                                     */
     uint64_t tick_args;     /* 256 bytes          per-tick input pointers of a captured tick (written by dd_engine_step) */
+    uint64_t timeline;      /* u64 [64,8,2]       config.timeline: per engine tick (mod 64) and kernel (prep, gate, gallery, match,
+                                                  apply, count-line, count-reduce): min start / max end in ns; the caller
+                                                  initialises starts to ~0 and ends to 0                         */
 } dd_tracker_layout;
 
 /* Host-only arithmetic: fills `host_out`.  No CUDA call. */
@@ -275,11 +283,14 @@ int dd_tracker_status(void* state, const dd_tracker_config* host_cfg, int32_t* h
  *                                 on the caller's stream -- when n_chunks == 1);
  *   line f64 [4] or [S,4]; partial_counts i64 [2,n_chunks,C,4]; total_counts i64 [C,4]; det_track_id i32 [S,Dmax];
  *   poll_every > 0: every that many ticks the chunk's pool counters are copied to pinned memory behind its tick
- *   (dd_engine_pool_latest reads them without synchronising). */
+ *   (dd_engine_pool_latest reads them without synchronising);
+ *   gallery_turns != 0 (n_chunks > 1): the chunks take turns on the HBM-bound gallery stream -- each one waits for the
+ *   previously enqueued one --, which keeps the chunks in anti-phase: the latency-bound matching of one chunk always
+ *   runs under the gallery stream of another (the tick is then captured as three graphs per chunk). */
 int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracker_config* const* host_cfgs,
                      const int32_t* host_first_stream, void* const* host_streams, void* aux_stream, const double* line,
                      int32_t line_per_stream, int64_t* partial_counts, int64_t* total_counts, int32_t* det_track_id,
-                     int32_t poll_every, void** host_out_engine);
+                     int32_t poll_every, int32_t gallery_turns, void** host_out_engine);
 int dd_engine_destroy(void* engine);
 /* A chunk's blob was re-laid out or its pool grew (cfg->n_segs / page_cap / segment pointers changed): its captured
  * graphs are dropped and re-captured at the next tick. */

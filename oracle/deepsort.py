@@ -3,8 +3,8 @@
 Every function cites the reference ``file:line`` it follows (paths relative to /root/reference).
 The numerics deliberately go through the same numpy / scipy routines as the reference (``np.dot``,
 ``np.linalg.multi_dot``, ``scipy.linalg.cho_factor`` ...) so that this restatement is bit-identical
-to the reference on the same inputs; ``tests/test_oracle_vs_reference.py`` checks that in the build
-container and ``tests/golden/`` carries reference-generated fixtures to the GPU box.
+to the reference on the same inputs; ``tests/test_golden.py`` checks it against the fixtures ``oracle/make_golden.py``
+generated from the unmodified reference in the build container (``tests/golden/``, which also travel to the GPU box).
 
 Pinned: against the unmodified reference run in this container (fixtures in tests/golden/).
 """
@@ -227,8 +227,8 @@ def lsap_port(cost):
         REVERSE order (remaining[it] = nc-1-it) and a scanned column is removed by swap-with-last;
       * scanning in list order, the running minimum is replaced when strictly lower, or when
         equal and the column is unassigned.
-    Returns (row_ind, col_ind) like scipy.  ``tests/test_oracle_lsap.py`` checks it against scipy
-    on tie-heavy matrices.
+    Returns (row_ind, col_ind) like scipy.  ``tests/test_hostemu.py::test_lsap_device_code_and_oracle_port_match_scipy``
+    checks it against scipy on tie-heavy matrices.
     """
     cost = np.asarray(cost, dtype=float)
     nr, nc = cost.shape

@@ -16,7 +16,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("DEEPDISH_REFERENCE", "/root/reference")
+def _reference_root():
+    """$DEEPDISH_REFERENCE, else an installed copy under baseline/_ref, else /root/reference."""
+    env = os.environ.get("DEEPDISH_REFERENCE")
+    if env:
+        return env
+    local = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if os.path.isdir(os.path.join(local, "deep_sort")):
+        return local
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available():

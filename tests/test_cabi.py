@@ -50,6 +50,14 @@ def test_layout_query_and_invalid_config():
     assert cfg.label_rank[0] == 2 and cfg.label_rank[1] == 0 and cfg.label_rank[2] == 1
 
 
+def test_engine_rejects_bad_arguments_without_touching_cuda():
+    _l, lib = _lib()
+    h = ctypes.c_void_p()
+    assert lib.dd_engine_create(0, None, None, None, None, None, None, 0, None, None, None, 0, 0, ctypes.byref(h)) == _l.DD_ERR_INVALID
+    assert lib.dd_engine_step(None, None, None, None, None, None, 0, None) == _l.DD_ERR_INVALID
+    assert lib.dd_engine_destroy(None) == _l.DD_ERR_INVALID
+
+
 def test_product_never_imports_oracle():
     """The product package must not reference oracle/ (no CPU fallback path)."""
     pkg = os.path.join(ROOT, "deepdish_b200")

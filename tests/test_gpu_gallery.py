@@ -40,6 +40,10 @@ def _history(impl, S, nobj, dmax, tmax, budget, frames, seed, feat_noise, big_bo
     ("short_gallery_budget_5", dict(S=4, nobj=12, dmax=16, tmax=48, budget=5, frames=40, seed=44, feat_noise=0.02)),
     ("many_candidates_two_gate_words", dict(S=3, nobj=40, dmax=48, tmax=128, budget=33, frames=40, seed=45,
                                             feat_noise=0.05, big_boxes=True)),
+    # identical rows x up to 8 gate-passing detections: more window candidates than a checker message lists (240), so
+    # the checker's evaluate-everything fallback runs
+    ("identical_rows_many_candidates", dict(S=3, nobj=30, dmax=40, tmax=96, budget=100, frames=115, seed=48,
+                                            feat_noise=0.0, big_boxes=True)),
     # nn_budget=None: galleries of ~300 rows span several 256-row blocks of the half pre-pass (running maximum)
     ("unbounded_multi_block", dict(S=2, nobj=8, dmax=12, tmax=32, budget=None, frames=340, seed=46, feat_noise=0.01)),
     ("unbounded_identical_rows", dict(S=2, nobj=6, dmax=8, tmax=32, budget=None, frames=300, seed=47, feat_noise=0.0)),
@@ -63,3 +67,5 @@ def test_half_prepass_costs_are_bit_identical_to_the_exact_pass(name, kw, impl):
     assert checked > 500
     if name == "many_candidates_two_gate_words":
         assert many > 8
+    if name == "identical_rows_many_candidates":
+        assert many >= 3

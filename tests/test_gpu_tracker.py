@@ -293,3 +293,33 @@ def test_unpack_detections_entry():
     valid = (torch.arange(D)[None, :] < b.count[:, None]).numpy()
     for got, exp in ((t, b.tlwh), (cf, b.conf), (lb, b.label), (ft, b.feat)):
         np.testing.assert_array_equal(got.cpu().numpy()[valid], exp.numpy()[valid])
+
+
+def test_engine_counts_launches_and_survives_mode_switches():
+    """The native tick engine (dd_engine_*): one captured graph per chunk and tick.  Its launch counter is what
+    bench.py reports as gpu_launches; ticks issued through it and call by call from Python (update / countline) can be
+    interleaved on the same tracker and still equal a tracker that only ever used one path."""
+    from deepdish_b200.batched import BatchedTracker
+    S = 6
+    a = BatchedTracker(S, LABELS3, max_tracks=48, max_dets=16, budget=20, max_age=30, n_chunks=2)
+    b = BatchedTracker(S, LABELS3, max_tracks=48, max_dets=16, budget=20, max_age=30, n_chunks=1)
+    sc = Scene(S, 10, 16, n_labels=3, seed=5)
+    for f in range(24):
+        fr = sc.step().to("cuda")
+        if f % 4 == 3:               # the per-call path: predict + update + countline
+            a.predict()
+            ia = a.update(fr.tlwh, fr.conf, fr.label, fr.feat, fr.count).cpu().numpy().copy()
+            a.countline()
+        else:
+            ia = a.step(fr, join=True, reduce=True).cpu().numpy().copy()
+        ib = b.step(fr, join=True, reduce=True).cpu().numpy().copy()
+        np.testing.assert_array_equal(ia, ib, err_msg="tick %d" % f)
+    ticks, launches, blocked = a.engine_stats()
+    assert ticks == 18 and launches == 18 * (2 * 9 + 1) and blocked >= 0.0
+    assert b.engine_stats()[1] == 24 * (9 + 1)
+    assert torch.equal(a.reduce_counts(), b.reduce_counts())
+    va, vb = a.host_view(["track_id", "state", "hits", "mean"]), b.host_view(["track_id", "state", "hits", "mean"])
+    for k in va:
+        np.testing.assert_array_equal(va[k], vb[k], err_msg=k)
+    a.check()
+    b.check()
