@@ -279,6 +279,9 @@ k_cosine_h(const DDView V, const DDTickArgs A) {
 #define DD_GS_MSG_CAP 240                    // candidates a message can list; a block with more (near-identical rows: legal,
                                              // never seen outside the adversarial tests) is re-evaluated in full by the checker
 #define DD_GS_MSG_BYTES (DD_GS_HDR_INTS * 4 + DD_GS_MSG_CAP * 2)    // checker message: header (32 ints; [6] = candidates) + list (u16)
+#ifndef DD_GS_DEBUG_SKIP
+#define DD_GS_DEBUG_SKIP 0   // timing experiments ONLY (wrong results): 1 = checker evaluates nothing, 2 = no candidate
+#endif                       // listing, 4 = no fragment loads / mma, 8 = one query row per job
 #define DD_GS_FIRST 1                        // first job / message of a detection group: reset the running maxima
 #define DD_GS_LAST 2                         // last one: the cost entries are final
 #define DD_GS_STOP 4
@@ -398,9 +401,9 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
                 }
                 if (lane < 8) { H[8 + lane] = cjl; H[16 + lane] = pidl; }
                 __syncwarp();
-                if (lane == 0) dd_mbar_expect_tx(P.hfull + hb, (unsigned)nq * 256u);
+                if (lane == 0) dd_mbar_expect_tx(P.hfull + hb, (DD_GS_DEBUG_SKIP & 8) ? 256u : (unsigned)nq * 256u);
                 __syncwarp();
-                if (lane < nq)
+                if (lane < ((DD_GS_DEBUG_SKIP & 8) ? 1 : nq))
                     dd_bulk_g2s(P.qbuf + hb * 2048 + lane * 256, V.det_feath + ((size_t)s * V.D + cjl) * DD_FEAT_DIM, 256u,
                                 P.hfull + hb);
                 hb ^= 1;
@@ -481,18 +484,27 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
             fphase ^= 1u << st;
             const uint4* pg = (const uint4*)(P.ring + (size_t)st * DD_PAGE_F16_BYTES);
             uint4 ga[4], gb[4];
+#if DD_GS_DEBUG_SKIP & 4
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ga[j] = make_uint4(lane, p, j, 1); gb[j] = ga[j]; }
+#else
 #pragma unroll
             for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + lane]; gb[j] = pg[j * 64 + 32 + lane]; }
+#endif
             __syncwarp();
             if (lane == 0) dd_mbar_arrive(P.empty + st);       // the stage is free again: its bytes are in registers
             st = st + 1 == stages ? 0 : st + 1;
             // two independent accumulator chains (any summation order satisfies the window bound)
             float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#if DD_GS_DEBUG_SKIP & 4
+            ca[0] = __uint_as_float(ga[0].x & 0xffu) * 1e-9f;
+#else
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 dd_mma_f16(ca, ga[j].x, gb[j].x, ga[j].y, gb[j].y, qb[j].x, qb[j].y);
                 dd_mma_f16(cb, ga[j].z, gb[j].z, ga[j].w, gb[j].w, qb[j].z, qb[j].w);
             }
+#endif
             float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2], c3 = ca[3] + cb[3];
             const int ra = p * 16 + gq, rb = ra + 8;
             if (ra >= nrows) { c0 = -3.0e38f; c1 = -3.0e38f; }     // rows past the end (stale stage bytes) never win
@@ -526,7 +538,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         unsigned short* mc = (unsigned short*)(M + DD_GS_HDR_INTS);
         M[lane] = lane == 6 ? 0 : hw;                          // word 6 = candidate counter
         __syncwarp();
-        for (int p = 0; p < npg; ++p) {
+        for (int p = 0; p < ((DD_GS_DEBUG_SKIP & 2) ? 0 : npg); ++p) {
             const int ra = p * 16 + gq, rb = ra + 8;
             const unsigned ua = P.approx[ra * 4 + tq], ub = P.approx[rb * 4 + tq];
             const float2 va = __half22float2(*(const __half2*)&ua);
@@ -562,7 +574,7 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
         const int nq = __shfl_sync(0xffffffffu, hw, 4), listed = __shfl_sync(0xffffffffu, hw, 6);
         // more candidates than a message holds: every (row, detection) of the block is evaluated exactly instead
         const bool all = listed > DD_GS_MSG_CAP;
-        const int ncand = all ? __shfl_sync(0xffffffffu, hw, 3) * nq : listed;
+        const int ncand = (DD_GS_DEBUG_SKIP & 1) ? 0 : (all ? __shfl_sync(0xffffffffu, hw, 3) * nq : listed);
         if (flags & DD_GS_FIRST) best = -3.0e38f;
         const float4* qbase = (const float4*)(V.det_featn + (size_t)s * V.D * DD_FEAT_DIM);
         for (int c0 = 0; c0 < ncand; c0 += CW) {
