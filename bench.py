@@ -269,14 +269,18 @@ def gpu_arm(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms = start.elapsed_time(end)
     state_bytes = bt.memory_bytes()
-    cdv = bt.v["cdesc"]
-    cd = cdv[..., 2]
-    cand_per_track = float(cd.sum()) / max(1, int((cd > 0).sum()))      # gate-passing detections per streamed track
-    # what the default gallery kernel must move from HBM for the last tick: every streamed track's half pages ONCE (a
-    # track with more than 8 gate-passing detections is streamed again per group of 8, but those passes hit L2), the
-    # detections' half rows, one 64-byte work record per track
-    g_streamed = float((cdv[..., 1] * (cd > 0)).sum())
-    q_rows, w_items = float(cd.sum()), float((cd > 0).sum())
+    # what the gallery kernel must move from HBM for the last tick, read from the work records k_gate wrote for it (one
+    # per streamed track: gallery rows, gate-passing detections): every streamed track's half pages ONCE (a track with
+    # more than 8 gate-passing detections is streamed again per group of 8, but those passes hit L2), the detections'
+    # half rows, one 64-byte work record per track
+    g_streamed = q_rows = w_items = 0.0
+    for c in bt.chunks:
+        n_work = int(c.v["work_ctl"][0])
+        rec = c.v["work_rec"][:n_work]
+        g_streamed += float(rec[:, 2].sum())
+        q_rows += float(rec[:, 3].sum())
+        w_items += float(n_work)
+    cand_per_track = q_rows / max(1.0, w_items)                         # gate-passing detections per streamed track
     g1 = int(bt.gallery_vectors().sum())
     conf1 = int(((bt.v["state"] == 2).sum()))
     bt.check()

@@ -32,8 +32,94 @@ __device__ __forceinline__ void bulk(void* dst, const void* src, unsigned bytes,
 }
 
 #define PAGE 4096
+__device__ __forceinline__ void mma_f16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 // pairs of warps (producer, consumer) per CTA; each pair owns `stages` ring slots; pages[] lists the page ids to read,
 // pair q of the grid takes entries q, q + n_pairs, ...
+template <int MODE>
+__global__ void k_stream3(const char* pool, const char* pool2, size_t pool2_rows, const int* pages, int n, int stages,
+                          unsigned long long* sink) {
+    extern __shared__ __align__(128) char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp / 3, role = warp % 3;
+    const int pairs_per_cta = blockDim.x / 96;
+    char* ring = smem + (size_t)pair * (stages * PAGE + 1024 + 256);
+    char* small = ring + stages * PAGE;
+    unsigned long long* full = (unsigned long long*)(small + 1024);
+    unsigned long long* empty = full + stages;
+    unsigned long long* sfull = empty + stages;
+    if (role == 0 && lane == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(sfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int q = blockIdx.x * pairs_per_cta + pair, nq = gridDim.x * pairs_per_cta;
+    int st = 0;
+    if (role == 0) {
+        unsigned ph = ~0u;
+        int k = 0;
+        for (int i = q; i < n; i += nq, ++k) {
+            if ((MODE & 4) && k % 7 == 0 && lane < 4)       // 4 small copies per 7 pages (nobody waits for them here)
+                bulk(small + lane * 256, pool2 + ((size_t)(pages[i] * 2654435761u + lane) % pool2_rows) * 512, 256, sfull);
+            mbar_wait(empty + st, (ph >> st) & 1u);
+            ph ^= 1u << st;
+            if (lane == 0) {
+                mbar_expect(full + st, PAGE);
+                bulk(ring + st * PAGE, pool + (size_t)pages[i] * PAGE, PAGE, full + st);
+            }
+            st = st + 1 == stages ? 0 : st + 1;
+        }
+    } else if (role == 1) {
+        unsigned ph = 0u;
+        float acc = 0.f;
+        for (int i = q; i < n; i += nq) {
+            mbar_wait(full + st, (ph >> st) & 1u);
+            ph ^= 1u << st;
+            const uint4* pg = (const uint4*)(ring + st * PAGE);
+            uint4 ga[4], gb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + lane]; gb[j] = pg[j * 64 + 32 + lane]; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + st);
+            st = st + 1 == stages ? 0 : st + 1;
+            if (MODE & 1) {
+                float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mma_f16(ca, ga[j].x, gb[j].x, ga[j].y, gb[j].y, ga[j].x, ga[j].y);
+                    mma_f16(cb, ga[j].z, gb[j].z, ga[j].w, gb[j].w, ga[j].z, ga[j].w);
+                }
+                acc += ca[0] + cb[0] + ca[1] + cb[1] + ca[2] + cb[2] + ca[3] + cb[3];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc += __uint_as_float((ga[j].x ^ gb[j].y) & 0x3fffffffu);
+            }
+        }
+        if (acc == 1.2345f) sink[0] = 1;
+    } else {
+        if (MODE & 2) {           // "checker": per 7 pages two dependent rounds of 4 random 512-byte rows
+            float acc = 0.f;
+            unsigned h = q * 2654435761u + 12345u;
+            for (int i = q; i < n; i += nq * 7) {
+                for (int r = 0; r < 2; ++r) {
+                    float4 a[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        h = h * 1664525u + 1013904223u + (unsigned)(acc != 7.f);
+                        a[k] = ((const float4*)(pool2 + ((size_t)h % pool2_rows) * 512))[lane];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc += a[k].x + a[k].y + a[k].z + a[k].w;
+                    acc = __shfl_xor_sync(0xffffffffu, acc, 1) + 1.f;      // next round depends on this one
+                }
+            }
+            if (acc == 1.2345f) sink[1] = 1;
+        }
+    }
+}
+
 __global__ void k_stream(const char* pool, const int* pages, int n, int stages, unsigned long long* sink) {
     extern __shared__ __align__(128) char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1, role = warp & 1;
@@ -127,6 +213,35 @@ int main(int argc, char** argv) {
                        ms, (double)n * PAGE / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
             }
         }
+    }
+    // ---- the same ring with the gallery stream's other ingredients added one by one (random pages, 7 triples x 4 stages)
+    {
+        const size_t pool2_rows = (size_t)2 * (1ull << 30) / 512;
+        char* pool2;
+        cudaMalloc(&pool2, pool2_rows * 512);
+        cudaMemset(pool2, 1, pool2_rows * 512);
+        std::vector<int> pages(n);
+        for (auto& p : pages) p = (int)(rng() % pool_pages);
+        cudaMemcpy(d_pages, pages.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+        const int triples = 7, stages = 4;
+        const size_t smem = (size_t)triples * (stages * PAGE + 1024 + 256);
+        auto run = [&](auto kern, int mode) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            for (int w = 0; w < 3; ++w) kern<<<sms, triples * 96, smem>>>(pool, pool2, pool2_rows, d_pages, n, stages, sink);
+            cudaEventRecord(a);
+            const int it = 10;
+            for (int w = 0; w < it; ++w) kern<<<sms, triples * 96, smem>>>(pool, pool2, pool2_rows, d_pages, n, stages, sink);
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            float ms;
+            cudaEventElapsedTime(&ms, a, b);
+            ms /= it;
+            printf("{\"triples\": 7, \"stages\": 4, \"mode\": %d, \"ms\": %.4f, \"page_GBps\": %.1f, \"err\": \"%s\", \"modes\": \"1 = 8 HMMA per page, 2 = third warp: 2 dependent rounds of 4 random 512 B rows per 7 pages, 4 = 4 small bulk copies per 7 pages\"}\n",
+                   mode, ms, (double)n * PAGE / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+        };
+        run(k_stream3<0>, 0); run(k_stream3<1>, 1); run(k_stream3<2>, 2); run(k_stream3<3>, 3); run(k_stream3<4>, 4); run(k_stream3<7>, 7);
     }
     return 0;
 }

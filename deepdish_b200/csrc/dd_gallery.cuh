@@ -279,9 +279,10 @@ k_cosine_h(const DDView V, const DDTickArgs A) {
 #define DD_GS_MSG_CAP 240                    // candidates a message can list; a block with more (near-identical rows: legal,
                                              // never seen outside the adversarial tests) is re-evaluated in full by the checker
 #define DD_GS_MSG_BYTES (DD_GS_HDR_INTS * 4 + DD_GS_MSG_CAP * 2)    // checker message: header (32 ints; [6] = candidates) + list (u16)
-#ifndef DD_GS_DEBUG_SKIP
-#define DD_GS_DEBUG_SKIP 0   // timing experiments ONLY (wrong results): 1 = checker evaluates nothing, 2 = no candidate
-#endif                       // listing, 4 = no fragment loads / mma, 8 = one query row per job
+// SKIP (template parameter of the role bodies): timing experiments only -- the product kernel is SKIP = 0; variants are
+// compiled under -DDD_GS_VARIANTS and replayed on a finished tick's work list by dd_gallery_replay (wrong costs, nothing
+// reads them): 1 = checker evaluates nothing, 2 = no candidate listing, 4 = no fragment loads / mma, 8 = one query row per
+// job, 16 = a ragged last page is copied whole.
 #define DD_GS_FIRST 1                        // first job / message of a detection group: reset the running maxima
 #define DD_GS_LAST 2                         // last one: the cost entries are final
 #define DD_GS_STOP 4
@@ -325,6 +326,7 @@ __device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDTripleSmem
 // quota: work-list entries this producer may claim (even; INT_MAX = until the list is empty).  With the one-triple-
 // per-CTA launch every CTA streams a bounded share and exits, so that its shared memory becomes available to
 // whatever kernel is waiting (the quotas of all CTAs together cover the list).
+template <int SKIP>
 __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSmem& P, int stages, int quota) {
     const int lane = threadIdx.x & 31;
     const int n = V.work_ctl[0];
@@ -401,9 +403,9 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
                 }
                 if (lane < 8) { H[8 + lane] = cjl; H[16 + lane] = pidl; }
                 __syncwarp();
-                if (lane == 0) dd_mbar_expect_tx(P.hfull + hb, (DD_GS_DEBUG_SKIP & 8) ? 256u : (unsigned)nq * 256u);
+                if (lane == 0) dd_mbar_expect_tx(P.hfull + hb, (SKIP & 8) ? 256u : (unsigned)nq * 256u);
                 __syncwarp();
-                if (lane < ((DD_GS_DEBUG_SKIP & 8) ? 1 : nq))
+                if (lane < ((SKIP & 8) ? 1 : nq))
                     dd_bulk_g2s(P.qbuf + hb * 2048 + lane * 256, V.det_feath + ((size_t)s * V.D + cjl) * DD_FEAT_DIM, 256u,
                                 P.hfull + hb);
                 hb ^= 1;
@@ -414,7 +416,7 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
                     const int valid = dd_imin(16, nrows - p * 16);
                     const char* src = dd_page_f16(V, __shfl_sync(0xffffffffu, pidl, p));
                     char* dst = P.ring + (size_t)st * DD_PAGE_F16_BYTES;
-                    if (valid == 16) {
+                    if (valid == 16 || (SKIP & 16)) {
                         if (lane == 0) {
                             dd_mbar_expect_tx(P.full + st, DD_PAGE_F16_BYTES);
                             dd_bulk_g2s(dst, src, DD_PAGE_F16_BYTES, P.full + st);
@@ -445,6 +447,7 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
     }
 }
 
+template <int SKIP>
 __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
     const int lane = threadIdx.x & 31;
     const int gq = lane >> 2, tq = lane & 3;
@@ -484,27 +487,27 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
             fphase ^= 1u << st;
             const uint4* pg = (const uint4*)(P.ring + (size_t)st * DD_PAGE_F16_BYTES);
             uint4 ga[4], gb[4];
-#if DD_GS_DEBUG_SKIP & 4
+            if (SKIP & 4) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ga[j] = make_uint4(lane, p, j, 1); gb[j] = ga[j]; }
-#else
+                for (int j = 0; j < 4; ++j) { ga[j] = make_uint4(lane, p, j, 1); gb[j] = ga[j]; }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + lane]; gb[j] = pg[j * 64 + 32 + lane]; }
-#endif
+                for (int j = 0; j < 4; ++j) { ga[j] = pg[j * 64 + lane]; gb[j] = pg[j * 64 + 32 + lane]; }
+            }
             __syncwarp();
             if (lane == 0) dd_mbar_arrive(P.empty + st);       // the stage is free again: its bytes are in registers
             st = st + 1 == stages ? 0 : st + 1;
             // two independent accumulator chains (any summation order satisfies the window bound)
             float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
-#if DD_GS_DEBUG_SKIP & 4
-            ca[0] = __uint_as_float(ga[0].x & 0xffu) * 1e-9f;
-#else
+            if (SKIP & 4) {
+                ca[0] = __uint_as_float(ga[0].x & 0xffu) * 1e-9f;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                dd_mma_f16(ca, ga[j].x, gb[j].x, ga[j].y, gb[j].y, qb[j].x, qb[j].y);
-                dd_mma_f16(cb, ga[j].z, gb[j].z, ga[j].w, gb[j].w, qb[j].z, qb[j].w);
+                for (int j = 0; j < 4; ++j) {
+                    dd_mma_f16(ca, ga[j].x, gb[j].x, ga[j].y, gb[j].y, qb[j].x, qb[j].y);
+                    dd_mma_f16(cb, ga[j].z, gb[j].z, ga[j].w, gb[j].w, qb[j].z, qb[j].w);
+                }
             }
-#endif
             float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2], c3 = ca[3] + cb[3];
             const int ra = p * 16 + gq, rb = ra + 8;
             if (ra >= nrows) { c0 = -3.0e38f; c1 = -3.0e38f; }     // rows past the end (stale stage bytes) never win
@@ -538,7 +541,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         unsigned short* mc = (unsigned short*)(M + DD_GS_HDR_INTS);
         M[lane] = lane == 6 ? 0 : hw;                          // word 6 = candidate counter
         __syncwarp();
-        for (int p = 0; p < ((DD_GS_DEBUG_SKIP & 2) ? 0 : npg); ++p) {
+        for (int p = 0; p < ((SKIP & 2) ? 0 : npg); ++p) {
             const int ra = p * 16 + gq, rb = ra + 8;
             const unsigned ua = P.approx[ra * 4 + tq], ub = P.approx[rb * 4 + tq];
             const float2 va = __half22float2(*(const __half2*)&ua);
@@ -556,7 +559,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
     }
 }
 
-template <int CW>
+template <int CW, int SKIP>
 __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSmem& P) {
     const int lane = threadIdx.x & 31;
     int mb = 0;
@@ -574,7 +577,7 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
         const int nq = __shfl_sync(0xffffffffu, hw, 4), listed = __shfl_sync(0xffffffffu, hw, 6);
         // more candidates than a message holds: every (row, detection) of the block is evaluated exactly instead
         const bool all = listed > DD_GS_MSG_CAP;
-        const int ncand = (DD_GS_DEBUG_SKIP & 1) ? 0 : (all ? __shfl_sync(0xffffffffu, hw, 3) * nq : listed);
+        const int ncand = (SKIP & 1) ? 0 : (all ? __shfl_sync(0xffffffffu, hw, 3) * nq : listed);
         if (flags & DD_GS_FIRST) best = -3.0e38f;
         const float4* qbase = (const float4*)(V.det_featn + (size_t)s * V.D * DD_FEAT_DIM);
         for (int c0 = 0; c0 < ncand; c0 += CW) {
@@ -632,11 +635,8 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
     }
 }
 
-// 72 registers (8 bytes of spills): the register file is four 16 K partitions, the CTA's 21 warps land 6 + 5 + 5 + 5,
-// and at 72 every partition still has room for one 80-register matching warp of another chunk (at 80 the six-warp
-// partition has not).
-__global__ void __maxnreg__(72)
-k_gallery_stream(const DDView V, int stages, int bounded) {
+template <int SKIP>
+__device__ __forceinline__ void dd_gs_body(const DDView& V, int stages, int bounded) {
     extern __shared__ __align__(128) char smem[];
     const int warp = threadIdx.x >> 5;
     const int triple = warp / 3, role = warp - triple * 3;
@@ -658,10 +658,27 @@ k_gallery_stream(const DDView V, int stages, int bounded) {
         quota = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 1) & ~1;
         if (quota < 2) quota = 2;
     }
-    if (role == 0) dd_gs_producer(V, P, stages, quota);
-    else if (role == 1) dd_gs_mma(P, stages);
+    if (role == 0) dd_gs_producer<SKIP>(V, P, stages, quota);
+    else if (role == 1) dd_gs_mma<SKIP>(P, stages);
     else {
-        dd_gs_checker<4>(V, P);
+        dd_gs_checker<4, SKIP>(V, P);
         if (V.tl && (threadIdx.x & 31) == 0) atomicMax(DD_TL_SLOT(2) + 1, dd_globaltimer());   // the checker drains last
     }
 }
+
+// 72 registers (8 bytes of spills): the register file is four 16 K partitions, the CTA's 21 warps land 6 + 5 + 5 + 5,
+// and at 72 every partition still has room for one 80-register matching warp of another chunk (at 80 the six-warp
+// partition has not).
+__global__ void __maxnreg__(72)
+k_gallery_stream(const DDView V, int stages, int bounded) {
+    dd_gs_body<0>(V, stages, bounded);
+}
+
+#ifdef DD_GS_VARIANTS
+template <int SKIP>
+__global__ void __maxnreg__(72)
+k_gallery_stream_dbg(const DDView V, int stages, int bounded) {
+    dd_gs_body<SKIP>(V, stages, bounded);
+}
+__global__ void k_reset_cursor(const DDView V) { V.work_ctl[32] = 0; }
+#endif

@@ -506,6 +506,34 @@ int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int r
     if (parts & DD_PART_TAIL) return dd_tick_tail(state, cfg, line, line_per_stream, nullptr, reduce != 0, st);
     return DD_OK;
 }
+#ifdef DD_GS_VARIANTS
+// Benchmark hook (A/B builds only, benchmarks/gallery_variants.py): run gallery-stream variant `skip` again on the work
+// list the last tick left behind.  Variants other than 0 write wrong costs -- nothing reads them before the next tick.
+extern "C" int dd_gallery_replay(void* state, const dd_tracker_config* cfg, int skip, void* stream) {
+    DDView V;
+    int rc = dd_make_view(state, cfg, &V);
+    if (rc != DD_OK) return rc;
+    int triples = 0, stages = 0, mw = 1;
+    rc = dd_tick_prepare(V, cfg, &triples, &stages, &mw);
+    if (rc != DD_OK || cfg->gallery_impl != 0) return DD_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t gsm = dd_gs_triple_bytes(stages) * triples;
+    k_reset_cursor<<<1, 1, 0, st>>>(V);
+#define DD_VARIANT(S) case S: \
+        cudaFuncSetAttribute(k_gallery_stream_dbg<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm); \
+        cudaFuncSetAttribute(k_gallery_stream_dbg<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        k_gallery_stream_dbg<S><<<dd_sm_count(), triples * 96, gsm, st>>>(V, stages, 0); break;
+    switch (skip) {
+        DD_VARIANT(0) DD_VARIANT(1) DD_VARIANT(2) DD_VARIANT(3) DD_VARIANT(4) DD_VARIANT(7) DD_VARIANT(8) DD_VARIANT(15)
+        DD_VARIANT(16) DD_VARIANT(31)
+        default: return DD_ERR_INVALID;
+    }
+#undef DD_VARIANT
+    DD_CHECK_LAUNCH();
+    return DD_OK;
+}
+#endif
+
 int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg) {
     DDView V;
     int rc = dd_make_view(state, cfg, &V);
