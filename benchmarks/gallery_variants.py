@@ -40,6 +40,8 @@ def main():
     rows, cands = int(rec[:, 2].sum()), int(rec[:, 3].sum())
     must = 256.0 * rows + 260.0 * cands + 64.0 * n
     sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    prof = (ctypes.c_uint64 * 16)()
+    lib.dd_gallery_prof.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_void_p]
     for skip in (0, 1, 2, 3, 4, 7, 8, 15, 16, 31, 0):
         for _ in range(3):
             _lib.check(lib.dd_gallery_replay(c.state, c.cfgp, skip, sp), "dd_gallery_replay")
@@ -53,8 +55,17 @@ def main():
             e.record()
             torch.cuda.synchronize()
             ms += s.elapsed_time(e) / 10
+        lib.dd_gallery_prof(prof, sp)                      # reset
+        _lib.check(lib.dd_gallery_replay(c.state, c.cfgp, skip, sp), "dd_gallery_replay")
+        lib.dd_gallery_prof(prof, sp)
+        p = [int(x) for x in prof]
+        frac = lambda a, b: round(a / max(1, b), 3)
+        roles = {"producer": {"wait_empty": frac(p[1], p[0]), "wait_hfree": frac(p[2], p[0])},
+                 "mma": {"wait_full": frac(p[5], p[4]), "wait_hfull": frac(p[6], p[4]), "wait_mfree": frac(p[7], p[4])},
+                 "checker": {"wait_mfull": frac(p[9], p[8])}}
         print(json.dumps({"skip": skip, "what": NAMES[skip], "ms": round(ms, 4), "work_items": n, "gallery_rows": rows,
-                          "must_move_GB": round(must / 1e9, 4), "GBps_of_must_move": round(must / ms / 1e6, 1)}), flush=True)
+                          "must_move_GB": round(must / 1e9, 4), "GBps_of_must_move": round(must / ms / 1e6, 1),
+                          "share_of_role_time_in_waits": roles}), flush=True)
 
 
 if __name__ == "__main__":

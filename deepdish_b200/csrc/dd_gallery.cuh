@@ -276,8 +276,11 @@ k_cosine_h(const DDView V, const DDTickArgs A) {
 
 #define DD_GS_BLOCK_ROWS 128                 // gallery rows per job (8 pages): the mma warp keeps 8 x 4 dots per lane
 #define DD_GS_HDR_INTS 32                    // job header: 0 slotg 1 stream 2 row0 3 nrows 4 nq 5 flags | 8.. cj[8] | 16.. pid[8]
-#define DD_GS_MSG_CAP 240                    // candidates a message can list; a block with more (near-identical rows: legal,
-                                             // never seen outside the adversarial tests) is re-evaluated in full by the checker
+#ifndef DD_GS_MQ
+#define DD_GS_MQ 2                           // checker messages in flight per triple: the checker's service time has a long
+#endif                                       // tail (dependent global reads), a shallow queue would stall the mma warp behind it
+#define DD_GS_MSG_CAP (DD_GS_MQ > 2 ? 112 : 240)   // candidates a message can list; a block with more (near-identical rows:
+                                             // legal, never seen outside the adversarial tests) is re-evaluated in full
 #define DD_GS_MSG_BYTES (DD_GS_HDR_INTS * 4 + DD_GS_MSG_CAP * 2)    // checker message: header (32 ints; [6] = candidates) + list (u16)
 // SKIP (template parameter of the role bodies): timing experiments only -- the product kernel is SKIP = 0; variants are
 // compiled under -DDD_GS_VARIANTS and replayed on a finished tick's work list by dd_gallery_replay (wrong costs, nothing
@@ -291,15 +294,30 @@ __host__ __device__ inline size_t dd_gs_triple_bytes(int stages) {
     const size_t b = (size_t)stages * DD_PAGE_F16_BYTES            // ring
                      + 2 * 8 * 256                                 // query half rows, double-buffered
                      + 2 * DD_GS_HDR_INTS * 4                      // job headers, double-buffered
-                     + 2 * DD_GS_MSG_BYTES                         // checker messages, double-buffered
+                     + DD_GS_MQ * DD_GS_MSG_BYTES                  // checker messages
                      + DD_GS_BLOCK_ROWS * 8 * 2                    // approximate dots of the block being streamed (half)
-                     + (size_t)(2 * stages + 8) * 8;               // mbarriers: full / empty [stages], hfull hfree mfull mfree [2]
+                     + (size_t)(2 * stages + 4 + 2 * DD_GS_MQ) * 8; // mbarriers: full / empty [stages], hfull hfree [2], mfull mfree [MQ]
     return (b + 127) & ~(size_t)127;
 }
 
 __device__ __forceinline__ void dd_mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dd_smem_u32(bar)) : "memory");
 }
+
+#ifdef DD_GS_VARIANTS
+// role-level cycle accounting of the variant builds (benchmarks/gallery_variants.py): cycles every role spent inside
+// its mbarrier waits, summed over all triples.  0 producer total, 1 wait empty, 2 wait hfree | 4 mma total, 5 wait full,
+// 6 wait hfull, 7 wait mfree | 8 checker total, 9 wait mfull
+__device__ unsigned long long dd_gs_prof[16];
+#define DD_GS_PROF_DECL unsigned long long pw_[4] = {0, 0, 0, 0}; const long long pt0_ = clock64();
+#define DD_GS_WAIT(k, bar, par) do { const long long c0_ = clock64(); dd_mbar_wait(bar, par); pw_[k] += (unsigned long long)(clock64() - c0_); } while (0)
+#define DD_GS_PROF_FLUSH(base) do { if ((threadIdx.x & 31) == 0) { atomicAdd(dd_gs_prof + (base), (unsigned long long)(clock64() - pt0_)); \
+        for (int k_ = 1; k_ < 4; ++k_) atomicAdd(dd_gs_prof + (base) + k_, pw_[k_]); } } while (0)
+#else
+#define DD_GS_PROF_DECL
+#define DD_GS_WAIT(k, bar, par) dd_mbar_wait(bar, par)
+#define DD_GS_PROF_FLUSH(base)
+#endif
 
 struct DDTripleSmem {
     char* ring;
@@ -314,13 +332,13 @@ __device__ __forceinline__ void dd_gs_carve(char* base, int stages, DDTripleSmem
     P.qbuf = P.ring + (size_t)stages * DD_PAGE_F16_BYTES;
     P.hdr = (int*)(P.qbuf + 2 * 8 * 256);
     P.msg = (char*)(P.hdr + 2 * DD_GS_HDR_INTS);
-    P.approx = (unsigned*)(P.msg + 2 * DD_GS_MSG_BYTES);
+    P.approx = (unsigned*)(P.msg + DD_GS_MQ * DD_GS_MSG_BYTES);
     P.full = (unsigned long long*)((char*)P.approx + DD_GS_BLOCK_ROWS * 8 * 2);
     P.empty = P.full + stages;
     P.hfull = P.empty + stages;
     P.hfree = P.hfull + 2;
     P.mfull = P.hfree + 2;
-    P.mfree = P.mfull + 2;
+    P.mfree = P.mfull + DD_GS_MQ;
 }
 
 // quota: work-list entries this producer may claim (even; INT_MAX = until the list is empty).  With the one-triple-
@@ -331,6 +349,7 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
     const int lane = threadIdx.x & 31;
     const int n = V.work_ctl[0];
     int claimed = 0;
+    DD_GS_PROF_DECL
     int st = 0;                  // next ring stage
     unsigned ephase = ~0u;       // bit s: parity to wait for on empty[s] (a fresh barrier passes a wait on parity 1)
     int hb = 0;
@@ -394,7 +413,7 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
                     pidl = b == 0 ? from_rec : (k < np ? V.ptab[(size_t)slotg * V.PT + k] : 0);
                 }
                 // ---- job header + query rows
-                dd_mbar_wait(P.hfree + hb, (hphase >> hb) & 1u);
+                DD_GS_WAIT(2, P.hfree + hb, (hphase >> hb) & 1u);
                 hphase ^= 1u << hb;
                 int* H = P.hdr + hb * DD_GS_HDR_INTS;
                 if (lane == 0) {
@@ -411,7 +430,7 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
                 hb ^= 1;
                 // ---- the block's pages
                 for (int p = 0; p < npg; ++p) {
-                    dd_mbar_wait(P.empty + st, (ephase >> st) & 1u);
+                    DD_GS_WAIT(1, P.empty + st, (ephase >> st) & 1u);
                     ephase ^= 1u << st;
                     const int valid = dd_imin(16, nrows - p * 16);
                     const char* src = dd_page_f16(V, __shfl_sync(0xffffffffu, pidl, p));
@@ -445,6 +464,7 @@ __device__ __forceinline__ void dd_gs_producer(const DDView& V, const DDTripleSm
         P.hdr[hb * DD_GS_HDR_INTS + 5] = DD_GS_STOP;
         dd_mbar_arrive(P.hfull + hb);
     }
+    DD_GS_PROF_FLUSH(0);
 }
 
 template <int SKIP>
@@ -454,10 +474,11 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
     int st = 0, hb = 0, mb = 0;
     unsigned fphase = 0u;        // bit s: parity to wait for on full[s]
     unsigned hphase = 0u;        // hfull[0..1]
-    unsigned mphase = 3u;        // mfree[0..1] (fresh barriers pass)
+    unsigned mphase = ~0u;       // mfree[0..MQ-1] (fresh barriers pass)
     float run0 = -3.0e38f, run1 = -3.0e38f;     // approximate maxima so far of detections 2 tq, 2 tq + 1 (over the group's blocks)
+    DD_GS_PROF_DECL
     for (;;) {
-        dd_mbar_wait(P.hfull + hb, (hphase >> hb) & 1u);
+        DD_GS_WAIT(2, P.hfull + hb, (hphase >> hb) & 1u);
         hphase ^= 1u << hb;
         const int hw = P.hdr[hb * DD_GS_HDR_INTS + lane];      // lane l keeps header word l
         const int flags = __shfl_sync(0xffffffffu, hw, 5);
@@ -467,6 +488,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
                 ((int*)(P.msg + mb * DD_GS_MSG_BYTES))[5] = DD_GS_STOP;
                 dd_mbar_arrive(P.mfull + mb);
             }
+            DD_GS_PROF_FLUSH(4);
             break;
         }
         const int nrows = __shfl_sync(0xffffffffu, hw, 3), nq = __shfl_sync(0xffffffffu, hw, 4);
@@ -483,7 +505,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         const int npg = (nrows + 15) >> 4;
         float mx0 = -3.0e38f, mx1 = -3.0e38f;
         for (int p = 0; p < npg; ++p) {                        // deliberately not unrolled: the loop must stay in the L0 i-cache
-            dd_mbar_wait(P.full + st, (fphase >> st) & 1u);
+            DD_GS_WAIT(1, P.full + st, (fphase >> st) & 1u);
             fphase ^= 1u << st;
             const uint4* pg = (const uint4*)(P.ring + (size_t)st * DD_PAGE_F16_BYTES);
             uint4 ga[4], gb[4];
@@ -535,7 +557,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         const float thr1 = 2 * tq + 1 < nq ? run1 - DD_H_WINDOW - 5.0e-4f : 3.0e38f;
         // ---- candidates -> checker message: every lane re-reads the dots it wrote and appends its own candidates
         // (a shared-memory counter hands out list positions; the order of the list does not matter to a maximum)
-        dd_mbar_wait(P.mfree + mb, (mphase >> mb) & 1u);
+        DD_GS_WAIT(3, P.mfree + mb, (mphase >> mb) & 1u);
         mphase ^= 1u << mb;
         int* M = (int*)(P.msg + mb * DD_GS_MSG_BYTES);
         unsigned short* mc = (unsigned short*)(M + DD_GS_HDR_INTS);
@@ -555,7 +577,7 @@ __device__ __forceinline__ void dd_gs_mma(const DDTripleSmem& P, int stages) {
         }
         __syncwarp();
         if (lane == 0) dd_mbar_arrive(P.mfull + mb);
-        mb ^= 1;
+        mb = mb + 1 == DD_GS_MQ ? 0 : mb + 1;
     }
 }
 
@@ -565,14 +587,15 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
     int mb = 0;
     unsigned mphase = 0u;
     float best = -3.0e38f;       // lane n: exact maximum of detection n of the current group
+    DD_GS_PROF_DECL
     for (;;) {
-        dd_mbar_wait(P.mfull + mb, (mphase >> mb) & 1u);
+        DD_GS_WAIT(1, P.mfull + mb, (mphase >> mb) & 1u);
         mphase ^= 1u << mb;
         const int* M = (const int*)(P.msg + mb * DD_GS_MSG_BYTES);
         const unsigned short* mc = (const unsigned short*)(M + DD_GS_HDR_INTS);
         const int hw = M[lane];
         const int flags = __shfl_sync(0xffffffffu, hw, 5);
-        if (flags & DD_GS_STOP) break;
+        if (flags & DD_GS_STOP) { DD_GS_PROF_FLUSH(8); break; }
         const int slotg = __shfl_sync(0xffffffffu, hw, 0), s = __shfl_sync(0xffffffffu, hw, 1);
         const int nq = __shfl_sync(0xffffffffu, hw, 4), listed = __shfl_sync(0xffffffffu, hw, 6);
         // more candidates than a message holds: every (row, detection) of the block is evaluated exactly instead
@@ -631,7 +654,7 @@ __device__ __forceinline__ void dd_gs_checker(const DDView& V, const DDTripleSme
         if ((flags & DD_GS_LAST) && lane < nq) V.cost[(size_t)slotg * V.D + dmine] = dd_subf(1.0f, best);
         __syncwarp();
         if (lane == 0) dd_mbar_arrive(P.mfree + mb);
-        mb ^= 1;
+        mb = mb + 1 == DD_GS_MQ ? 0 : mb + 1;
     }
 }
 
@@ -645,10 +668,8 @@ __device__ __forceinline__ void dd_gs_body(const DDView& V, int stages, int boun
     dd_gs_carve(smem + (size_t)triple * dd_gs_triple_bytes(stages), stages, P);
     if (role == 0 && (threadIdx.x & 31) == 0) {
         for (int i = 0; i < stages; ++i) { dd_mbar_init(P.full + i, 1); dd_mbar_init(P.empty + i, 1); }
-        for (int i = 0; i < 2; ++i) {
-            dd_mbar_init(P.hfull + i, 1); dd_mbar_init(P.hfree + i, 1);
-            dd_mbar_init(P.mfull + i, 1); dd_mbar_init(P.mfree + i, 1);
-        }
+        for (int i = 0; i < 2; ++i) { dd_mbar_init(P.hfull + i, 1); dd_mbar_init(P.hfree + i, 1); }
+        for (int i = 0; i < DD_GS_MQ; ++i) { dd_mbar_init(P.mfull + i, 1); dd_mbar_init(P.mfree + i, 1); }
         dd_mbar_fence_init();
     }
     __syncthreads();

@@ -532,6 +532,15 @@ extern "C" int dd_gallery_replay(void* state, const dd_tracker_config* cfg, int 
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
+// read (and reset) the role-level cycle counters of the variant kernels: host_out16 u64[16]
+extern "C" int dd_gallery_prof(unsigned long long* host_out16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return DD_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(host_out16, dd_gs_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return DD_ERR_CUDA;
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(dd_gs_prof, z, sizeof(z)) != cudaSuccess) return DD_ERR_CUDA;
+    return DD_OK;
+}
 #endif
 
 int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg) {
