@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--gallery-waves", type=int, default=0)
     ap.add_argument("--gallery-impl", default="default")
     ap.add_argument("--no-turns", action="store_true")
+    ap.add_argument("--host", action="store_true", help="end-to-end ticks from ragged pinned host batches (step_host_packed)")
     a = ap.parse_args()
     S = B.S_PER_GPU
     bt = BatchedTracker(S, B.LABELS, max_tracks=B.TMAX, max_dets=B.DMAX, budget=B.BUDGET, max_age=B.MAX_AGE,
@@ -45,8 +46,15 @@ def main():
         c.v["timeline"][:, :, 1] = 0
     torch.cuda.synchronize()
     t0 = bt.engine_stats()[0]
-    for b in frames:
-        bt.step(b, join=False, reduce=True)
+    if a.host:
+        ids_host = torch.empty((S, B.DMAX), dtype=torch.int32).pin_memory()
+        packed = [bt.pack_host(b) for b in frames]
+        torch.cuda.synchronize()
+        for hb in packed:
+            bt.step_host_packed(hb, ids_host)
+    else:
+        for b in frames:
+            bt.step(b, join=False, reduce=True)
     bt.join()
     torch.cuda.synchronize()
     tl = [c.v["timeline"].cpu().numpy() for c in bt.chunks]

@@ -44,8 +44,10 @@ struct Chunk {
     void* state = nullptr;
     dd_tracker_config cfg;
     int lo = 0, n = 0;
-    cudaStream_t st = nullptr, copy_st = nullptr;
-    cudaEvent_t done = nullptr, copied = nullptr, unpacked[2] = {nullptr, nullptr}, gal_done = nullptr;
+    cudaStream_t st = nullptr, copy_st = nullptr, copy_st2 = nullptr, d2h_st = nullptr;
+    cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, unpacked[2] = {nullptr, nullptr}, gal_done = nullptr;
+    cudaEvent_t tick_end = nullptr, d2h_done = nullptr;      // the det -> track ids leave on their own stream
+    bool d2h_valid = false;
     bool unpacked_valid[2] = {false, false};
     // captured pieces of a tick, [ragged][reduce][piece]: 0 = everything (or, with gallery turns, the kernels before the
     // gallery stream), 1 = the gallery stream, 2 = the kernels behind it
@@ -142,6 +144,10 @@ int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce
     if (rc != DD_OK) return rc;
     cudaGraphExec_t* g = c.graph[ragged][reduce];
     DDTickArgs* dst = (DDTickArgs*)((char*)c.state + dd_tick_args_offset(&c.cfg));
+    if (c.d2h_valid) {                       // the previous tick's ids must have left before this tick's matching rewrites them
+        DD_CU(cudaStreamWaitEvent(st, c.d2h_done, 0));
+        c.d2h_valid = false;
+    }
     k_set_args<<<1, 32, 0, st>>>(dst, A);
     DD_CU(cudaGetLastError());
     if (ragged) {
@@ -238,6 +244,9 @@ int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracke
         ok = c.cfg.max_dets == E->D && c.cfg.n_labels * 4 == E->C4 &&
              cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.copied, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.copied2, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.tick_end, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.d2h_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.gal_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.unpacked[0], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.unpacked[1], cudaEventDisableTiming) == cudaSuccess &&
@@ -261,7 +270,9 @@ int dd_engine_destroy(void* engine) {
     for (auto& c : E->ch) {
         drop_graphs(c);
         if (c.copy_st) cudaStreamDestroy(c.copy_st);
-        for (cudaEvent_t e : {c.done, c.copied, c.gal_done, c.unpacked[0], c.unpacked[1], c.poll_ev[0], c.poll_ev[1]})
+        if (c.copy_st2) cudaStreamDestroy(c.copy_st2);
+        if (c.d2h_st) cudaStreamDestroy(c.d2h_st);
+        for (cudaEvent_t e : {c.done, c.copied, c.copied2, c.gal_done, c.tick_end, c.d2h_done, c.unpacked[0], c.unpacked[1], c.poll_ev[0], c.poll_ev[1]})
             if (e) cudaEventDestroy(e);
         if (c.poll_host) cudaFreeHost(c.poll_host);
     }
@@ -295,6 +306,8 @@ int dd_engine_bind_host(void* engine, int32_t chunk, void* dev_blob0, void* dev_
     c.blob_cap = blob_capacity;
     c.s_tlwh = det_tlwh; c.s_conf = det_conf; c.s_label = det_label; c.s_count = det_count;
     if (!c.copy_st) DD_CU(cudaStreamCreateWithFlags(&c.copy_st, cudaStreamNonBlocking));
+    if (!c.copy_st2) DD_CU(cudaStreamCreateWithFlags(&c.copy_st2, cudaStreamNonBlocking));
+    if (!c.d2h_st) DD_CU(cudaStreamCreateWithFlags(&c.d2h_st, cudaStreamNonBlocking));
     return DD_OK;
 }
 
@@ -354,11 +367,25 @@ int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint6
     for (int i = 0; i < E->P; ++i) {
         Chunk& c = E->ch[i];
         cudaStream_t st = multi ? c.st : cur;
-        // upload on the chunk's copy stream into the buffer the tick before last has finished reading
-        if (c.unpacked_valid[par]) DD_CU(cudaStreamWaitEvent(c.copy_st, c.unpacked[par], 0));
-        DD_CU(cudaMemcpyAsync(c.dev_blob[par], host_blobs[i], host_blob_bytes[i], cudaMemcpyHostToDevice, c.copy_st));
+        // upload on the chunk's copy streams into the buffer the tick before last has finished reading.  Two halves on
+        // two streams: one DMA stream alone does not saturate the host link on every box (41 vs 54 GB/s measured), and
+        // the chunks' uploads do not otherwise overlap in time
+        const size_t total = (size_t)host_blob_bytes[i];
+        size_t half = total > ((size_t)4 << 20) ? ((total / 2 + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1)) : total;
+        if (half > total) half = total;
+        if (c.unpacked_valid[par]) {
+            DD_CU(cudaStreamWaitEvent(c.copy_st, c.unpacked[par], 0));
+            if (half < total) DD_CU(cudaStreamWaitEvent(c.copy_st2, c.unpacked[par], 0));
+        }
+        DD_CU(cudaMemcpyAsync(c.dev_blob[par], host_blobs[i], half, cudaMemcpyHostToDevice, c.copy_st));
         DD_CU(cudaEventRecord(c.copied, c.copy_st));
         DD_CU(cudaStreamWaitEvent(st, c.copied, 0));
+        if (half < total) {
+            DD_CU(cudaMemcpyAsync(c.dev_blob[par] + half, (const char*)host_blobs[i] + half, total - half, cudaMemcpyHostToDevice,
+                                  c.copy_st2));
+            DD_CU(cudaEventRecord(c.copied2, c.copy_st2));
+            DD_CU(cudaStreamWaitEvent(st, c.copied2, 0));
+        }
         const size_t o = (size_t)c.lo * E->D;
         const int64_t* of = host_offsets4 + 4 * i;
         DDTickArgs A;
@@ -373,8 +400,19 @@ int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint6
         const int rc = launch_tick(*E, c, A, 1, 1, st, c.unpacked[par]);
         if (rc != DD_OK) return rc;
         c.unpacked_valid[par] = true;
-        if (host_out_ids)
-            DD_CU(cudaMemcpyAsync(host_out_ids + o, E->ids + o, (size_t)c.n * E->D * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (host_out_ids) {
+            const size_t nb = (size_t)c.n * E->D * sizeof(int);
+            if (multi) {
+                // off the chunk's stream: the read-back would otherwise sit in the chunk's chain in front of the next tick
+                DD_CU(cudaEventRecord(c.tick_end, st));
+                DD_CU(cudaStreamWaitEvent(c.d2h_st, c.tick_end, 0));
+                DD_CU(cudaMemcpyAsync(host_out_ids + o, E->ids + o, nb, cudaMemcpyDeviceToHost, c.d2h_st));
+                DD_CU(cudaEventRecord(c.d2h_done, c.d2h_st));
+                c.d2h_valid = true;
+            } else {
+                DD_CU(cudaMemcpyAsync(host_out_ids + o, E->ids + o, nb, cudaMemcpyDeviceToHost, st));
+            }
+        }
         if (multi) DD_CU(cudaEventRecord(c.done, st));
     }
     const int rc = sum_partials(*E, par, cur);
@@ -391,6 +429,7 @@ int dd_engine_join(void* engine, void* caller_stream) {
     for (auto& c : E->ch) {
         DD_CU(cudaEventRecord(c.done, c.st));
         DD_CU(cudaStreamWaitEvent(cur, c.done, 0));
+        if (c.d2h_valid) DD_CU(cudaStreamWaitEvent(cur, c.d2h_done, 0));
     }
     if (E->last_sum >= 0) DD_CU(cudaStreamWaitEvent(cur, E->sum_done[E->last_sum], 0));
     return DD_OK;
