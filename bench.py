@@ -404,8 +404,8 @@ def gpu_arm(args):
                     "host_throttled_ms_per_step": e2e_blocked_ms / K, "rank0_cpu_affinity": numa},
             "host_enqueue_ms_per_step": (enq_ms - blocked_ms) / K,
             "host_throttled_ms_per_step": blocked_ms / K,
-            "host_note": "host_enqueue = host time to issue a tick (one call into the native engine: per chunk an argument "
-                         "kernel + one cudaGraphLaunch); host_throttled = time the host was additionally BLOCKED because it "
+            "host_note": "host_enqueue = host time to issue a tick (one call into the native engine: per chunk the prep kernel "
+                         "+ the captured graphs of the rest); host_throttled = time the host was additionally BLOCKED because it "
                          "may not run more than 3 ticks ahead of the device (page-pool polls)",
             "gpu_launches": launches,
             "clocks": clocks,

@@ -701,15 +701,17 @@ class BatchedTracker:
     def check(self):
         """Raise if any stream overflowed its capacities (never silently truncated)."""
         f = self.status()
+        # storage first: once appends are dropped the tracks that got no gallery depend on the order the CTAs reached the
+        # pool, and what follows (spurious new tracks, even a track overflow) is a consequence
+        if f & _lib.FLAG_POOL_EXHAUSTED:
+            raise RuntimeError("gallery page pool exhausted (a feature was not appended); construct the tracker with a "
+                               "larger pool_pages / pool_fraction")
         if f & _lib.FLAG_TRACK_OVERFLOW:
             raise RuntimeError("track capacity exceeded (max_tracks=%d)" % self.max_tracks)
         if f & _lib.FLAG_DET_OVERFLOW:
             raise RuntimeError("detection capacity exceeded (max_dets=%d)" % self.max_dets)
         if f & _lib.FLAG_LSAP_INFEASIBLE:
             raise ValueError("cost matrix is infeasible")
-        if f & _lib.FLAG_POOL_EXHAUSTED:
-            raise RuntimeError("gallery page pool exhausted (a feature was not appended); construct the tracker with a "
-                               "larger pool_pages / pool_fraction")
         if f & _lib.FLAG_GALLERY_OVERFLOW:
             raise RuntimeError("a gallery outgrew its page table (page_cap); call maintain() more often")
         if f & _lib.FLAG_BAD_LABEL:

@@ -5,7 +5,8 @@
 //
 // Why native: the reference's per-frame driver loop is Python (deepdish.py:1245-1262); batched over 1024 streams the
 // tick is 0.5 ms of device time, and 14 launches + a dozen event / stream calls per tick through ctypes cost as much on
-// the host.  Here a tick costs the host one C call: per chunk a 1-CTA argument kernel + one cudaGraphLaunch.
+// the host.  Here a tick costs the host one C call: per chunk one plain kernel launch (detection prep, which carries the tick's inputs) + the
+// captured graph(s) of the rest.
 // A graph's kernel parameters are frozen at capture, so the per-tick inputs (detection arrays, the ragged blob and
 // its section offsets, the output slots) travel through the blob's tick_args words (DDTickArgs, dd_view.h).
 #include <cuda_runtime.h>
@@ -17,6 +18,7 @@
 int dd_capture_tick(void* state, const dd_tracker_config* cfg, int ragged, int reduce, int parts, const double* line,
                     int line_per_stream, cudaStream_t st);
 int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg);
+int dd_launch_prep_publishing(void* state, const dd_tracker_config* cfg, const DDTickArgs* A, cudaStream_t st);
 enum { PART_PREP = 1, PART_GATE = 2, PART_GALLERY = 4, PART_POST = 8, PART_TAIL = 16 };      // DD_PART_* of dd_tracker.cu
 size_t dd_tick_args_offset(const dd_tracker_config* cfg);
 
@@ -24,10 +26,6 @@ size_t dd_tick_args_offset(const dd_tracker_config* cfg);
 
 #include <chrono>
 extern "C" int dd_engine_destroy(void* engine);
-
-__global__ void k_set_args(DDTickArgs* dst, const DDTickArgs a) {
-    if (threadIdx.x == 0) *dst = a;
-}
 
 // total[e] = sum over chunks of partial[c][e]
 __global__ void k_sum_partials(const long long* __restrict__ partial, int n_chunks, int n, long long* __restrict__ total) {
@@ -78,7 +76,7 @@ struct Engine {
     long long *partial = nullptr, *total = nullptr;
     int* ids = nullptr;
     long long tick = 0;
-    long long launches = 0;          // kernels launched through graphs + argument kernels (bench.py's gpu_launches)
+    long long launches = 0;          // kernels launched: prep kernels + graph nodes + count summations (bench.py gpu_launches)
     double blocked_ms = 0.0;         // host time spent waiting on the run-ahead throttle (pool polls)
 };
 
@@ -123,17 +121,16 @@ int ensure_graphs(Engine& E, Chunk& c, int ragged, int reduce) {
     if (g[0]) return DD_OK;
     static bool carve_set = false;       // see dd_tick_prepare: every kernel of the tick asks for the maximum carve-out
     if (!carve_set) {
-        cudaFuncSetAttribute(k_set_args, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_sum_partials, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carve_set = true;
     }
     int rc = dd_tick_prepare_host(c.state, &c.cfg);        // function attributes: outside the capture
     if (rc != DD_OK) return rc;
-    const int prep = ragged ? 0 : PART_PREP;               // a ragged tick's prep kernel runs in front of the graphs
-    if (!E.turns) return capture_piece(E, c, ragged, reduce, prep | PART_GATE | PART_GALLERY | PART_POST | PART_TAIL, &g[0]);
+    // the detection-prep kernel runs in front of the graphs (launch_tick): it carries the tick's arguments by value
+    if (!E.turns) return capture_piece(E, c, ragged, reduce, PART_GATE | PART_GALLERY | PART_POST | PART_TAIL, &g[0]);
     rc = capture_piece(E, c, ragged, reduce, PART_GALLERY, &g[1]);
     if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, PART_POST | PART_TAIL, &g[2]);
-    if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, prep | PART_GATE, &g[0]);
+    if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, PART_GATE, &g[0]);
     return rc;
 }
 
@@ -143,19 +140,15 @@ int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce
     int rc = ensure_graphs(E, c, ragged, reduce);
     if (rc != DD_OK) return rc;
     cudaGraphExec_t* g = c.graph[ragged][reduce];
-    DDTickArgs* dst = (DDTickArgs*)((char*)c.state + dd_tick_args_offset(&c.cfg));
     if (c.d2h_valid) {                       // the previous tick's ids must have left before this tick's matching rewrites them
         DD_CU(cudaStreamWaitEvent(st, c.d2h_done, 0));
         c.d2h_valid = false;
     }
-    k_set_args<<<1, 32, 0, st>>>(dst, A);
-    DD_CU(cudaGetLastError());
-    if (ragged) {
-        const double* line = E.line + (E.line_per_stream ? (size_t)c.lo * 4 : 0);
-        rc = dd_capture_tick(c.state, &c.cfg, 1, reduce, PART_PREP, line, E.line_per_stream, st);      // plain launch
-        if (rc != DD_OK) return rc;
-        if (consumed) DD_CU(cudaEventRecord(consumed, st));
-    }
+    // the first kernel of the tick is launched plainly with the tick's arguments by value; it publishes them into the
+    // blob's tick_args words, from which the captured kernels behind it read (a graph's parameters are frozen)
+    rc = dd_launch_prep_publishing(c.state, &c.cfg, &A, st);
+    if (rc != DD_OK) return rc;
+    if (ragged && consumed) DD_CU(cudaEventRecord(consumed, st));
     DD_CU(cudaGraphLaunch(g[0], st));
     if (E.turns) {
         // the gallery stream is the HBM-bound kernel: two of them side by side gain nothing, and chunks that drift into
@@ -168,7 +161,7 @@ int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce
         E.last_gal = c.gal_done;
         DD_CU(cudaGraphLaunch(g[2], st));
     }
-    E.launches += 8 + (reduce ? 1 : 0);      // argument kernel + the tick's 7 (8) kernels
+    E.launches += 7 + (reduce ? 1 : 0);      // the tick's 7 (8) kernels
     if (E.poll_every > 0 && E.tick % E.poll_every == 0) {
         // the slot written two polls ago is reused: its copy has long completed unless the host runs far ahead
         const int k = c.poll_turn;

@@ -29,7 +29,8 @@
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_prep(const DDView V, const DDTickArgs A) {
-    DDTlScope tl_(V, 0);
+    DDTlScope tl_(V, 0, A.tick);
+    if (A.publish && blockIdx.x == 0 && threadIdx.x == 0) *const_cast<DDTickArgs*>(V.targs) = A;
     const double* __restrict__ det_tlwh = DD_ARG(det_tlwh);
     const float* __restrict__ det_feat = DD_ARG(det_feat);
     const int* __restrict__ det_count = DD_ARG(det_count);
@@ -67,7 +68,8 @@ struct DDRagged {
 
 __global__ void __launch_bounds__(DD_WARPS * 32)
 k_prep_ragged(const DDView V, const DDTickArgs A) {
-    DDTlScope tl_(V, 0);
+    DDTlScope tl_(V, 0, A.tick);
+    if (A.publish && blockIdx.x == 0 && threadIdx.x == 0) *const_cast<DDTickArgs*>(V.targs) = A;
     DDRagged R;
     R.blob = DD_ARG(blob);
     R.off_tlwh = DD_ARG(off_tlwh); R.off_conf = DD_ARG(off_conf); R.off_label = DD_ARG(off_label); R.off_feat = DD_ARG(off_feat);
@@ -488,6 +490,7 @@ static DDTickArgs dd_args_padded(const double* det_tlwh, const float* det_conf, 
     A.off_tlwh = A.off_conf = A.off_label = A.off_feat = 0;
     A.indirect = 0;
     A.tick = 0;
+    A.publish = 0;
     return A;
 }
 
@@ -542,6 +545,15 @@ extern "C" int dd_gallery_prof(unsigned long long* host_out16, void* stream) {
     return DD_OK;
 }
 #endif
+
+// The detection-prep kernel of an engine tick: launched plainly (not captured) with the tick's arguments by value, which
+// it publishes into the blob's tick_args words for the captured kernels behind it.
+int dd_launch_prep_publishing(void* state, const dd_tracker_config* cfg, const DDTickArgs* A, cudaStream_t st) {
+    DDTickArgs a = *A;
+    a.indirect = 0;
+    a.publish = 1;
+    return dd_update_impl(state, cfg, a, st, nullptr, true, DD_PART_PREP);
+}
 
 int dd_tick_prepare_host(void* state, const dd_tracker_config* cfg) {
     DDView V;

@@ -19,6 +19,8 @@ struct DDTickArgs {
     long long off_tlwh, off_conf, off_label, off_feat;
     int indirect;
     int tick;                    // engine tick number (timeline slot)
+    int publish;                 // detection-prep kernel only: copy these arguments into the blob's tick_args words for
+                                 // the captured kernels behind it
 };
 #define DD_ARG(f) (A.indirect ? V.targs->f : A.f)
 // timeline stamps (config.timeline, captured ticks only): kernel k's earliest CTA start / latest CTA end of this tick
@@ -30,7 +32,8 @@ __device__ __forceinline__ unsigned long long dd_globaltimer() {
 #endif
     return t;
 }
-#define DD_TL_SLOT(k) (V.tl + (size_t)(((V.targs->tick & 63) * 8 + (k)) * 2))
+#define DD_TL_SLOT_AT(tick, k) (V.tl + (size_t)((((tick) & 63) * 8 + (k)) * 2))
+#define DD_TL_SLOT(k) DD_TL_SLOT_AT(V.targs->tick, k)
 #define DD_TL_BEGIN(k) do { if (V.tl && threadIdx.x == 0) atomicMin(DD_TL_SLOT(k), dd_globaltimer()); } while (0)
 #define DD_TL_END(k) do { if (V.tl && threadIdx.x == 0) atomicMax(DD_TL_SLOT(k) + 1, dd_globaltimer()); } while (0)
 #endif
@@ -88,8 +91,17 @@ DD_HD int dd_half_chunk_off(int r, int c) {
 struct DDTlScope {
     const DDView& V;
     const int k;
-    __device__ __forceinline__ DDTlScope(const DDView& v, int k_) : V(v), k(k_) { DD_TL_BEGIN(k); }
-    __device__ __forceinline__ ~DDTlScope() { DD_TL_END(k); }
+    int tick;
+    __device__ __forceinline__ DDTlScope(const DDView& v, int k_) : V(v), k(k_), tick(0) {
+        if (V.tl && threadIdx.x == 0) { tick = V.targs->tick; atomicMin(DD_TL_SLOT_AT(tick, k), dd_globaltimer()); }
+    }
+    // the detection-prep kernel publishes the tick's arguments itself: it takes the tick number from its own copy
+    __device__ __forceinline__ DDTlScope(const DDView& v, int k_, int tick_) : V(v), k(k_), tick(tick_) {
+        if (V.tl && threadIdx.x == 0) atomicMin(DD_TL_SLOT_AT(tick, k), dd_globaltimer());
+    }
+    __device__ __forceinline__ ~DDTlScope() {
+        if (V.tl && threadIdx.x == 0) atomicMax(DD_TL_SLOT_AT(tick, k) + 1, dd_globaltimer());
+    }
 };
 #endif
 

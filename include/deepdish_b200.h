@@ -272,8 +272,8 @@ int dd_tracker_status(void* state, const dd_tracker_config* host_cfg, int32_t* h
  * Tick engine: the native executor of the batched per-frame loop (the batched form of the reference's driver loop,
  * deepdish.py:1245-1262 -> Pipeline.process_results :1035-1114 around Tracker.predict / update).  One engine drives
  * the n_chunks trackers ("stream chunks": contiguous blocks of streams with their own state blob and CUDA stream) of
- * one GPU: per chunk and tick ONE captured CUDA graph (the 7-8 kernels of dd_tracker_tick) preceded by a 1-CTA kernel
- * that writes the tick's input pointers into the blob's tick_args words; chunks overlap freely across tick
+ * one GPU: per chunk and tick the detection-prep kernel launched with the tick's inputs by value -- it publishes them into the
+ * blob's tick_args words -- followed by ONE captured CUDA graph of the remaining 6-7 kernels of dd_tracker_tick; chunks overlap freely across tick
  * boundaries; the chunks' partial counters are summed into total_counts on the auxiliary stream.
  * The engine is a HOST object owning only CUDA events / graphs / one capture stream / per-chunk copy streams and 32
  * bytes of pinned memory per chunk; all device buffers stay caller-owned.  Not thread-safe.
@@ -320,7 +320,7 @@ int dd_engine_wait_counts(void* engine, void* caller_stream);
  * and the tick it was taken behind (-1: none yet).  If the newest poll is still in flight and the engine is already
  * max_age_ticks ticks past it, waits for it: the host never runs further ahead than the forecast covers. */
 int dd_engine_pool_latest(void* engine, int32_t chunk, int32_t max_age_ticks, int32_t* host_out4, int64_t* host_out_tick);
-/* Ticks stepped, kernels launched (graph nodes + argument kernels), host milliseconds spent blocked in the run-ahead
+/* Ticks stepped, kernels launched (prep kernels + graph nodes + count summations), host milliseconds spent blocked in the run-ahead
  * throttle.  Any output may be NULL. */
 int dd_engine_stats(void* engine, int64_t* host_out_ticks, int64_t* host_out_launches, double* host_out_blocked_ms);
 

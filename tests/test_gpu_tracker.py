@@ -74,8 +74,12 @@ def test_pool_exhaustion_is_reported_not_silent():
     bt = BatchedTracker(2, LABELS3, max_tracks=32, max_dets=12, budget=40, max_age=30, pool_pages=8, seg_pages=8)
     bt._poll_pool = False                          # no growth: the 8-page pool must run dry
     sc = Scene(2, 10, 12, n_labels=3, seed=5)
+    from deepdish_b200 import _lib
     for _ in range(30):
         bt.step(sc.step().to("cuda"))
+    # which appends are dropped once the pool is dry depends on the order the CTAs reach it, so what follows (ids, even a
+    # track overflow) is not deterministic -- the flag and the error are
+    assert bt.status() & _lib.FLAG_POOL_EXHAUSTED
     with pytest.raises(RuntimeError, match="pool exhausted"):
         bt.check()
 
@@ -315,8 +319,8 @@ def test_engine_counts_launches_and_survives_mode_switches():
         ib = b.step(fr, join=True, reduce=True).cpu().numpy().copy()
         np.testing.assert_array_equal(ia, ib, err_msg="tick %d" % f)
     ticks, launches, blocked = a.engine_stats()
-    assert ticks == 18 and launches == 18 * (2 * 9 + 1) and blocked >= 0.0
-    assert b.engine_stats()[1] == 24 * (9 + 1)
+    assert ticks == 18 and launches == 18 * (2 * 8 + 1) and blocked >= 0.0
+    assert b.engine_stats()[1] == 24 * (8 + 1)
     assert torch.equal(a.reduce_counts(), b.reduce_counts())
     va, vb = a.host_view(["track_id", "state", "hits", "mean"]), b.host_view(["track_id", "state", "hits", "mean"])
     for k in va:
