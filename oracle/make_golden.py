@@ -26,8 +26,8 @@ def scene_checksum(batches):
     return h.hexdigest()
 
 
-def run_reference_tracker(R, batches, labels, budget, max_age, n_init=3, tcap=64):
-    """Reference Tracker + the reference's own Pipeline.process_results on one stream."""
+def run_reference_tracker(R, batches, labels, budget, max_age, n_init=3, tcap=64, stream=0):
+    """Reference Tracker + the reference's own Pipeline.process_results on one stream (`stream` of the batches)."""
     metric = R.deep_sort_nn_matching.NearestNeighborDistanceMetric("cosine", 0.2, budget)
     trk = R.deep_sort_tracker.Tracker(metric, max_iou_distance=0.7, max_age=max_age, n_init=n_init)
     cnt = refload.RefCounter(trk, labels, oc.default_line(640, 480))
@@ -44,7 +44,7 @@ def run_reference_tracker(R, batches, labels, budget, max_age, n_init=3, tcap=64
     track_labels = np.full((F, tcap), -1, np.int32)
     gal_len = np.zeros((F, tcap), np.int32)        # len(metric.samples[track]) after the update (nn_matching.py:137-154)
     for f, b in enumerate(batches):
-        tlwh, conf, lab, feat = b.stream(0)
+        tlwh, conf, lab, feat = b.stream(stream)
         dets = [R.deep_sort_detection.Detection(tlwh[i], labels[lab[i]], conf[i], feat[i])
                 for i in range(len(conf))]
         trk.predict()
@@ -319,6 +319,34 @@ def golden_yolo(R):
     np.savez_compressed(os.path.join(OUT, "yolo.npz"), head=head, wanted=np.array(wanted),
                         names=np.array(names), **out)
     print("yolo.npz", [len(out["tlwh%d" % f]) for f in range(frames)], [len(out["keep%d" % f]) for f in range(frames)])
+
+
+def golden_yolo_full(R, frames=2, na=25200, seed=11):
+    """The reference on a FULL-SIZE head (BASELINE configs[1]: 25200 anchors x 85, ~500 confident rows per frame):
+    YOLOV5.detect_image + the reference's box filter + the reference's NMS.  The 17 MB head is not stored: tests
+    regenerate it from the seed with this module's synth_yolo_head and verify the checksum."""
+    from PIL import Image
+    os.environ["DEEPDISHHOME"] = refload.REFERENCE_ROOT
+    head = synth_yolo_head(np.random.default_rng(seed), frames, na)
+    wanted = ["person", "bicycle", "car", "motorbike"]
+    det = R.tools_yolov5.YOLOV5(wanted_labels=wanted, model_file="synthetic.tflite")
+    names = [det.labels[i] for i in range(80)]
+    img = Image.new("RGB", (640, 480))
+    out = {}
+    for f in range(frames):
+        refload.FakeInterpreter.outputs = [head[f:f + 1]]
+        boxes, labels, scores = det.detect_image(img)
+        ib, kept = ref_box_filter(boxes, labels, scores)
+        sc = np.array(scores, np.float32)[kept]
+        keep = R.deep_sort_preprocessing.non_max_suppression(np.array(ib), 0.6, sc) if len(ib) else []
+        out["fbox%d" % f] = np.asarray(ib, np.float64).reshape(-1, 4)
+        out["fscore%d" % f] = sc
+        out["fcls%d" % f] = np.array([names.index(labels[i]) for i in kept], np.int32)
+        out["keep%d" % f] = np.array(keep, np.int32)
+        assert len(set(sc.tolist())) == len(sc)          # unique scores: numpy's unstable sort order cannot matter
+    np.savez_compressed(os.path.join(OUT, "yolo_full.npz"), frames=frames, na=na, seed=seed, wanted=np.array(wanted),
+                        names=np.array(names), checksum=hashlib.sha256(head.tobytes()).hexdigest(), **out)
+    print("yolo_full.npz", [len(out["fbox%d" % f]) for f in range(frames)], [len(out["keep%d" % f]) for f in range(frames)])
 
 
 def golden_ssd_post(R):
@@ -621,6 +649,25 @@ def golden_yolo3(R):
         print("yolo3.npz (x86 SIMD exp pass)", [len(res["lab%d" % f]) for f in range(frames)])
 
 
+def golden_tracker_multi(R, name="tracker_multi.npz", seed=105, streams=6, n_obj=14, dmax=20, frames=120, budget=30,
+                         max_age=30):
+    """Several cameras: one unmodified reference Tracker + Pipeline.process_results PER STREAM on the streams of one
+    Scene -- what the batched tracker (stream chunks, captured ticks, ragged host batches) must reproduce stream by
+    stream, and whose summed counters the count reduction must equal."""
+    from deepdish_b200.scene import Scene
+    sc = Scene(streams, n_obj, dmax, n_labels=3, seed=seed)
+    batches = [sc.step() for _ in range(frames)]
+    per = [run_reference_tracker(R, batches, LABELS3, budget, max_age, stream=s) for s in range(streams)]
+    out = {k: np.stack([p[k] for p in per]) for k in ("det_ids", "n_tracks", "ids", "states", "tsu", "deleted", "counts",
+                                                       "track_labels")}
+    out["means"] = np.stack([p["means"][-1] for p in per])          # final frame only
+    out["covs"] = np.stack([p["covs"][-1] for p in per])
+    out.update(seed=seed, streams=streams, n_obj=n_obj, dmax=dmax, frames=frames, budget=budget, max_age=max_age,
+               checksum=scene_checksum(batches))
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, "streams", streams, "next ids", out["ids"].max(axis=(1, 2)).tolist(), "counts", out["counts"][:, -1].sum(axis=0).tolist())
+
+
 def golden_unbounded(R):
     """nn_budget=None -- the only way deepdish.py:515-516 ever builds its metric: galleries are never trimmed
     (nn_matching.py:137-154).  820 frames, 6 long-lived objects (no re-spawns): every track is matched ~740 times."""
@@ -656,6 +703,12 @@ def main():
     if os.environ.get("DD_GOLDEN_ONLY") == "nms_ties":
         golden_nms_ties(R)
         return
+    if os.environ.get("DD_GOLDEN_ONLY") == "yolo_full":
+        golden_yolo_full(R)
+        return
+    if os.environ.get("DD_GOLDEN_ONLY") == "multi":
+        golden_tracker_multi(R)
+        return
     golden_tflite_adapter(R)
     golden_framerecords(R)
     golden_patches(R)
@@ -674,6 +727,8 @@ def main():
     golden_tracker(R, "tracker_delcount.npz", seed=103, n_obj=10, dmax=12, frames=240, budget=100, max_age=5,
                    store_inputs=False, clutter_mean=0.0, respawn_prob=0.03)
     golden_unbounded(R)
+    golden_tracker_multi(R)
+    golden_yolo_full(R)
 
 
 if __name__ == "__main__":

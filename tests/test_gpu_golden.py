@@ -208,3 +208,75 @@ def test_kalman_metric_iou_vs_reference_fixture():
     cost = ops.iou_cost(ops._dev(m["trk_tlwh"], torch.float64), torch.ones(len(m["trk_tlwh"]), dtype=torch.int32, device="cuda"),
                         ops._dev(m["det_tlwh"], torch.float64))
     np.testing.assert_array_equal(cost.cpu().numpy(), 1. - m["iou"])
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3])
+def test_batched_tracker_vs_multi_stream_reference_fixture(n_chunks):
+    """Six cameras against six unmodified reference Trackers + Pipeline.process_results (tracker_multi.npz): the batched
+    tracker -- stream chunks on their own CUDA streams, captured ticks through the native engine, alternating between
+    HBM-resident batches and ragged pinned host batches -- reproduces every stream's det->track ids, track lists, states
+    and counters tick by tick, and its count reduction equals the sum of the six reference counters."""
+    from deepdish_b200.batched import BatchedTracker
+    g = goldens.load("tracker_multi.npz")
+    batches = goldens.multi_batches(g)
+    if batches is None:
+        pytest.skip("regenerated inputs do not match the fixture checksum")
+    S, D = int(g["streams"]), int(g["dmax"])
+    bt = BatchedTracker(S, LABELS3, max_tracks=96, max_dets=D, budget=int(g["budget"]), max_age=int(g["max_age"]),
+                        n_chunks=n_chunks)
+    ids_host = torch.empty((S, D), dtype=torch.int32).pin_memory()
+    for f, b in enumerate(batches):
+        if f % 2 == 0:
+            bt.step(b.to("cuda"), join=False, reduce=True)
+            bt.join()
+            got = bt.det_track_id.cpu().numpy()
+        else:
+            bt.step_host_packed(bt.pack_host(b), ids_host)
+            bt.join()
+            torch.cuda.synchronize()
+            got = ids_host.numpy().copy()
+        np.testing.assert_array_equal(bt.total_counts.cpu().numpy(), g["counts"][:, f].sum(axis=0), err_msg="tick %d" % f)
+        v = bt.host_view(["n_tracks", "order", "track_id", "state", "tsu", "n_deleted", "deleted", "counts"])
+        for s in range(S):
+            n = int(b.count[s])
+            assert list(got[s, :n]) == list(g["det_ids"][s, f, :n]), (f, s)
+            nt = int(v["n_tracks"][s]); sl = v["order"][s, :nt]
+            assert nt == int(g["n_tracks"][s, f])
+            assert list(v["track_id"][s, sl]) == list(g["ids"][s, f, :nt])
+            assert list(v["state"][s, sl]) == list(g["states"][s, f, :nt])
+            assert list(v["tsu"][s, sl]) == list(g["tsu"][s, f, :nt])
+            dl = v["deleted"][s, :int(v["n_deleted"][s])]
+            assert list(v["track_id"][s, dl]) == [x for x in g["deleted"][s, f] if x >= 0]
+            np.testing.assert_array_equal(v["counts"][s], g["counts"][s, f])
+    bt.check()
+    vm = bt.host_view(["n_tracks", "order", "mean", "cov"])
+    for s in range(S):
+        nt = int(vm["n_tracks"][s]); sl = vm["order"][s, :nt]
+        np.testing.assert_allclose(vm["mean"][s, sl], g["means"][s, :nt], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(vm["cov"][s, sl], g["covs"][s, :nt], rtol=1e-4, atol=1e-12)
+
+
+def test_yolo_decode_and_nms_full_size_vs_reference_fixture():
+    """BASELINE configs[1] size: [frames, 25200, 85] head through dd_yolo_decode (TMA-staged tiles, fused box filter) and
+    dd_nms against the unmodified reference's detect_image + box filter + NMS (yolo_full.npz): boxes, scores, classes
+    and keep lists bit-exact."""
+    from deepdish_b200 import ops
+    g = goldens.load("yolo_full.npz")
+    head_np = goldens.yolo_full_head(g)
+    if head_np is None:
+        pytest.skip("regenerated head does not match the fixture checksum")
+    names, wanted = list(g["names"]), list(g["wanted"])
+    mask = torch.tensor([1 if n in wanted else 0 for n in names], dtype=torch.uint8, device="cuda")
+    head = torch.from_numpy(head_np).cuda()
+    out = ops.yolo_decode(head, mask, 0.25, (640, 480), (640, 480), ncap=1024)
+    keep, nkeep = ops.nms(out["tlwh"], out["score"], out["count"], 0.6)
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    keep, nkeep = keep.cpu().numpy(), nkeep.cpu().numpy()
+    for f in range(head.shape[0]):
+        n = int(o["count"][f])
+        assert n == len(g["fbox%d" % f]) and n > 200
+        np.testing.assert_array_equal(o["tlwh"][f, :n], g["fbox%d" % f])
+        np.testing.assert_array_equal(o["score"][f, :n], g["fscore%d" % f])
+        np.testing.assert_array_equal(o["cls"][f, :n], g["fcls%d" % f])
+        assert list(keep[f, :nkeep[f]]) == list(g["keep%d" % f])
+    assert int(o["flags"].sum()) == 0
