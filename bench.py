@@ -362,7 +362,7 @@ def gpu_arm(args):
         tick_bytes = 512.0 * (G + Dn + Dn) + 1152.0 * (TC * 1.1) + 44.0 * Dn      # SURVEY 8d B_trk summed over streams
         f32_bytes = 512.0 * G + 512.0 * Dn + 16.0 * TC                            # SURVEY 8d figure for this kernel (f32 rows)
         half = args.gallery_impl != "exact"
-        kname = {"default": "k_gallery_stream", "half_warp": "k_cosine_h", "exact": "k_cosine"}[args.gallery_impl]
+        kname = {"default": "k_gallery_stream", "exact": "k_cosine"}[args.gallery_impl]
         traffic = load_traffic(kname) if WORKLOAD_NAME == "c3" else None
         # bytes the kernel MUST move from HBM: the half page rows of every streamed track (once), the detections' half
         # rows and the work records; the exact re-check (a few f32 rows per track) comes on top and is in `traffic`
@@ -446,8 +446,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C2 / C4 / C5 measurements folded into `configs` (N = 1 only)")
     ap.add_argument("--no-affinity", action="store_true", help="multi-GPU: do not pin each rank to its GPU's CPUs")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"], help="c3 = the metric's configuration (default)")
-    ap.add_argument("--gallery-impl", default="default", choices=["default", "exact", "half_warp"],
-                    help="A/B knob: gallery kernel (all bit-identical): default, exact f32 pass, half pre-pass with per-warp loads")
+    ap.add_argument("--gallery-impl", default="default", choices=["default", "exact"],
+                    help="A/B knob: gallery kernel (bit-identical): default (half pre-pass stream), exact f32 pass")
     ap.add_argument("--cosine-ctas", type=int, default=0, help="A/B knob: CTAs per SM of the persistent gallery kernel")
     ap.add_argument("--gallery-stages", type=int, default=0, help="A/B knob: ring stages per warp pair of the default gallery kernel")
     ap.add_argument("--gallery-waves", type=int, default=0, help="A/B knob: 0 = one persistent gallery CTA per SM (default), W = one warp triple per CTA in W waves")

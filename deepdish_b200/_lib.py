@@ -15,7 +15,7 @@ DD_MAX_SEGS = 16
 PAGE_ROWS, PAGE_F32_BYTES, PAGE_F16_BYTES = 16, 8192, 4096
 FLAG_TRACK_OVERFLOW, FLAG_DET_OVERFLOW, FLAG_LSAP_INFEASIBLE = 1, 2, 4
 FLAG_POOL_EXHAUSTED, FLAG_GALLERY_OVERFLOW, FLAG_BAD_LABEL = 8, 16, 32
-GALLERY_IMPLS = {"default": 0, "exact": 1, "half_warp": 2}
+GALLERY_IMPLS = {"default": 0, "exact": 1}
 
 _i32, _f64, _u64, _vp = ctypes.c_int32, ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p
 

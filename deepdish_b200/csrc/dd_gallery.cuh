@@ -1,8 +1,9 @@
 // dd_gallery.cuh -- the gallery kernels: min cosine distance between the gate-passing detections of a track and the
 // track's feature gallery (nn_matching.py:31-54,78-96 under tracker.py:97-105), over paged galleries.
 //
-//   k_cosine      exact f32 pass, one warp per track index (gallery_impl = 1; defines the result)
-//   k_cosine_h    half-precision pre-pass on tensor cores + exact re-check, per-warp global loads (gallery_impl = 2)
+//   k_cosine          exact f32 pass, one warp per track index (gallery_impl = 1; defines the result)
+//   k_gallery_stream  half-precision pre-pass on tensor cores + exact re-check, as a producer / mma / checker warp
+//                     pipeline over TMA-fed shared-memory rings (gallery_impl = 0, the default)
 //
 // The half pre-pass ("half the bytes, the same bits").  The exact pass is bound by the 512 B per gallery row it must
 // read, so every gallery page has a round-to-nearest HALF shadow (256 B per row) and the kernels stream that:
@@ -13,7 +14,7 @@
 // r* that maximises e satisfies a(r*, n) >= m - 2E, so the exact maximum is the maximum of e over the rows with
 // a >= m - 2E -- typically one or two rows, read from the f32 page and evaluated with exactly the arithmetic of
 // the exact pass.  The cost matrix is therefore bit-identical, whatever the data; only the number of re-checked
-// rows (speed) depends on it.  Galleries longer than DD_H_BLOCK_ROWS are processed block by block with the running
+// rows (speed) depends on it.  Galleries longer than DD_GS_BLOCK_ROWS are processed block by block with the running
 // maximum m' <= m of the blocks so far: the window only gets wider, never wrong.
 // Fragment trick: a dot product does not care about the order of its terms, so lane 4 g + t feeds the mma with the
 // eight consecutive halves of one 16-byte chunk (chunk t + 4 j of rows g and g + 8, j = 0..3) and takes the B operand
@@ -24,7 +25,6 @@
 
 #define DD_WARPS 4
 #define DD_H_WINDOW 2.2e-3f
-#define DD_H_BLOCK_ROWS 256
 
 __global__ void __launch_bounds__(DD_WARPS * 32, 7)
 k_cosine(const DDView V, const DDTickArgs A) {
@@ -43,221 +43,10 @@ __device__ __forceinline__ void dd_mma_f16(float (&c)[4], unsigned a0, unsigned 
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-struct DDHalfSmem {          // per warp
-    float* approx;           // [rows_blk][8]  a(r, n); overwritten with e(r, n) for the re-checked entries
-    unsigned short* cand;    // [rows_blk * 8] re-check list, entry = row << 3 | n
-    float* thr;              // [8]            m - 2E per query
-    int* cj;                 // [8]            detection index of each query column
-};
-__host__ __device__ inline int dd_half_rows_blk(int B) {
-    const int pad = (B + 15) & ~15;
-    return (B > 0 && pad < DD_H_BLOCK_ROWS) ? pad : DD_H_BLOCK_ROWS;
-}
-__host__ __device__ inline size_t dd_half_smem_per_warp(int B) {
-    return (size_t)dd_half_rows_blk(B) * 8 * 6 + 64;
-}
-__device__ __forceinline__ void dd_half_carve(char* mine, int rows_blk, DDHalfSmem& sm) {
-    sm.approx = (float*)mine;
-    sm.cand = (unsigned short*)(mine + (size_t)rows_blk * 8 * 4);
-    sm.thr = (float*)(mine + (size_t)rows_blk * 8 * 6);
-    sm.cj = (int*)(mine + (size_t)rows_blk * 8 * 6 + 32);
-}
-
-// Exact values of the listed (row, query) entries of one gallery block, 4 per round: the exact pass's arithmetic, bit
-// for bit.  mypid: lane i holds the page id of the block's i-th page.  The totals replace the approximate values.
-__device__ __forceinline__ void dd_half_recheck(const WarpG& g, const DDView& V, int s, const DDHalfSmem& sm,
-                                                int ncand, int mypid) {
-    for (int c0 = 0; c0 < ncand; c0 += 4) {
-        float v[4];
-        float4 a[4], q[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int e = sm.cand[dd_imin(c0 + k, ncand - 1)];
-            const int d = sm.cj[e & 7];
-            const int row = e >> 3;
-            const int pid = __shfl_sync(0xffffffffu, mypid, row >> 4);
-            a[k] = dd_page_f32(V, pid)[(size_t)(row & 15) * (DD_FEAT_DIM / 4) + g.lane];
-            q[k] = ((const float4*)(V.det_featn + ((size_t)s * V.D + d) * DD_FEAT_DIM))[g.lane];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float p = dd_fmaf(a[k].x, q[k].x, 0.f);
-            p = dd_fmaf(a[k].y, q[k].y, p);
-            p = dd_fmaf(a[k].z, q[k].z, p);
-            p = dd_fmaf(a[k].w, q[k].w, p);
-            v[k] = p;
-        }
-        int n = 4, o = 16;                          // transposing butterfly, as dd_fold_max
-#pragma unroll
-        for (; n > 1; n >>= 1, o >>= 1) {
-            const bool up = (g.lane & o) != 0;
-            const int half = n >> 1;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-                const float send = up ? v[i] : v[i + half];
-                const float keep = up ? v[i + half] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-            }
-        }
-#pragma unroll
-        for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-        const int k = g.lane >> 3;                  // lane L owns the total of entry c0 + (L >> 3)
-        if ((g.lane & 7) == 0 && c0 + k < ncand) sm.approx[sm.cand[c0 + k]] = v[0];
-    }
-}
-
-// one track index: all its gate-passing detections, 8 at a time
-__device__ __forceinline__ void dd_cosine_track_half(const WarpG& g, const DDView& V, int s, int t,
-                                                     const int* __restrict__ det_count, const DDHalfSmem& sm,
-                                                     int rows_blk) {
-    const int4 dsc = *(const int4*)(V.cdesc + ((size_t)s * V.T + t) * 4);
-    if (dsc.z <= 0) return;
-    const size_t slot = (size_t)s * V.T + dsc.x;
-    const int glen = dsc.y;
-    int nd = det_count[s];
-    if (nd > V.D) nd = V.D;
-    const int gq = g.lane >> 2, tq = g.lane & 3;
-    const int* pt = V.ptab + slot * V.PT;
-    int base = 0;
-    unsigned word = nd > 0 ? V.gate[slot * V.DW] : 0u;
-    for (;;) {
-        // ---- next group of <= 8 gate-passing detections
-        int nq = 0;
-        while (nq < 8) {
-            if (!word) {
-                base += 32;
-                if (base >= nd) break;
-                word = V.gate[slot * V.DW + (base >> 5)];
-                continue;
-            }
-            if (g.lane == 0) sm.cj[nq] = base + dd_ctz(word);
-            ++nq;
-            word &= word - 1;
-        }
-        if (nq == 0) break;
-        __syncwarp();
-        const int myq = gq < nq ? sm.cj[gq] : 0;       // detection whose half row feeds column gq
-        if (glen <= 0) {
-            if (g.lane < nq) V.cost[slot * V.D + sm.cj[g.lane]] = dd_subf(1.0f, -3.0e38f);
-            __syncwarp();
-            continue;
-        }
-        uint4 qb[4];
-        {
-            const uint4* qh = (const uint4*)(V.det_feath + ((size_t)s * V.D + myq) * DD_FEAT_DIM);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) qb[j] = gq < nq ? qh[tq + 4 * j] : make_uint4(0u, 0u, 0u, 0u);
-        }
-        float best = -3.0e38f;                          // lane n < nq: exact maximum of query n so far
-        float run0 = -3.0e38f, run1 = -3.0e38f;         // approximate maxima so far of queries 2 tq, 2 tq + 1
-        for (int row0 = 0; row0 < glen; row0 += rows_blk) {
-            const int nrows = dd_imin(rows_blk, glen - row0);
-            const int nsteps = (nrows + 15) >> 4;       // pages of this block
-            const int mypid = pt[(row0 >> 4) + dd_imin(g.lane, nsteps - 1)];
-            // ---- stream the half pages, one page (16 rows) per step, two steps in flight
-            uint4 ga[2][4], gb[2][4];
-            // rows past the end of the gallery are not loaded (sector-granular: 2 lanes share a 32-byte sector of one row)
-            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int st = 0; st < 2; ++st) {
-                const uint4* pg = (const uint4*)dd_page_f16(V, __shfl_sync(0xffffffffu, mypid, dd_imin(st, nsteps - 1)));
-                const bool va = st * 16 + gq < nrows, vb = st * 16 + gq + 8 < nrows;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ga[st][j] = va ? pg[j * 64 + g.lane] : zero4;
-                    gb[st][j] = vb ? pg[j * 64 + 32 + g.lane] : zero4;
-                }
-            }
-            float mx0 = -3.0e38f, mx1 = -3.0e38f;
-            for (int step = 0; step < nsteps; step += 2) {
-#pragma unroll
-                for (int st = 0; st < 2; ++st) {
-                    const int cur = step + st;
-                    if (cur >= nsteps) break;
-                    float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dd_mma_f16(c, ga[st][j].x, gb[st][j].x, ga[st][j].y, gb[st][j].y, qb[j].x, qb[j].y);
-                        dd_mma_f16(c, ga[st][j].z, gb[st][j].z, ga[st][j].w, gb[st][j].w, qb[j].z, qb[j].w);
-                    }
-                    const int nxt = cur + 2;
-                    if (nxt < nsteps) {
-                        const uint4* pg = (const uint4*)dd_page_f16(V, __shfl_sync(0xffffffffu, mypid, nxt));
-                        const bool va = nxt * 16 + gq < nrows, vb = nxt * 16 + gq + 8 < nrows;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            ga[st][j] = va ? pg[j * 64 + g.lane] : zero4;
-                            gb[st][j] = vb ? pg[j * 64 + 32 + g.lane] : zero4;
-                        }
-                    }
-                    const int ra = cur * 16 + gq, rb = ra + 8;
-                    if (ra >= nrows) { c[0] = -3.0e38f; c[1] = -3.0e38f; }      // rows past the end never win
-                    if (rb >= nrows) { c[2] = -3.0e38f; c[3] = -3.0e38f; }
-                    *(float2*)(sm.approx + ra * 8 + 2 * tq) = make_float2(c[0], c[1]);
-                    *(float2*)(sm.approx + rb * 8 + 2 * tq) = make_float2(c[2], c[3]);
-                    mx0 = fmaxf(mx0, fmaxf(c[0], c[2]));
-                    mx1 = fmaxf(mx1, fmaxf(c[1], c[3]));
-                }
-            }
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
-                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
-            }
-            run0 = fmaxf(run0, mx0);
-            run1 = fmaxf(run1, mx1);
-            if (gq == 0) { sm.thr[2 * tq] = run0 - DD_H_WINDOW; sm.thr[2 * tq + 1] = run1 - DD_H_WINDOW; }
-            __syncwarp();
-            // ---- re-check list: every (row, query) whose approximate dot is within the window of the maximum
-            int ncand = 0;
-            const int total = nsteps * 16 * 8;
-            for (int i0 = 0; i0 < total; i0 += 32) {
-                const int i = i0 + g.lane;
-                const int n = i & 7;
-                const bool p = n < nq && sm.approx[i] >= sm.thr[n];
-                const unsigned m = __ballot_sync(0xffffffffu, p);
-                if (p) sm.cand[ncand + __popc(m & ((1u << g.lane) - 1u))] = (unsigned short)i;
-                ncand += __popc(m);
-            }
-            __syncwarp();
-            dd_half_recheck(g, V, s, sm, ncand, mypid);
-            __syncwarp();
-            if (g.lane < nq) {                              // exact maximum per query over its re-checked rows
-                for (int i = 0; i < ncand; ++i) {
-                    const int e = sm.cand[i];
-                    if ((e & 7) == g.lane) best = fmaxf(best, sm.approx[e]);
-                }
-            }
-            __syncwarp();
-        }
-        if (g.lane < nq) V.cost[slot * V.D + sm.cj[g.lane]] = dd_subf(1.0f, best);
-        __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(DD_WARPS * 32, 4)
-k_cosine_h(const DDView V, const DDTickArgs A) {
-    const int* __restrict__ det_count = DD_ARG(det_count);
-    extern __shared__ __align__(16) char smem[];
-    WarpG g;
-    const int rows_blk = dd_half_rows_blk(V.B);
-    DDHalfSmem sm;
-    dd_half_carve(smem + (size_t)(threadIdx.x >> 5) * dd_half_smem_per_warp(V.B), rows_blk, sm);
-    const int n = V.work_ctl[0];
-    for (;;) {
-        int i = 0;
-        if (g.lane == 0) i = atomicAdd(V.work_ctl + 32, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= n) break;
-        const int w = V.work[i];
-        dd_cosine_track_half(g, V, w / V.T, w % V.T, det_count, sm, rows_blk);
-    }
-}
-
 // ---- k_gallery_stream: the half pre-pass as a three-stage warp pipeline (gallery_impl = 0, the default) -----------
-// The per-warp kernel above keeps its in-flight gallery bytes in registers and serialises, per track, a chain of
-// dependent latencies (claim -> descriptor -> gate word -> queries -> rows ... -> candidate list -> f32 re-check rows).
-// Here every link of that chain is its own warp and the bytes in flight live in shared memory.  A CTA is a set of
+// A per-warp kernel (round 1's k_cosine_h) keeps its in-flight gallery bytes in registers and serialises, per track, a
+// chain of dependent latencies (claim -> descriptor -> gate word -> queries -> rows ... -> candidate list -> f32 re-check
+// rows).  Here every link of that chain is its own warp and the bytes in flight live in shared memory.  A CTA is a set of
 // warp TRIPLES, one CTA per SM:
 //   producer P   walks the work list (self-contained records written by k_gate, claimed two entries ahead) and, for
 //                every job = (track, group of <= 8 gate-passing detections, block of <= 128 gallery rows), posts a job

@@ -329,7 +329,7 @@ static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* t
     int mw = cfg->match_warps;
     if (mw != 1 && mw != 4 && mw != 8) mw = (V.T > 160 || V.D > 160) ? 4 : 1;
     if (mw > 1 && smem + 256 > 227 * 1024) mw = 1;
-    static size_t match_set = 0, cta_set = 0, gsm_set = 0, hsm_set = 0;     // the attributes only ever grow
+    static size_t match_set = 0, cta_set = 0, gsm_set = 0;     // the attributes only ever grow
     // Shared-memory carve-out: an SM's L1 / shared split is fixed by the first CTA that lands on it and cannot change
     // while CTAs are resident.  The driver would give the gallery stream the smallest configuration that holds ONE of
     // its CTAs (196 KB for 170 KB), leaving 25 KB -- one matching warp -- for everything else of the other stream
@@ -338,7 +338,7 @@ static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* t
     if (!carve_set) {
         const int mx = cudaSharedmemCarveoutMaxShared;
         const void* ks[] = {(const void*)k_prep, (const void*)k_prep_ragged, (const void*)k_gate<true>, (const void*)k_gate<false>,
-                            (const void*)k_gallery_stream, (const void*)k_cosine_h, (const void*)k_cosine, (const void*)k_match,
+                            (const void*)k_gallery_stream, (const void*)k_cosine, (const void*)k_match,
                             (const void*)k_match_cta<4>, (const void*)k_match_cta<8>, (const void*)k_apply,
                             (const void*)k_countline, (const void*)k_count_reduce, (const void*)k_predict};
         for (const void* k : ks)
@@ -371,13 +371,6 @@ static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* t
                 return DD_ERR_CUDA;
             gsm_set = gsm;
         }
-    } else if (cfg->gallery_impl == 2) {
-        const size_t hsm = dd_half_smem_per_warp(V.B) * DD_WARPS;
-        if (hsm > 48 * 1024 && hsm > hsm_set) {
-            if (cudaFuncSetAttribute(k_cosine_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm) != cudaSuccess)
-                return DD_ERR_CUDA;
-            hsm_set = hsm;
-        }
     }
     *triples_out = triples; *stages_out = stages; *mw_out = mw;
     return DD_OK;
@@ -394,17 +387,12 @@ static int dd_launch_gallery(const DDView& V, const dd_tracker_config* cfg, cons
         else
             k_gallery_stream<<<dd_sm_count(), triples * 96, dd_gs_triple_bytes(stages) * triples, st>>>(V, stages, 0);
     } else {
-        const int per_sm = cfg->cosine_ctas_per_sm > 0 ? cfg->cosine_ctas_per_sm : 4;
-        long long grid = (long long)dd_sm_count() * per_sm;
-        const long long need = warps_to_blocks((long long)V.S * V.T);
-        if (grid > need) grid = need;
-        k_cosine_h<<<(unsigned)grid, DD_WARPS * 32, dd_half_smem_per_warp(V.B) * DD_WARPS, st>>>(V, A);
+        return DD_ERR_INVALID;
     }
     DD_CHECK_LAUNCH();
     return DD_OK;
 }
 
-// `prepared`: dd_tick_prepare already ran for this (V, cfg) -- the captured path calls it before the capture begins.
 // parts: which kernels of the update to launch (the engine captures a tick in pieces so that it can put events between them)
 #define DD_PART_PREP 1      // detection prep (the only reader of a ragged blob)
 #define DD_PART_GATE 2      // Track.predict + gating + work list

@@ -82,10 +82,10 @@ typedef struct dd_tracker_config {
     int32_t seg_pages;          /* pages per pool segment, a power of two                               */
     int32_t n_segs;             /* segments attached so far, 1..DD_MAX_SEGS (dd_tracker_pool_attach)    */
     /* per-tracker tuning (A/B measurements; 0 = default everywhere) */
-    int32_t gallery_impl;       /* 0 = default (the half-precision producer/consumer stream), 1 = exact f32 pass,
-                                   2 = half pre-pass with per-warp global loads (both bit-identical to 0) */
-    int32_t cosine_ctas_per_sm; /* impl 2: persistent grid = SMs x this (default 4); impl 0: warp triples (producer,
-                                   mma, checker) per SM (default 7; at most 7, 8 with gallery_waves)   */
+    int32_t gallery_impl;       /* 0 = default (the half-precision producer / mma / checker stream), 1 = exact f32
+                                   pass (bit-identical to 0; defines the result)                        */
+    int32_t cosine_ctas_per_sm; /* impl 0: warp triples (producer, mma, checker) per SM (default 7; at most 7, 8 with
+                                   gallery_waves)                                                       */
     int32_t match_warps;        /* matching kernel: 0 = by problem size, 1 / 4 / 8 warps per stream     */
     int32_t gallery_stages;     /* impl 0: 4 KB ring stages per warp triple (default 4)                 */
     int32_t gallery_waves;      /* impl 0: 0 = one persistent CTA per SM holding all the triples (default); W > 0 = one

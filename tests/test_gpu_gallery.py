@@ -48,7 +48,7 @@ def _history(impl, S, nobj, dmax, tmax, budget, frames, seed, feat_noise, big_bo
     ("unbounded_multi_block", dict(S=2, nobj=8, dmax=12, tmax=32, budget=None, frames=340, seed=46, feat_noise=0.01)),
     ("unbounded_identical_rows", dict(S=2, nobj=6, dmax=8, tmax=32, budget=None, frames=300, seed=47, feat_noise=0.0)),
 ])
-@pytest.mark.parametrize("impl", ["default", "half_warp"])
+@pytest.mark.parametrize("impl", ["default"])
 def test_half_prepass_costs_are_bit_identical_to_the_exact_pass(name, kw, impl):
     half = _history(impl, **kw)
     exact = _history("exact", **kw)

@@ -1,4 +1,4 @@
-"""The error bound behind the gallery kernel's half-precision pre-pass (`k_cosine_h`):
+"""The error bound behind the gallery kernel's half-precision pre-pass (`k_gallery_stream`):
 for unit vectors g, q the dot product of their round-to-nearest float16 copies, accumulated in float32, differs from
 the float32 dot product by at most E = 1.1e-3, so the row with the largest exact dot always lies within 2E of the
 largest approximate dot.  Checked here on random galleries, on vectors built to make every rounding error push the
