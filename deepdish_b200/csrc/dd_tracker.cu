@@ -22,8 +22,8 @@
 #define DD_MATCH_MIN_CTAS 24     // <= 80 registers: a matching warp must fit beside the gallery stream of another chunk
 #endif
 #ifndef DD_APPLY_MIN_CTAS
-#define DD_APPLY_MIN_CTAS 10     // <= 96 registers (88 bytes of spills): an apply warp must fit into what a register-file
-#endif                           // partition has left beside five gallery warps of another chunk
+#define DD_APPLY_MIN_CTAS 8      // <= 128 registers, no spills: an apply warp (4 K registers) must fit into what a
+#endif                           // register-file partition has left beside five 72-register gallery warps of another chunk
 #define DD_SUB 8
 #define DD_ITEMS_PER_CTA (DD_WARPS * 32 / DD_SUB)
 
@@ -97,8 +97,16 @@ k_prep_ragged(const DDView V, const DDTickArgs A) {
     dd_prep_det_at(g, V, s, d, box, (const float*)(R.blob + R.off_feat) + src * DD_FEAT_DIM);
 }
 
+#ifndef DD_GATE_MIN_CTAS
+#define DD_GATE_MIN_CTAS 8      // 64 registers, no spills: 32 warps per SM instead of 28 (the kernel is bound by f64 dependency latency)
+#endif
+#if DD_GATE_MIN_CTAS > 0
+#define DD_GATE_BOUNDS __launch_bounds__(DD_WARPS * 32, DD_GATE_MIN_CTAS)
+#else
+#define DD_GATE_BOUNDS __launch_bounds__(DD_WARPS * 32)
+#endif
 template <bool PREDICT>
-__global__ void __launch_bounds__(DD_WARPS * 32)
+__global__ void DD_GATE_BOUNDS
 k_gate(const DDView V, const DDTickArgs A) {
     DDTlScope tl_(V, 1);
     const int* __restrict__ det_count = DD_ARG(det_count);
@@ -181,8 +189,8 @@ k_match_cta(const DDView V, const DDTickArgs A) {
     dd_match_stream(g, V, blockIdx.x, DD_ARG(det_tlwh), DD_ARG(det_count), DD_ARG(out_ids), smem + 256);
 }
 
-// 64-thread CTAs: at ~150 registers per thread a 128-thread CTA would not fit beside the persistent gallery CTA of
-// another chunk (672 threads x 80 registers leave 11.7 K of the SM's 64 K) and the whole kernel would wait for it.
+// 64-thread CTAs at <= 128 registers: at ~150 registers per thread a warp would not fit into any register-file
+// partition beside the persistent gallery CTA of another chunk, and the whole kernel would wait for it to drain.
 #define DD_APPLY_WARPS 2
 #define DD_APPLY_ITEMS (DD_APPLY_WARPS * 32 / DD_SUB)
 __global__ void __launch_bounds__(DD_APPLY_WARPS * 32, DD_APPLY_MIN_CTAS)
