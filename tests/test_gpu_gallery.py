@@ -44,6 +44,10 @@ def _history(impl, S, nobj, dmax, tmax, budget, frames, seed, feat_noise, big_bo
     # the checker's evaluate-everything fallback runs
     ("identical_rows_many_candidates", dict(S=3, nobj=30, dmax=40, tmax=96, budget=100, frames=115, seed=48,
                                             feat_noise=0.0, big_boxes=True)),
+    # a crowd: more than 16 gate-passing detections per track (three and more jobs per gallery), five gate words, the
+    # four-warp matching kernel
+    ("crowd_many_jobs_per_track", dict(S=2, nobj=70, dmax=144, tmax=192, budget=33, frames=30, seed=49,
+                                      feat_noise=0.05, big_boxes=True)),
     # nn_budget=None: galleries of ~300 rows span several 256-row blocks of the half pre-pass (running maximum)
     ("unbounded_multi_block", dict(S=2, nobj=8, dmax=12, tmax=32, budget=None, frames=340, seed=46, feat_noise=0.01)),
     ("unbounded_identical_rows", dict(S=2, nobj=6, dmax=8, tmax=32, budget=None, frames=300, seed=47, feat_noise=0.0)),
@@ -69,3 +73,5 @@ def test_half_prepass_costs_are_bit_identical_to_the_exact_pass(name, kw, impl):
         assert many > 8
     if name == "identical_rows_many_candidates":
         assert many >= 3
+    if name == "crowd_many_jobs_per_track":
+        assert many > 16
