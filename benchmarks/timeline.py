@@ -44,6 +44,7 @@ def main():
     for c in bt.chunks:
         c.v["timeline"][:, :, 0] = torch.iinfo(torch.int64).max
         c.v["timeline"][:, :, 1] = 0
+        c.v["timeline"][:, 7, 0] = 0          # slot 7: latest k_match CTA start (max), longest single k_match CTA (max)
     torch.cuda.synchronize()
     t0 = bt.engine_stats()[0]
     if a.host:
@@ -76,6 +77,13 @@ def main():
     for k in range(6):
         d = [iv[(t, c, k)][1] - iv[(t, c, k)][0] for t in ticks for c in range(a.chunks)]
         print("%-10s mean %.4f ms  (min %.4f max %.4f)" % (NAMES[k], sum(d) / len(d), min(d), max(d)))
+    late, longest = [], []
+    for t in ticks:
+        for c in range(a.chunks):
+            late.append((int(tl[c][t, 7, 0]) - base) / 1e6 - iv[(t, c, 3)][0])
+            longest.append(int(tl[c][t, 7, 1]) / 1e6)
+    print("k_match: last CTA starts %.4f ms after the first (mean; max %.4f); longest single CTA %.4f ms (mean; max %.4f)"
+          % (sum(late) / len(late), max(late), sum(longest) / len(longest), max(longest)))
     cov = []
     for t in ticks:
         for c in range(a.chunks):

@@ -175,7 +175,15 @@ k_match(const DDView V, const DDTickArgs A) {
     DDTlScope tl_(V, 3);
     extern __shared__ __align__(128) char smem[];
     WarpG g;
+    // timeline slot 7 (config.timeline only): [0] = latest CTA start, [1] = longest single CTA, both relative quantities
+    // that tell a placement delay (CTAs waiting for room on an SM) from a slow-down of the matching itself
+    unsigned long long t0 = 0;
+    if (V.tl && threadIdx.x == 0) t0 = dd_globaltimer();
     dd_match_stream(g, V, blockIdx.x, DD_ARG(det_tlwh), DD_ARG(det_count), DD_ARG(out_ids), smem);
+    if (V.tl && threadIdx.x == 0) {
+        atomicMax(DD_TL_SLOT(7), t0);
+        atomicMax(DD_TL_SLOT(7) + 1, dd_globaltimer() - t0);
+    }
 }
 
 // Crowded scenes (C4: ~260 tracks x ~180 detections per stream): the same matching body run by 4 (or 8) warps of
