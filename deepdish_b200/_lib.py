@@ -144,7 +144,7 @@ def lib():
                              _vp, _i32, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(_vp)],
         "dd_engine_destroy": [_vp],
         "dd_engine_rebind": [_vp, _i32, _vp, cfgp],
-        "dd_engine_bind_host": [_vp, _i32, _vp, _vp, _u64, _vp, _vp, _vp, _vp],
+        "dd_engine_bind_host": [_vp, _i32, ctypes.POINTER(_vp), _i32, _u64, _vp, _vp, _vp, _vp],
         "dd_engine_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
         "dd_engine_step_host": [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_int64), _vp, _vp],
         "dd_engine_join": [_vp, _vp],

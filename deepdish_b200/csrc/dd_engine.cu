@@ -43,15 +43,16 @@ struct Chunk {
     dd_tracker_config cfg;
     int lo = 0, n = 0;
     cudaStream_t st = nullptr, copy_st = nullptr, copy_st2 = nullptr, d2h_st = nullptr;
-    cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, unpacked[2] = {nullptr, nullptr}, gal_done = nullptr;
+    cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, unpacked[4] = {nullptr, nullptr, nullptr, nullptr}, gal_done = nullptr;
     cudaEvent_t tick_end = nullptr, d2h_done = nullptr;      // the det -> track ids leave on their own stream
     bool d2h_valid = false;
-    bool unpacked_valid[2] = {false, false};
+    bool unpacked_valid[4] = {false, false, false, false};
     // captured pieces of a tick, [ragged][reduce][piece]: 0 = everything (or, with gallery turns, the kernels before the
     // gallery stream), 1 = the gallery stream, 2 = the kernels behind it
     cudaGraphExec_t graph[2][2][3] = {};
     // host path (dd_engine_bind_host): double-buffered device blob + the small padded arrays the tick fills
-    unsigned char* dev_blob[2] = {nullptr, nullptr};
+    unsigned char* dev_blob[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_blob = 0;              // upload buffers in rotation (2 .. 4)
     size_t blob_cap = 0;
     double* s_tlwh = nullptr;
     float* s_conf = nullptr;
@@ -243,6 +244,8 @@ int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracke
              cudaEventCreateWithFlags(&c.gal_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.unpacked[0], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.unpacked[1], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.unpacked[2], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.unpacked[3], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.poll_ev[0], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c.poll_ev[1], cudaEventDisableTiming) == cudaSuccess &&
              cudaHostAlloc((void**)&c.poll_host, 8 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
@@ -265,7 +268,7 @@ int dd_engine_destroy(void* engine) {
         if (c.copy_st) cudaStreamDestroy(c.copy_st);
         if (c.copy_st2) cudaStreamDestroy(c.copy_st2);
         if (c.d2h_st) cudaStreamDestroy(c.d2h_st);
-        for (cudaEvent_t e : {c.done, c.copied, c.copied2, c.gal_done, c.tick_end, c.d2h_done, c.unpacked[0], c.unpacked[1], c.poll_ev[0], c.poll_ev[1]})
+        for (cudaEvent_t e : {c.done, c.copied, c.copied2, c.gal_done, c.tick_end, c.d2h_done, c.unpacked[0], c.unpacked[1], c.unpacked[2], c.unpacked[3], c.poll_ev[0], c.poll_ev[1]})
             if (e) cudaEventDestroy(e);
         if (c.poll_host) cudaFreeHost(c.poll_host);
     }
@@ -287,15 +290,17 @@ int dd_engine_rebind(void* engine, int32_t chunk, void* state, const dd_tracker_
     return DD_OK;
 }
 
-int dd_engine_bind_host(void* engine, int32_t chunk, void* dev_blob0, void* dev_blob1, uint64_t blob_capacity,
+int dd_engine_bind_host(void* engine, int32_t chunk, void* const* host_dev_blobs, int32_t n_blobs, uint64_t blob_capacity,
                         double* det_tlwh, float* det_conf, int32_t* det_label, int32_t* det_count) {
     Engine* E = (Engine*)engine;
-    if (!E || chunk < 0 || chunk >= E->P || !dev_blob0 || !dev_blob1 || !det_tlwh || !det_conf || !det_label || !det_count)
+    if (!E || chunk < 0 || chunk >= E->P || !host_dev_blobs || n_blobs < 2 || n_blobs > 4 || !det_tlwh || !det_conf ||
+        !det_label || !det_count)
         return DD_ERR_INVALID;
-    if (((uintptr_t)dev_blob0 & 15) || ((uintptr_t)dev_blob1 & 15)) return DD_ERR_INVALID;
+    for (int k = 0; k < n_blobs; ++k)
+        if (!host_dev_blobs[k] || ((uintptr_t)host_dev_blobs[k] & 15)) return DD_ERR_INVALID;
     Chunk& c = E->ch[chunk];
-    c.dev_blob[0] = (unsigned char*)dev_blob0;
-    c.dev_blob[1] = (unsigned char*)dev_blob1;
+    for (int k = 0; k < n_blobs; ++k) c.dev_blob[k] = (unsigned char*)host_dev_blobs[k];
+    c.n_blob = n_blobs;
     c.blob_cap = blob_capacity;
     c.s_tlwh = det_tlwh; c.s_conf = det_conf; c.s_label = det_label; c.s_count = det_count;
     if (!c.copy_st) DD_CU(cudaStreamCreateWithFlags(&c.copy_st, cudaStreamNonBlocking));
@@ -352,7 +357,7 @@ int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint6
     const bool multi = E->P > 1;
     for (int i = 0; i < E->P; ++i) {
         const int64_t* of = host_offsets4 + 4 * i;
-        if (!host_blobs[i] || !E->ch[i].dev_blob[0] || host_blob_bytes[i] > E->ch[i].blob_cap) return DD_ERR_INVALID;
+        if (!host_blobs[i] || E->ch[i].n_blob < 2 || host_blob_bytes[i] > E->ch[i].blob_cap) return DD_ERR_INVALID;
         if ((of[0] & 7) || (of[1] & 3) || (of[2] & 3) || (of[3] & 15)) return DD_ERR_INVALID;
     }
     if (multi && E->sum_valid[par])
@@ -366,15 +371,16 @@ int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint6
         const size_t total = (size_t)host_blob_bytes[i];
         size_t half = total > ((size_t)4 << 20) ? ((total / 2 + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1)) : total;
         if (half > total) half = total;
-        if (c.unpacked_valid[par]) {
-            DD_CU(cudaStreamWaitEvent(c.copy_st, c.unpacked[par], 0));
-            if (half < total) DD_CU(cudaStreamWaitEvent(c.copy_st2, c.unpacked[par], 0));
+        const int bi = (int)(E->tick % c.n_blob);         // upload buffer of this tick: free once the tick n_blob back consumed it
+        if (c.unpacked_valid[bi]) {
+            DD_CU(cudaStreamWaitEvent(c.copy_st, c.unpacked[bi], 0));
+            if (half < total) DD_CU(cudaStreamWaitEvent(c.copy_st2, c.unpacked[bi], 0));
         }
-        DD_CU(cudaMemcpyAsync(c.dev_blob[par], host_blobs[i], half, cudaMemcpyHostToDevice, c.copy_st));
+        DD_CU(cudaMemcpyAsync(c.dev_blob[bi], host_blobs[i], half, cudaMemcpyHostToDevice, c.copy_st));
         DD_CU(cudaEventRecord(c.copied, c.copy_st));
         DD_CU(cudaStreamWaitEvent(st, c.copied, 0));
         if (half < total) {
-            DD_CU(cudaMemcpyAsync(c.dev_blob[par] + half, (const char*)host_blobs[i] + half, total - half, cudaMemcpyHostToDevice,
+            DD_CU(cudaMemcpyAsync(c.dev_blob[bi] + half, (const char*)host_blobs[i] + half, total - half, cudaMemcpyHostToDevice,
                                   c.copy_st2));
             DD_CU(cudaEventRecord(c.copied2, c.copy_st2));
             DD_CU(cudaStreamWaitEvent(st, c.copied2, 0));
@@ -385,14 +391,14 @@ int dd_engine_step_host(void* engine, const void* const* host_blobs, const uint6
         A.det_tlwh = c.s_tlwh; A.det_conf = c.s_conf; A.det_label = c.s_label; A.det_feat = nullptr; A.det_count = c.s_count;
         A.out_ids = E->ids + o;
         A.out_counts = E->partial + ((size_t)par * E->P + i) * E->C4;
-        A.blob = c.dev_blob[par];
+        A.blob = c.dev_blob[bi];
         A.off_tlwh = of[0]; A.off_conf = of[1]; A.off_label = of[2]; A.off_feat = of[3];
         A.indirect = 0;
         A.tick = (int)E->tick;
         // only the tick's first kernel reads the blob (later kernels read the small padded arrays it fills)
-        const int rc = launch_tick(*E, c, A, 1, 1, st, c.unpacked[par]);
+        const int rc = launch_tick(*E, c, A, 1, 1, st, c.unpacked[bi]);
         if (rc != DD_OK) return rc;
-        c.unpacked_valid[par] = true;
+        c.unpacked_valid[bi] = true;
         if (host_out_ids) {
             const size_t nb = (size_t)c.n * E->D * sizeof(int);
             if (multi) {

@@ -295,10 +295,12 @@ int dd_engine_destroy(void* engine);
 /* A chunk's blob was re-laid out or its pool grew (cfg->n_segs / page_cap / segment pointers changed): its captured
  * graphs are dropped and re-captured at the next tick. */
 int dd_engine_rebind(void* engine, int32_t chunk, void* state, const dd_tracker_config* host_cfg);
-/* Buffers of the end-to-end path of one chunk: two device blobs of blob_capacity bytes (16-byte aligned) the ragged
- * host batches are uploaded into alternately, and the small padded arrays (f64 [n,Dmax,4], f32 [n,Dmax], i32 [n,Dmax],
- * i32 [n]) the tick's first kernel expands box / confidence / label / count into. */
-int dd_engine_bind_host(void* engine, int32_t chunk, void* dev_blob0, void* dev_blob1, uint64_t blob_capacity,
+/* Buffers of the end-to-end path of one chunk: n_blobs (2 .. 4) device blobs of blob_capacity bytes (16-byte aligned;
+ * host_dev_blobs is a HOST array of their device pointers) the ragged host batches are uploaded into in rotation -- the
+ * upload of tick k + n_blobs can start as soon as tick k has consumed its blob, so more buffers decouple the host link
+ * from the device tick --, and the small padded arrays (f64 [n,Dmax,4], f32 [n,Dmax], i32 [n,Dmax], i32 [n]) the
+ * tick's first kernel expands box / confidence / label / count into. */
+int dd_engine_bind_host(void* engine, int32_t chunk, void* const* host_dev_blobs, int32_t n_blobs, uint64_t blob_capacity,
                         double* det_tlwh, float* det_conf, int32_t* det_label, int32_t* det_count);
 /* One tick of every chunk from a padded, HBM-resident batch of all S streams (arrays as dd_tracker_update);
  * det_track_id is written; reduce != 0: counters reduced into total_counts (valid after dd_engine_join).  Only
