@@ -120,10 +120,11 @@ int capture_piece(Engine& E, Chunk& c, int ragged, int reduce, int parts, cudaGr
 int ensure_graphs(Engine& E, Chunk& c, int ragged, int reduce) {
     cudaGraphExec_t* g = c.graph[ragged][reduce];
     if (g[0]) return DD_OK;
-    static bool carve_set = false;       // see dd_tick_prepare: every kernel of the tick asks for the maximum carve-out
-    if (!carve_set) {
+    static bool carve_set[64] = {};      // per device; see dd_tick_prepare: every kernel of the tick asks for the maximum carve-out
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !carve_set[dev]) {
         cudaFuncSetAttribute(k_sum_partials, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carve_set = true;
+        carve_set[dev] = true;
     }
     int rc = dd_tick_prepare_host(c.state, &c.cfg);        // function attributes: outside the capture
     if (rc != DD_OK) return rc;

@@ -345,12 +345,18 @@ static int dd_tick_prepare(const DDView& V, const dd_tracker_config* cfg, int* t
     int mw = cfg->match_warps;
     if (mw != 1 && mw != 4 && mw != 8) mw = (V.T > 160 || V.D > 160) ? 4 : 1;
     if (mw > 1 && smem + 256 > 227 * 1024) mw = 1;
-    static size_t match_set = 0, cta_set = 0, gsm_set = 0;     // the attributes only ever grow
+    // Function attributes belong to a device: the caches below (what has been opted in so far; the attributes only ever
+    // grow) are kept per device, so a process that drives several GPUs sets them on each.
+    struct Opted { size_t match = 0, cta = 0, gsm = 0; bool carve = false; };
+    static Opted opted[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DD_ERR_CUDA;
+    size_t &match_set = opted[dev].match, &cta_set = opted[dev].cta, &gsm_set = opted[dev].gsm;
+    bool& carve_set = opted[dev].carve;
     // Shared-memory carve-out: an SM's L1 / shared split is fixed by the first CTA that lands on it and cannot change
     // while CTAs are resident.  The driver would give the gallery stream the smallest configuration that holds ONE of
     // its CTAs (196 KB for 170 KB), leaving 25 KB -- one matching warp -- for everything else of the other stream
     // chunks.  Every tick kernel therefore asks for the maximum carve-out (228 KB), whichever reaches an idle SM first.
-    static bool carve_set = false;
     if (!carve_set) {
         const int mx = cudaSharedmemCarveoutMaxShared;
         const void* ks[] = {(const void*)k_prep, (const void*)k_prep_ragged, (const void*)k_gate<true>, (const void*)k_gate<false>,

@@ -10,7 +10,8 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous
  *     with respect to the host, outputs are valid after the stream is synchronised;
  *   - return value: DD_OK or a negative DD_ERR_* code; nothing is thrown across the ABI;
- *   - the caller (PyTorch, cudaMalloc, ...) owns every buffer; the library keeps no global state;
+ *   - the caller (PyTorch, cudaMalloc, ...) owns every buffer; the library keeps no state of its own beyond per-device
+ *     caches of the kernel attributes it has opted into (shared-memory sizes, carve-out);
  *   - row-major, densely packed arrays; f64 = double, f32 = float, i32 = int32_t, i64 = int64_t.
  */
 #ifndef DEEPDISH_B200_H
