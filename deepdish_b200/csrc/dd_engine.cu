@@ -133,6 +133,9 @@ int ensure_graphs(Engine& E, Chunk& c, int ragged, int reduce) {
     rc = capture_piece(E, c, ragged, reduce, PART_GALLERY, &g[1]);
     if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, PART_POST | PART_TAIL, &g[2]);
     if (rc == DD_OK) rc = capture_piece(E, c, ragged, reduce, PART_GATE, &g[0]);
+    if (rc != DD_OK)                     // all pieces or none: g[0] is what marks the set as captured
+        for (int k = 0; k < 3; ++k)
+            if (g[k]) { cudaGraphExecDestroy(g[k]); g[k] = nullptr; }
     return rc;
 }
 
