@@ -386,6 +386,7 @@ struct DDMatchSmem {
 // only).  The matching warp's shared memory decides how many streams fit on an SM beside another chunk's gallery
 // stream, so every kilobyte here is occupancy.
 #define DD_CVAL 4       // gate-passing costs per track kept in shared memory (the rest is read from global)
+#define DD_MB 4         // iterations per batch of the matching warp's staging loops (loads first, then stores)
 DD_HD size_t dd_match_union_bytes(int T, int D, int tab_cap) {
     const size_t a = (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4;
     const size_t b = (size_t)tab_cap * 2 * 3;
@@ -557,15 +558,37 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
         const int ndel = V.n_deleted[s];
         for (int k = g.lane; k < ndel; k += G::NL) V.state[sT + V.deleted[sT + k]] = DD_STATE_FREE;
     }
-    for (int t = g.lane; t < nT; t += G::NL) {
-        const int slot = V.order[sT + t];
-        m.trk_slot[t] = (short)slot;
-        m.trk_tsu[t] = (short)V.tsu[sT + slot];
-        m.trk_state[t] = (unsigned char)V.state[sT + slot];
-        m.trk_det[t] = -1;
+    // Staging loops of this function: the compiler cannot move a global load over the shared-memory store of the
+    // iteration before it, so a plain loop pays one memory round trip per iteration -- and this warp is all latency.
+    // They are therefore written in batches of DD_MB iterations: all loads of a batch first, then its stores.
+    for (int t0 = g.lane; t0 < nT; t0 += DD_MB * G::NL) {
+        int slot[DD_MB], tsu[DD_MB], st[DD_MB];
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) slot[u] = t0 + u * G::NL < nT ? V.order[sT + t0 + u * G::NL] : 0;
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) {
+            tsu[u] = V.tsu[sT + slot[u]];
+            st[u] = V.state[sT + slot[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) {
+            const int t = t0 + u * G::NL;
+            if (t >= nT) break;
+            m.trk_slot[t] = (short)slot[u];
+            m.trk_tsu[t] = (short)tsu[u];
+            m.trk_state[t] = (unsigned char)st[u];
+            m.trk_det[t] = -1;
+        }
     }
     for (int d = g.lane; d < nd; d += G::NL) m.undA[d] = (short)d;
-    for (int e = g.lane; e < nd * 4; e += G::NL) m.dbox[e] = det_tlwh[sD * 4 + e];
+    for (int e0 = g.lane; e0 < nd * 4; e0 += DD_MB * G::NL) {
+        double b[DD_MB];
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) b[u] = e0 + u * G::NL < nd * 4 ? det_tlwh[sD * 4 + e0 + u * G::NL] : 0.0;
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u)
+            if (e0 + u * G::NL < nd * 4) m.dbox[e0 + u * G::NL] = b[u];
+    }
     g.sync();
     short *und = m.undA, *und_next = m.undB;
     int nund = nd;
@@ -589,22 +612,48 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
 
     // ---- matching cascade (linear_assignment.py:121-139)
     {
-        for (int e = g.lane; e < nT * V.DW; e += G::NL) {      // stage the gate words (by track index)
-            const int t = e / V.DW, w = e - t * V.DW;
-            m.gate_sm[e] = m.trk_state[t] == DD_STATE_CONFIRMED ? V.gate[(sT + m.trk_slot[t]) * V.DW + w] : 0u;
+        for (int e0 = g.lane; e0 < nT * V.DW; e0 += DD_MB * G::NL) {      // stage the gate words (by track index)
+            unsigned gw[DD_MB];
+#pragma unroll
+            for (int u = 0; u < DD_MB; ++u) {
+                const int e = e0 + u * G::NL;
+                gw[u] = 0u;
+                if (e < nT * V.DW) {
+                    const int t = e / V.DW, w = e - t * V.DW;
+                    if (m.trk_state[t] == DD_STATE_CONFIRMED) gw[u] = V.gate[(sT + m.trk_slot[t]) * V.DW + w];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < DD_MB; ++u)
+                if (e0 + u * G::NL < nT * V.DW) m.gate_sm[e0 + u * G::NL] = gw[u];
         }
         g.sync();
-        for (int e = g.lane; e < nT * DD_CVAL; e += G::NL) {   // stage the first gate-passing costs per track
-            const int t = e / DD_CVAL, k = e - t * DD_CVAL;
-            int seen = 0, d = -1;
-            for (int w = 0; w < V.DW && d < 0; ++w) {
-                unsigned word = m.gate_sm[t * V.DW + w];
-                const int pc = dd_popc(word);
-                if (seen + pc <= k) { seen += pc; continue; }
-                for (int q = seen; q < k; ++q) word &= word - 1;
-                d = w * 32 + dd_ctz(word);
+        for (int e0 = g.lane; e0 < nT * DD_CVAL; e0 += DD_MB * G::NL) {   // stage the first gate-passing costs per track
+            float cv[DD_MB];
+            bool has[DD_MB];
+#pragma unroll
+            for (int u = 0; u < DD_MB; ++u) {
+                const int e = e0 + u * G::NL;
+                has[u] = false;
+                cv[u] = 0.0f;
+                if (e >= nT * DD_CVAL) continue;
+                const int t = e / DD_CVAL, k = e - t * DD_CVAL;
+                int seen = 0, d = -1;
+                for (int w = 0; w < V.DW && d < 0; ++w) {
+                    unsigned word = m.gate_sm[t * V.DW + w];
+                    const int pc = dd_popc(word);
+                    if (seen + pc <= k) { seen += pc; continue; }
+                    for (int q = seen; q < k; ++q) word &= word - 1;
+                    d = w * 32 + dd_ctz(word);
+                }
+                if (d >= 0) {
+                    has[u] = true;
+                    cv[u] = V.cost[(sT + m.trk_slot[t]) * V.D + d];
+                }
             }
-            if (d >= 0) m.cval[e] = V.cost[(sT + m.trk_slot[t]) * V.D + d];
+#pragma unroll
+            for (int u = 0; u < DD_MB; ++u)
+                if (has[u]) m.cval[e0 + u * G::NL] = cv[u];
         }
         g.sync();
         DDCosineCost cc;
@@ -726,46 +775,70 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
         if (out_det_track_id) out_det_track_id[sD + d] = -1;
     }
     g.sync();
-    for (int t = g.lane; t < nT; t += G::NL) {
-        const size_t slot = sT + m.trk_slot[t];
-        const int d = m.trk_det[t];
-        int st = m.trk_state[t];
-        if (d >= 0) {
-            const int hits = V.hits[slot] + 1;
-            V.hits[slot] = hits;
-            V.tsu[slot] = 0;
-            if (st == DD_STATE_TENTATIVE && hits >= V.n_init) st = DD_STATE_CONFIRMED;
-            V.det_kind[sD + d] = 1;
-            V.det_slot[sD + d] = m.trk_slot[t];
-            if (out_det_track_id) out_det_track_id[sD + d] = V.track_id[slot];
-        } else {
-            if (st == DD_STATE_TENTATIVE) st = DD_STATE_DELETED;
-            else if (m.trk_tsu[t] > V.max_age) st = DD_STATE_DELETED;
+    for (int t0 = g.lane; t0 < nT; t0 += DD_MB * G::NL) {
+        int hit[DD_MB], tid[DD_MB];
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) {        // hits and ids of the matched tracks of the batch, loaded together
+            const int t = t0 + u * G::NL;
+            hit[u] = tid[u] = 0;
+            if (t < nT && m.trk_det[t] >= 0) {
+                const size_t slot = sT + m.trk_slot[t];
+                hit[u] = V.hits[slot];
+                tid[u] = V.track_id[slot];
+            }
         }
-        V.state[slot] = st;
-        m.trk_state[t] = (unsigned char)st;
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) {
+            const int t = t0 + u * G::NL;
+            if (t >= nT) break;
+            const size_t slot = sT + m.trk_slot[t];
+            const int d = m.trk_det[t];
+            int st = m.trk_state[t];
+            if (d >= 0) {
+                const int hits = hit[u] + 1;
+                V.hits[slot] = hits;
+                V.tsu[slot] = 0;
+                if (st == DD_STATE_TENTATIVE && hits >= V.n_init) st = DD_STATE_CONFIRMED;
+                V.det_kind[sD + d] = 1;
+                V.det_slot[sD + d] = m.trk_slot[t];
+                if (out_det_track_id) out_det_track_id[sD + d] = tid[u];
+            } else {
+                if (st == DD_STATE_TENTATIVE) st = DD_STATE_DELETED;
+                else if (m.trk_tsu[t] > V.max_age) st = DD_STATE_DELETED;
+            }
+            V.state[slot] = st;
+            m.trk_state[t] = (unsigned char)st;
+        }
     }
     g.sync();
     // free slots in ascending slot order -> lista; a free slot that still holds gallery pages (its track was
     // deleted by the previous update, or dropped by a host edit) returns them to the pool first
     int nfree = 0;
-    for (int base = 0; base < V.T; base += G::NL) {
-        const int k = base + g.lane;
-        const bool p = k < V.T && V.state[sT + k] == DD_STATE_FREE;
-        if (p) {
-            const int np = V.gal_np[sT + k];
-            if (np > 0) {
+    for (int base0 = 0; base0 < V.T; base0 += DD_MB * G::NL) {
+        int sst[DD_MB], snp[DD_MB];
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) {
+            const int k = base0 + u * G::NL + g.lane;
+            sst[u] = k < V.T ? V.state[sT + k] : -1;
+            snp[u] = k < V.T ? V.gal_np[sT + k] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < DD_MB; ++u) {
+            if (base0 + u * G::NL >= V.T) break;
+            const int k = base0 + u * G::NL + g.lane;
+            const bool p = k < V.T && sst[u] == DD_STATE_FREE;
+            if (p && snp[u] > 0) {
                 const int* pt = V.ptab + (sT + k) * V.PT;
-                for (int i = 0; i < np; ++i) dd_page_free(V, pt[i]);
+                for (int i = 0; i < snp[u]; ++i) dd_page_free(V, pt[i]);
                 V.gal_np[sT + k] = 0;
                 V.gal_len[sT + k] = 0;
                 V.gal_pos[sT + k] = 0;
             }
+            int tot;
+            const int pos = g.scan_excl(p, tot);
+            if (p) m.lista[nfree + pos] = (short)k;
+            nfree += tot;
         }
-        int tot;
-        const int pos = g.scan_excl(p, tot);
-        if (p) m.lista[nfree + pos] = (short)k;
-        nfree += tot;
     }
     g.sync();
     int nnew = nund;
