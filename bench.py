@@ -217,7 +217,8 @@ def gpu_arm(args):
 
     P = args.chunks
     knobs = dict(gallery_impl=args.gallery_impl, cosine_ctas_per_sm=args.cosine_ctas, match_warps=args.match_warps,
-                 gallery_stages=args.gallery_stages, gallery_waves=args.gallery_waves, gallery_turns=not args.no_turns)
+                 gallery_stages=args.gallery_stages, gallery_waves=args.gallery_waves, gallery_turns=not args.no_turns,
+                 engine_graphs=not args.no_graphs)
     bt = BatchedTracker(S, LABELS, max_tracks=TMAX, max_dets=DMAX, budget=BUDGET, max_age=MAX_AGE, device=dev,
                         n_chunks=P, **knobs)
     scene = Scene(S, N_OBJECTS, DMAX, n_labels=len(LABELS), seed=1234 + rank, device=dev)
@@ -452,6 +453,7 @@ def main():
     ap.add_argument("--gallery-stages", type=int, default=0, help="A/B knob: ring stages per warp pair of the default gallery kernel")
     ap.add_argument("--gallery-waves", type=int, default=0, help="A/B knob: 0 = one persistent gallery CTA per SM (default), W = one warp triple per CTA in W waves")
     ap.add_argument("--no-turns", action="store_true", help="A/B knob: chunks do not take turns on the gallery stream")
+    ap.add_argument("--no-graphs", action="store_true", help="A/B knob: the engine launches the tick's kernels plainly instead of replaying captured graphs")
     ap.add_argument("--match-warps", type=int, default=0, help="A/B knob: warps per stream in the matching kernel (0 = by size)")
     ap.add_argument("--chunks", type=int, default=2, help="stream chunks pipelined on separate CUDA streams")
     args = ap.parse_args()

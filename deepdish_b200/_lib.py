@@ -143,6 +143,7 @@ def lib():
         "dd_engine_create": [_i32, ctypes.POINTER(_vp), ctypes.POINTER(cfgp), ctypes.POINTER(_i32), ctypes.POINTER(_vp), _vp,
                              _vp, _i32, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(_vp)],
         "dd_engine_destroy": [_vp],
+        "dd_engine_set_graphs": [_vp, _i32],
         "dd_engine_rebind": [_vp, _i32, _vp, cfgp],
         "dd_engine_bind_host": [_vp, _i32, ctypes.POINTER(_vp), _i32, _u64, _vp, _vp, _vp, _vp],
         "dd_engine_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],

@@ -141,7 +141,7 @@ class BatchedTracker:
                  line=None, frame_size=(640, 480), device="cuda", n_chunks=1,
                  pool_pages=None, pool_fraction=0.5, seg_pages=None, page_cap=0,
                  gallery_impl="default", cosine_ctas_per_sm=0, match_warps=0, gallery_stages=0, gallery_waves=0,
-                 timeline=0, gallery_turns=True):
+                 timeline=0, gallery_turns=True, engine_graphs=True):
         """budget=None is the reference's nn_budget=None (deepdish.py:515-516): galleries grow without bound; the
         page pool and the per-slot page tables are grown between ticks (``maintain``).
 
@@ -152,7 +152,7 @@ class BatchedTracker:
         self.pool_pages, self.pool_fraction, self.seg_pages, self.page_cap = pool_pages, pool_fraction, seg_pages, page_cap
         self.gallery_impl, self.cosine_ctas_per_sm, self.match_warps = gallery_impl, cosine_ctas_per_sm, match_warps
         self.gallery_stages, self.gallery_waves = gallery_stages, gallery_waves
-        self.timeline, self.gallery_turns = timeline, gallery_turns
+        self.timeline, self.gallery_turns, self.engine_graphs = timeline, gallery_turns, engine_graphs
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedTracker runs on a CUDA device only (no CPU fallback)")
@@ -213,6 +213,8 @@ class BatchedTracker:
                                                  ctypes.byref(h)),
                        "dd_engine_create")
             self._engine = h
+            if not self.engine_graphs:        # the tick's kernels launched plainly by the engine instead of replayed graphs
+                _lib.check(self.lib.dd_engine_set_graphs(h, 0), "dd_engine_set_graphs")
         return self._engine
 
     def __del__(self):

@@ -67,6 +67,7 @@ struct Chunk {
 struct Engine {
     int P = 0, D = 0, C4 = 0, line_per_stream = 0, poll_every = 0;
     bool turns = false;              // chunks take turns on the gallery stream (see dd_engine_create)
+    bool graphs = true;              // replay captured graphs (dd_engine_set_graphs(0): launch the tick's kernels plainly)
     cudaEvent_t last_gal = nullptr;  // end of the most recently enqueued gallery stream
     std::vector<Chunk> ch;
     cudaStream_t aux = nullptr, cap = nullptr;
@@ -142,9 +143,16 @@ int ensure_graphs(Engine& E, Chunk& c, int ragged, int reduce) {
 // consumed: (ragged ticks) recorded right behind the detection-prep kernel, the only reader of the uploaded blob
 int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce, cudaStream_t st,
                 cudaEvent_t consumed = nullptr) {
-    int rc = ensure_graphs(E, c, ragged, reduce);
+    int rc = E.graphs ? ensure_graphs(E, c, ragged, reduce) : dd_tick_prepare_host(c.state, &c.cfg);
     if (rc != DD_OK) return rc;
     cudaGraphExec_t* g = c.graph[ragged][reduce];
+    const double* line = E.line + (E.line_per_stream ? (size_t)c.lo * 4 : 0);
+    // one piece of the tick behind the prep kernel: its captured graph, or the same kernels launched plainly (they read
+    // the tick's inputs through tick_args either way)
+    auto piece = [&](int k, int parts) -> int {
+        if (E.graphs) return cudaGraphLaunch(g[k], st) == cudaSuccess ? DD_OK : DD_ERR_CUDA;
+        return dd_capture_tick(c.state, &c.cfg, ragged, reduce, parts, line, E.line_per_stream, st);
+    };
     if (c.d2h_valid) {                       // the previous tick's ids must have left before this tick's matching rewrites them
         DD_CU(cudaStreamWaitEvent(st, c.d2h_done, 0));
         c.d2h_valid = false;
@@ -154,17 +162,20 @@ int launch_tick(Engine& E, Chunk& c, const DDTickArgs& A, int ragged, int reduce
     rc = dd_launch_prep_publishing(c.state, &c.cfg, &A, st);
     if (rc != DD_OK) return rc;
     if (ragged && consumed) DD_CU(cudaEventRecord(consumed, st));
-    DD_CU(cudaGraphLaunch(g[0], st));
+    rc = piece(0, E.turns ? PART_GATE : PART_GATE | PART_GALLERY | PART_POST | PART_TAIL);
+    if (rc != DD_OK) return rc;
     if (E.turns) {
         // the gallery stream is the HBM-bound kernel: two of them side by side gain nothing, and chunks that drift into
         // phase run their gallery streams AND their latency-bound kernels at the same time.  So every gallery stream
         // waits for the previously enqueued one (of another chunk): chunks stay in anti-phase, the matching of one runs
         // under the gallery stream of the other.
         if (E.last_gal && E.last_gal != c.gal_done) DD_CU(cudaStreamWaitEvent(st, E.last_gal, 0));
-        DD_CU(cudaGraphLaunch(g[1], st));
+        rc = piece(1, PART_GALLERY);
+        if (rc != DD_OK) return rc;
         DD_CU(cudaEventRecord(c.gal_done, st));
         E.last_gal = c.gal_done;
-        DD_CU(cudaGraphLaunch(g[2], st));
+        rc = piece(2, PART_POST | PART_TAIL);
+        if (rc != DD_OK) return rc;
     }
     E.launches += 7 + (reduce ? 1 : 0);      // the tick's 7 (8) kernels
     if (E.poll_every > 0 && E.tick % E.poll_every == 0) {
@@ -280,6 +291,13 @@ int dd_engine_destroy(void* engine) {
         if (e) cudaEventDestroy(e);
     if (E->cap) cudaStreamDestroy(E->cap);
     delete E;
+    return DD_OK;
+}
+
+int dd_engine_set_graphs(void* engine, int32_t use_graphs) {
+    Engine* E = (Engine*)engine;
+    if (!E) return DD_ERR_INVALID;
+    E->graphs = use_graphs != 0;
     return DD_OK;
 }
 

@@ -293,6 +293,11 @@ int dd_engine_create(int32_t n_chunks, void* const* host_states, const dd_tracke
                      int32_t line_per_stream, int64_t* partial_counts, int64_t* total_counts, int32_t* det_track_id,
                      int32_t poll_every, int32_t gallery_turns, void** host_out_engine);
 int dd_engine_destroy(void* engine);
+/* use_graphs != 0 (the default): the tick's kernels behind the detection-prep kernel are replayed from captured CUDA
+ * graphs; 0: the same kernels are launched plainly from the engine's C++ loop.  Same results, same order on the same
+ * streams; graphs cost the host less per tick, plain launches leave shorter gaps where a tick is cut into several
+ * graphs (gallery_turns).  May be switched between ticks. */
+int dd_engine_set_graphs(void* engine, int32_t use_graphs);
 /* A chunk's blob was re-laid out or its pool grew (cfg->n_segs / page_cap / segment pointers changed): its captured
  * graphs are dropped and re-captured at the next tick. */
 int dd_engine_rebind(void* engine, int32_t chunk, void* state, const dd_tracker_config* host_cfg);

@@ -327,3 +327,29 @@ def test_engine_counts_launches_and_survives_mode_switches():
         np.testing.assert_array_equal(va[k], vb[k], err_msg=k)
     a.check()
     b.check()
+
+
+def test_engine_plain_launches_equal_graph_replay():
+    """dd_engine_set_graphs(0): the engine launches the tick's kernels plainly instead of replaying captured graphs --
+    same kernels, same order, same streams, so ids, counters and state are identical tick by tick."""
+    from deepdish_b200.batched import BatchedTracker
+    S = 6
+    kw = dict(max_tracks=48, max_dets=16, budget=20, max_age=30, n_chunks=2)
+    a = BatchedTracker(S, LABELS3, engine_graphs=False, **kw)
+    b = BatchedTracker(S, LABELS3, **kw)
+    c = BatchedTracker(S, LABELS3, engine_graphs=False, gallery_turns=False, **kw)
+    sc = Scene(S, 10, 16, n_labels=3, seed=11)
+    for f in range(30):
+        fr = sc.step().to("cuda")
+        ia = a.step(fr, join=True, reduce=True).cpu().numpy().copy()
+        ib = b.step(fr, join=True, reduce=True).cpu().numpy().copy()
+        ic = c.step(fr, join=True, reduce=True).cpu().numpy().copy()
+        np.testing.assert_array_equal(ia, ib, err_msg="tick %d" % f)
+        np.testing.assert_array_equal(ic, ib, err_msg="tick %d (no turns)" % f)
+    assert a.engine_stats()[:2] == b.engine_stats()[:2]
+    assert torch.equal(a.reduce_counts(), b.reduce_counts()) and torch.equal(c.reduce_counts(), b.reduce_counts())
+    va, vb = a.host_view(["track_id", "state", "hits", "mean"]), b.host_view(["track_id", "state", "hits", "mean"])
+    for k in va:
+        np.testing.assert_array_equal(va[k], vb[k], err_msg=k)
+    a.check()
+    c.check()
