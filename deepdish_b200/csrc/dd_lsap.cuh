@@ -276,11 +276,20 @@ DD_HD int dd_set_difference_order_serial(const short* a, int na, const unsigned 
 //   (n >> 2) > nm  : set_copy_and_difference -> ascending survivors (caller already has them);
 //   otherwise      : the survivors, in ascending order, are inserted into a fresh set with CPython's
 //                    growth rule and read back in slot order (dd_set_order_from_survivors).
-DD_HD int dd_set_order_from_survivors(const short* surv_asc, int k, short* out, short* bufA, short* bufB) {
+// Only the insertions are inherently serial; dd_set_build_from_survivors does them (one lane) and returns
+// (table << 16) | mask -- table 0: the set lives in bufA, 1: in bufB -- so that a group can read the slots back with an
+// ordered compaction (dd_match_stream).
+DD_HD int dd_set_build_from_survivors(const short* surv_asc, int k, short* bufA, short* bufB) {
     short *R = bufA, *Rt = bufB;
     int maskR = 7, fillR = 0;
     for (int i = 0; i < 8; ++i) R[i] = 0;
     for (int i = 0; i < k; ++i) dd_set_add(R, Rt, maskR, fillR, surv_asc[i]);
+    return ((R == bufA ? 0 : 1) << 16) | maskR;
+}
+DD_HD int dd_set_order_from_survivors(const short* surv_asc, int k, short* out, short* bufA, short* bufB) {
+    const int tm = dd_set_build_from_survivors(surv_asc, k, bufA, bufB);
+    const short* R = (tm >> 16) ? bufB : bufA;
+    const int maskR = tm & 0xffff;
     int n_out = 0;
     for (int i = 0; i <= maskR; ++i)
         if (R[i]) out[n_out++] = (short)(R[i] - 1);

@@ -715,8 +715,21 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
             for (int k = g.lane; k < nsurv; k += G::NL) m.listb[k] = m.rows[k];
             n_unm_a = nsurv;
         } else if (contig) {
-            if (g.lane == 0) n_unm_a = dd_set_order_from_survivors(m.rows, nsurv, m.listb, m.tabA, m.tabB);
-            n_unm_a = g.imax(n_unm_a);
+            // one lane inserts (serial by nature), the group reads the slots back in order
+            int tm = 0;
+            if (g.lane == 0) tm = dd_set_build_from_survivors(m.rows, nsurv, m.tabA, m.tabB);
+            tm = g.imax(tm);
+            g.sync();
+            const short* R = (tm >> 16) ? m.tabB : m.tabA;
+            const int slots = (tm & 0xffff) + 1;
+            for (int base = 0; base < slots; base += G::NL) {
+                const int i = base + g.lane;
+                const int e = i < slots ? R[i] : 0;
+                int tot;
+                const int pos = g.scan_excl(e != 0, tot);
+                if (e) m.listb[n_unm_a + pos] = (short)(e - 1);
+                n_unm_a += tot;
+            }
         } else {
             for (int k = g.lane; k < nT; k += G::NL) m.flag[k] = 0;
             g.sync();
