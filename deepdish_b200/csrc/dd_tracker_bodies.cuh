@@ -385,8 +385,12 @@ struct DDMatchSmem {
 // only), the three CPython-set tables (set-order step between the cascade and the IoU stage) and tbox (IoU stage
 // only).  The matching warp's shared memory decides how many streams fit on an SM beside another chunk's gallery
 // stream, so every kilobyte here is occupancy.
+#ifndef DD_CVAL
 #define DD_CVAL 4       // gate-passing costs per track kept in shared memory (the rest is read from global)
+#endif
+#ifndef DD_MB
 #define DD_MB 4         // iterations per batch of the matching warp's staging loops (loads first, then stores)
+#endif
 DD_HD size_t dd_match_union_bytes(int T, int D, int tab_cap) {
     const size_t a = (size_t)T * ((D + 31) / 32) * 4 + (size_t)T * DD_CVAL * 4;
     const size_t b = (size_t)tab_cap * 2 * 3;
@@ -628,32 +632,28 @@ DD_HD void dd_match_stream(const G& g, const DDView& V, int s, const double* det
                 if (e0 + u * G::NL < nT * V.DW) m.gate_sm[e0 + u * G::NL] = gw[u];
         }
         g.sync();
-        for (int e0 = g.lane; e0 < nT * DD_CVAL; e0 += DD_MB * G::NL) {   // stage the first gate-passing costs per track
-            float cv[DD_MB];
-            bool has[DD_MB];
+        // stage the first DD_CVAL gate-passing costs of every track: one track per lane, a cursor over its gate words,
+        // the (<= DD_CVAL) loads of a track issued together from one 4*D-byte cost row
+        for (int t = g.lane; t < nT; t += G::NL) {
+            const float* crow = V.cost + (sT + m.trk_slot[t]) * V.D;
+            const unsigned* gwp = m.gate_sm + t * V.DW;
+            float cv[DD_CVAL];
+            bool has[DD_CVAL];
+            int w = 0;
+            unsigned word = gwp[0];
 #pragma unroll
-            for (int u = 0; u < DD_MB; ++u) {
-                const int e = e0 + u * G::NL;
-                has[u] = false;
-                cv[u] = 0.0f;
-                if (e >= nT * DD_CVAL) continue;
-                const int t = e / DD_CVAL, k = e - t * DD_CVAL;
-                int seen = 0, d = -1;
-                for (int w = 0; w < V.DW && d < 0; ++w) {
-                    unsigned word = m.gate_sm[t * V.DW + w];
-                    const int pc = dd_popc(word);
-                    if (seen + pc <= k) { seen += pc; continue; }
-                    for (int q = seen; q < k; ++q) word &= word - 1;
-                    d = w * 32 + dd_ctz(word);
-                }
-                if (d >= 0) {
-                    has[u] = true;
-                    cv[u] = V.cost[(sT + m.trk_slot[t]) * V.D + d];
+            for (int k = 0; k < DD_CVAL; ++k) {
+                while (!word && ++w < V.DW) word = gwp[w];
+                has[k] = word != 0u;
+                cv[k] = 0.0f;
+                if (has[k]) {
+                    cv[k] = crow[w * 32 + dd_ctz(word)];
+                    word &= word - 1;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < DD_MB; ++u)
-                if (has[u]) m.cval[e0 + u * G::NL] = cv[u];
+            for (int k = 0; k < DD_CVAL; ++k)
+                if (has[k]) m.cval[t * DD_CVAL + k] = cv[k];
         }
         g.sync();
         DDCosineCost cc;
