@@ -80,6 +80,37 @@ def test_trajectory_parity_host_emulation():
     assert int(ctl[0]) + int(np_.sum()) == int(ctl[1])
 
 
+def test_two_gate_words_host_emulation():
+    """More than 32 detections per stream (two gate words per track) in a dense scene: the matching warp's cost staging
+    walks a cursor across the words, tracks with more than DD_CVAL gate-passing detections read the rest of their costs
+    from the global cost rows, and the unmatched-track set is read back from whichever table the growth left it in."""
+    S = 2
+    cfg = L.make_config(S, 96, 40, 30, LABELS3, max_age=12)
+    emu = hd.HostEmuTracker(cfg)
+    orc = OracleStreams(S, LABELS3, budget=30, max_age=12)
+    sc = Scene(S, 34, 40, n_labels=3, seed=23)
+    many, two_words, checked = 0, 0, 0
+    for f in range(45):
+        b = sc.step()
+        pre = {k: emu.v[k].copy() for k in ("n_tracks", "order", "track_id")}
+        ids = orc.step(b)
+        emu.predict()
+        got = emu.update(b.tlwh.numpy(), b.conf.numpy(), b.label.numpy(), b.feat.numpy(), b.count.numpy())
+        emu.countline()
+        gate = emu.v["gate"].view(np.uint32)
+        pc = np.array([[bin(int(w)).count("1") for w in row] for row in gate.reshape(-1, gate.shape[-1])])
+        many += int((pc.sum(axis=1) > 4).sum())
+        two_words += int((pc[:, 1] > 0).sum())
+        for s in range(S):
+            n = int(b.count[s])
+            assert list(got[s, :n]) == ids[s], (f, s)
+            compare_stream(orc.trk[s], orc.cnt[s], emu.v, s, LABELS3)
+            if f > 5:
+                checked += compare_costs(orc.trk[s], pre, emu.v, s)
+    assert int(emu.v["err"].sum()) == 0 and checked > 500
+    assert many > 0 and two_words > 0, (many, two_words)       # the paths this test is for were taken
+
+
 @pytest.mark.parametrize("budget", [None, 5, 16, 37])
 def test_paged_galleries_host_emulation(budget):
     """nn_budget=None (deepdish.py:515-516: galleries never trimmed, nn_matching.py:137-154) and ring budgets that
